@@ -1,0 +1,80 @@
+"""ctypes binding of the C ABI in include/leco_b200.h.
+
+The product path has NO fallback: if the shared library is missing or a call fails,
+this module raises.  (`python -m leco_b200.build` or `__graft_entry__.build()` builds it.)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_void_p
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libleco_b200.so")
+_lib = None
+
+
+class LecoError(RuntimeError):
+    pass
+
+
+class GemmArgs(Structure):
+    _fields_ = [
+        ("a", c_void_p), ("b", c_void_p), ("d", c_void_p),
+        ("mode", c_int32), ("M", c_int32), ("N", c_int32), ("K", c_int32),
+        ("lda", c_int64), ("ldb", c_int64), ("ldd", c_int64),
+        ("batch0", c_int32), ("batch1", c_int32),
+        ("a_bs0", c_int64), ("a_bs1", c_int64), ("b_bs0", c_int64), ("b_bs1", c_int64),
+        ("d_bs0", c_int64), ("d_bs1", c_int64),
+        ("cn", c_int32), ("ch", c_int32), ("cw", c_int32), ("cc", c_int32),
+        ("a2", c_void_p), ("b2", c_void_p), ("K2", c_int32),
+        ("lda2", c_int64), ("ldb2", c_int64),
+        ("bias", c_void_p), ("rowbias", c_void_p), ("rows_per_group", c_int32),
+        ("ld_rowbias", c_int64),
+        ("residual", c_void_p), ("ldr", c_int64),
+        ("epilogue", c_int32), ("alpha", c_float), ("out_fp32", c_int32), ("block_n", c_int32),
+    ]
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """dlopen the library (works without a GPU: no CUDA call happens at load time)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise LecoError(
+            f"{_LIB_PATH} not built. Run `python -m leco_b200.build` (needs nvcc). "
+            "leco_b200 has no CPU / PyTorch fallback path.")
+    lib = ctypes.CDLL(_LIB_PATH)
+    lib.leco_last_error.restype = c_char_p
+    lib.leco_abi_version.restype = c_int32
+    lib.leco_launch_count.restype = c_int64
+    lib.leco_device_info.argtypes = [POINTER(c_int32)] * 3
+    lib.leco_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
+    _declare_ops(lib)
+    _lib = lib
+    return lib
+
+
+# (name, argtypes) of every other entry point; filled in as kernels are added
+_OPS: list[tuple[str, list]] = []
+
+
+def _declare_ops(lib):
+    for name, argtypes in _OPS:
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int32
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().leco_last_error().decode(errors="replace")
+        raise LecoError(f"{what} failed (rc={rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().leco_launch_count())

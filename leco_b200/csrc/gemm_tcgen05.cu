@@ -1,0 +1,491 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D = epi( alpha * ( sum_k A[m,k] B[n,k]  +  sum_k2 A2[m,k2] B2[n,k2] ) )
+//
+// * operands are bf16, K-major; tiles are staged HBM -> smem by TMA (128B swizzle),
+//   multiplied by tcgen05.mma (one elected thread), accumulated in TMEM (fp32) and read
+//   back with tcgen05.ld by four epilogue warps while the next tile's MMAs already run
+//   (two TMEM accumulator stages).
+// * mode 0: plain / batched matrices.  mode 1: implicit-GEMM 3x3 convolution over an NHWC
+//   image: the A tile for filter tap (kh,kw) is ONE 4-D TMA box {64 ch, W, Hb, Nb} at
+//   coordinates (c0, kw-1, h0+kh-1, n0); out-of-image pixels are zero-filled by TMA, so
+//   padding costs nothing and no im2col buffer exists.
+// * the optional second K segment is the LoRA residual of lora.py:102-106: A2 is
+//   scale*lora_down(x) (K2 <= 64), B2 the lora_up weight: one extra UMMA K-step instead
+//   of three extra kernels.
+// * epilogue: bias, per-row-group bias (the ResnetBlock2D time-embedding add), residual
+//   add, GEGLU, bf16 or fp32 store.
+//
+// Roles: warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (TMEM lane quadrant = warp % 4).
+#include <stdio.h>
+
+#include "../../include/leco_b200.h"
+#include "common.cuh"
+
+namespace leco {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;               // 64 bf16 = 128 B = one swizzle row
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int GEMM_THREADS = 256;
+
+struct GemmParams {
+  CUtensorMap tm_a, tm_b, tm_a2, tm_b2;
+  int mode, M, N;
+  int chunks1, ksteps_last1, cin_chunks;
+  int has_seg2, ksteps2;
+  int tiles_m, tiles_n, batch0, batch1;
+  int cn, ch, cw, hb, nb, tiles_per_img, rows_per_tile;
+  void* d;
+  long long ldd, d_bs0, d_bs1;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* rowbias;
+  int rows_per_group;
+  long long ld_rowbias;
+  const __nv_bfloat16* residual;
+  long long ldr;
+  int epilogue;
+  float alpha;
+  int out_fp32;
+  unsigned a_tx_bytes;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 160 ? 5 : 6);
+  // accumulator stage stride in TMEM columns (power of two so a stage never straddles an
+  // alignment boundary): 64 / 128 / 256
+  static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void epi_store_bf16(__nv_bfloat16* dst, const float (&v)[32], int ncols_valid) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (g * 8 < ncols_valid) {
+      uint4 o;
+      o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+      o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+      o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+      o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+      *reinterpret_cast<uint4*>(dst + g * 8) = o;
+    }
+  }
+}
+__device__ __forceinline__ void epi_store_f32(float* dst, const float (&v)[32], int ncols_valid) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    if (g * 4 < ncols_valid) {
+      *reinterpret_cast<float4*>(dst + g * 4) =
+          make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+    }
+  }
+}
+// v[j] += src[j] for 32 bf16 (16-byte vector loads), guarded in groups of 8 columns
+__device__ __forceinline__ void epi_add_bf16(float (&v)[32], const __nv_bfloat16* src, int ncols_valid) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (g * 8 < ncols_valid) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + g * 8));
+      v[g * 8 + 0] += bf16_lo(q.x);
+      v[g * 8 + 1] += bf16_hi(q.x);
+      v[g * 8 + 2] += bf16_lo(q.y);
+      v[g * 8 + 3] += bf16_hi(q.y);
+      v[g * 8 + 4] += bf16_lo(q.z);
+      v[g * 8 + 5] += bf16_hi(q.z);
+      v[g * 8 + 6] += bf16_lo(q.w);
+      v[g * 8 + 7] += bf16_hi(q.w);
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * STAGES;      // [2]       MMA -> epilogue
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_a);
+    tma_prefetch_desc(&p.tm_b);
+    if (p.has_seg2) {
+      tma_prefetch_desc(&p.tm_a2);
+      tma_prefetch_desc(&p.tm_b2);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int total_tiles = tiles_mn * p.batch0 * p.batch1;
+  const int total_chunks = p.chunks1 + p.has_seg2;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int bidx = tile / tiles_mn;
+      const int rem = tile - bidx * tiles_mn;
+      const int nt = rem / p.tiles_m;
+      const int mt = rem - nt * p.tiles_m;
+      const int b1 = bidx / p.batch0;
+      const int b0 = bidx - b1 * p.batch0;
+      const int n0 = nt * BN;
+      int m0 = mt * BLOCK_M, img_n0 = 0, img_h0 = 0;
+      if (p.mode == 1) {
+        if (p.nb > 1) {
+          img_n0 = mt * p.nb;
+        } else {
+          img_n0 = mt / p.tiles_per_img;
+          img_h0 = (mt - img_n0 * p.tiles_per_img) * p.hb;
+        }
+        m0 = (img_n0 * p.ch + img_h0) * p.cw;
+      }
+      for (int c = 0; c < total_chunks; ++c) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+        uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+        if (c < p.chunks1) {
+          mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes + Cfg::B_STAGE_BYTES);
+          if (p.mode == 0) {
+            tma_load_4d(sa, &p.tm_a, &full_bar[stage], c * BLOCK_K, m0, b0, b1);
+          } else {
+            const int tap = c / p.cin_chunks;
+            const int cc = c - tap * p.cin_chunks;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            tma_load_4d(sa, &p.tm_a, &full_bar[stage], cc * BLOCK_K, kw - 1, img_h0 + kh - 1, img_n0);
+          }
+          tma_load_4d(sb, &p.tm_b, &full_bar[stage], c * BLOCK_K, n0, b0, b1);
+        } else {
+          mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
+          tma_load_4d(sa, &p.tm_a2, &full_bar[stage], 0, m0, 0, 0);
+          tma_load_4d(sb, &p.tm_b2, &full_bar[stage], 0, n0, 0, 0);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // -------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = umma_idesc_bf16_m128(BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
+      for (int c = 0; c < total_chunks; ++c) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const int ksteps = (c < p.chunks1 - 1) ? 4 : (c == p.chunks1 - 1 ? p.ksteps_last1 : p.ksteps2);
+        const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
+        const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
+        for (int j = 0; j < ksteps; ++j) {
+          // +32 bytes (16 bf16) along K inside the 128B swizzle row: +2 in the >>4 address field
+          umma_bf16(tmem_d, da + 2 * j, db + 2 * j, idesc, (c | j) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;                  // TMEM lane quadrant of this warp
+    const int r = q * 32 + lane;             // row inside the tile
+    const bool geglu = (p.epilogue == 1);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int bidx = tile / tiles_mn;
+      const int rem = tile - bidx * tiles_mn;
+      const int nt = rem / p.tiles_m;
+      const int mt = rem - nt * p.tiles_m;
+      const int b1 = bidx / p.batch0;
+      const int b0 = bidx - b1 * p.batch0;
+      const int n0 = nt * BN;
+      long long m;
+      bool row_ok;
+      if (p.mode == 0) {
+        m = static_cast<long long>(mt) * BLOCK_M + r;
+        row_ok = m < p.M;
+      } else {
+        int img_n0 = 0, img_h0 = 0;
+        if (p.nb > 1) {
+          img_n0 = mt * p.nb;
+          row_ok = (r < p.rows_per_tile) && (img_n0 + r / (p.ch * p.cw) < p.cn);
+        } else {
+          img_n0 = mt / p.tiles_per_img;
+          img_h0 = (mt - img_n0 * p.tiles_per_img) * p.hb;
+          row_ok = (r < p.rows_per_tile) && (img_h0 + r / p.cw < p.ch);
+        }
+        m = static_cast<long long>(img_n0 * p.ch + img_h0) * p.cw + r;
+      }
+      const long long boff = b0 * p.d_bs0 + b1 * p.d_bs1;
+
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
+
+      if (!geglu) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t raw[32];
+          tmem_ld_32x32b_x32(trow + c * 32, raw);
+          tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          const int nvalid = p.N - col0;  // may be <= 0 or > 32
+          if (row_ok && nvalid > 0) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+            if (p.bias) epi_add_bf16(v, p.bias + col0, nvalid);
+            if (p.rowbias)
+              epi_add_bf16(v, p.rowbias + (m / p.rows_per_group) * p.ld_rowbias + col0, nvalid);
+            if (p.residual) epi_add_bf16(v, p.residual + boff + m * p.ldr + col0, nvalid);
+            if (p.out_fp32)
+              epi_store_f32(reinterpret_cast<float*>(p.d) + boff + m * p.ldd + col0, v, nvalid);
+            else
+              epi_store_bf16(reinterpret_cast<__nv_bfloat16*>(p.d) + boff + m * p.ldd + col0, v, nvalid);
+          }
+        }
+      } else {
+        // tile columns [0,BN/2) = hidden block, [BN/2,BN) = matching gate block
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          uint32_t rh[32], rg[32];
+          tmem_ld_32x32b_x32(trow + c * 32, rh);
+          tmem_ld_32x32b_x32(trow + BN / 2 + c * 32, rg);
+          tmem_ld_wait();
+          const int ocol0 = nt * (BN / 2) + c * 32;
+          const int nvalid = p.N / 2 - ocol0;
+          if (row_ok && nvalid > 0) {
+            float h[32], g[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              h[j] = __uint_as_float(rh[j]) * p.alpha;
+              g[j] = __uint_as_float(rg[j]) * p.alpha;
+            }
+            if (p.bias) {
+              epi_add_bf16(h, p.bias + n0 + c * 32, 32);
+              epi_add_bf16(g, p.bias + n0 + BN / 2 + c * 32, 32);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h[j] = h[j] * gelu_erf_f(g[j]);
+            epi_store_bf16(reinterpret_cast<__nv_bfloat16*>(p.d) + boff + m * p.ldd + ocol0, h, nvalid);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ host side
+static int pick_block_n(const leco_gemm_args& a, int tiles_m, int batches, int nsm) {
+  if (a.epilogue == 1) return 128;
+  if (a.block_n) return a.block_n;
+  const int cand[4] = {256, 160, 128, 64};
+  const double rate[4] = {1.0, 0.95, 0.9, 0.6};
+  double best = -1;
+  int best_bn = 128;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cand[i];
+    const int tn = (a.N + bn - 1) / bn;
+    const double util_n = double(a.N) / double(tn * bn);  // ragged last tile wastes MMA
+    const long long tiles = 1LL * tiles_m * tn * batches;
+    const long long waves = (tiles + nsm - 1) / nsm;
+    const double eff = double(tiles) / double(waves * nsm);
+    const double score = rate[i] * util_n * eff;
+    if (score > best + 1e-9) {
+      best = score;
+      best_bn = bn;
+    }
+  }
+  return best_bn;
+}
+
+template <int BN>
+static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LECO_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+void count_launch();
+
+}  // namespace leco
+
+extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
+  using namespace leco;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LECO_REQUIRE(a && a->a && a->b && a->d, "leco_gemm_bf16: null operand");
+  LECO_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "leco_gemm_bf16: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+  LECO_REQUIRE(a->N % 8 == 0 && a->K % 16 == 0, "leco_gemm_bf16: N%%8 / K%%16 violated (N=%d K=%d)", a->N, a->K);
+  LECO_REQUIRE(a->ldd % 8 == 0 && a->ldb % 8 == 0, "leco_gemm_bf16: ldd/ldb must be multiples of 8");
+  const int batch0 = a->batch0 > 0 ? a->batch0 : 1, batch1 = a->batch1 > 0 ? a->batch1 : 1;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = a->mode;
+  p.M = a->M;
+  p.N = a->N;
+  p.batch0 = batch0;
+  p.batch1 = batch1;
+  p.chunks1 = (a->K + BLOCK_K - 1) / BLOCK_K;
+  p.ksteps_last1 = ((a->K - 1) % BLOCK_K) / 16 + 1;
+  uint32_t box_a[4] = {BLOCK_K, BLOCK_M, 1, 1};
+  if (a->mode == 0) {
+    LECO_REQUIRE(a->lda % 8 == 0, "leco_gemm_bf16: lda must be a multiple of 8");
+    p.tiles_m = (a->M + BLOCK_M - 1) / BLOCK_M;
+    const uint64_t dims[4] = {(uint64_t)a->K, (uint64_t)a->M, (uint64_t)batch0, (uint64_t)batch1};
+    const uint64_t bs0 = batch0 > 1 ? (uint64_t)a->a_bs0 : (uint64_t)a->lda * a->M;
+    const uint64_t bs1 = batch1 > 1 ? (uint64_t)a->a_bs1 : bs0 * batch0;
+    const uint64_t str[3] = {(uint64_t)a->lda * 2, bs0 * 2, bs1 * 2};
+    if (make_tmap_bf16_4d(&p.tm_a, a->a, dims, str, box_a)) return -3;
+    p.a_tx_bytes = A_STAGE_BYTES;
+  } else if (a->mode == 1) {
+    LECO_REQUIRE(batch0 == 1 && batch1 == 1, "leco_gemm_bf16: conv mode is not batched");
+    LECO_REQUIRE(a->cc % 64 == 0 && a->K == 9 * a->cc, "leco_gemm_bf16: conv needs C%%64==0 and K==9C (C=%d K=%d)", a->cc, a->K);
+    LECO_REQUIRE(a->cw >= 1 && a->cw <= 128 && a->M == a->cn * a->ch * a->cw, "leco_gemm_bf16: conv geometry (n=%d h=%d w=%d M=%d)", a->cn, a->ch, a->cw, a->M);
+    p.cn = a->cn;
+    p.ch = a->ch;
+    p.cw = a->cw;
+    p.cin_chunks = a->cc / 64;
+    p.ksteps_last1 = 4;
+    int hb = 128 / a->cw;
+    if (hb > a->ch) hb = a->ch;
+    int nb = 1;
+    if (hb == a->ch) {
+      nb = 128 / (a->ch * a->cw);
+      if (nb < 1) nb = 1;
+      if (nb > 256) nb = 256;
+    }
+    p.hb = hb;
+    p.nb = nb;
+    p.tiles_per_img = (a->ch + hb - 1) / hb;
+    p.rows_per_tile = a->cw * hb * nb;
+    p.tiles_m = nb > 1 ? (a->cn + nb - 1) / nb : a->cn * p.tiles_per_img;
+    const uint64_t dims[4] = {(uint64_t)a->cc, (uint64_t)a->cw, (uint64_t)a->ch, (uint64_t)a->cn};
+    const uint64_t str[3] = {(uint64_t)a->cc * 2, (uint64_t)a->cc * a->cw * 2, (uint64_t)a->cc * a->cw * a->ch * 2};
+    box_a[1] = a->cw;
+    box_a[2] = hb;
+    box_a[3] = nb;
+    if (make_tmap_bf16_4d(&p.tm_a, a->a, dims, str, box_a)) return -3;
+    p.a_tx_bytes = (unsigned)p.rows_per_tile * BLOCK_K * 2;
+  } else {
+    LECO_REQUIRE(false, "leco_gemm_bf16: unknown mode %d", a->mode);
+  }
+
+  const int nsm = sm_count();
+  const int bn = pick_block_n(*a, p.tiles_m, batch0 * batch1, nsm);
+  LECO_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "leco_gemm_bf16: unsupported block_n %d", bn);
+  if (a->epilogue == 1) LECO_REQUIRE(a->N % 128 == 0 && !a->out_fp32 && !a->residual && !a->rowbias, "leco_gemm_bf16: GEGLU needs N%%128==0, bf16 out, no residual/rowbias");
+  p.tiles_n = (a->N + bn - 1) / bn;
+  {
+    const uint64_t dims[4] = {(uint64_t)a->K, (uint64_t)a->N, (uint64_t)batch0, (uint64_t)batch1};
+    const uint64_t bs0 = batch0 > 1 ? (uint64_t)a->b_bs0 : (uint64_t)a->ldb * a->N;
+    const uint64_t bs1 = batch1 > 1 ? (uint64_t)a->b_bs1 : bs0 * batch0;
+    const uint64_t str[3] = {(uint64_t)a->ldb * 2, bs0 * 2, bs1 * 2};
+    const uint32_t box_b[4] = {BLOCK_K, (uint32_t)bn, 1, 1};
+    if (make_tmap_bf16_4d(&p.tm_b, a->b, dims, str, box_b)) return -3;
+  }
+  if (a->a2) {
+    LECO_REQUIRE(a->b2 && a->K2 > 0 && a->K2 <= 64 && a->K2 % 16 == 0, "leco_gemm_bf16: LoRA segment needs K2 in {16,32,48,64} (K2=%d)", a->K2);
+    LECO_REQUIRE(a->lda2 % 8 == 0 && a->ldb2 % 8 == 0 && batch0 == 1 && batch1 == 1, "leco_gemm_bf16: LoRA segment strides / batching");
+    p.has_seg2 = 1;
+    p.ksteps2 = a->K2 / 16;
+    const uint64_t dims_a[4] = {(uint64_t)a->K2, (uint64_t)a->M, 1, 1};
+    const uint64_t str_a[3] = {(uint64_t)a->lda2 * 2, (uint64_t)a->lda2 * a->M * 2, (uint64_t)a->lda2 * a->M * 2};
+    const uint32_t box2[4] = {BLOCK_K, BLOCK_M, 1, 1};
+    if (make_tmap_bf16_4d(&p.tm_a2, a->a2, dims_a, str_a, box2)) return -3;
+    const uint64_t dims_b[4] = {(uint64_t)a->K2, (uint64_t)a->N, 1, 1};
+    const uint64_t str_b[3] = {(uint64_t)a->ldb2 * 2, (uint64_t)a->ldb2 * a->N * 2, (uint64_t)a->ldb2 * a->N * 2};
+    const uint32_t box_b2[4] = {BLOCK_K, (uint32_t)bn, 1, 1};
+    if (make_tmap_bf16_4d(&p.tm_b2, a->b2, dims_b, str_b, box_b2)) return -3;
+  }
+  p.d = a->d;
+  p.ldd = a->ldd;
+  p.d_bs0 = batch0 > 1 ? a->d_bs0 : 0;
+  p.d_bs1 = batch1 > 1 ? a->d_bs1 : 0;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(a->bias);
+  p.rowbias = reinterpret_cast<const __nv_bfloat16*>(a->rowbias);
+  p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
+  p.ld_rowbias = a->ld_rowbias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+  p.ldr = a->ldr;
+  if (a->residual) LECO_REQUIRE(a->ldr % 8 == 0, "leco_gemm_bf16: ldr must be a multiple of 8");
+  if (a->rowbias) LECO_REQUIRE(a->ld_rowbias % 8 == 0, "leco_gemm_bf16: ld_rowbias must be a multiple of 8");
+  p.epilogue = a->epilogue;
+  p.alpha = a->alpha == 0.0f ? 1.0f : a->alpha;
+  p.out_fp32 = a->out_fp32;
+
+  const long long total_tiles = 1LL * p.tiles_m * p.tiles_n * batch0 * batch1;
+  const int grid = (int)(total_tiles < nsm ? total_tiles : nsm);
+  count_launch();
+  switch (bn) {
+    case 64: return launch_gemm<64>(p, grid, stream);
+    case 128: return launch_gemm<128>(p, grid, stream);
+    case 160: return launch_gemm<160>(p, grid, stream);
+    default: return launch_gemm<256>(p, grid, stream);
+  }
+}

@@ -1,0 +1,227 @@
+"""Generates the committed golden fixtures by running the reference's OWN unmodified code.
+
+Runs only in the build container (needs /root/reference).  What it does:
+  1. imports the reference's lora.py / train_util.py / prompt_util.py / config_util.py /
+     train_lora.py unmodified (a name-only `diffusers` stub is on sys.path; the UNet and
+     scheduler objects the reference drives are the oracle's restatements with seeded
+     synthetic weights, because diffusers / checkpoints do not exist in this sandbox);
+  2. runs train_lora.train() itself on CPU/fp32 for a few iterations (model loading and
+     text encoding are the only things patched out, SURVEY.md §2 marks them out of scope);
+  3. records per-iteration losses, k, the saved .safetensors keys / checksums;
+  4. runs oracle/leco_ref.py on the same seeds and REQUIRES bit-identical results;
+  5. writes tests/golden/*.json.
+
+    python tests/golden/make_golden.py
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import json
+import os
+import sys
+import tempfile
+import zlib
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import leco_ref  # noqa: E402
+from oracle.ref_loader import load_reference  # noqa: E402
+from oracle.sched_ref import create_noise_scheduler  # noqa: E402
+from oracle.unet_ref import CONFIGS, build_unet  # noqa: E402
+
+GOLDEN_DIR = os.path.dirname(os.path.abspath(__file__))
+SEED = 1234
+
+
+def synthetic_embedding(prompt: str, dim: int) -> torch.Tensor:
+    """Stand-in for train_util.encode_prompts (out of scope): N(0,1) [1,77,D] per distinct
+    prompt, seeded by the prompt text."""
+    g = torch.Generator(device="cpu").manual_seed(zlib.crc32(prompt.encode()) & 0x7FFFFFFF)
+    return torch.randn((1, 77, dim), generator=g)
+
+
+def tensor_digest(t: torch.Tensor) -> dict:
+    t = t.detach().to(torch.float64).flatten()
+    return {"n": t.numel(), "sum": float(t.sum()), "abs": float(t.abs().sum()),
+            "head": [float(x) for x in t[:4]]}
+
+
+PROMPTS_YAML = """
+- target: "van gogh"
+  positive: "van gogh"
+  unconditional: ""
+  neutral: ""
+  action: "erase"
+  guidance_scale: 1.0
+  resolution: 128
+  dynamic_resolution: false
+  batch_size: 2
+- target: "cat"
+  positive: "a photo of a cat"
+  unconditional: ""
+  neutral: "animal"
+  action: "enhance"
+  guidance_scale: 1.5
+  resolution: 128
+  batch_size: 1
+"""
+
+CONFIG_YAML = """
+prompts_file: "{prompts}"
+pretrained_model:
+  name_or_path: "synthetic:{arch}"
+  v2: true
+  v_pred: {v_pred}
+network:
+  type: "lierla"
+  rank: 4
+  alpha: 1.0
+  training_method: "full"
+train:
+  precision: "float32"
+  noise_scheduler: "ddim"
+  iterations: {iters}
+  lr: 1e-3
+  optimizer: "AdamW"
+  lr_scheduler: "constant"
+  max_denoising_steps: {max_steps}
+save:
+  name: "golden"
+  path: "{out}"
+  per_steps: 200
+  precision: "float32"
+logging:
+  use_wandb: false
+  verbose: false
+other:
+  use_xformers: false
+"""
+
+
+def run_reference_train(arch: str, iters: int, max_steps: int, v_pred: bool):
+    ref = load_reference()
+    import importlib
+    os.environ.setdefault("WANDB_MODE", "disabled")
+    train_lora = importlib.import_module("train_lora")
+    assert os.path.abspath(train_lora.__file__).startswith("/root/reference")
+    cfg = CONFIGS[arch]
+    unet = build_unet(arch, seed=0)
+
+    class _Dummy:
+        def to(self, *a, **k):
+            return self
+
+        def eval(self):
+            return self
+
+    def fake_load_models(name, scheduler_name, v2=False, v_pred=False, weight_dtype=torch.float32):
+        sched = create_noise_scheduler(scheduler_name, "v_prediction" if v_pred else "epsilon")
+        return _Dummy(), _Dummy(), unet, sched
+
+    def fake_encode(tokenizer, text_encoder, prompts):
+        return torch.cat([synthetic_embedding(p, cfg.cross_attention_dim) for p in prompts])
+
+    losses, ks = [], []
+    orig_loss = ref.prompt_util.PromptEmbedsPair.loss
+
+    def rec_loss(self, **kw):
+        out = orig_loss(self, **kw)
+        losses.append(float(out.item()))
+        return out
+
+    orig_diffusion = ref.train_util.diffusion
+
+    def rec_diffusion(*a, **kw):
+        ks.append(int(kw["total_timesteps"]))
+        return orig_diffusion(*a, **kw)
+
+    with tempfile.TemporaryDirectory() as tmp:
+        pfile = os.path.join(tmp, "prompts.yaml")
+        open(pfile, "w").write(PROMPTS_YAML)
+        cfile = os.path.join(tmp, "config.yaml")
+        open(cfile, "w").write(CONFIG_YAML.format(prompts=pfile, arch=arch, iters=iters,
+                                                 max_steps=max_steps, out=os.path.join(tmp, "out"),
+                                                 v_pred=str(v_pred).lower()))
+        config = ref.config_util.load_config_from_yaml(cfile)
+        prompts = ref.prompt_util.load_prompts_from_yaml(config.prompts_file)
+        patches = [(ref.model_util, "load_models", fake_load_models),
+                   (ref.train_util, "encode_prompts", fake_encode),
+                   (ref.train_util, "diffusion", rec_diffusion),
+                   (ref.prompt_util.PromptEmbedsPair, "loss", rec_loss),
+                   (train_lora, "DEVICE_CUDA", torch.device("cpu"))]
+        saved = [(o, n, getattr(o, n)) for o, n, _ in patches]
+        try:
+            for o, n, v in patches:
+                setattr(o, n, v)
+            ref.prompt_util.PromptEmbedsCache.prompts.clear()
+            torch.manual_seed(SEED)
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                train_lora.train(config, prompts)
+        finally:
+            for o, n, v in saved:
+                setattr(o, n, v)
+        from safetensors.torch import load_file
+        sd = load_file(os.path.join(tmp, "out", "golden_last.safetensors"))
+    # un-patch the oracle unet's Linear forwards for the next user
+    return losses, ks, sd, prompts
+
+
+def run_oracle_train(arch: str, iters: int, max_steps: int, v_pred: bool, prompt_settings):
+    cfg = CONFIGS[arch]
+    unet = build_unet(arch, seed=0)
+    sched = create_noise_scheduler("ddim", "v_prediction" if v_pred else "epsilon")
+    torch.manual_seed(SEED)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = leco_ref.LoRANetworkRef(unet, rank=4, multiplier=1.0, alpha=1.0, train_method="full")
+    opt = torch.optim.AdamW(net.prepare_optimizer_params(), lr=1e-3)
+    lrs = torch.optim.lr_scheduler.ConstantLR(opt, factor=1)
+    pairs = []
+    for s in prompt_settings:
+        emb = {p: synthetic_embedding(p, cfg.cross_attention_dim)
+               for p in (s.target, s.positive, s.unconditional, s.neutral)}
+        pairs.append(leco_ref.PromptPairRef(
+            target=emb[s.target], positive=emb[s.positive], unconditional=emb[s.unconditional],
+            neutral=emb[s.neutral], guidance_scale=s.guidance_scale, resolution=s.resolution,
+            dynamic_resolution=s.dynamic_resolution, batch_size=s.batch_size, action=s.action))
+    losses, ks = [], []
+    for _ in range(iters):
+        rec = {}
+        losses.append(leco_ref.leco_iteration(unet, sched, net, opt, lrs, pairs,
+                                              max_denoising_steps=max_steps, record=rec))
+        ks.append(rec["k"])
+    return losses, ks, net.lora_state_dict(torch.float32)
+
+
+def main():
+    torch.set_num_threads(4)
+    out = {}
+    for arch, iters, max_steps, v_pred in (("tiny21", 4, 8, True), ("tiny15", 3, 6, False)):
+        ref_losses, ref_ks, ref_sd, prompts = run_reference_train(arch, iters, max_steps, v_pred)
+        ora_losses, ora_ks, ora_sd = run_oracle_train(arch, iters, max_steps, v_pred, prompts)
+        assert ref_ks == ora_ks, (ref_ks, ora_ks)
+        assert ref_losses == ora_losses, (ref_losses, ora_losses)
+        assert sorted(ref_sd.keys()) == sorted(ora_sd.keys())  # safetensors re-orders keys on disk
+        for k in ref_sd:
+            assert torch.equal(ref_sd[k], ora_sd[k]), k
+        keys = sorted(ref_sd.keys())
+        out[arch] = {
+            "seed": SEED, "iters": iters, "max_denoising_steps": max_steps, "v_pred": v_pred,
+            "lr": 1e-3, "losses": ref_losses, "k": ref_ks, "n_keys": len(keys),
+            "first_keys": keys[:6], "last_keys": keys[-3:],
+            "digests": {k: tensor_digest(ref_sd[k]) for k in keys[:12] + keys[-12:]},
+            "total_abs": float(sum(v.double().abs().sum() for v in ref_sd.values())),
+        }
+        print(arch, "reference == oracle bit-exact;", "losses", ref_losses, "k", ref_ks)
+    out["_meta"] = {"torch": torch.__version__,
+                    "how": "reference train_lora.train() (unmodified) on oracle UNet/DDIM, CPU fp32"}
+    with open(os.path.join(GOLDEN_DIR, "leco_train_golden.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", os.path.join(GOLDEN_DIR, "leco_train_golden.json"))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,244 @@
+"""GPU check harness for leco_gemm_bf16 (run on the B200 box through gpurun).
+
+Every case runs in its own subprocess under a timeout so that a trap / hang in one case
+cannot take the others down.  Results -> gpurun_out/gemm_cases.json.  The comparison is a
+plain PyTorch fp32 reference of the same op on the same bf16-rounded inputs.
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+
+def _rand(shape, scale=1.0, seed=0):
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).cuda()
+
+
+def _cmp(out, ref, tol=2e-2):
+    import torch
+    out = out.float()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    finite = bool(torch.isfinite(out).all().item())
+    return {"max_abs_err": err, "ref_absmax": scale, "rel": err / scale, "ok": finite and err / scale < tol}
+
+
+def case_matrix(M, N, K, block_n=0, bias=False, rowbias=0, residual=False, lora=0, geglu=False,
+                alpha=1.0, out_fp32=False, strided=False):
+    import torch
+    from leco_b200 import ops
+    a = _rand((M, K), seed=1)
+    if strided:  # A is a column slice of a wider buffer (like Q inside a fused QKV output)
+        wide = _rand((M, K * 3), seed=1)
+        a = wide[:, K:2 * K]
+    b = _rand((N, K), scale=K ** -0.5, seed=2)
+    ref = a.float() @ b.float().t()
+    kw = {}
+    if lora:
+        t = _rand((M, lora), seed=3)
+        up = _rand((N, lora), scale=0.1, seed=4)
+        ref = ref + t.float() @ up.float().t()
+        kw.update(lora_t=t, lora_up=up)
+    ref = ref * alpha
+    if bias:
+        bv = _rand((N,), seed=5)
+        ref = ref + bv.float()[None]
+        kw["bias"] = bv
+    if rowbias:
+        groups = (M + rowbias - 1) // rowbias
+        rb = _rand((groups, N), seed=6)
+        ref = ref + rb.float().repeat_interleave(rowbias, 0)[:M]
+        kw.update(rowbias=rb, rows_per_group=rowbias)
+    if geglu:
+        # library layout: rows interleaved in blocks of 64 (hidden j, gate j)
+        h, gte = ref[:, :N // 2], ref[:, N // 2:]
+        ref = h * torch.nn.functional.gelu(gte)
+        perm = torch.arange(N).reshape(2, N // 128, 64).permute(1, 0, 2).reshape(-1).cuda()
+        b = b[perm].contiguous()
+        if bias:
+            kw["bias"] = kw["bias"][perm].contiguous()
+        if lora:
+            kw["lora_up"] = kw["lora_up"][perm].contiguous()
+    if residual:
+        r = _rand(ref.shape, seed=7)
+        ref = ref + r.float()
+        kw["residual"] = r
+    out = ops.gemm(a, b, geglu=geglu, alpha=alpha, out_fp32=out_fp32, block_n=block_n, **kw)
+    torch.cuda.synchronize()
+    return _cmp(out, ref)
+
+
+def case_batched(B1, B0, M, N, K, out_fp32=True, alpha=0.125):
+    """S = alpha * Q K^T with Q,K strided views into a fused [B1*M, 3*B0*K] projection output."""
+    import torch
+    from leco_b200 import ops
+    C = B0 * K
+    qkv = _rand((B1 * max(M, N), 3 * C), seed=11)
+    q = qkv[: B1 * M, 0:C].unflatten(0, (B1, M)).unflatten(2, (B0, K)).permute(0, 2, 1, 3)
+    k = qkv[: B1 * N, C:2 * C].unflatten(0, (B1, N)).unflatten(2, (B0, K)).permute(0, 2, 1, 3)
+    out = torch.empty((B1, B0, M, N), device="cuda", dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    ops.gemm_batched(q, k, out, alpha=alpha)
+    torch.cuda.synchronize()
+    ref = alpha * torch.einsum("bhmk,bhnk->bhmn", q.float(), k.float())
+    return _cmp(out, ref)
+
+
+def case_conv(n, h, w, cin, cout, block_n=0, bias=True, rowbias=True, residual=True, lora=0):
+    import torch
+    import torch.nn.functional as F
+    from leco_b200 import ops
+    x = _rand((n, h, w, cin), seed=21)                       # NHWC
+    wt = _rand((cout, cin, 3, 3), scale=(9 * cin) ** -0.5, seed=22)  # OIHW
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1).permute(0, 2, 3, 1).reshape(n * h * w, cout)
+    wk = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()  # [O, (kh,kw,c)]
+    kw = {}
+    if lora:
+        t = _rand((n * h * w, lora), seed=23)
+        up = _rand((cout, lora), scale=0.1, seed=24)
+        ref = ref + t.float() @ up.float().t()
+        kw.update(lora_t=t, lora_up=up)
+    if bias:
+        bv = _rand((cout,), seed=25)
+        ref = ref + bv.float()[None]
+        kw["bias"] = bv
+    if rowbias:
+        rb = _rand((n, cout), seed=26)
+        ref = ref + rb.float().repeat_interleave(h * w, 0)
+        kw.update(rowbias=rb, rows_per_group=h * w)
+    if residual:
+        r = _rand(ref.shape, seed=27)
+        ref = ref + r.float()
+        kw["residual"] = r
+    out = ops.gemm(x.reshape(n * h * w, cin), wk, conv_nhw=(n, h, w), block_n=block_n, **kw)
+    torch.cuda.synchronize()
+    return _cmp(out, ref)
+
+
+def case_perf(M, N, K, block_n=0, conv=None, iters=20):
+    import torch
+    from leco_b200 import ops
+    if conv:
+        n, h, w, cin = conv
+        a = _rand((n * h * w, cin), seed=31)
+        K = 9 * cin
+        M = n * h * w
+    else:
+        a = _rand((M, K), seed=31)
+    b = _rand((N, K), scale=K ** -0.5, seed=32)
+    out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    kw = dict(conv_nhw=conv[:3]) if conv else {}
+    for _ in range(3):
+        ops.gemm(a, b, out, block_n=block_n, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ops.gemm(a, b, out, block_n=block_n, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+    # cuBLAS yardstick (reference only, never on the product path)
+    if not conv:
+        for _ in range(3):
+            torch.matmul(a, b.t())
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            torch.matmul(a, b.t())
+        e1.record()
+        torch.cuda.synchronize()
+        ms_ref = e0.elapsed_time(e1) / iters
+    else:
+        ms_ref = None
+    return {"ok": True, "ms": ms, "tflops": tf, "cublas_ms": ms_ref}
+
+
+CASES = [
+    ("basic_bn128", case_matrix, dict(M=256, N=256, K=256, block_n=128)),
+    ("basic_bn64", case_matrix, dict(M=256, N=256, K=256, block_n=64)),
+    ("basic_bn160", case_matrix, dict(M=256, N=320, K=256, block_n=160)),
+    ("basic_bn256", case_matrix, dict(M=256, N=512, K=256, block_n=256)),
+    ("multi_tile_persist", case_matrix, dict(M=4096, N=2560, K=320)),
+    ("ragged_m308_n320", case_matrix, dict(M=308, N=320, K=1024)),
+    ("tiny_m4", case_matrix, dict(M=4, N=1280, K=320, bias=True)),
+    ("k80", case_matrix, dict(M=256, N=128, K=80)),
+    ("k48", case_matrix, dict(M=128, N=64, K=48)),
+    ("n_ragged_n72", case_matrix, dict(M=256, N=72, K=128, block_n=64)),
+    ("bias_rowbias_res", case_matrix, dict(M=512, N=320, K=320, bias=True, rowbias=128, residual=True)),
+    ("lora16", case_matrix, dict(M=1024, N=960, K=320, lora=16)),
+    ("lora32_bias_res", case_matrix, dict(M=1024, N=640, K=640, lora=32, bias=True, residual=True)),
+    ("lora_only_small_n16", case_matrix, dict(M=1024, N=16, K=320, alpha=0.25)),
+    ("geglu", case_matrix, dict(M=512, N=2560, K=320, geglu=True, bias=True)),
+    ("geglu_lora", case_matrix, dict(M=300, N=1024, K=128, geglu=True, bias=True, lora=16)),
+    ("fp32_out_alpha", case_matrix, dict(M=256, N=256, K=64, alpha=0.125, out_fp32=True)),
+    ("strided_a", case_matrix, dict(M=512, N=128, K=128, strided=True)),
+    ("batched_qk_d64", case_batched, dict(B1=2, B0=5, M=1024, N=1024, K=64)),
+    ("batched_qk_cross77", case_batched, dict(B1=4, B0=5, M=256, N=80, K=64)),
+    ("batched_bf16out", case_batched, dict(B1=2, B0=2, M=128, N=128, K=64, out_fp32=False)),
+    ("conv_64x64_c64", case_conv, dict(n=2, h=64, w=64, cin=64, cout=64)),
+    ("conv_32x32_c128_n320", case_conv, dict(n=2, h=32, w=32, cin=128, cout=320)),
+    ("conv_16x16", case_conv, dict(n=4, h=16, w=16, cin=192, cout=128)),
+    ("conv_8x8_n3", case_conv, dict(n=3, h=8, w=8, cin=128, cout=256)),
+    ("conv_4x4", case_conv, dict(n=4, h=4, w=4, cin=64, cout=64)),
+    ("conv_2x2", case_conv, dict(n=4, h=2, w=2, cin=64, cout=64)),
+    ("conv_40x40", case_conv, dict(n=2, h=40, w=40, cin=64, cout=64)),
+    ("conv_24x40_rect", case_conv, dict(n=1, h=24, w=40, cin=64, cout=64)),
+    ("conv_lora16", case_conv, dict(n=2, h=32, w=32, cin=128, cout=128, lora=16)),
+    ("conv_plain", case_conv, dict(n=2, h=32, w=32, cin=64, cout=64, bias=False, rowbias=False, residual=False)),
+    ("perf_ff1", case_perf, dict(M=16384, N=2560, K=320)),
+    ("perf_ff2", case_perf, dict(M=16384, N=320, K=1280)),
+    ("perf_8k", case_perf, dict(M=8192, N=8192, K=8192, iters=5)),
+    ("perf_8k_bn128", case_perf, dict(M=8192, N=8192, K=8192, block_n=128, iters=5)),
+    ("perf_conv_64_320", case_perf, dict(M=0, N=320, K=0, conv=(4, 64, 64, 320))),
+    ("perf_conv_16_1280", case_perf, dict(M=0, N=1280, K=0, conv=(4, 16, 16, 1280))),
+]
+
+
+def main():
+    if len(sys.argv) >= 3 and sys.argv[1] == "--case":
+        name = sys.argv[2]
+        for n, fn, kw in CASES:
+            if n == name:
+                res = fn(**kw)
+                print("RESULT " + json.dumps(res))
+                return
+        raise SystemExit(f"unknown case {name}")
+    only = sys.argv[1:] if len(sys.argv) > 1 else None
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    results = {}
+    for name, _, kw in CASES:
+        if only and not any(name.startswith(o) for o in only):
+            continue
+        t0 = time.time()
+        try:
+            pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", name],
+                                capture_output=True, text=True, timeout=180)
+            line = [l for l in pr.stdout.splitlines() if l.startswith("RESULT ")]
+            if pr.returncode == 0 and line:
+                res = json.loads(line[-1][7:])
+            else:
+                res = {"ok": False, "rc": pr.returncode, "stderr": pr.stderr[-1500:], "stdout": pr.stdout[-500:]}
+        except subprocess.TimeoutExpired:
+            res = {"ok": False, "timeout": True}
+        res["secs"] = round(time.time() - t0, 1)
+        res["args"] = {k: v for k, v in kw.items()}
+        results[name] = res
+        print(name, json.dumps(res)[:300], flush=True)
+        with open(os.path.join(out_dir, "gemm_cases.json"), "w") as f:
+            json.dump(results, f, indent=1)
+    nfail = sum(1 for r in results.values() if not r.get("ok"))
+    print(f"SUMMARY {len(results) - nfail}/{len(results)} ok")
+
+
+if __name__ == "__main__":
+    main()
