@@ -36,8 +36,8 @@ int leco_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
  * mode 1: A is an NHWC image [cn][ch][cw][cc]; implicit 3x3 / stride 1 / pad 1 conv,
  *         B is [N][9*cc] with k = (kh*3+kw)*cc + c  (nn.Conv2d weight permuted OHWI).
  * epilogue: + bias[n] + rowbias[m / rows_per_group][n] + residual[m][n];
- *           epilogue==1: GEGLU (attention.py GEGLU: hidden * gelu(gate)), B rows
- *           interleaved in blocks of 64 (hidden block j, gate block j), D has N/2 cols.
+ *           epilogue==1: GEGLU (diffusers attention.py GEGLU: hidden * gelu(gate)); B keeps the
+ *           nn.Linear row order [hidden rows ; gate rows]; D has N/2 columns.
  * ------------------------------------------------------------------------------- */
 typedef struct leco_gemm_args {
   const void* a;
@@ -63,8 +63,77 @@ typedef struct leco_gemm_args {
   float alpha;
   int32_t out_fp32;
   int32_t block_n; /* 0 = heuristic; else 64 / 128 / 160 / 256 */
+  int32_t b_rows;  /* rows of B that exist per batch entry (0 = N); rows in [b_rows,N) read as 0 */
 } leco_gemm_args;
 int leco_gemm_bf16(const leco_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Boundary convolutions (diffusers UNet2DConditionModel.conv_in / conv_out, called from
+ * train_util.py:156-160).  conv_in: NCHW [n,4,h,w] (fp32 or bf16) -> NHWC bf16, w OIHW.
+ * conv_out: NHWC bf16 -> NCHW fp32, w [cout][9][c] (OHWI).  conv_out_bwd: d(input).
+ * ------------------------------------------------------------------------------- */
+int leco_conv_in(const void* x, int x_is_fp32, const void* w, const void* bias, void* y, int n, int h, int w_,
+                 int cout, void* stream);
+int leco_conv_out(const void* x, const void* w, const void* bias, float* y, int n, int h, int w_, int c, int cout,
+                  void* stream);
+int leco_conv_out_bwd(const float* dy, const void* w, void* dx, int n, int h, int w_, int c, int cout, void* stream);
+
+/* diffusers Timesteps(flip_sin_to_cos=True, freq_shift=0): out[n][dim] = [cos | sin] (bf16) */
+int leco_timestep_embedding(const float* t, void* out, int n, int dim, void* stream);
+
+/* elementwise / data-movement glue (bf16, sizes multiples of 8) */
+int leco_silu(const void* x, void* y, int64_t numel, void* stream);
+int leco_add_inplace(void* y, const void* x, int64_t numel, void* stream);
+int leco_geglu_fwd(const void* pre, void* out, int64_t M, int H, void* stream);
+int leco_geglu_bwd(const void* pre, const void* dout, void* dpre, int64_t M, int H, void* stream);
+int leco_copy_cols(const void* src, int64_t lds, int scol0, void* dst, int64_t ldd, int dcol0, int64_t M, int ncols,
+                   void* stream);
+int leco_upsample2x(const void* x, void* y, int n, int h, int w, int c, void* stream);
+int leco_upsample2x_bwd(const void* dy, void* dx, int n, int h, int w, int c, void* stream);
+int leco_im2col_s2(const void* x, void* col, int n, int h, int w, int c, void* stream);
+int leco_col2im_s2(const void* dcol, void* dx, int n, int h, int w, int c, void* stream);
+int leco_transpose(const void* in, void* out, int rows, int cols, int rows_pad, int64_t in_ld, int64_t in_bs0,
+                   int64_t in_bs1, int64_t out_ld, int64_t out_bs0, int64_t out_bs1, int batch0, int batch1,
+                   void* stream);
+int leco_softmax_rows(const float* s, void* p, int64_t rows, int n_valid, int n_pad, int64_t ld_s, int64_t ld_p,
+                      void* stream);
+int leco_softmax_bwd_rows(const void* p, const float* dp, void* ds, int64_t rows, int n_valid, int n_pad,
+                          int64_t ld_p, int64_t ld_dp, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * GroupNorm(+SiLU) / LayerNorm (diffusers ResnetBlock2D.norm1/2, Transformer2DModel.norm,
+ * BasicTransformerBlock.norm1-3), forward and backward-data.  stats = float2 (mean, rstd).
+ * ------------------------------------------------------------------------------- */
+int64_t leco_group_norm_workspace_bytes(int n, int G);
+int leco_group_norm(const void* x, void* y, void* stats, const void* gamma, const void* beta, int n, int hw, int C,
+                    int G, float eps, int silu, void* workspace, void* stream);
+int leco_group_norm_bwd(const void* x, const void* dz, void* dx, const void* stats, const void* gamma,
+                        const void* beta, int n, int hw, int C, int G, int silu, void* workspace, void* stream);
+int leco_layer_norm(const void* x, void* y, void* stats, const void* gamma, const void* beta, int64_t M, int C,
+                    float eps, void* stream);
+int leco_layer_norm_bwd(const void* x, const void* dy, void* dx, const void* stats, const void* gamma, int64_t M,
+                        int C, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Training-side kernels.
+ * leco_tn_reduce: out[N1,N2] (fp32, +=; or out[N2,N1] with transpose_out) = scale * A[M,N1]^T B[M,N2] — the LoRA weight gradients that
+ *   autograd derives from lora.py:102-106 (dB = dY^T down(x), dA = (dY B)^T x).
+ * leco_adamw_flat: torch.optim.AdamW semantics (train_lora.py:89,280) over one flat buffer;
+ *   hyper_dev = fp32[8] {lr, beta1, beta2, eps, weight_decay, step, grad_scale, -}.
+ * leco_guided_step: CFG combine (train_util.py:163-166) + DDIM eta=0 update as x' = cx x + ce guided;
+ *   coef_dev = fp32[3] {guidance, cx, ce}.
+ * leco_loss: prompt_util.py:107-135 erase/enhance MSE and d(loss)/d(target).
+ * ------------------------------------------------------------------------------- */
+int leco_tn_reduce(const void* a, int64_t lda, const void* b, int64_t ldb, float* out, int64_t ldo, int64_t M, int N1,
+                   int N2, float scale, int transpose_out, void* stream);
+int leco_adamw_flat(void* params_bf16, float* grads, void* exp_avg, void* exp_avg_sq, int state_is_fp32,
+                    const void* mask_u8, const float* hyper_dev, int64_t n, int zero_grad, void* stream);
+int leco_guided_step(const float* eps_pair, const float* x, float* x_out, float* guided_out, const float* coef_dev,
+                     int64_t half_numel, void* stream);
+int leco_loss(const float* target, const float* positive, const float* neutral, const float* uncond,
+              float sign_times_guidance, float* loss_out, float* dtarget, int64_t numel, void* stream);
+int leco_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
+int leco_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,6 +9,8 @@ import ctypes
 import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_void_p
 
+P, I, L, F = c_void_p, c_int32, c_int64, c_float
+
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libleco_b200.so")
 _lib = None
 
@@ -32,6 +34,7 @@ class GemmArgs(Structure):
         ("ld_rowbias", c_int64),
         ("residual", c_void_p), ("ldr", c_int64),
         ("epilogue", c_int32), ("alpha", c_float), ("out_fp32", c_int32), ("block_n", c_int32),
+        ("b_rows", c_int32),
     ]
 
 
@@ -54,13 +57,46 @@ def load():
     lib.leco_launch_count.restype = c_int64
     lib.leco_device_info.argtypes = [POINTER(c_int32)] * 3
     lib.leco_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
+    lib.leco_group_norm_workspace_bytes.restype = c_int64
+    lib.leco_group_norm_workspace_bytes.argtypes = [c_int32, c_int32]
     _declare_ops(lib)
     _lib = lib
     return lib
 
 
 # (name, argtypes) of every other entry point; filled in as kernels are added
-_OPS: list[tuple[str, list]] = []
+_OPS: list[tuple[str, list]] = [
+    ("leco_conv_in", [P, I, P, P, P, I, I, I, I, P]),
+    ("leco_conv_out", [P, P, P, P, I, I, I, I, I, P]),
+    ("leco_conv_out_bwd", [P, P, P, I, I, I, I, I, P]),
+    ("leco_timestep_embedding", [P, P, I, I, P]),
+    ("leco_silu", [P, P, L, P]),
+    ("leco_add_inplace", [P, P, L, P]),
+    ("leco_geglu_fwd", [P, P, L, I, P]),
+    ("leco_geglu_bwd", [P, P, P, L, I, P]),
+    ("leco_copy_cols", [P, L, I, P, L, I, L, I, P]),
+    ("leco_upsample2x", [P, P, I, I, I, I, P]),
+    ("leco_upsample2x_bwd", [P, P, I, I, I, I, P]),
+    ("leco_im2col_s2", [P, P, I, I, I, I, P]),
+    ("leco_col2im_s2", [P, P, I, I, I, I, P]),
+    ("leco_transpose", [P, P, I, I, I, L, L, L, L, L, L, I, I, P]),
+    ("leco_softmax_rows", [P, P, L, I, I, L, L, P]),
+    ("leco_softmax_bwd_rows", [P, P, P, L, I, I, L, L, F, P]),
+    ("leco_group_norm", [P, P, P, P, P, I, I, I, I, F, I, P, P]),
+    ("leco_group_norm_bwd", [P, P, P, P, P, P, I, I, I, I, I, P, P]),
+    ("leco_layer_norm", [P, P, P, P, P, L, I, F, P]),
+    ("leco_layer_norm_bwd", [P, P, P, P, P, L, I, P]),
+    ("leco_tn_reduce", [P, L, P, L, P, L, L, I, I, F, I, P]),
+    ("leco_adamw_flat", [P, P, P, P, I, P, P, L, I, P]),
+    ("leco_guided_step", [P, P, P, P, P, L, P]),
+    ("leco_loss", [P, P, P, P, F, P, P, L, P]),
+    ("leco_cast_f32_to_bf16", [P, P, L, P]),
+    ("leco_cast_bf16_to_f32", [P, P, L, P]),
+]
+
+# every symbol include/leco_b200.h declares (tests check the .so exports all of them)
+EXPORTED = ["leco_last_error", "leco_abi_version", "leco_launch_count", "leco_device_info",
+            "leco_gemm_bf16", "leco_group_norm_workspace_bytes"] + [n for n, _ in _OPS]
 
 
 def _declare_ops(lib):

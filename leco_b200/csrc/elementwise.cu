@@ -1,0 +1,552 @@
+// HBM-bound glue kernels of the UNet step: boundary convolutions (conv_in K=36, conv_out N=4),
+// timestep sinusoid, SiLU, GEGLU (fwd/bwd), channel concat/split, nearest 2x upsample (fwd/bwd),
+// stride-2 im2col/col2im, batched transpose, row softmax (fwd/bwd) and axpy.  All are
+// coalesced 16-byte-vector kernels; none of them is worth a tensor core.
+#include "../../include/leco_b200.h"
+#include "common.cuh"
+
+namespace leco {
+void count_launch();
+
+static inline int grid_for(long long work, int block) {
+  long long g = (work + block - 1) / block;
+  const long long cap = 148LL * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+struct alignas(16) bf16x8 {
+  uint32_t u[4];
+};
+__device__ __forceinline__ void unpack8(const bf16x8& q, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = bf16_lo(q.u[i]);
+    f[2 * i + 1] = bf16_hi(q.u[i]);
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
+  bf16x8 q;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q.u[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+  return q;
+}
+
+// ------------------------------------------------------------------ conv_in (3x3, Cin=4)
+// x: NCHW [n,4,h,w] (fp32 or bf16) -> y: NHWC [n*h*w, cout] bf16.  w: OIHW [cout,4,3,3] bf16.
+template <typename TIn>
+__global__ void conv_in_kernel(const TIn* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                               const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                               int n, int h, int wd, int cout) {
+  const int groups = cout / 8;
+  const long long total = 1LL * n * h * wd * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long pix = i / groups;
+    const int px = (int)(pix % wd);
+    const int py = (int)((pix / wd) % h);
+    const int img = (int)(pix / ((long long)wd * h));
+    float patch[36];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yy = py + ky - 1, xx = px + kx - 1;
+          float v = 0.f;
+          if (yy >= 0 && yy < h && xx >= 0 && xx < wd)
+            v = static_cast<float>(x[((1LL * img * 4 + c) * h + yy) * wd + xx]);
+          patch[c * 9 + ky * 3 + kx] = v;
+        }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __nv_bfloat16* wr = w + (size_t)(g * 8 + j) * 36;
+      float a = bias ? __bfloat162float(bias[g * 8 + j]) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 36; ++k) a = fmaf(patch[k], __bfloat162float(__ldg(wr + k)), a);
+      acc[j] = a;
+    }
+    *reinterpret_cast<bf16x8*>(y + pix * cout + g * 8) = pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------ conv_out (3x3, Cout<=8)
+// x: NHWC [n*h*w, c] bf16 -> y: NCHW [n,cout,h,w] fp32.  w: [cout][9][c] bf16 (OHWI).
+__global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                const __nv_bfloat16* __restrict__ bias, float* __restrict__ y, int n,
+                                int h, int wd, int c, int cout) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long npix = 1LL * n * h * wd;
+  const int vpp = c / 8;
+  for (long long pix = warp; pix < npix; pix += nwarps) {
+    const int px = (int)(pix % wd);
+    const int py = (int)((pix / wd) % h);
+    const int img = (int)(pix / ((long long)wd * h));
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+      if (yy < 0 || yy >= h || xx < 0 || xx >= wd) continue;
+      const __nv_bfloat16* xr = x + ((1LL * img * h + yy) * wd + xx) * c;
+      for (int v = lane; v < vpp; v += 32) {
+        float xv[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(xr + v * 8), xv);
+        for (int o = 0; o < cout; ++o) {
+          float wv[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(w + ((size_t)o * 9 + tap) * c + v * 8), wv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[o] = fmaf(xv[j], wv[j], acc[o]);
+        }
+      }
+    }
+    for (int o = 0; o < cout; ++o) {
+      float a = acc[o];
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+      if (lane == 0)
+        y[((1LL * img * cout + o) * h + py) * wd + px] = a + (bias ? __bfloat162float(bias[o]) : 0.f);
+    }
+  }
+}
+
+// conv_out backward-data: dy NCHW fp32 [n,cout,h,w] -> dx NHWC bf16 [n*h*w, c]
+// dx[p, ci] = sum_{o,tap} dy[o, p - off(tap)] * w[o][tap][ci]
+__global__ void conv_out_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ w,
+                                    __nv_bfloat16* __restrict__ dx, int n, int h, int wd, int c, int cout) {
+  const int vpp = c / 8;
+  const long long total = 1LL * n * h * wd * vpp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpp);
+    const long long pix = i / vpp;
+    const int px = (int)(pix % wd);
+    const int py = (int)((pix / wd) % h);
+    const int img = (int)(pix / ((long long)wd * h));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      // output pixel q that used input p with this tap: q = p - (tap offset)
+      const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);
+      if (yy < 0 || yy >= h || xx < 0 || xx >= wd) continue;
+      for (int o = 0; o < cout; ++o) {
+        const float g = dy[((1LL * img * cout + o) * h + yy) * wd + xx];
+        float wv[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(w + ((size_t)o * 9 + tap) * c + v * 8), wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(g, wv[j], acc[j]);
+      }
+    }
+    *reinterpret_cast<bf16x8*>(dx + pix * c + v * 8) = pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------ timestep sinusoid
+// diffusers get_timestep_embedding(flip_sin_to_cos=True, freq_shift=0): [cos | sin]
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out,
+                                          int n, int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * half) return;
+  const int j = i % half, r = i / half;
+  const float freq = expf(-9.210340371976184f * (float)j / (float)half);
+  const float a = t[r] * freq;
+  out[(size_t)r * dim + j] = __float2bfloat16(cosf(a));
+  out[(size_t)r * dim + half + j] = __float2bfloat16(sinf(a));
+}
+
+// ------------------------------------------------------------------ elementwise
+__global__ void silu_kernel(const bf16x8* __restrict__ x, bf16x8* __restrict__ y, long long nvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8(x[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+    y[i] = pack8(f);
+  }
+}
+// y += x   (gradient accumulation)
+__global__ void add_inplace_kernel(bf16x8* __restrict__ y, const bf16x8* __restrict__ x, long long nvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    unpack8(y[i], a);
+    unpack8(x[i], b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    y[i] = pack8(a);
+  }
+}
+// GEGLU: pre [M, 2H] = [hidden | gate] -> out [M,H] = hidden * gelu(gate)
+__global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfloat16* __restrict__ out,
+                                 long long M, int H) {
+  const int vpr = H / 8;
+  const long long total = M * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vpr;
+    const int v = (int)(i % vpr);
+    float h[8], g[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(pre + r * 2 * H + v * 8), h);
+    unpack8(*reinterpret_cast<const bf16x8*>(pre + r * 2 * H + H + v * 8), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] *= gelu_erf_f(g[j]);
+    *reinterpret_cast<bf16x8*>(out + r * H + v * 8) = pack8(h);
+  }
+}
+__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dout,
+                                 __nv_bfloat16* __restrict__ dpre, long long M, int H) {
+  const int vpr = H / 8;
+  const long long total = M * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vpr;
+    const int v = (int)(i % vpr);
+    float h[8], g[8], d[8], dh[8], dg[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(pre + r * 2 * H + v * 8), h);
+    unpack8(*reinterpret_cast<const bf16x8*>(pre + r * 2 * H + H + v * 8), g);
+    unpack8(*reinterpret_cast<const bf16x8*>(dout + r * H + v * 8), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float cdf = 0.5f * (1.0f + erff(g[j] * 0.70710678118654752440f));
+      const float pdf = 0.3989422804014327f * __expf(-0.5f * g[j] * g[j]);
+      dh[j] = d[j] * g[j] * cdf;
+      dg[j] = d[j] * h[j] * (cdf + g[j] * pdf);
+    }
+    *reinterpret_cast<bf16x8*>(dpre + r * 2 * H + v * 8) = pack8(dh);
+    *reinterpret_cast<bf16x8*>(dpre + r * 2 * H + H + v * 8) = pack8(dg);
+  }
+}
+
+// generic strided row copy: dst[r, dcol0 + j] = src[r, scol0 + j], j < ncols (all multiples of 8)
+__global__ void copy_cols_kernel(const __nv_bfloat16* __restrict__ src, long long lds, int scol0,
+                                 __nv_bfloat16* __restrict__ dst, long long ldd, int dcol0, long long M,
+                                 int ncols) {
+  const int vpr = ncols / 8;
+  const long long total = M * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vpr;
+    const int v = (int)(i % vpr);
+    *reinterpret_cast<bf16x8*>(dst + r * ldd + dcol0 + v * 8) =
+        *reinterpret_cast<const bf16x8*>(src + r * lds + scol0 + v * 8);
+  }
+}
+
+// nearest 2x upsample NHWC: y[n, 2h, 2w, c]
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n,
+                                  int h, int w, int c) {
+  const int vpp = c / 8;
+  const long long total = 1LL * n * 2 * h * 2 * w * vpp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpp);
+    long long p = i / vpp;
+    const int ox = (int)(p % (2 * w));
+    p /= 2 * w;
+    const int oy = (int)(p % (2 * h));
+    const int img = (int)(p / (2 * h));
+    const long long src = ((1LL * img * h + oy / 2) * w + ox / 2) * c + v * 8;
+    *reinterpret_cast<bf16x8*>(y + (i / vpp) * c + v * 8) = *reinterpret_cast<const bf16x8*>(x + src);
+  }
+}
+// backward: dx[n,h,w,c] = sum of the 2x2 block of dy[n,2h,2w,c]
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
+                                      int n, int h, int w, int c) {
+  const int vpp = c / 8;
+  const long long total = 1LL * n * h * w * vpp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpp);
+    long long p = i / vpp;
+    const int ix = (int)(p % w);
+    p /= w;
+    const int iy = (int)(p % h);
+    const int img = (int)(p / h);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dyy = 0; dyy < 2; ++dyy)
+#pragma unroll
+      for (int dxx = 0; dxx < 2; ++dxx) {
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(
+                    dy + ((1LL * img * 2 * h + 2 * iy + dyy) * 2 * w + 2 * ix + dxx) * c + v * 8),
+                f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    *reinterpret_cast<bf16x8*>(dx + (i / vpp) * c + v * 8) = pack8(acc);
+  }
+}
+
+// stride-2 3x3 pad-1 im2col: x NHWC [n,h,w,c] -> col [n*(h/2)*(w/2), 9*c] (k = tap*c + ch)
+__global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, int n,
+                                 int h, int w, int c) {
+  const int vpp = c / 8, oh = h / 2, ow = w / 2;
+  const long long total = 1LL * n * oh * ow * 9 * vpp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpp);
+    long long p = i / vpp;
+    const int tap = (int)(p % 9);
+    p /= 9;
+    const int ox = (int)(p % ow);
+    const int oy = (int)((p / ow) % oh);
+    const int img = (int)(p / ((long long)ow * oh));
+    const int yy = 2 * oy + tap / 3 - 1, xx = 2 * ox + tap % 3 - 1;
+    bf16x8 q = {{0, 0, 0, 0}};
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+      q = *reinterpret_cast<const bf16x8*>(x + ((1LL * img * h + yy) * w + xx) * c + v * 8);
+    *reinterpret_cast<bf16x8*>(col + p * 9 * c + (size_t)tap * c + v * 8) = q;
+  }
+}
+// col2im (gather form): dx[n,h,w,c] = sum over (out pixel, tap) that read this input pixel
+__global__ void col2im_s2_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx, int n,
+                                 int h, int w, int c) {
+  const int vpp = c / 8, oh = h / 2, ow = w / 2;
+  const long long total = 1LL * n * h * w * vpp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpp);
+    long long p = i / vpp;
+    const int ix = (int)(p % w);
+    const int iy = (int)((p / w) % h);
+    const int img = (int)(p / ((long long)w * h));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ny = iy - (tap / 3 - 1), nx = ix - (tap % 3 - 1);  // = 2*oy, 2*ox
+      if (ny < 0 || nx < 0 || (ny & 1) || (nx & 1)) continue;
+      const int oy = ny >> 1, ox = nx >> 1;
+      if (oy >= oh || ox >= ow) continue;
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dcol + ((1LL * img * oh + oy) * ow + ox) * 9 * c +
+                                               (size_t)tap * c + v * 8),
+              f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    *reinterpret_cast<bf16x8*>(dx + p * c + v * 8) = pack8(acc);
+  }
+}
+
+// batched 2-D transpose with arbitrary strides: out[b1,b0,c,r] = in[b1,b0,r,c]
+// (zero-fills out columns r in [rows, rows_pad))
+__global__ void transpose_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                 int rows, int cols, int rows_pad, long long in_ld, long long in_bs0,
+                                 long long in_bs1, long long out_ld, long long out_bs0, long long out_bs1,
+                                 int batch0) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int b = blockIdx.z;
+  const int b1 = b / batch0, b0 = b % batch0;
+  const __nv_bfloat16* src = in + b0 * in_bs0 + b1 * in_bs1;
+  __nv_bfloat16* dst = out + b0 * out_bs0 + b1 * out_bs1;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(long long)r * in_ld + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows_pad) dst[(long long)c * out_ld + r] = tile[threadIdx.x][i];
+  }
+}
+
+// row softmax: s fp32 [rows, ld_s] (first n_valid columns valid) -> p bf16 [rows, ld_p], columns
+// [n_valid, n_pad) written as 0.  One warp per row.
+__global__ void softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, long long rows,
+                                    int n_valid, int n_pad, long long ld_s, long long ld_p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const float* sr = s + r * ld_s;
+    float mx = -INFINITY;
+    for (int j = lane; j < n_valid; j += 32) mx = fmaxf(mx, sr[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < n_valid; j += 32) sum += __expf(sr[j] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    __nv_bfloat16* pr = p + r * ld_p;
+    for (int j = lane; j < n_pad; j += 32)
+      pr[j] = __float2bfloat16(j < n_valid ? __expf(sr[j] - mx) * inv : 0.f);
+  }
+}
+// softmax backward: ds = p * (dp - sum_j p_j dp_j) * scale ; dp fp32 [rows, ld], p bf16, ds bf16
+__global__ void softmax_bwd_rows_kernel(const __nv_bfloat16* __restrict__ p, const float* __restrict__ dp,
+                                        __nv_bfloat16* __restrict__ ds, long long rows, int n_valid, int n_pad,
+                                        long long ld_p, long long ld_dp, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const __nv_bfloat16* pr = p + r * ld_p;
+    const float* dr = dp + r * ld_dp;
+    float dot = 0.f;
+    for (int j = lane; j < n_valid; j += 32) dot += __bfloat162float(pr[j]) * dr[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    __nv_bfloat16* dsr = ds + r * ld_p;
+    for (int j = lane; j < n_pad; j += 32)
+      dsr[j] = __float2bfloat16(j < n_valid ? __bfloat162float(pr[j]) * (dr[j] - dot) * scale : 0.f);
+  }
+}
+
+}  // namespace leco
+
+using namespace leco;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+#define BFW(p) reinterpret_cast<__nv_bfloat16*>(p)
+
+extern "C" int leco_conv_in(const void* x, int x_is_fp32, const void* w, const void* bias, void* y, int n, int h,
+                            int wd, int cout, void* stream) {
+  LECO_REQUIRE(x && w && y && cout % 8 == 0, "leco_conv_in: bad args");
+  const long long work = 1LL * n * h * wd * (cout / 8);
+  count_launch();
+  if (x_is_fp32)
+    conv_in_kernel<float><<<grid_for(work, 128), 128, 0, STREAM(stream)>>>(
+        reinterpret_cast<const float*>(x), BF(w), BF(bias), BFW(y), n, h, wd, cout);
+  else
+    conv_in_kernel<__nv_bfloat16><<<grid_for(work, 128), 128, 0, STREAM(stream)>>>(BF(x), BF(w), BF(bias),
+                                                                                   BFW(y), n, h, wd, cout);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_conv_out(const void* x, const void* w, const void* bias, float* y, int n, int h, int wd, int c,
+                             int cout, void* stream) {
+  LECO_REQUIRE(x && w && y && c % 8 == 0 && cout >= 1 && cout <= 8, "leco_conv_out: bad args");
+  count_launch();
+  conv_out_kernel<<<grid_for(1LL * n * h * wd * 32, 256), 256, 0, STREAM(stream)>>>(BF(x), BF(w), BF(bias), y, n,
+                                                                                   h, wd, c, cout);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_conv_out_bwd(const float* dy, const void* w, void* dx, int n, int h, int wd, int c, int cout,
+                                 void* stream) {
+  LECO_REQUIRE(dy && w && dx && c % 8 == 0 && cout >= 1 && cout <= 8, "leco_conv_out_bwd: bad args");
+  count_launch();
+  conv_out_bwd_kernel<<<grid_for(1LL * n * h * wd * (c / 8), 256), 256, 0, STREAM(stream)>>>(dy, BF(w), BFW(dx),
+                                                                                           n, h, wd, c, cout);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_timestep_embedding(const float* t, void* out, int n, int dim, void* stream) {
+  LECO_REQUIRE(t && out && dim % 2 == 0, "leco_timestep_embedding: bad args");
+  count_launch();
+  timestep_embedding_kernel<<<(n * dim / 2 + 127) / 128, 128, 0, STREAM(stream)>>>(t, BFW(out), n, dim);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_silu(const void* x, void* y, int64_t numel, void* stream) {
+  LECO_REQUIRE(x && y && numel % 8 == 0, "leco_silu: numel must be a multiple of 8");
+  count_launch();
+  silu_kernel<<<grid_for(numel / 8, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const bf16x8*>(x),
+                                                                   reinterpret_cast<bf16x8*>(y), numel / 8);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_add_inplace(void* y, const void* x, int64_t numel, void* stream) {
+  LECO_REQUIRE(x && y && numel % 8 == 0, "leco_add_inplace: numel must be a multiple of 8");
+  count_launch();
+  add_inplace_kernel<<<grid_for(numel / 8, 256), 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<bf16x8*>(y), reinterpret_cast<const bf16x8*>(x), numel / 8);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_geglu_fwd(const void* pre, void* out, int64_t M, int H, void* stream) {
+  LECO_REQUIRE(pre && out && H % 8 == 0, "leco_geglu_fwd: bad args");
+  count_launch();
+  geglu_fwd_kernel<<<grid_for(M * (H / 8), 256), 256, 0, STREAM(stream)>>>(BF(pre), BFW(out), M, H);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_geglu_bwd(const void* pre, const void* dout, void* dpre, int64_t M, int H, void* stream) {
+  LECO_REQUIRE(pre && dout && dpre && H % 8 == 0, "leco_geglu_bwd: bad args");
+  count_launch();
+  geglu_bwd_kernel<<<grid_for(M * (H / 8), 256), 256, 0, STREAM(stream)>>>(BF(pre), BF(dout), BFW(dpre), M, H);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_copy_cols(const void* src, int64_t lds, int scol0, void* dst, int64_t ldd, int dcol0,
+                              int64_t M, int ncols, void* stream) {
+  LECO_REQUIRE(src && dst && ncols % 8 == 0 && scol0 % 8 == 0 && dcol0 % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0,
+               "leco_copy_cols: columns / strides must be multiples of 8");
+  count_launch();
+  copy_cols_kernel<<<grid_for(M * (ncols / 8), 256), 256, 0, STREAM(stream)>>>(BF(src), lds, scol0, BFW(dst),
+                                                                               ldd, dcol0, M, ncols);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_upsample2x(const void* x, void* y, int n, int h, int w, int c, void* stream) {
+  LECO_REQUIRE(x && y && c % 8 == 0, "leco_upsample2x: bad args");
+  count_launch();
+  upsample2x_kernel<<<grid_for(4LL * n * h * w * (c / 8), 256), 256, 0, STREAM(stream)>>>(BF(x), BFW(y), n, h, w,
+                                                                                        c);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_upsample2x_bwd(const void* dy, void* dx, int n, int h, int w, int c, void* stream) {
+  LECO_REQUIRE(dy && dx && c % 8 == 0, "leco_upsample2x_bwd: bad args");
+  count_launch();
+  upsample2x_bwd_kernel<<<grid_for(1LL * n * h * w * (c / 8), 256), 256, 0, STREAM(stream)>>>(BF(dy), BFW(dx), n,
+                                                                                            h, w, c);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_im2col_s2(const void* x, void* col, int n, int h, int w, int c, void* stream) {
+  LECO_REQUIRE(x && col && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "leco_im2col_s2: bad args");
+  count_launch();
+  im2col_s2_kernel<<<grid_for(1LL * n * (h / 2) * (w / 2) * 9 * (c / 8), 256), 256, 0, STREAM(stream)>>>(
+      BF(x), BFW(col), n, h, w, c);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_col2im_s2(const void* dcol, void* dx, int n, int h, int w, int c, void* stream) {
+  LECO_REQUIRE(dcol && dx && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "leco_col2im_s2: bad args");
+  count_launch();
+  col2im_s2_kernel<<<grid_for(1LL * n * h * w * (c / 8), 256), 256, 0, STREAM(stream)>>>(BF(dcol), BFW(dx), n, h,
+                                                                                       w, c);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_transpose(const void* in, void* out, int rows, int cols, int rows_pad, int64_t in_ld,
+                              int64_t in_bs0, int64_t in_bs1, int64_t out_ld, int64_t out_bs0, int64_t out_bs1,
+                              int batch0, int batch1, void* stream) {
+  LECO_REQUIRE(in && out && rows > 0 && cols > 0 && rows_pad >= rows && batch0 > 0 && batch1 > 0,
+               "leco_transpose: bad args");
+  LECO_REQUIRE(1LL * batch0 * batch1 <= 65535, "leco_transpose: too many batches");
+  dim3 grid((cols + 31) / 32, (rows_pad + 31) / 32, batch0 * batch1), block(32, 8);
+  count_launch();
+  transpose_kernel<<<grid, block, 0, STREAM(stream)>>>(BF(in), BFW(out), rows, cols, rows_pad, in_ld, in_bs0,
+                                                       in_bs1, out_ld, out_bs0, out_bs1, batch0);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_softmax_rows(const float* s, void* p, int64_t rows, int n_valid, int n_pad, int64_t ld_s,
+                                 int64_t ld_p, void* stream) {
+  LECO_REQUIRE(s && p && n_valid > 0 && n_pad >= n_valid, "leco_softmax_rows: bad args");
+  count_launch();
+  softmax_rows_kernel<<<grid_for(rows * 32, 256), 256, 0, STREAM(stream)>>>(s, BFW(p), rows, n_valid, n_pad, ld_s,
+                                                                           ld_p);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_softmax_bwd_rows(const void* p, const float* dp, void* ds, int64_t rows, int n_valid,
+                                     int n_pad, int64_t ld_p, int64_t ld_dp, float scale, void* stream) {
+  LECO_REQUIRE(p && dp && ds && n_valid > 0 && n_pad >= n_valid, "leco_softmax_bwd_rows: bad args");
+  count_launch();
+  softmax_bwd_rows_kernel<<<grid_for(rows * 32, 256), 256, 0, STREAM(stream)>>>(BF(p), dp, BFW(ds), rows, n_valid,
+                                                                               n_pad, ld_p, ld_dp, scale);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

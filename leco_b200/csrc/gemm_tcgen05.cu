@@ -192,11 +192,24 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             const int kh = tap / 3, kw = tap - kh * 3;
             tma_load_4d(sa, &p.tm_a, &full_bar[stage], cc * BLOCK_K, kw - 1, img_h0 + kh - 1, img_n0);
           }
-          tma_load_4d(sb, &p.tm_b, &full_bar[stage], c * BLOCK_K, n0, b0, b1);
+          if (p.epilogue == 1) {
+            // GEGLU: tile columns [0,BN/2) <- hidden rows, [BN/2,BN) <- the matching gate rows
+            tma_load_4d(sb, &p.tm_b, &full_bar[stage], c * BLOCK_K, nt * (BN / 2), b0, b1);
+            tma_load_4d(sb + (BN / 2) * BLOCK_K * 2, &p.tm_b, &full_bar[stage], c * BLOCK_K,
+                        p.N / 2 + nt * (BN / 2), b0, b1);
+          } else {
+            tma_load_4d(sb, &p.tm_b, &full_bar[stage], c * BLOCK_K, n0, b0, b1);
+          }
         } else {
           mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
           tma_load_4d(sa, &p.tm_a2, &full_bar[stage], 0, m0, 0, 0);
-          tma_load_4d(sb, &p.tm_b2, &full_bar[stage], 0, n0, 0, 0);
+          if (p.epilogue == 1) {
+            tma_load_4d(sb, &p.tm_b2, &full_bar[stage], 0, nt * (BN / 2), 0, 0);
+            tma_load_4d(sb + (BN / 2) * BLOCK_K * 2, &p.tm_b2, &full_bar[stage], 0,
+                        p.N / 2 + nt * (BN / 2), 0, 0);
+          } else {
+            tma_load_4d(sb, &p.tm_b2, &full_bar[stage], 0, n0, 0, 0);
+          }
         }
         if (++stage == STAGES) {
           stage = 0;
@@ -313,8 +326,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
               g[j] = __uint_as_float(rg[j]) * p.alpha;
             }
             if (p.bias) {
-              epi_add_bf16(h, p.bias + n0 + c * 32, 32);
-              epi_add_bf16(g, p.bias + n0 + BN / 2 + c * 32, 32);
+              epi_add_bf16(h, p.bias + ocol0, 32);
+              epi_add_bf16(g, p.bias + p.N / 2 + ocol0, 32);
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) h[j] = h[j] * gelu_erf_f(g[j]);
@@ -380,7 +393,7 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   LECO_REQUIRE(a && a->a && a->b && a->d, "leco_gemm_bf16: null operand");
   LECO_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "leco_gemm_bf16: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
-  LECO_REQUIRE(a->N % 8 == 0 && a->K % 16 == 0, "leco_gemm_bf16: N%%8 / K%%16 violated (N=%d K=%d)", a->N, a->K);
+  LECO_REQUIRE(a->N % 8 == 0 && a->K % 8 == 0, "leco_gemm_bf16: N%%8 / K%%8 violated (N=%d K=%d)", a->N, a->K);
   LECO_REQUIRE(a->ldd % 8 == 0 && a->ldb % 8 == 0, "leco_gemm_bf16: ldd/ldb must be multiples of 8");
   const int batch0 = a->batch0 > 0 ? a->batch0 : 1, batch1 = a->batch1 > 0 ? a->batch1 : 1;
 
@@ -392,7 +405,7 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
   p.batch0 = batch0;
   p.batch1 = batch1;
   p.chunks1 = (a->K + BLOCK_K - 1) / BLOCK_K;
-  p.ksteps_last1 = ((a->K - 1) % BLOCK_K) / 16 + 1;
+  p.ksteps_last1 = ((a->K - 1) % BLOCK_K) / 16 + 1;  // K%16==8: the tail k-step reads TMA zero fill
   uint32_t box_a[4] = {BLOCK_K, BLOCK_M, 1, 1};
   if (a->mode == 0) {
     LECO_REQUIRE(a->lda % 8 == 0, "leco_gemm_bf16: lda must be a multiple of 8");
@@ -442,11 +455,11 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
   if (a->epilogue == 1) LECO_REQUIRE(a->N % 128 == 0 && !a->out_fp32 && !a->residual && !a->rowbias, "leco_gemm_bf16: GEGLU needs N%%128==0, bf16 out, no residual/rowbias");
   p.tiles_n = (a->N + bn - 1) / bn;
   {
-    const uint64_t dims[4] = {(uint64_t)a->K, (uint64_t)a->N, (uint64_t)batch0, (uint64_t)batch1};
+    const uint64_t dims[4] = {(uint64_t)a->K, (uint64_t)(a->b_rows > 0 ? a->b_rows : a->N), (uint64_t)batch0, (uint64_t)batch1};
     const uint64_t bs0 = batch0 > 1 ? (uint64_t)a->b_bs0 : (uint64_t)a->ldb * a->N;
     const uint64_t bs1 = batch1 > 1 ? (uint64_t)a->b_bs1 : bs0 * batch0;
     const uint64_t str[3] = {(uint64_t)a->ldb * 2, bs0 * 2, bs1 * 2};
-    const uint32_t box_b[4] = {BLOCK_K, (uint32_t)bn, 1, 1};
+    const uint32_t box_b[4] = {BLOCK_K, (uint32_t)(a->epilogue == 1 ? bn / 2 : bn), 1, 1};
     if (make_tmap_bf16_4d(&p.tm_b, a->b, dims, str, box_b)) return -3;
   }
   if (a->a2) {
@@ -460,7 +473,7 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
     if (make_tmap_bf16_4d(&p.tm_a2, a->a2, dims_a, str_a, box2)) return -3;
     const uint64_t dims_b[4] = {(uint64_t)a->K2, (uint64_t)a->N, 1, 1};
     const uint64_t str_b[3] = {(uint64_t)a->ldb2 * 2, (uint64_t)a->ldb2 * a->N * 2, (uint64_t)a->ldb2 * a->N * 2};
-    const uint32_t box_b2[4] = {BLOCK_K, (uint32_t)bn, 1, 1};
+    const uint32_t box_b2[4] = {BLOCK_K, (uint32_t)(a->epilogue == 1 ? bn / 2 : bn), 1, 1};
     if (make_tmap_bf16_4d(&p.tm_b2, a->b2, dims_b, str_b, box_b2)) return -3;
   }
   p.d = a->d;

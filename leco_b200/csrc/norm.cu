@@ -1,0 +1,408 @@
+// GroupNorm(+SiLU) and LayerNorm, forward and backward-data, on NHWC / token-major bf16
+// activations.  HBM-bound warp-shuffle / shared-atomic reductions (no tensor-core work):
+//   GroupNorm: pass 1 = per-(sample,split) partial group sums, pass 2 = normalise (+SiLU);
+//   LayerNorm: one warp per row, row held in registers, exact two-pass variance.
+// Statistics are fp32; gamma/beta are frozen (no parameter gradients are ever needed:
+// LECO trains only the LoRA matrices, train_lora.py:69).
+#include "../../include/leco_b200.h"
+#include "common.cuh"
+
+namespace leco {
+void count_launch();
+
+using v8 = uint4;
+__device__ __forceinline__ void up8(const v8& q, float (&f)[8]) {
+  f[0] = bf16_lo(q.x); f[1] = bf16_hi(q.x);
+  f[2] = bf16_lo(q.y); f[3] = bf16_hi(q.y);
+  f[4] = bf16_lo(q.z); f[5] = bf16_hi(q.z);
+  f[6] = bf16_lo(q.w); f[7] = bf16_hi(q.w);
+}
+__device__ __forceinline__ v8 pk8(const float (&f)[8]) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+__device__ __forceinline__ float dsilu_f(float y) {
+  const float s = 1.0f / (1.0f + __expf(-y));
+  return s * (1.0f + y * (1.0f - s));
+}
+
+constexpr int GN_MAX_GROUPS = 64;
+
+// ---- pass 1 (forward): partial[n][split][g] = (sum x, sum x^2)
+// blockDim.x = vpp * R (vpp = C/8 vector columns, R row lanes); each thread owns one vector column.
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ partial, int hw, int C,
+                                int G, int vpp, int splits) {
+  __shared__ float sm[GN_MAX_GROUPS][2];
+  const int n = blockIdx.x, sp = blockIdx.y;
+  for (int i = threadIdx.x; i < G * 2; i += blockDim.x) (&sm[0][0])[i] = 0.f;
+  __syncthreads();
+  const int R = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp, rl = threadIdx.x / vpp;
+  const int rows_per = (hw + splits - 1) / splits;
+  const int r0 = sp * rows_per, r1 = min(hw, r0 + rows_per);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (rl < R) {
+    const __nv_bfloat16* base = x + ((size_t)n * hw) * C + v * 8;
+    for (int r = r0 + rl; r < r1; r += R) {
+      float f[8];
+      up8(*reinterpret_cast<const v8*>(base + (size_t)r * C), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += f[j];
+        s2[j] = fmaf(f[j], f[j], s2[j]);
+      }
+    }
+    const int cpg = C / G;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (v * 8 + j) / cpg;
+      atomicAdd(&sm[g][0], s1[j]);
+      atomicAdd(&sm[g][1], s2[j]);
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x)
+    partial[((size_t)n * splits + sp) * G + g] = make_float2(sm[g][0], sm[g][1]);
+}
+
+// ---- pass 2 (forward): y = (x-mean)*rstd*gamma+beta [silu]; also writes stats[n][g] = (mean, rstd)
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                const float2* __restrict__ partial, float2* __restrict__ stats,
+                                const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                                int hw, int C, int G, int splits, float eps, int silu) {
+  __shared__ float2 ms[GN_MAX_GROUPS];
+  const int n = blockIdx.x;
+  const int cpg = C / G;
+  if (threadIdx.x < G) {
+    float a = 0.f, b = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      const float2 p = partial[((size_t)n * splits + s) * G + threadIdx.x];
+      a += p.x;
+      b += p.y;
+    }
+    const float cnt = (float)hw * (float)cpg;
+    const float mean = a / cnt;
+    const float var = fmaxf(b / cnt - mean * mean, 0.f);
+    const float2 r = make_float2(mean, rsqrtf(var + eps));
+    ms[threadIdx.x] = r;
+    if (blockIdx.y == 0) stats[(size_t)n * G + threadIdx.x] = r;
+  }
+  __syncthreads();
+  const int vpp = C / 8;
+  const long long total = (long long)hw * vpp;
+  const __nv_bfloat16* xb = x + (size_t)n * hw * C;
+  __nv_bfloat16* yb = y + (size_t)n * hw * C;
+  for (long long i = blockIdx.y * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.y * blockDim.x) {
+    const int v = (int)(i % vpp);
+    float f[8], gm[8], bt[8];
+    up8(*reinterpret_cast<const v8*>(xb + i * 8), f);
+    up8(__ldg(reinterpret_cast<const v8*>(gamma + v * 8)), gm);
+    up8(__ldg(reinterpret_cast<const v8*>(beta + v * 8)), bt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 m = ms[(v * 8 + j) / cpg];
+      float o = (f[j] - m.x) * m.y * gm[j] + bt[j];
+      if (silu) o = silu_f(o);
+      f[j] = o;
+    }
+    *reinterpret_cast<v8*>(yb + i * 8) = pk8(f);
+  }
+}
+
+// ---- backward pass 1: partial[n][split][g] = (sum g, sum g*xhat) with g = dy*gamma (dy through SiLU')
+__global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
+                                    const float2* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
+                                    const __nv_bfloat16* __restrict__ beta, float2* __restrict__ partial, int hw,
+                                    int C, int G, int vpp, int splits, int silu) {
+  __shared__ float sm[GN_MAX_GROUPS][2];
+  __shared__ float2 ms[GN_MAX_GROUPS];
+  const int n = blockIdx.x, sp = blockIdx.y;
+  for (int i = threadIdx.x; i < G * 2; i += blockDim.x) (&sm[0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < G; i += blockDim.x) ms[i] = stats[(size_t)n * G + i];
+  __syncthreads();
+  const int R = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp, rl = threadIdx.x / vpp;
+  const int rows_per = (hw + splits - 1) / splits;
+  const int r0 = sp * rows_per, r1 = min(hw, r0 + rows_per);
+  const int cpg = C / G;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (rl < R) {
+    float gm[8], bt[8];
+    up8(__ldg(reinterpret_cast<const v8*>(gamma + v * 8)), gm);
+    up8(__ldg(reinterpret_cast<const v8*>(beta + v * 8)), bt);
+    const size_t off = ((size_t)n * hw) * C + v * 8;
+    for (int r = r0 + rl; r < r1; r += R) {
+      float f[8], d[8];
+      up8(*reinterpret_cast<const v8*>(x + off + (size_t)r * C), f);
+      up8(*reinterpret_cast<const v8*>(dz + off + (size_t)r * C), d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 m = ms[(v * 8 + j) / cpg];
+        const float xh = (f[j] - m.x) * m.y;
+        float dy = d[j];
+        if (silu) dy *= dsilu_f(xh * gm[j] + bt[j]);
+        const float g = dy * gm[j];
+        s1[j] += g;
+        s2[j] = fmaf(g, xh, s2[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (v * 8 + j) / cpg;
+      atomicAdd(&sm[g][0], s1[j]);
+      atomicAdd(&sm[g][1], s2[j]);
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x)
+    partial[((size_t)n * splits + sp) * G + g] = make_float2(sm[g][0], sm[g][1]);
+}
+
+// ---- backward pass 2: dx = rstd * (g - mean(g) - xhat * mean(g*xhat))
+__global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
+                                    __nv_bfloat16* __restrict__ dx, const float2* __restrict__ stats,
+                                    const float2* __restrict__ partial, const __nv_bfloat16* __restrict__ gamma,
+                                    const __nv_bfloat16* __restrict__ beta, int hw, int C, int G, int splits,
+                                    int silu) {
+  __shared__ float2 ms[GN_MAX_GROUPS];
+  __shared__ float2 gs[GN_MAX_GROUPS];
+  const int n = blockIdx.x;
+  const int cpg = C / G;
+  if (threadIdx.x < G) {
+    float a = 0.f, b = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      const float2 p = partial[((size_t)n * splits + s) * G + threadIdx.x];
+      a += p.x;
+      b += p.y;
+    }
+    const float cnt = (float)hw * (float)cpg;
+    gs[threadIdx.x] = make_float2(a / cnt, b / cnt);
+    ms[threadIdx.x] = stats[(size_t)n * G + threadIdx.x];
+  }
+  __syncthreads();
+  const int vpp = C / 8;
+  const long long total = (long long)hw * vpp;
+  const size_t base = (size_t)n * hw * C;
+  for (long long i = blockIdx.y * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.y * blockDim.x) {
+    const int v = (int)(i % vpp);
+    float f[8], d[8], gm[8], bt[8];
+    up8(*reinterpret_cast<const v8*>(x + base + i * 8), f);
+    up8(*reinterpret_cast<const v8*>(dz + base + i * 8), d);
+    up8(__ldg(reinterpret_cast<const v8*>(gamma + v * 8)), gm);
+    up8(__ldg(reinterpret_cast<const v8*>(beta + v * 8)), bt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (v * 8 + j) / cpg;
+      const float2 m = ms[g];
+      const float xh = (f[j] - m.x) * m.y;
+      float dy = d[j];
+      if (silu) dy *= dsilu_f(xh * gm[j] + bt[j]);
+      const float gg = dy * gm[j];
+      f[j] = m.y * (gg - gs[g].x - xh * gs[g].y);
+    }
+    *reinterpret_cast<v8*>(dx + base + i * 8) = pk8(f);
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm
+constexpr int LN_MAX_VEC = 8;  // per lane -> C <= 2048
+
+__global__ void ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                              float2* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
+                              const __nv_bfloat16* __restrict__ beta, long long M, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int vpr = C / 8;
+  for (long long r = warp; r < M; r += nwarps) {
+    float f[LN_MAX_VEC][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int v = lane + 32 * i;
+      if (v < vpr) {
+        up8(*reinterpret_cast<const v8*>(x + r * C + v * 8), f[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[i][j];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int v = lane + 32 * i;
+      if (v < vpr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = f[i][j] - mean;
+          q = fmaf(d, d, q);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)C + eps);
+    if (lane == 0 && stats) stats[r] = make_float2(mean, rstd);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int v = lane + 32 * i;
+      if (v < vpr) {
+        float gm[8], bt[8], o[8];
+        up8(__ldg(reinterpret_cast<const v8*>(gamma + v * 8)), gm);
+        up8(__ldg(reinterpret_cast<const v8*>(beta + v * 8)), bt);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * gm[j] + bt[j];
+        *reinterpret_cast<v8*>(y + r * C + v * 8) = pk8(o);
+      }
+    }
+  }
+}
+
+__global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                              __nv_bfloat16* __restrict__ dx, const float2* __restrict__ stats,
+                              const __nv_bfloat16* __restrict__ gamma, long long M, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int vpr = C / 8;
+  for (long long r = warp; r < M; r += nwarps) {
+    const float2 m = stats[r];
+    float xh[LN_MAX_VEC][8], g[LN_MAX_VEC][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int v = lane + 32 * i;
+      if (v < vpr) {
+        float f[8], d[8], gm[8];
+        up8(*reinterpret_cast<const v8*>(x + r * C + v * 8), f);
+        up8(*reinterpret_cast<const v8*>(dy + r * C + v * 8), d);
+        up8(__ldg(reinterpret_cast<const v8*>(gamma + v * 8)), gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (f[j] - m.x) * m.y;
+          g[i][j] = d[j] * gm[j];
+          s1 += g[i][j];
+          s2 = fmaf(g[i][j], xh[i][j], s2);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float m1 = s1 / (float)C, m2 = s2 / (float)C;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int v = lane + 32 * i;
+      if (v < vpr) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = m.y * (g[i][j] - m1 - xh[i][j] * m2);
+        *reinterpret_cast<v8*>(dx + r * C + v * 8) = pk8(o);
+      }
+    }
+  }
+}
+
+static int gn_launch_cfg(int hw, int C, int* vpp, int* threads, int* splits) {
+  *vpp = C / 8;
+  if (*vpp > 1024) return -1;
+  int R = 256 / *vpp;
+  if (R < 1) R = 1;
+  *threads = *vpp * R;
+  int s = hw / 64;
+  if (s < 1) s = 1;
+  if (s > 32) s = 32;
+  *splits = s;
+  return 0;
+}
+
+}  // namespace leco
+
+using namespace leco;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+#define BFW(p) reinterpret_cast<__nv_bfloat16*>(p)
+
+// workspace: float2[n * 32 splits * G]  (leco_group_norm_workspace_bytes)
+extern "C" int64_t leco_group_norm_workspace_bytes(int n, int G) { return (int64_t)n * 32 * G * 8; }
+
+extern "C" int leco_group_norm(const void* x, void* y, void* stats /*float2[n*G]*/, const void* gamma,
+                               const void* beta, int n, int hw, int C, int G, float eps, int silu,
+                               void* workspace, void* stream) {
+  LECO_REQUIRE(x && y && stats && gamma && beta && workspace, "leco_group_norm: null pointer");
+  LECO_REQUIRE(C % 8 == 0 && G > 0 && G <= GN_MAX_GROUPS && C % G == 0, "leco_group_norm: C=%d G=%d unsupported", C, G);
+  int vpp, threads, splits;
+  LECO_REQUIRE(gn_launch_cfg(hw, C, &vpp, &threads, &splits) == 0, "leco_group_norm: C=%d too wide", C);
+  count_launch();
+  gn_stats_kernel<<<dim3(n, splits), threads, 0, STREAM(stream)>>>(BF(x), reinterpret_cast<float2*>(workspace), hw,
+                                                                  C, G, vpp, splits);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  long long work = (long long)hw * vpp;
+  int gy = (int)((work + 255) / 256);
+  if (gy > 592) gy = 592;
+  if (gy < 1) gy = 1;
+  count_launch();
+  gn_apply_kernel<<<dim3(n, gy), 256, 0, STREAM(stream)>>>(BF(x), BFW(y), reinterpret_cast<const float2*>(workspace),
+                                                          reinterpret_cast<float2*>(stats), BF(gamma), BF(beta), hw,
+                                                          C, G, splits, eps, silu);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int leco_group_norm_bwd(const void* x, const void* dz, void* dx, const void* stats, const void* gamma,
+                                   const void* beta, int n, int hw, int C, int G, int silu, void* workspace,
+                                   void* stream) {
+  LECO_REQUIRE(x && dz && dx && stats && gamma && beta && workspace, "leco_group_norm_bwd: null pointer");
+  LECO_REQUIRE(C % 8 == 0 && G > 0 && G <= GN_MAX_GROUPS && C % G == 0, "leco_group_norm_bwd: C=%d G=%d", C, G);
+  int vpp, threads, splits;
+  LECO_REQUIRE(gn_launch_cfg(hw, C, &vpp, &threads, &splits) == 0, "leco_group_norm_bwd: C=%d too wide", C);
+  count_launch();
+  gn_bwd_stats_kernel<<<dim3(n, splits), threads, 0, STREAM(stream)>>>(
+      BF(x), BF(dz), reinterpret_cast<const float2*>(stats), BF(gamma), BF(beta),
+      reinterpret_cast<float2*>(workspace), hw, C, G, vpp, splits, silu);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  long long work = (long long)hw * vpp;
+  int gy = (int)((work + 255) / 256);
+  if (gy > 592) gy = 592;
+  if (gy < 1) gy = 1;
+  count_launch();
+  gn_bwd_apply_kernel<<<dim3(n, gy), 256, 0, STREAM(stream)>>>(
+      BF(x), BF(dz), BFW(dx), reinterpret_cast<const float2*>(stats), reinterpret_cast<const float2*>(workspace),
+      BF(gamma), BF(beta), hw, C, G, splits, silu);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int leco_layer_norm(const void* x, void* y, void* stats /*float2[M] or NULL*/, const void* gamma,
+                               const void* beta, int64_t M, int C, float eps, void* stream) {
+  LECO_REQUIRE(x && y && gamma && beta, "leco_layer_norm: null pointer");
+  LECO_REQUIRE(C % 8 == 0 && C <= 8 * 32 * LN_MAX_VEC, "leco_layer_norm: C=%d unsupported", C);
+  long long blocks = (M + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  count_launch();
+  ln_fwd_kernel<<<(int)blocks, 256, 0, STREAM(stream)>>>(BF(x), BFW(y), reinterpret_cast<float2*>(stats), BF(gamma),
+                                                       BF(beta), M, C, eps);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_layer_norm_bwd(const void* x, const void* dy, void* dx, const void* stats, const void* gamma,
+                                   int64_t M, int C, void* stream) {
+  LECO_REQUIRE(x && dy && dx && stats && gamma, "leco_layer_norm_bwd: null pointer");
+  LECO_REQUIRE(C % 8 == 0 && C <= 8 * 32 * LN_MAX_VEC, "leco_layer_norm_bwd: C=%d unsupported", C);
+  long long blocks = (M + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  count_launch();
+  ln_bwd_kernel<<<(int)blocks, 256, 0, STREAM(stream)>>>(BF(x), BF(dy), BFW(dx), reinterpret_cast<const float2*>(stats),
+                                                       BF(gamma), M, C);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

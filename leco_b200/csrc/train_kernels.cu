@@ -1,0 +1,249 @@
+// Training-side kernels of the LECO step:
+//   * tn_reduce    : out[N1,N2] += scale * A[M,N1]^T . B[M,N2]  (the skinny LoRA weight gradients
+//                    dB = dY^T (s x A^T), dA = (s dY B)^T x; N2 = padded rank <= 64) — HBM-bound:
+//                    A is streamed exactly once.
+//   * adamw_flat   : fused decoupled-weight-decay Adam over ONE flat LoRA parameter buffer
+//                    (replaces torch.optim.AdamW over 384 tensors, train_lora.py:89,280).
+//   * guided_step  : classifier-free-guidance combine (train_util.py:163-166) fused with the
+//                    DDIM update (scheduling_ddim.py step, eta=0) as one affine map.
+//   * leco_loss    : erase/enhance MSE objective (prompt_util.py:107-135) + its gradient
+//                    w.r.t. the target prediction, on device (the reference does this on the CPU).
+#include "../../include/leco_b200.h"
+#include "common.cuh"
+
+namespace leco {
+void count_launch();
+
+constexpr int TN_TILE_N1 = 128;
+constexpr int TN_ROWS = 32;
+
+__global__ void __launch_bounds__(256)
+tn_reduce_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __nv_bfloat16* __restrict__ B,
+                 long long ldb, float* __restrict__ out, long long ldo, long long M, int N1, int N2, float scale,
+                 int rows_per_split, int transpose_out) {
+  __shared__ __align__(16) __nv_bfloat16 sA[TN_ROWS][TN_TILE_N1];
+  __shared__ __align__(16) __nv_bfloat16 sB[TN_ROWS][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * TN_TILE_N1;
+  const long long m_begin = (long long)blockIdx.y * rows_per_split;
+  const long long m_end = min(M, m_begin + rows_per_split);
+  const int JB = (N2 + 7) / 8;  // b-columns per thread (ty*JB + jj)
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (long long m0 = m_begin; m0 < m_end; m0 += TN_ROWS) {
+    // A tile: 32 rows x 128 cols = 512 16-byte vectors, 2 per thread
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int vi = threadIdx.x + t * 256;
+      const int r = vi >> 4, cv = vi & 15;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (m0 + r < m_end && n0 + cv * 8 < N1)
+        q = *reinterpret_cast<const uint4*>(A + (m0 + r) * lda + n0 + cv * 8);
+      *reinterpret_cast<uint4*>(&sA[r][cv * 8]) = q;
+    }
+    {  // B tile: 32 rows x 64 cols = 256 vectors, 1 per thread
+      const int r = threadIdx.x >> 3, cv = threadIdx.x & 7;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (m0 + r < m_end && cv * 8 < N2) q = *reinterpret_cast<const uint4*>(B + (m0 + r) * ldb + cv * 8);
+      *reinterpret_cast<uint4*>(&sB[r][cv * 8]) = q;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < TN_ROWS; ++r) {
+      const uint2 av = *reinterpret_cast<const uint2*>(&sA[r][tx * 4]);
+      const float a0 = bf16_lo(av.x), a1 = bf16_hi(av.x), a2 = bf16_lo(av.y), a3 = bf16_hi(av.y);
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        if (jj < JB) {
+          const float b = __bfloat162float(sB[r][ty * JB + jj]);
+          acc[0][jj] = fmaf(a0, b, acc[0][jj]);
+          acc[1][jj] = fmaf(a1, b, acc[1][jj]);
+          acc[2][jj] = fmaf(a2, b, acc[2][jj]);
+          acc[3][jj] = fmaf(a3, b, acc[3][jj]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + tx * 4 + i;
+    if (n >= N1) continue;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = ty * JB + jj;
+      if (jj < JB && j < N2)
+        atomicAdd(transpose_out ? out + (long long)j * ldo + n : out + (long long)n * ldo + j, acc[i][jj] * scale);
+    }
+  }
+}
+
+// hyper (device, fp32[8]): lr, beta1, beta2, eps, weight_decay, step, grad_scale, unused
+template <typename TState>
+__global__ void adamw_flat_kernel(__nv_bfloat16* __restrict__ p, float* __restrict__ g, TState* __restrict__ m,
+                                  TState* __restrict__ v, const uint8_t* __restrict__ mask,
+                                  const float* __restrict__ hyper, long long n, int zero_grad) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], step = hyper[5],
+              gs = hyper[6];
+  const float bc1 = 1.0f - powf(b1, step), bc2 = 1.0f - powf(b2, step);
+  const float step_size = lr / bc1;
+  const float inv_bc2_sqrt = rsqrtf(bc2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (mask && !mask[i]) {
+      if (zero_grad) g[i] = 0.f;
+      continue;
+    }
+    // the reference holds parameters, grads and Adam state in the training dtype (bf16,
+    // train_lora.py:78): round the gradient the same way before it enters the moments
+    const float grad = __bfloat162float(__float2bfloat16(g[i] * gs));
+    float w = __bfloat162float(p[i]);
+    w *= (1.0f - lr * wd);
+    const float mi = (float)m[i] * b1 + (1.0f - b1) * grad;  // lerp
+    const float vi = (float)v[i] * b2 + (1.0f - b2) * grad * grad;
+    m[i] = (TState)mi;
+    v[i] = (TState)vi;
+    const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
+    w -= step_size * (mi / denom);
+    p[i] = __float2bfloat16(w);
+    if (zero_grad) g[i] = 0.f;
+  }
+}
+
+// guided = e_u + g (e_c - e_u);  x' = cx * x + ce * guided   (coef = {g, cx, ce})
+// eps: fp32 NCHW [2B, chw] (first B uncond, last B cond); x fp32 [B, chw]
+__global__ void guided_step_kernel(const float* __restrict__ eps, const float* __restrict__ x,
+                                   float* __restrict__ x_out, float* __restrict__ guided_out,
+                                   const float* __restrict__ coef, long long half) {
+  const float g = coef[0], cx = coef[1], ce = coef[2];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < half;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float eu = eps[i], ec = eps[half + i];
+    const float gd = eu + g * (ec - eu);
+    if (guided_out) guided_out[i] = gd;
+    if (x_out) x_out[i] = cx * x[i] + ce * gd;
+  }
+}
+
+// loss = mean((t - (nn + sgn*gs*(pp - uu)))^2);  dt = 2 (t - goal) / numel.   single block, deterministic
+__global__ void leco_loss_kernel(const float* __restrict__ t, const float* __restrict__ pp,
+                                 const float* __restrict__ nn, const float* __restrict__ uu, float sgn_gs,
+                                 float* __restrict__ loss, float* __restrict__ dt, long long numel) {
+  __shared__ float red[32];
+  float s = 0.f;
+  const float inv = 1.0f / (float)numel;
+  for (long long i = threadIdx.x; i < numel; i += blockDim.x) {
+    const float goal = nn[i] + sgn_gs * (pp[i] - uu[i]);
+    const float d = t[i] - goal;
+    s = fmaf(d, d, s);
+    if (dt) dt[i] = 2.0f * d * inv;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *loss = s * inv;
+  }
+}
+
+// fp32 -> bf16 / bf16 -> fp32 flat casts, and scaled fp32 fill (graph-friendly helpers)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16(x[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = __bfloat162float(x[i]);
+}
+
+}  // namespace leco
+
+using namespace leco;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+#define BFW(p) reinterpret_cast<__nv_bfloat16*>(p)
+
+extern "C" int leco_tn_reduce(const void* a, int64_t lda, const void* b, int64_t ldb, float* out, int64_t ldo,
+                              int64_t M, int N1, int N2, float scale, int transpose_out, void* stream) {
+  LECO_REQUIRE(a && b && out && M > 0, "leco_tn_reduce: null / empty");
+  LECO_REQUIRE(N1 % 8 == 0 && N2 % 8 == 0 && N2 <= 64 && lda % 8 == 0 && ldb % 8 == 0,
+               "leco_tn_reduce: N1%%8, N2%%8, N2<=64, strides%%8 required (N1=%d N2=%d)", N1, N2);
+  int splits = (int)((M + 511) / 512);
+  if (splits > 64) splits = 64;
+  int rows_per = (int)((M + splits - 1) / splits);
+  rows_per = (rows_per + TN_ROWS - 1) / TN_ROWS * TN_ROWS;
+  splits = (int)((M + rows_per - 1) / rows_per);
+  dim3 grid((N1 + TN_TILE_N1 - 1) / TN_TILE_N1, splits);
+  count_launch();
+  tn_reduce_kernel<<<grid, 256, 0, STREAM(stream)>>>(BF(a), lda, BF(b), ldb, out, ldo, M, N1, N2, scale, rows_per, transpose_out);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int leco_adamw_flat(void* params_bf16, float* grads, void* exp_avg, void* exp_avg_sq, int state_is_fp32,
+                               const void* mask_u8, const float* hyper_dev, int64_t n, int zero_grad, void* stream) {
+  LECO_REQUIRE(params_bf16 && grads && exp_avg && exp_avg_sq && hyper_dev && n > 0, "leco_adamw_flat: null / empty");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  count_launch();
+  if (state_is_fp32)
+    adamw_flat_kernel<float><<<(int)blocks, 256, 0, STREAM(stream)>>>(
+        BFW(params_bf16), grads, reinterpret_cast<float*>(exp_avg), reinterpret_cast<float*>(exp_avg_sq),
+        reinterpret_cast<const uint8_t*>(mask_u8), hyper_dev, n, zero_grad);
+  else
+    adamw_flat_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, STREAM(stream)>>>(
+        BFW(params_bf16), grads, BFW(exp_avg), BFW(exp_avg_sq), reinterpret_cast<const uint8_t*>(mask_u8),
+        hyper_dev, n, zero_grad);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int leco_guided_step(const float* eps_pair, const float* x, float* x_out, float* guided_out,
+                                const float* coef_dev, int64_t half_numel, void* stream) {
+  LECO_REQUIRE(eps_pair && coef_dev && (x_out || guided_out) && (!x_out || x), "leco_guided_step: null pointer");
+  long long blocks = (half_numel + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  count_launch();
+  guided_step_kernel<<<(int)blocks, 256, 0, STREAM(stream)>>>(eps_pair, x, x_out, guided_out, coef_dev, half_numel);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int leco_loss(const float* target, const float* positive, const float* neutral, const float* uncond,
+                         float sign_times_guidance, float* loss_out, float* dtarget, int64_t numel, void* stream) {
+  LECO_REQUIRE(target && positive && neutral && uncond && loss_out && numel > 0, "leco_loss: null / empty");
+  count_launch();
+  leco_loss_kernel<<<1, 1024, 0, STREAM(stream)>>>(target, positive, neutral, uncond, sign_times_guidance, loss_out,
+                                                  dtarget, numel);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int leco_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
+  LECO_REQUIRE(x && y, "leco_cast: null");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  count_launch();
+  cast_f32_bf16_kernel<<<(int)blocks, 256, 0, STREAM(stream)>>>(x, BFW(y), n);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
+  LECO_REQUIRE(x && y, "leco_cast: null");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  count_launch();
+  cast_bf16_f32_kernel<<<(int)blocks, 256, 0, STREAM(stream)>>>(BF(x), y, n);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -93,7 +93,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
 
 
 def gemm_batched(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 1.0,
-                 block_n: int = 0) -> torch.Tensor:
+                 block_n: int = 0, n_pad: int = 0) -> torch.Tensor:
     """out[b1,b0,M,N] = alpha * a[b1,b0,M,K] @ b[b1,b0,N,K]^T over arbitrary-strided 4-D views
     (inner stride 1).  out may be bf16 or fp32."""
     lib = capi.load()
@@ -102,8 +102,11 @@ def gemm_batched(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: 
     assert a.stride(3) == 1 and b.stride(3) == 1 and out.stride(3) == 1
     B1, B0, M, K = a.shape
     N = b.shape[2]
-    assert b.shape == (B1, B0, N, K) and out.shape == (B1, B0, M, N)
+    assert b.shape == (B1, B0, N, K)
     g = GemmArgs()
+    if n_pad:  # B has N real rows; output columns [N, n_pad) are produced as zeros
+        g.b_rows, N = N, n_pad
+    assert out.shape == (B1, B0, M, N)
     g.a, g.b, g.d = _ptr(a), _ptr(b), _ptr(out)
     g.M, g.N, g.K = M, N, K
     g.lda, g.ldb, g.ldd = a.stride(2), b.stride(2), out.stride(2)
@@ -116,3 +119,322 @@ def gemm_batched(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: 
     g.block_n = block_n
     capi.check(lib.leco_gemm_bf16(ctypes.byref(g), _stream()), "leco_gemm_bf16(batched)")
     return out
+
+
+# --------------------------------------------------------------------------------------
+# everything below: one thin wrapper per C entry point (allocation + pointer passing only)
+# --------------------------------------------------------------------------------------
+def _lib():
+    return capi.load()
+
+
+def conv_in(x_nchw: torch.Tensor, w_oihw: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    n, c, h, w = x_nchw.shape
+    assert c == 4 and x_nchw.is_contiguous() and x_nchw.dtype in (torch.float32, BF16)
+    cout = w_oihw.shape[0]
+    y = torch.empty((n * h * w, cout), device=x_nchw.device, dtype=BF16)
+    capi.check(_lib().leco_conv_in(_ptr(x_nchw), int(x_nchw.dtype == torch.float32), _ptr(w_oihw), _ptr(bias),
+                                   _ptr(y), n, h, w, cout, _stream()), "leco_conv_in")
+    return y
+
+
+def conv_out(x: torch.Tensor, w_ohwi: torch.Tensor, bias: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
+    cout, c = w_ohwi.shape[0], x.shape[1]
+    y = torch.empty((n, cout, h, w), device=x.device, dtype=torch.float32)
+    capi.check(_lib().leco_conv_out(_ptr(x), _ptr(w_ohwi), _ptr(bias), _ptr(y), n, h, w, c, cout, _stream()),
+               "leco_conv_out")
+    return y
+
+
+def conv_out_bwd(dy: torch.Tensor, w_ohwi: torch.Tensor, c: int) -> torch.Tensor:
+    n, cout, h, w = dy.shape
+    assert dy.dtype == torch.float32 and dy.is_contiguous()
+    dx = torch.empty((n * h * w, c), device=dy.device, dtype=BF16)
+    capi.check(_lib().leco_conv_out_bwd(_ptr(dy), _ptr(w_ohwi), _ptr(dx), n, h, w, c, cout, _stream()),
+               "leco_conv_out_bwd")
+    return dx
+
+
+def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
+    assert t.dtype == torch.float32 and t.dim() == 1
+    out = torch.empty((t.shape[0], dim), device=t.device, dtype=BF16)
+    capi.check(_lib().leco_timestep_embedding(_ptr(t), _ptr(out), t.shape[0], dim, _stream()),
+               "leco_timestep_embedding")
+    return out
+
+
+def silu(x: torch.Tensor) -> torch.Tensor:
+    y = torch.empty_like(x)
+    capi.check(_lib().leco_silu(_ptr(x), _ptr(y), x.numel(), _stream()), "leco_silu")
+    return y
+
+
+def add_(y: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    assert y.shape == x.shape and y.is_contiguous() and x.is_contiguous()
+    capi.check(_lib().leco_add_inplace(_ptr(y), _ptr(x), y.numel(), _stream()), "leco_add_inplace")
+    return y
+
+
+def geglu_fwd(pre: torch.Tensor) -> torch.Tensor:
+    M, H2 = pre.shape
+    out = torch.empty((M, H2 // 2), device=pre.device, dtype=BF16)
+    capi.check(_lib().leco_geglu_fwd(_ptr(pre), _ptr(out), M, H2 // 2, _stream()), "leco_geglu_fwd")
+    return out
+
+
+def geglu_bwd(pre: torch.Tensor, dout: torch.Tensor) -> torch.Tensor:
+    M, H2 = pre.shape
+    dpre = torch.empty_like(pre)
+    capi.check(_lib().leco_geglu_bwd(_ptr(pre), _ptr(dout), _ptr(dpre), M, H2 // 2, _stream()), "leco_geglu_bwd")
+    return dpre
+
+
+def copy_cols(src: torch.Tensor, scol0: int, dst: torch.Tensor, dcol0: int, ncols: int):
+    assert src.stride(1) == 1 and dst.stride(1) == 1 and src.shape[0] == dst.shape[0]
+    capi.check(_lib().leco_copy_cols(_ptr(src), src.stride(0), scol0, _ptr(dst), dst.stride(0), dcol0,
+                                     src.shape[0], ncols, _stream()), "leco_copy_cols")
+
+
+def concat2(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    out = torch.empty((a.shape[0], a.shape[1] + b.shape[1]), device=a.device, dtype=BF16)
+    copy_cols(a, 0, out, 0, a.shape[1])
+    copy_cols(b, 0, out, a.shape[1], b.shape[1])
+    return out
+
+
+def split2(x: torch.Tensor, c1: int):
+    a = torch.empty((x.shape[0], c1), device=x.device, dtype=BF16)
+    b = torch.empty((x.shape[0], x.shape[1] - c1), device=x.device, dtype=BF16)
+    copy_cols(x, 0, a, 0, c1)
+    copy_cols(x, c1, b, 0, x.shape[1] - c1)
+    return a, b
+
+
+def upsample2x(x: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
+    c = x.shape[1]
+    y = torch.empty((n * 4 * h * w, c), device=x.device, dtype=BF16)
+    capi.check(_lib().leco_upsample2x(_ptr(x), _ptr(y), n, h, w, c, _stream()), "leco_upsample2x")
+    return y
+
+
+def upsample2x_bwd(dy: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
+    c = dy.shape[1]
+    dx = torch.empty((n * h * w, c), device=dy.device, dtype=BF16)
+    capi.check(_lib().leco_upsample2x_bwd(_ptr(dy), _ptr(dx), n, h, w, c, _stream()), "leco_upsample2x_bwd")
+    return dx
+
+
+def im2col_s2(x: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
+    c = x.shape[1]
+    col = torch.empty((n * (h // 2) * (w // 2), 9 * c), device=x.device, dtype=BF16)
+    capi.check(_lib().leco_im2col_s2(_ptr(x), _ptr(col), n, h, w, c, _stream()), "leco_im2col_s2")
+    return col
+
+
+def col2im_s2(dcol: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
+    c = dcol.shape[1] // 9
+    dx = torch.empty((n * h * w, c), device=dcol.device, dtype=BF16)
+    capi.check(_lib().leco_col2im_s2(_ptr(dcol), _ptr(dx), n, h, w, c, _stream()), "leco_col2im_s2")
+    return dx
+
+
+def transpose_batched(src: torch.Tensor, cols_pad: int = 0) -> torch.Tensor:
+    """src: 4-D view [b1,b0,rows,cols] (inner stride 1) -> new [b1,b0,cols,rows_pad] (zero padded)."""
+    _req_bf16(src, "src")
+    B1, B0, rows, cols = src.shape
+    rows_pad = max(cols_pad, rows)
+    out = torch.empty((B1, B0, cols, rows_pad), device=src.device, dtype=BF16)
+    capi.check(_lib().leco_transpose(_ptr(src), _ptr(out), rows, cols, rows_pad, src.stride(2), src.stride(1),
+                                     src.stride(0), out.stride(2), out.stride(1), out.stride(0), B0, B1,
+                                     _stream()), "leco_transpose")
+    return out
+
+
+def softmax_rows(s: torch.Tensor, n_valid: int, n_pad: int) -> torch.Tensor:
+    """s: fp32 [..., ld] contiguous -> p bf16 [..., n_pad]."""
+    assert s.dtype == torch.float32 and s.is_contiguous()
+    rows = s.numel() // s.shape[-1]
+    p = torch.empty(s.shape[:-1] + (n_pad,), device=s.device, dtype=BF16)
+    capi.check(_lib().leco_softmax_rows(_ptr(s), _ptr(p), rows, n_valid, n_pad, s.shape[-1], n_pad, _stream()),
+               "leco_softmax_rows")
+    return p
+
+
+def softmax_bwd_rows(p: torch.Tensor, dp: torch.Tensor, n_valid: int, scale: float) -> torch.Tensor:
+    assert dp.dtype == torch.float32 and dp.is_contiguous() and p.is_contiguous()
+    rows = p.numel() // p.shape[-1]
+    ds = torch.empty_like(p)
+    capi.check(_lib().leco_softmax_bwd_rows(_ptr(p), _ptr(dp), _ptr(ds), rows, n_valid, p.shape[-1], p.shape[-1],
+                                            dp.shape[-1], scale, _stream()), "leco_softmax_bwd_rows")
+    return ds
+
+
+_gn_ws = {}
+
+
+def _gn_workspace(dev, n, G):
+    key = (dev, n, G)
+    if key not in _gn_ws:
+        _gn_ws[key] = torch.empty(int(_lib().leco_group_norm_workspace_bytes(n, G)), device=dev,
+                                  dtype=torch.uint8)
+    return _gn_ws[key]
+
+
+def group_norm(x: torch.Tensor, n: int, hw: int, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float,
+               silu_act: bool):
+    C = x.shape[1]
+    assert x.is_contiguous() and x.shape[0] == n * hw
+    y = torch.empty_like(x)
+    stats = torch.empty((n, groups, 2), device=x.device, dtype=torch.float32)
+    ws = torch.empty(int(_lib().leco_group_norm_workspace_bytes(n, groups)), device=x.device, dtype=torch.uint8)
+    capi.check(_lib().leco_group_norm(_ptr(x), _ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), n, hw, C, groups,
+                                      eps, int(silu_act), _ptr(ws), _stream()), "leco_group_norm")
+    return y, stats
+
+
+def group_norm_bwd(x, dz, stats, gamma, beta, n, hw, groups, silu_act):
+    C = x.shape[1]
+    dx = torch.empty_like(x)
+    ws = torch.empty(int(_lib().leco_group_norm_workspace_bytes(n, groups)), device=x.device, dtype=torch.uint8)
+    capi.check(_lib().leco_group_norm_bwd(_ptr(x), _ptr(dz), _ptr(dx), _ptr(stats), _ptr(gamma), _ptr(beta), n, hw,
+                                          C, groups, int(silu_act), _ptr(ws), _stream()), "leco_group_norm_bwd")
+    return dx
+
+
+def layer_norm(x: torch.Tensor, gamma, beta, eps: float, want_stats: bool = False):
+    M, C = x.shape
+    assert x.is_contiguous()
+    y = torch.empty_like(x)
+    stats = torch.empty((M, 2), device=x.device, dtype=torch.float32) if want_stats else None
+    capi.check(_lib().leco_layer_norm(_ptr(x), _ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), M, C, eps,
+                                      _stream()), "leco_layer_norm")
+    return y, stats
+
+
+def layer_norm_bwd(x, dy, stats, gamma):
+    M, C = x.shape
+    dx = torch.empty_like(x)
+    capi.check(_lib().leco_layer_norm_bwd(_ptr(x), _ptr(dy), _ptr(dx), _ptr(stats), _ptr(gamma), M, C, _stream()),
+               "leco_layer_norm_bwd")
+    return dx
+
+
+def tn_reduce(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, scale: float = 1.0,
+              transpose_out: bool = False):
+    """out[N1,N2] += scale * a[M,N1]^T @ b[M,N2]   (out fp32; with transpose_out it is [N2,N1])."""
+    assert out.dtype == torch.float32 and out.stride(1) == 1 and a.stride(1) == 1 and b.stride(1) == 1
+    assert out.shape == ((b.shape[1], a.shape[1]) if transpose_out else (a.shape[1], b.shape[1]))
+    capi.check(_lib().leco_tn_reduce(_ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0),
+                                     a.shape[0], a.shape[1], b.shape[1], scale, int(transpose_out), _stream()),
+               "leco_tn_reduce")
+
+
+def adamw_flat(params, grads, exp_avg, exp_avg_sq, mask, hyper, zero_grad=True):
+    capi.check(_lib().leco_adamw_flat(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq),
+                                      int(exp_avg.dtype == torch.float32), _ptr(mask), _ptr(hyper),
+                                      params.numel(), int(zero_grad), _stream()), "leco_adamw_flat")
+
+
+def guided_step(eps_pair, x, coef, want_x=True, want_guided=False):
+    half = eps_pair.numel() // 2
+    shape = (eps_pair.shape[0] // 2,) + tuple(eps_pair.shape[1:])
+    x_out = torch.empty(shape, device=eps_pair.device, dtype=torch.float32) if want_x else None
+    g_out = torch.empty(shape, device=eps_pair.device, dtype=torch.float32) if want_guided else None
+    capi.check(_lib().leco_guided_step(_ptr(eps_pair), _ptr(x), _ptr(x_out), _ptr(g_out), _ptr(coef), half,
+                                       _stream()), "leco_guided_step")
+    return x_out, g_out
+
+
+def leco_loss(target, positive, neutral, uncond, sign_times_guidance: float, want_grad=True):
+    loss = torch.empty((1,), device=target.device, dtype=torch.float32)
+    dt = torch.empty_like(target) if want_grad else None
+    capi.check(_lib().leco_loss(_ptr(target), _ptr(positive), _ptr(neutral), _ptr(uncond), sign_times_guidance,
+                                _ptr(loss), _ptr(dt), target.numel(), _stream()), "leco_loss")
+    return loss, dt
+
+
+def cast_f32_to_bf16(x):
+    y = torch.empty(x.shape, device=x.device, dtype=BF16)
+    capi.check(_lib().leco_cast_f32_to_bf16(_ptr(x), _ptr(y), x.numel(), _stream()), "leco_cast")
+    return y
+
+
+def cast_bf16_to_f32(x):
+    y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    capi.check(_lib().leco_cast_bf16_to_f32(_ptr(x), _ptr(y), x.numel(), _stream()), "leco_cast")
+    return y
+
+
+# --------------------------------------------------------------------------------------
+# plumbing helpers (allocation / memset / tiny copies: torch's allocator, no math)
+# --------------------------------------------------------------------------------------
+def clone(x):
+    return x.clone()
+
+
+def zeros_like(x):
+    return torch.zeros_like(x)
+
+
+def empty_like(x):
+    return torch.empty_like(x)
+
+
+def zeros(shape, like, dtype=None):
+    return torch.zeros(shape, device=like.device, dtype=dtype or like.dtype)
+
+
+def cat_cols(a, b):
+    return torch.cat([a, b], dim=1).contiguous()
+
+
+def transpose2d(x: torch.Tensor) -> torch.Tensor:
+    """[R,C] -> contiguous [C,R]."""
+    return transpose_batched(x.unsqueeze(0).unsqueeze(0)).squeeze(0).squeeze(0)
+
+
+# --------------------------------------------------------------------------------------
+# attention v0: S = scale QK^T (tcgen05 batched GEMM, fp32) -> row softmax -> P V (tcgen05)
+# P is materialised; the fused flash kernel replaces this on the no-grad path.
+# --------------------------------------------------------------------------------------
+def _heads_view(t2d: torch.Tensor, nb: int, s: int, heads: int, d: int) -> torch.Tensor:
+    """[nb*s, heads*d] (row stride free) -> strided view [nb, heads, s, d]."""
+    return t2d.unflatten(0, (nb, s)).unflatten(2, (heads, d)).permute(0, 2, 1, 3)
+
+
+def attention(qt, kt, vt, nb, sq, skv, heads, d, scale, save_for_bwd=False):
+    skv_pad = (skv + 15) // 16 * 16
+    q4, k4, v4 = _heads_view(qt, nb, sq, heads, d), _heads_view(kt, nb, skv, heads, d), _heads_view(vt, nb, skv, heads, d)
+    S = torch.empty((nb, heads, sq, skv_pad), device=qt.device, dtype=torch.float32)
+    gemm_batched(q4, k4, S, alpha=scale, n_pad=skv_pad if skv_pad != skv else 0)
+    P = softmax_rows(S, skv, skv_pad)
+    del S
+    Vt = transpose_batched(v4, cols_pad=skv_pad)               # [nb, heads, d, skv_pad]
+    o = torch.empty((nb * sq, heads * d), device=qt.device, dtype=BF16)
+    gemm_batched(P, Vt, _heads_view(o, nb, sq, heads, d))
+    return o, ((P,) if save_for_bwd else None)
+
+
+def attention_bwd(go, qt, kt, vt, saved, nb, sq, skv, heads, d, scale, dq_out, dk_out, dv_out):
+    """Writes d(q), d(k), d(v) into the given [rows, heads*d] views (any may be None)."""
+    (P,) = saved
+    skv_pad = P.shape[-1]
+    pad = skv_pad if skv_pad != skv else 0
+    q4, k4, v4 = _heads_view(qt, nb, sq, heads, d), _heads_view(kt, nb, skv, heads, d), _heads_view(vt, nb, skv, heads, d)
+    go4 = _heads_view(go, nb, sq, heads, d)
+    dP = torch.empty((nb, heads, sq, skv_pad), device=go.device, dtype=torch.float32)
+    gemm_batched(go4, v4, dP, n_pad=pad)                         # dP = dO V^T
+    dS = softmax_bwd_rows(P, dP, skv, scale)                     # scale * P o (dP - rowsum(P o dP))
+    del dP
+    if dv_out is not None:
+        Pt = transpose_batched(P)                                # [.., skv_pad, sq]
+        goT = transpose_batched(go4)                             # [.., d, sq]
+        gemm_batched(Pt[:, :, :skv], goT, _heads_view(dv_out, nb, skv, heads, d))
+        del Pt, goT
+    if dq_out is not None:
+        Kt = transpose_batched(k4, cols_pad=skv_pad)             # [.., d, skv_pad]
+        gemm_batched(dS, Kt, _heads_view(dq_out, nb, sq, heads, d))
+    if dk_out is not None:
+        dSt = transpose_batched(dS)                              # [.., skv_pad, sq]
+        Qt = transpose_batched(q4)                               # [.., d, sq]
+        gemm_batched(dSt[:, :, :skv], Qt, _heads_view(dk_out, nb, skv, heads, d))

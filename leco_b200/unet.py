@@ -1,0 +1,821 @@
+"""Engine-backed UNet: the object handed to the reference as `unet`.
+
+Drop-in boundary.  `EngineUNet` is what `lora.LoRANetwork(unet, ...)`
+(lora.py:109-156) walks and what `train_util.predict_noise` (train_util.py:156-160) calls:
+
+  * `named_modules()` yields a tree with diffusers' class names and attribute paths
+    (`Transformer2DModel`, `ResnetBlock2D`, `Downsample2D`, `Upsample2D` holding real
+    `nn.Linear` / `nn.Conv2d` children) so the reference's string matching (lora.py:62,68,
+    188-197) finds the same 192 / 278 / 722 targets and exports the same key names;
+  * the children only OWN the frozen weights.  Nothing here ever calls their `forward`:
+    the network is executed by hand-written sm_100a kernels through `leco_b200.ops`
+    (tcgen05 GEMM / implicit-GEMM conv with the LoRA residual as an extra K-segment,
+    GroupNorm/LayerNorm/attention kernels);
+  * `LoRAModule.apply_to` (lora.py:97-100) replaces `child.forward` by the adapter's bound
+    method; the engine recognises that patch (`child.forward.__self__`) and reads
+    `lora_down/lora_up/multiplier/scale` LIVE from it, so `with network:` (lora.py:231-237)
+    and `optimizer.step()` behave exactly as with the reference UNet;
+  * backward (only d(input) chains and the LoRA weight gradients exist — every other
+    parameter is frozen, train_lora.py:69) is a reverse walk over a tape of engine ops.
+
+The numerical backend is injected (`backend=`): the product uses `leco_b200.ops` (CUDA, no
+fallback); the CPU test-suite injects a plain-torch double to validate this file's wiring
+(forward order, skip connections, chain rule) against the oracle.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+# --------------------------------------------------------------------------- configs
+@dataclass
+class UNetSpec:
+    """Public unet/config.json values (diffusers 0.20) that define the topology."""
+    name: str
+    block_out_channels: Sequence[int] = (320, 640, 1280, 1280)
+    attn_levels: Sequence[bool] = (True, True, True, False)
+    layers_per_block: int = 2
+    cross_attention_dim: int = 768
+    num_heads: Sequence[int] = (8, 8, 8, 8)
+    transformer_depth: Sequence[int] = (1, 1, 1, 1)
+    use_linear_projection: bool = False
+    norm_groups: int = 32
+    text_time: bool = False  # SDXL addition_embed_type="text_time"
+    add_time_dim: int = 256
+    add_proj_in: int = 2816
+    in_channels: int = 4
+    out_channels: int = 4
+
+    @property
+    def temb_dim(self) -> int:
+        return self.block_out_channels[0] * 4
+
+
+SPECS: Dict[str, UNetSpec] = {
+    "sd15": UNetSpec("sd15", cross_attention_dim=768, num_heads=(8, 8, 8, 8)),
+    "sd21": UNetSpec("sd21", cross_attention_dim=1024, num_heads=(5, 10, 20, 20), use_linear_projection=True),
+    "sdxl": UNetSpec("sdxl", block_out_channels=(320, 640, 1280), attn_levels=(False, True, True),
+                     cross_attention_dim=2048, num_heads=(5, 10, 20), transformer_depth=(1, 2, 10),
+                     use_linear_projection=True, text_time=True),
+    "tiny21": UNetSpec("tiny21", block_out_channels=(64, 128, 256, 256), cross_attention_dim=128,
+                       num_heads=(1, 2, 4, 4), use_linear_projection=True),
+    "tiny15": UNetSpec("tiny15", block_out_channels=(64, 128, 256, 256), cross_attention_dim=96,
+                       num_heads=(8, 8, 8, 8)),
+    "tinyxl": UNetSpec("tinyxl", block_out_channels=(64, 128, 256), attn_levels=(False, True, True),
+                       cross_attention_dim=128, num_heads=(1, 2, 4), transformer_depth=(1, 2, 3),
+                       use_linear_projection=True, text_time=True, add_time_dim=32, add_proj_in=32 * 6 + 64),
+}
+
+
+# --------------------------------------------------------------------------- module tree
+# Parameter holders only.  Class names / attribute paths mirror diffusers because the
+# reference matches on them (lora.py:188-197).  `forward` of a holder is never used.
+class _Holder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover - engine never dispatches through modules
+        raise RuntimeError("leco_b200 modules are parameter holders; call EngineUNet instead")
+
+
+class TimestepEmbedding(_Holder):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.linear_1 = nn.Linear(cin, cout)
+        self.linear_2 = nn.Linear(cout, cout)
+
+
+class ResnetBlock2D(_Holder):
+    def __init__(self, cin, cout, temb, groups):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, cin, eps=1e-5)
+        self.conv1 = nn.Conv2d(cin, cout, 3, 1, 1)
+        self.time_emb_proj = nn.Linear(temb, cout)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=1e-5)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1)
+        self.conv_shortcut = nn.Conv2d(cin, cout, 1, 1, 0) if cin != cout else None
+
+
+class Downsample2D(_Holder):
+    def __init__(self, ch):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, 2, 1)
+
+
+class Upsample2D(_Holder):
+    def __init__(self, ch):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, 1, 1)
+
+
+class Attention(_Holder):
+    def __init__(self, qdim, ctx_dim, heads, dim_head):
+        super().__init__()
+        inner = heads * dim_head
+        self.heads, self.dim_head = heads, dim_head
+        self.to_q = nn.Linear(qdim, inner, bias=False)
+        self.to_k = nn.Linear(ctx_dim or qdim, inner, bias=False)
+        self.to_v = nn.Linear(ctx_dim or qdim, inner, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(inner, qdim), nn.Identity()])
+
+
+class GEGLU(_Holder):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.proj = nn.Linear(cin, cout * 2)
+
+
+class FeedForward(_Holder):
+    def __init__(self, dim):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * 4), nn.Identity(), nn.Linear(dim * 4, dim)])
+
+
+class BasicTransformerBlock(_Holder):
+    def __init__(self, dim, heads, dim_head, ctx_dim):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn1 = Attention(dim, None, heads, dim_head)
+        self.norm2 = nn.LayerNorm(dim)
+        self.attn2 = Attention(dim, ctx_dim, heads, dim_head)
+        self.norm3 = nn.LayerNorm(dim)
+        self.ff = FeedForward(dim)
+
+
+class Transformer2DModel(_Holder):
+    def __init__(self, heads, dim_head, ch, depth, ctx_dim, linear_proj, groups):
+        super().__init__()
+        inner = heads * dim_head
+        self.norm = nn.GroupNorm(groups, ch, eps=1e-6)
+        self.proj_in = nn.Linear(ch, inner) if linear_proj else nn.Conv2d(ch, inner, 1, 1, 0)
+        self.transformer_blocks = nn.ModuleList(
+            [BasicTransformerBlock(inner, heads, dim_head, ctx_dim) for _ in range(depth)])
+        self.proj_out = nn.Linear(inner, ch) if linear_proj else nn.Conv2d(inner, ch, 1, 1, 0)
+
+
+class _Block(_Holder):
+    def __init__(self, resnets, attentions, sampler_name=None, sampler=None):
+        super().__init__()
+        self.resnets = nn.ModuleList(resnets)
+        if attentions is not None:
+            self.attentions = nn.ModuleList(attentions)
+        if sampler is not None:
+            setattr(self, sampler_name, nn.ModuleList([sampler]))
+
+
+def _build_tree(root: nn.Module, s: UNetSpec):
+    ch = list(s.block_out_channels)
+    L = len(ch)
+    temb = s.temb_dim
+
+    def tr(c, heads, depth):
+        return Transformer2DModel(heads, c // heads, c, depth, s.cross_attention_dim,
+                                  s.use_linear_projection, s.norm_groups)
+
+    root.conv_in = nn.Conv2d(s.in_channels, ch[0], 3, 1, 1)
+    root.time_embedding = TimestepEmbedding(ch[0], temb)
+    if s.text_time:
+        root.add_embedding = TimestepEmbedding(s.add_proj_in, temb)
+    downs = []
+    out = ch[0]
+    for i in range(L):
+        cin, out = out, ch[i]
+        res = [ResnetBlock2D(cin if j == 0 else out, out, temb, s.norm_groups) for j in range(s.layers_per_block)]
+        att = [tr(out, s.num_heads[i], s.transformer_depth[i]) for _ in range(s.layers_per_block)] \
+            if s.attn_levels[i] else None
+        downs.append(_Block(res, att, "downsamplers", Downsample2D(out) if i != L - 1 else None))
+    root.down_blocks = nn.ModuleList(downs)
+    root.mid_block = _Block([ResnetBlock2D(ch[-1], ch[-1], temb, s.norm_groups) for _ in range(2)],
+                            [tr(ch[-1], s.num_heads[-1], s.transformer_depth[-1])])
+    ups = []
+    rch, rheads = ch[::-1], list(s.num_heads)[::-1]
+    rdepth, rattn = list(s.transformer_depth)[::-1], list(s.attn_levels)[::-1]
+    out = rch[0]
+    for i in range(L):
+        prev, out = out, rch[i]
+        cin = rch[min(i + 1, L - 1)]
+        n = s.layers_per_block + 1
+        res = []
+        for j in range(n):
+            skip = cin if j == n - 1 else out
+            rin = prev if j == 0 else out
+            res.append(ResnetBlock2D(rin + skip, out, temb, s.norm_groups))
+        att = [tr(out, rheads[i], rdepth[i]) for _ in range(n)] if rattn[i] else None
+        ups.append(_Block(res, att, "upsamplers", Upsample2D(out) if i != L - 1 else None))
+    root.up_blocks = nn.ModuleList(ups)
+    root.conv_norm_out = nn.GroupNorm(s.norm_groups, ch[0], eps=1e-5)
+    root.conv_out = nn.Conv2d(ch[0], s.out_channels, 3, 1, 1)
+
+
+# --------------------------------------------------------------------------- tape
+class Act:
+    """An activation tensor plus 'does anything trainable sit upstream of it'."""
+    __slots__ = ("t", "rg")
+
+    def __init__(self, t, rg=False):
+        self.t, self.rg = t, rg
+
+
+class Tape:
+    """Reverse-mode tape over engine ops.  Gradients are keyed by tensor identity."""
+
+    def __init__(self, be):
+        self.be = be
+        self.nodes: List[Callable[[], None]] = []
+        self.grads: Dict[int, torch.Tensor] = {}
+        self._keep: List[torch.Tensor] = []
+        self._aliased: set = set()
+
+    def record(self, fn):
+        self.nodes.append(fn)
+
+    def grad(self, t):
+        return self.grads.get(id(t))
+
+    def accum(self, t, g, owned: bool):
+        """grads[t] += g.  `owned`=False means g is someone else's buffer (aliasing is allowed
+        once per buffer; a second alias is copied so in-place accumulation stays safe)."""
+        k = id(t)
+        if k in self.grads:
+            self.be.add_(self.grads[k], g)
+            return
+        if not owned:
+            if id(g) in self._aliased:
+                g = self.be.clone(g)
+            else:
+                self._aliased.add(id(g))
+        self.grads[k] = g
+        self._keep.append(t)
+
+    def backward(self):
+        for fn in reversed(self.nodes):
+            fn()
+        self.nodes.clear()
+
+
+# --------------------------------------------------------------------------- LoRA discovery
+def find_adapter(child: nn.Module):
+    """The LoRAModule whose bound `forward` replaced child.forward (lora.py:97-100), or None."""
+    owner = getattr(getattr(child, "forward", None), "__self__", None)
+    if owner is None or owner is child:
+        return None
+    if hasattr(owner, "lora_down") and hasattr(owner, "lora_up"):
+        return owner
+    return None
+
+
+class LoraSite:
+    """One fused GEMM site with up to three adapted nn.Linear / 1x1-conv members sharing an
+    input (q,k,v / k,v) or a single member.  Holds the padded tensor-core operands:
+        ad  [Kl, K]  rows = stacked lora_down weights (zero rows pad Kl to a multiple of 16)
+        bup [N, Kl]  block structure: member i occupies rows n_off_i.., cols k_off_i..
+    Values are re-copied from the adapter parameters whenever their version counters move."""
+
+    def __init__(self, members: List[nn.Module], n_offsets: List[int], n_total: int, k_in: int):
+        self.members, self.n_offsets, self.n_total, self.k_in = members, n_offsets, n_total, k_in
+        self.ad = self.bup = None
+        self._versions = None
+        self._adapters = None
+
+    def adapters(self):
+        ads = [find_adapter(m) for m in self.members]
+        if all(a is None for a in ads):
+            return None
+        if any(a is None for a in ads):
+            raise RuntimeError("leco_b200: partially adapted fused projection group is unsupported")
+        return ads
+
+    def active(self):
+        """(adapters, multiplier) if the LoRA branch contributes, else None (multiplier == 0 is
+        skipped: exact)."""
+        ads = self.adapters()
+        if ads is None:
+            return None
+        mult = float(ads[0].multiplier)
+        if any(float(a.multiplier) != mult for a in ads):
+            raise RuntimeError("leco_b200: adapters of one fused site disagree on multiplier")
+        if mult == 0.0:
+            return None
+        return ads, mult
+
+    def refresh(self, ads, device, dtype):
+        ranks = [a.lora_down.weight.shape[0] for a in ads]
+        kl = (sum(ranks) + 15) // 16 * 16
+        if kl > 64:
+            raise RuntimeError(f"leco_b200: fused LoRA rank {sum(ranks)} > 64 is unsupported")
+        vers = tuple((a.lora_down.weight._version, a.lora_up.weight._version, a.lora_down.weight.data_ptr())
+                     for a in ads)
+        if self.ad is None or self.ad.shape[0] != kl or self.ad.device != device:
+            self.ad = torch.zeros((kl, self.k_in), device=device, dtype=dtype)
+            self.bup = torch.zeros((self.n_total, kl), device=device, dtype=dtype)
+            self._versions = None
+        if vers != self._versions:
+            k0 = 0
+            for a, n0, r in zip(ads, self.n_offsets, ranks):
+                wd = a.lora_down.weight.detach()
+                wu = a.lora_up.weight.detach()
+                self.ad[k0:k0 + r].copy_(wd.reshape(r, -1))
+                n = wu.shape[0]
+                self.bup[n0:n0 + n, k0:k0 + r].copy_(wu.reshape(n, r))
+                k0 += r
+            self._versions = vers
+        self.ranks = ranks
+        return self.ad, self.bup
+
+    # fp32 gradient accumulators in operand layout (zeroed per backward)
+    def begin_grad(self, be):
+        self.g_ad = self.g_bup = None
+
+    def grad_ad(self, be):
+        if self.g_ad is None:
+            self.g_ad = be.zeros(self.ad.shape, self.ad, torch.float32)
+        return self.g_ad
+
+    def grad_bup(self, be):
+        if self.g_bup is None:
+            self.g_bup = be.zeros(self.bup.shape, self.bup, torch.float32)
+        return self.g_bup
+
+    def collect_grads(self, be):
+        """[d lora_down.weight, d lora_up.weight] per member, in the adapters' own shapes/dtypes."""
+        out, k0 = [], 0
+        ads = self.adapters()
+        for a, n0, r in zip(ads, self.n_offsets, self.ranks):
+            wd, wu = a.lora_down.weight, a.lora_up.weight
+            n = wu.shape[0]
+            gd = None if self.g_ad is None else self.g_ad[k0:k0 + r].reshape(wd.shape).to(wd.dtype)
+            gu = None if self.g_bup is None else self.g_bup[n0:n0 + n, k0:k0 + r].reshape(wu.shape).to(wu.dtype)
+            out += [gd, gu]
+            k0 += r
+        self.g_ad = self.g_bup = None
+        return out
+
+
+# --------------------------------------------------------------------------- packed weights
+class LinearPack:
+    """Frozen weights of one GEMM site in kernel layout (bf16): w [N,K], wt [K,N], bias [N]."""
+
+    def __init__(self, mods: List[nn.Module], device, dtype, need_wt=True):
+        ws, bs = [], []
+        for m in mods:
+            w = m.weight.detach()
+            ws.append(w.reshape(w.shape[0], -1))
+            if m.bias is not None:
+                bs.append(m.bias.detach())
+        w = torch.cat(ws, 0).to(device=device, dtype=dtype).contiguous()
+        self.w = w
+        self.wt = w.t().contiguous() if need_wt else None
+        self.bias = torch.cat(bs).to(device=device, dtype=dtype).contiguous() if bs else None
+        n_off, o = [], 0
+        for x in ws:
+            n_off.append(o)
+            o += x.shape[0]
+        self.site = LoraSite(mods, n_off, o, w.shape[1])
+        self.n, self.k = w.shape
+
+
+class ConvPack:
+    """3x3 conv in implicit-GEMM layout: w [O, 9*I] (k = tap*I + c); wt_flip [I, 9*O] for d(input)."""
+
+    def __init__(self, m: nn.Conv2d, device, dtype):
+        w = m.weight.detach().to(device=device, dtype=dtype)  # OIHW
+        O, I = w.shape[0], w.shape[1]
+        self.w = w.permute(0, 2, 3, 1).reshape(O, 9 * I).contiguous()
+        # d(input)[p, i] = sum_{tap, o} dy[p - off(tap), o] w[o, i, tap] = conv3x3(dy, flipped/transposed w)
+        self.wt_flip = w.flip(2, 3).permute(1, 2, 3, 0).reshape(I, 9 * O).contiguous()
+        self.wt = self.w.t().contiguous()  # [9I, O] for the stride-2 (im2col) variant's d(col)
+        self.bias = m.bias.detach().to(device=device, dtype=dtype).contiguous() if m.bias is not None else None
+        self.stride = m.stride[0]
+        self.cin, self.cout = I, O
+        self.module = m
+
+
+class NormPack:
+    def __init__(self, m, device, dtype):
+        self.gamma = m.weight.detach().to(device=device, dtype=dtype).contiguous()
+        self.beta = m.bias.detach().to(device=device, dtype=dtype).contiguous()
+        self.eps = m.eps
+        self.groups = getattr(m, "num_groups", None)
+
+
+# --------------------------------------------------------------------------- the engine
+class EngineUNet(nn.Module):
+    """`unet` duck type of the reference: callable
+    `unet(sample[2B,4,h,w], timestep, encoder_hidden_states=[2B,77,D], added_cond_kwargs=None).sample`,
+    plus `.to / .requires_grad_ / .eval / .enable_xformers_memory_efficient_attention`."""
+
+    def __init__(self, spec: UNetSpec, backend=None):
+        super().__init__()
+        self.spec = spec
+        self.config = SimpleNamespace(in_channels=spec.in_channels,
+                                      addition_embed_type="text_time" if spec.text_time else None)
+        _build_tree(self, spec)
+        self._be = backend
+        self._packed = False
+        self._act_dtype = torch.bfloat16
+        self._last_tape: Optional[Tape] = None
+        self.attention_impl = "auto"
+
+    # ---- reference-facing no-ops -------------------------------------------------------
+    def enable_xformers_memory_efficient_attention(self, *a, **k):  # train_lora.py:68
+        return None
+
+    @property
+    def backend(self):
+        if self._be is None:
+            from . import ops  # product path: CUDA only, raises if the library is missing
+            self._be = ops
+        return self._be
+
+    # ---- weight packing ----------------------------------------------------------------
+    def pack(self, device=None, dtype=None):
+        """(Re)build kernel-layout copies of the frozen weights on `device`."""
+        p = next(self.parameters())
+        device = device or p.device
+        dtype = dtype or self._act_dtype
+        s = self.spec
+        P = SimpleNamespace()
+        P.conv_in_w = self.conv_in.weight.detach().to(device=device, dtype=dtype).contiguous()
+        P.conv_in_b = self.conv_in.bias.detach().to(device=device, dtype=dtype).contiguous()
+        P.time1 = LinearPack([self.time_embedding.linear_1], device, dtype, need_wt=False)
+        P.time2 = LinearPack([self.time_embedding.linear_2], device, dtype, need_wt=False)
+        if s.text_time:
+            P.add1 = LinearPack([self.add_embedding.linear_1], device, dtype, need_wt=False)
+            P.add2 = LinearPack([self.add_embedding.linear_2], device, dtype, need_wt=False)
+        resnets: List[ResnetBlock2D] = [m for m in self.modules() if isinstance(m, ResnetBlock2D)]
+        P.temb_all = LinearPack([r.time_emb_proj for r in resnets], device, dtype, need_wt=False)
+        P.res = {}
+        off = 0
+        for r in resnets:
+            rp = SimpleNamespace(norm1=NormPack(r.norm1, device, dtype), conv1=ConvPack(r.conv1, device, dtype),
+                                 norm2=NormPack(r.norm2, device, dtype), conv2=ConvPack(r.conv2, device, dtype),
+                                 shortcut=LinearPack([r.conv_shortcut], device, dtype) if r.conv_shortcut is not None else None,
+                                 temb_off=off, cout=r.conv1.out_channels)
+            off += r.conv1.out_channels
+            P.res[id(r)] = rp
+        P.tr = {}
+        for t in (m for m in self.modules() if isinstance(m, Transformer2DModel)):
+            tp = SimpleNamespace(norm=NormPack(t.norm, device, dtype),
+                                 proj_in=LinearPack([t.proj_in], device, dtype),
+                                 proj_out=LinearPack([t.proj_out], device, dtype), blocks=[])
+            for b in t.transformer_blocks:
+                tp.blocks.append(SimpleNamespace(
+                    norm1=NormPack(b.norm1, device, dtype), norm2=NormPack(b.norm2, device, dtype),
+                    norm3=NormPack(b.norm3, device, dtype),
+                    qkv=LinearPack([b.attn1.to_q, b.attn1.to_k, b.attn1.to_v], device, dtype),
+                    out1=LinearPack([b.attn1.to_out[0]], device, dtype),
+                    q2=LinearPack([b.attn2.to_q], device, dtype),
+                    kv2=LinearPack([b.attn2.to_k, b.attn2.to_v], device, dtype),
+                    out2=LinearPack([b.attn2.to_out[0]], device, dtype),
+                    ff1=LinearPack([b.ff.net[0].proj], device, dtype),
+                    ff2=LinearPack([b.ff.net[2]], device, dtype),
+                    heads=b.attn1.heads, dim_head=b.attn1.dim_head))
+            P.tr[id(t)] = tp
+        P.samp = {}
+        for m in self.modules():
+            if isinstance(m, (Downsample2D, Upsample2D)):
+                P.samp[id(m)] = ConvPack(m.conv, device, dtype)
+        P.norm_out = NormPack(self.conv_norm_out, device, dtype)
+        wo = self.conv_out.weight.detach().to(device=device, dtype=dtype)
+        P.conv_out_w = wo.permute(0, 2, 3, 1).reshape(wo.shape[0], 9, wo.shape[1]).contiguous()
+        P.conv_out_b = self.conv_out.bias.detach().to(device=device, dtype=dtype).contiguous()
+        self._P = P
+        self._packed = True
+        self._pack_device = device
+        return self
+
+    def _ensure_packed(self, device):
+        if not self._packed or self._pack_device != device:
+            self.pack(device)
+
+    # ---- ops with backward rules ---------------------------------------------------------
+    def _linear(self, be, tape, x: Act, pk: LinearPack, residual: Optional[Act] = None, geglu=False,
+                conv_nhw=None):
+        """y = x W^T + b (+ s*(x A^T) B^T) (+ residual)   — lora.py:102-106 fused."""
+        act = pk.site.active()
+        kw = {}
+        T = ad = bup = None
+        scale = mult = 1.0
+        if act is not None:
+            ads, mult = act
+            ad, bup = pk.site.refresh(ads, x.t.device, x.t.dtype)
+            scale = float(ads[0].scale)
+            T = be.gemm(x.t, ad, alpha=scale * mult)          # T = s*m * x A^T   [M, Kl]
+            kw.update(lora_t=T, lora_up=bup)
+        rg_out = x.rg or (residual is not None and residual.rg) or act is not None
+        y = be.gemm(x.t, pk.w, bias=pk.bias, residual=None if residual is None else residual.t, geglu=geglu, **kw)
+        out = Act(y, rg_out and tape is not None)
+        if tape is not None and out.rg:
+            assert not geglu, "GEGLU epilogue is used on the no-grad path only"
+
+            def bwd():
+                gy = tape.grad(y)
+                if gy is None:
+                    return
+                if residual is not None and residual.rg:
+                    tape.accum(residual.t, gy, owned=False)
+                kw2 = {}
+                if act is not None:
+                    sm = scale * mult
+                    bupT = be.transpose2d(bup)                       # [Kl, N]
+                    dT = be.gemm(gy, bupT, alpha=sm)                 # s*m * dY B      [M, Kl]
+                    # dB[n,k] += sum_m dY[m,n] T[m,k]   (T already carries s*m)
+                    be.tn_reduce(gy, T, pk.site.grad_bup(be))
+                    # dA[k,j] += sum_m dT[m,k] x[m,j]   -> accumulated transposed-in-place
+                    be.tn_reduce(x.t, dT, pk.site.grad_ad(be), transpose_out=True)
+                    if x.rg:
+                        kw2.update(lora_t=dT, lora_up=be.transpose2d(ad))   # + dT A
+                if x.rg:
+                    dx = be.gemm(gy, pk.wt, **kw2)
+                    tape.accum(x.t, dx, owned=True)
+            tape.record(bwd)
+        return out
+
+    def _conv3x3(self, be, tape, x: Act, pk: ConvPack, n, h, w, rowbias=None, residual: Optional[Act] = None):
+        if find_adapter(pk.module) is not None:
+            raise NotImplementedError("leco_b200: conv (c3lier) LoRA sites are not wired yet")
+        y = be.gemm(x.t, pk.w, bias=pk.bias, rowbias=rowbias, rows_per_group=h * w,
+                    residual=None if residual is None else residual.t, conv_nhw=(n, h, w))
+        out = Act(y, (x.rg or (residual is not None and residual.rg)) and tape is not None)
+        if out.rg:
+            def bwd():
+                gy = tape.grad(y)
+                if gy is None:
+                    return
+                if residual is not None and residual.rg:
+                    tape.accum(residual.t, gy, owned=False)
+                if x.rg:
+                    tape.accum(x.t, be.gemm(gy, pk.wt_flip, conv_nhw=(n, h, w)), owned=True)
+            tape.record(bwd)
+        return out
+
+    def _conv_s2(self, be, tape, x: Act, pk: ConvPack, n, h, w):
+        if find_adapter(pk.module) is not None:
+            raise NotImplementedError("leco_b200: conv (c3lier) LoRA sites are not wired yet")
+        col = be.im2col_s2(x.t, n, h, w)
+        y = be.gemm(col, pk.w, bias=pk.bias)
+        out = Act(y, x.rg and tape is not None)
+        if out.rg:
+            def bwd():
+                gy = tape.grad(y)
+                if gy is not None:
+                    tape.accum(x.t, be.col2im_s2(be.gemm(gy, pk.wt), n, h, w), owned=True)
+            tape.record(bwd)
+        return out
+
+    def _group_norm(self, be, tape, x: Act, pk: NormPack, n, hw, silu):
+        y, stats = be.group_norm(x.t, n, hw, pk.gamma, pk.beta, pk.groups, pk.eps, silu)
+        out = Act(y, x.rg and tape is not None)
+        if out.rg:
+            def bwd():
+                gy = tape.grad(y)
+                if gy is not None:
+                    tape.accum(x.t, be.group_norm_bwd(x.t, gy, stats, pk.gamma, pk.beta, n, hw, pk.groups, silu),
+                               owned=True)
+            tape.record(bwd)
+        return out
+
+    def _layer_norm(self, be, tape, x: Act, pk: NormPack):
+        want = x.rg and tape is not None
+        y, stats = be.layer_norm(x.t, pk.gamma, pk.beta, pk.eps, want)
+        out = Act(y, want)
+        if want:
+            def bwd():
+                gy = tape.grad(y)
+                if gy is not None:
+                    tape.accum(x.t, be.layer_norm_bwd(x.t, gy, stats, pk.gamma), owned=True)
+            tape.record(bwd)
+        return out
+
+    def _attention(self, be, tape, qa: Act, qc: int, ka: Act, kc: int, va: Act, vc: int, nb, sq, skv, heads, d):
+        """softmax(Q K^T / sqrt(d)) V per (sample, head).  Q/K/V are column blocks (offsets qc/kc/vc,
+        width heads*d) of the fused projection outputs owned by the Acts qa/ka/va."""
+        C = heads * d
+        scale = d ** -0.5
+        qt, kt, vt = qa.t[:, qc:qc + C], ka.t[:, kc:kc + C], va.t[:, vc:vc + C]
+        rg = (qa.rg or ka.rg or va.rg) and tape is not None
+        o, saved = be.attention(qt, kt, vt, nb, sq, skv, heads, d, scale, rg)
+        out = Act(o, rg)
+        if rg:
+            def bwd():
+                go = tape.grad(o)
+                if go is None:
+                    return
+                # the projections feed only this attention: their gradient buffers are written here
+                bufs = {}
+                for owner in (qa, ka, va):
+                    if owner.rg and id(owner.t) not in bufs:
+                        assert tape.grad(owner.t) is None
+                        bufs[id(owner.t)] = be.empty_like(owner.t)
+
+                def view(owner, c0):
+                    return bufs[id(owner.t)][:, c0:c0 + C] if owner.rg else None
+                be.attention_bwd(go, qt, kt, vt, saved, nb, sq, skv, heads, d, scale,
+                                 view(qa, qc), view(ka, kc), view(va, vc))
+                for owner in (qa, ka, va):
+                    if owner.rg and id(owner.t) in bufs:
+                        tape.accum(owner.t, bufs.pop(id(owner.t)), owned=True)
+            tape.record(bwd)
+        return out
+
+    # ---- network pieces ---------------------------------------------------------------
+    def _resnet(self, be, tape, x: Act, rp, temb_all, n, h, w):
+        hw = h * w
+        hdn = self._group_norm(be, tape, x, rp.norm1, n, hw, True)
+        rb = temb_all[:, rp.temb_off:rp.temb_off + rp.cout]
+        hdn = self._conv3x3(be, tape, hdn, rp.conv1, n, h, w, rowbias=rb)
+        hdn = self._group_norm(be, tape, hdn, rp.norm2, n, hw, True)
+        sc = x if rp.shortcut is None else self._linear(be, tape, x, rp.shortcut)
+        return self._conv3x3(be, tape, hdn, rp.conv2, n, h, w, residual=sc)
+
+    def _transformer(self, be, tape, x: Act, tp, ctx: Act, n, h, w):
+        hw = h * w
+        hdn = self._group_norm(be, tape, x, tp.norm, n, hw, False)
+        hdn = self._linear(be, tape, hdn, tp.proj_in)
+        for bp in tp.blocks:
+            C = bp.heads * bp.dim_head
+            n1 = self._layer_norm(be, tape, hdn, bp.norm1)
+            qkv = self._linear(be, tape, n1, bp.qkv)
+            a = self._attention(be, tape, qkv, 0, qkv, C, qkv, 2 * C, n, hw, hw, bp.heads, bp.dim_head)
+            hdn = self._linear(be, tape, a, bp.out1, residual=hdn)
+            n2 = self._layer_norm(be, tape, hdn, bp.norm2)
+            q2 = self._linear(be, tape, n2, bp.q2)
+            kv = self._linear(be, tape, ctx, bp.kv2)
+            skv = ctx.t.shape[0] // n
+            a = self._attention(be, tape, q2, 0, kv, 0, kv, C, n, hw, skv, bp.heads, bp.dim_head)
+            hdn = self._linear(be, tape, a, bp.out2, residual=hdn)
+            n3 = self._layer_norm(be, tape, hdn, bp.norm3)
+            if tape is None:
+                f = self._linear(be, None, n3, bp.ff1, geglu=True)
+            else:
+                pre = self._linear(be, tape, n3, bp.ff1)
+                f = self._geglu(be, tape, pre)
+            hdn = self._linear(be, tape, f, bp.ff2, residual=hdn)
+        return self._linear(be, tape, hdn, tp.proj_out, residual=x)
+
+    def _geglu(self, be, tape, pre: Act):
+        y = be.geglu_fwd(pre.t)
+        out = Act(y, pre.rg and tape is not None)
+        if out.rg:
+            def bwd():
+                gy = tape.grad(y)
+                if gy is not None:
+                    tape.accum(pre.t, be.geglu_bwd(pre.t, gy), owned=True)
+            tape.record(bwd)
+        return out
+
+    def _concat(self, be, tape, a: Act, b: Act):
+        y = be.concat2(a.t, b.t)
+        out = Act(y, (a.rg or b.rg) and tape is not None)
+        if out.rg:
+            ca = a.t.shape[1]
+
+            def bwd():
+                gy = tape.grad(y)
+                if gy is None:
+                    return
+                ga, gb = be.split2(gy, ca)
+                if a.rg:
+                    tape.accum(a.t, ga, owned=True)
+                if b.rg:
+                    tape.accum(b.t, gb, owned=True)
+            tape.record(bwd)
+        return out
+
+    def _upsample(self, be, tape, x: Act, n, h, w):
+        y = be.upsample2x(x.t, n, h, w)
+        out = Act(y, x.rg and tape is not None)
+        if out.rg:
+            def bwd():
+                gy = tape.grad(y)
+                if gy is not None:
+                    tape.accum(x.t, be.upsample2x_bwd(gy, n, h, w), owned=True)
+            tape.record(bwd)
+        return out
+
+    # ---- the forward program -----------------------------------------------------------
+    def run(self, sample: torch.Tensor, t: torch.Tensor, ctx2d: torch.Tensor, added: Optional[dict] = None,
+            tape: Optional[Tape] = None):
+        """sample NCHW [N,4,h,w] (fp32 or activation dtype), t fp32 [N], ctx2d [N*S, D] activation
+        dtype -> (eps NCHW fp32 [N,4,h,w], final Act).  With `tape`, records the backward."""
+        be, s, P = self.backend, self.spec, self._P
+        N, _, H, W = sample.shape
+        # -- time embedding (no trainable inputs in scope: time_emb_proj is only adapted by c3lier)
+        te = be.timestep_embedding(t, s.block_out_channels[0])
+        emb = be.gemm(be.silu(be.gemm(te, P.time1.w, bias=P.time1.bias)), P.time2.w, bias=P.time2.bias)
+        if s.text_time:
+            ids = added["time_ids"].reshape(-1).to(torch.float32)
+            tid = be.timestep_embedding(ids, s.add_time_dim).reshape(N, -1)
+            add_in = be.cat_cols(added["text_embeds"].to(tid.dtype), tid)
+            aug = be.gemm(be.silu(be.gemm(add_in, P.add1.w, bias=P.add1.bias)), P.add2.w, bias=P.add2.bias)
+            emb = be.add_(emb, aug)
+        if any(find_adapter(m) is not None for m in P.temb_all.site.members):
+            raise NotImplementedError("leco_b200: time_emb_proj (c3lier) LoRA sites are not wired yet")
+        temb_all = be.gemm(be.silu(emb), P.temb_all.w, bias=P.temb_all.bias)
+
+        ctx = Act(ctx2d, False)
+        x = Act(be.conv_in(sample, P.conv_in_w, P.conv_in_b), False)
+        skips: List[Tuple[Act, int, int]] = [(x, H, W)]
+        h, w = H, W
+        for blk in self.down_blocks:
+            for i, r in enumerate(blk.resnets):
+                x = self._resnet(be, tape, x, P.res[id(r)], temb_all, N, h, w)
+                if hasattr(blk, "attentions"):
+                    x = self._transformer(be, tape, x, P.tr[id(blk.attentions[i])], ctx, N, h, w)
+                skips.append((x, h, w))
+            if hasattr(blk, "downsamplers"):
+                x = self._conv_s2(be, tape, x, P.samp[id(blk.downsamplers[0])], N, h, w)
+                h, w = h // 2, w // 2
+                skips.append((x, h, w))
+        mb = self.mid_block
+        x = self._resnet(be, tape, x, P.res[id(mb.resnets[0])], temb_all, N, h, w)
+        x = self._transformer(be, tape, x, P.tr[id(mb.attentions[0])], ctx, N, h, w)
+        x = self._resnet(be, tape, x, P.res[id(mb.resnets[1])], temb_all, N, h, w)
+        for blk in self.up_blocks:
+            for i, r in enumerate(blk.resnets):
+                sk, sh, sw = skips.pop()
+                assert (sh, sw) == (h, w)
+                x = self._concat(be, tape, x, sk)
+                x = self._resnet(be, tape, x, P.res[id(r)], temb_all, N, h, w)
+                if hasattr(blk, "attentions"):
+                    x = self._transformer(be, tape, x, P.tr[id(blk.attentions[i])], ctx, N, h, w)
+            if hasattr(blk, "upsamplers"):
+                x = self._upsample(be, tape, x, N, h, w)
+                h, w = h * 2, w * 2
+                x = self._conv3x3(be, tape, x, P.samp[id(blk.upsamplers[0])], N, h, w)
+        xn = self._group_norm(be, tape, x, P.norm_out, N, h * w, True)
+        eps = be.conv_out(xn.t, P.conv_out_w, P.conv_out_b, N, h, w)
+        if tape is not None and xn.rg:
+            C0 = s.block_out_channels[0]
+
+            def bwd():
+                g = tape.grads.get("eps")
+                if g is not None:
+                    tape.accum(xn.t, be.conv_out_bwd(g, P.conv_out_w, C0), owned=True)
+            tape.record(bwd)
+        return eps
+
+    # ---- reference call surface -----------------------------------------------------------
+    def lora_sites(self) -> List[LoraSite]:
+        out = []
+        P = self._P
+        for tp in P.tr.values():
+            out += [tp.proj_in.site, tp.proj_out.site]
+            for bp in tp.blocks:
+                out += [bp.qkv.site, bp.out1.site, bp.q2.site, bp.kv2.site, bp.out2.site, bp.ff1.site, bp.ff2.site]
+        return out
+
+    def forward(self, sample, timestep, encoder_hidden_states=None, added_cond_kwargs=None, **_):
+        """train_util.py:156-160 / :239-244.  Under autograd (grad enabled and an adapter with
+        multiplier != 0 attached) the result carries a grad_fn that routes d(sample) into the
+        adapters' `.grad` through the engine's own backward."""
+        dev = sample.device
+        self._ensure_packed(dev)
+        be = self.backend
+        N = sample.shape[0]
+        t = timestep
+        if not torch.is_tensor(t):
+            t = torch.tensor([float(t)], dtype=torch.float32)
+        t = t.reshape(-1).to(device=dev, dtype=torch.float32).expand(N).contiguous()
+        ctx2d = encoder_hidden_states.to(device=dev, dtype=self._act_dtype).reshape(
+            -1, encoder_hidden_states.shape[-1]).contiguous()
+        x_in = sample.detach().contiguous()
+        if x_in.dtype not in (torch.float32, self._act_dtype):
+            x_in = x_in.float()
+        sites = [s for s in self.lora_sites() if s.active() is not None]
+        if torch.is_grad_enabled() and sites:
+            params = []
+            for st in sites:
+                for a in st.adapters():
+                    params += [a.lora_down.weight, a.lora_up.weight]
+            eps = _EngineFn.apply(self, x_in, t, ctx2d, added_cond_kwargs, sites, *params)
+        else:
+            eps = self.run(x_in, t, ctx2d, added_cond_kwargs, None)
+        return SimpleNamespace(sample=eps.to(sample.dtype))
+
+
+class _EngineFn(torch.autograd.Function):
+    """One autograd node for the whole UNet: forward = engine program with a tape, backward =
+    tape walk producing the adapters' weight gradients (the only trainable tensors)."""
+
+    @staticmethod
+    def forward(ctx, eng: EngineUNet, x, t, ctx2d, added, sites, *params):
+        be = eng.backend
+        tape = Tape(be)
+        for st in sites:
+            st.begin_grad(be)
+        eps = eng.run(x, t, ctx2d, added, tape)
+        ctx.tape, ctx.sites, ctx.be = tape, sites, be
+        return eps
+
+    @staticmethod
+    def backward(ctx, g_eps):
+        tape, be = ctx.tape, ctx.be
+        tape.grads["eps"] = g_eps.contiguous().float()
+        tape.backward()
+        grads = []
+        for st in ctx.sites:
+            grads += st.collect_grads(be)
+        return (None, None, None, None, None, None, *grads)

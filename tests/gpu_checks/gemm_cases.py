@@ -58,15 +58,8 @@ def case_matrix(M, N, K, block_n=0, bias=False, rowbias=0, residual=False, lora=
         ref = ref + rb.float().repeat_interleave(rowbias, 0)[:M]
         kw.update(rowbias=rb, rows_per_group=rowbias)
     if geglu:
-        # library layout: rows interleaved in blocks of 64 (hidden j, gate j)
         h, gte = ref[:, :N // 2], ref[:, N // 2:]
         ref = h * torch.nn.functional.gelu(gte)
-        perm = torch.arange(N).reshape(2, N // 128, 64).permute(1, 0, 2).reshape(-1).cuda()
-        b = b[perm].contiguous()
-        if bias:
-            kw["bias"] = kw["bias"][perm].contiguous()
-        if lora:
-            kw["lora_up"] = kw["lora_up"][perm].contiguous()
     if residual:
         r = _rand(ref.shape, seed=7)
         ref = ref + r.float()

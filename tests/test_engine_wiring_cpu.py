@@ -1,0 +1,94 @@
+"""CPU: the engine's forward program and tape backward (leco_b200/unet.py) driven by the
+plain-torch test double must reproduce the oracle UNet (forward) and the oracle's autograd
+LoRA gradients, in fp32.  This validates wiring/algebra only; kernels are checked on the GPU."""
+import contextlib
+import io
+
+import pytest
+import torch
+
+from leco_b200.unet import SPECS, EngineUNet
+from oracle import leco_ref
+from oracle.unet_ref import CONFIGS, build_unet
+from tests import torch_backend
+
+
+def _inputs(arch, n=2, hw=16, seed=3):
+    cfg = CONFIGS[arch]
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((n, 4, hw, hw), generator=g)
+    ctx = torch.randn((n, 77, cfg.cross_attention_dim), generator=g)
+    added = None
+    if cfg.addition_embed_type:
+        pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
+        added = {"text_embeds": torch.randn((n, pooled), generator=g),
+                 "time_ids": torch.tensor([[128., 128, 0, 0, 128, 128]] * n)}
+    return x, ctx, added
+
+
+def _engine(arch, oracle):
+    eng = EngineUNet(SPECS[arch], backend=torch_backend)
+    eng.load_state_dict(oracle.state_dict())
+    eng._act_dtype = torch.float32
+    eng.requires_grad_(False)
+    return eng
+
+
+@pytest.mark.parametrize("arch", ["tiny21", "tiny15", "tinyxl"])
+def test_forward_matches_oracle(arch):
+    torch.manual_seed(0)
+    oracle = build_unet(arch)
+    eng = _engine(arch, oracle)
+    x, ctx, added = _inputs(arch)
+    t = torch.tensor(481)
+    with torch.no_grad():
+        ref = oracle(x, t, ctx, added).sample
+        out = eng(x, t, encoder_hidden_states=ctx, added_cond_kwargs=added).sample
+    assert out.shape == ref.shape
+    err = (out - ref).abs().max().item()
+    assert err < 2e-4 * ref.abs().max().item() + 1e-5, err
+
+
+@pytest.mark.parametrize("arch", ["tiny21", "tiny15"])
+def test_lora_forward_and_grads_match_oracle_autograd(arch):
+    oracle = build_unet(arch)
+    eng = _engine(arch, oracle)
+    x, ctx, added = _inputs(arch, n=2, hw=8)
+    t = torch.tensor(261)
+
+    def make(unet):
+        torch.manual_seed(11)
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = leco_ref.LoRANetworkRef(unet, rank=4, multiplier=1.0, alpha=1.0)
+        g = torch.Generator().manual_seed(5)
+        for l in net.unet_loras:  # lora_up is zero at init: randomise so the branch contributes
+            l.lora_up.weight.data = 0.05 * torch.randn(l.lora_up.weight.shape, generator=g)
+        return net
+
+    net_o, net_e = make(oracle), make(eng)
+    assert len(net_o.unet_loras) == len(net_e.unet_loras) == 192
+    assert [l.lora_name for l in net_o.unet_loras] == [l.lora_name for l in net_e.unet_loras]
+    goal = torch.randn((2, 4, 8, 8), generator=torch.Generator().manual_seed(9))
+
+    def loss_of(unet, net):
+        with net:
+            y = unet(x, t, encoder_hidden_states=ctx).sample
+        return torch.nn.functional.mse_loss(y.float(), goal), y
+
+    lo, yo = loss_of(oracle, net_o)
+    le, ye = loss_of(eng, net_e)
+    assert (yo - ye).abs().max().item() < 2e-4 * yo.abs().max().item() + 1e-5
+    lo.backward()
+    le.backward()
+    worst = 0.0
+    for a, b in zip(net_o.unet_loras, net_e.unet_loras):
+        for pa, pb in ((a.lora_down.weight, b.lora_down.weight), (a.lora_up.weight, b.lora_up.weight)):
+            assert pb.grad is not None, b.lora_name
+            scale = pa.grad.abs().max().item() + 1e-8
+            worst = max(worst, (pa.grad - pb.grad).abs().max().item() / scale)
+    assert worst < 5e-3, worst
+    # multiplier == 0 (outside `with network:`) must equal the frozen network exactly
+    with torch.no_grad():
+        base = _engine(arch, build_unet(arch))(x, t, encoder_hidden_states=ctx).sample
+        off = eng(x, t, encoder_hidden_states=ctx).sample
+    assert torch.equal(base, off)
