@@ -132,6 +132,8 @@ int leco_guided_step(const float* eps_pair, const float* x, float* x_out, float*
                      int64_t half_numel, void* stream);
 int leco_loss(const float* target, const float* positive, const float* neutral, const float* uncond,
               float sign_times_guidance, float* loss_out, float* dtarget, int64_t numel, void* stream);
+/* out = a*x + b*y (the DDIM update for drop-in scheduler.step callers, train_util.py:190) */
+int leco_axpby(const void* x, const void* y, void* out, float a, float b, int64_t n, int is_fp32, void* stream);
 int leco_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
 int leco_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
 

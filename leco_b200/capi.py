@@ -90,6 +90,7 @@ _OPS: list[tuple[str, list]] = [
     ("leco_adamw_flat", [P, P, P, P, I, P, P, L, I, P]),
     ("leco_guided_step", [P, P, P, P, P, L, P]),
     ("leco_loss", [P, P, P, P, F, P, P, L, P]),
+    ("leco_axpby", [P, P, P, F, F, L, I, P]),
     ("leco_cast_f32_to_bf16", [P, P, L, P]),
     ("leco_cast_bf16_to_f32", [P, P, L, P]),
 ]

@@ -166,6 +166,14 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float*
     y[i] = __bfloat162float(x[i]);
 }
 
+template <typename T>
+__global__ void axpby_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ out, float a, float b,
+                             long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = static_cast<T>(a * static_cast<float>(x[i]) + b * static_cast<float>(y[i]));
+}
+
 }  // namespace leco
 
 using namespace leco;
@@ -244,6 +252,22 @@ extern "C" int leco_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* s
   if (blocks > 148 * 8) blocks = 148 * 8;
   count_launch();
   cast_bf16_f32_kernel<<<(int)blocks, 256, 0, STREAM(stream)>>>(BF(x), y, n);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int leco_axpby(const void* x, const void* y, void* out, float a, float b, int64_t n, int is_fp32,
+                          void* stream) {
+  LECO_REQUIRE(x && y && out, "leco_axpby: null");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  count_launch();
+  if (is_fp32)
+    axpby_kernel<float><<<(int)blocks, 256, 0, STREAM(stream)>>>(reinterpret_cast<const float*>(x),
+                                                                reinterpret_cast<const float*>(y),
+                                                                reinterpret_cast<float*>(out), a, b, n);
+  else
+    axpby_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, STREAM(stream)>>>(BF(x), BF(y), BFW(out), a, b, n);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

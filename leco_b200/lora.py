@@ -1,0 +1,246 @@
+"""LoRA adapter network with the reference's call surface, stored the way the kernels want it.
+
+Host-side mirror of lora.py (reference) for the drop-in boundary:
+
+    LoRANetwork(unet, rank=4, multiplier=1.0, alpha=1.0, train_method="full")   lora.py:110-117
+    .unet_loras[i].{lora_name, lora_dim, lora_down, lora_up, alpha, scale, multiplier, org_forward}
+    .prepare_optimizer_params() -> [{"params": [...]}]                          lora.py:201-210
+    .save_weights(file, dtype=None, metadata=None)                               lora.py:212-229
+    with network: ...   (multiplier 1.0 inside, 0 outside)                       lora.py:231-237
+
+Same discovery rule (class-name strings, outer-block train_method filter, lora.py:169-197),
+same key names / order, same initialisation draws from the global CPU generator
+(kaiming-uniform(a=sqrt 5) down, zeros up, lora.py:91-92), same error behaviour.
+
+What is different is the storage.  When the network sits on a CUDA device and adapts a
+`leco_b200.unet.EngineUNet`, all adapter weights live in ONE flat bf16 buffer laid out as
+the tensor-core operands of the engine's fused GEMM sites (`ad [Kl,K]`, `bup [N,Kl]` per
+site, see unet.LoraSite); every `lora_down.weight` / `lora_up.weight` Parameter is a VIEW
+into it.  Consequences: the forward needs no packing, the backward accumulates straight
+into a flat fp32 gradient buffer, AdamW is one fused kernel over the flat buffer
+(`FlatAdamW`) and data-parallel training all-reduces that one buffer.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+PREFIX = "lora_unet"
+# The reference keeps these as module-level lists and EXTENDS THE FIRST IN PLACE for c3lier
+# (train_lora.py:44-46): callers that do the same to `DEFAULT_TARGET_REPLACE` here get the
+# same behaviour, because the constructor reads the list at call time.
+UNET_TARGET_REPLACE_MODULE_TRANSFORMER = ["Transformer2DModel"]
+UNET_TARGET_REPLACE_MODULE_CONV = ["ResnetBlock2D", "Downsample2D", "Upsample2D"]
+DEFAULT_TARGET_REPLACE = UNET_TARGET_REPLACE_MODULE_TRANSFORMER
+TRAINING_METHODS = ("noxattn", "innoxattn", "selfattn", "xattn", "full")
+
+
+def _skip_block(method: str, block_name: str) -> bool:
+    if method == "full":
+        return False
+    if method == "noxattn":
+        return "attn2" in block_name or "time_embed" in block_name
+    if method == "innoxattn":
+        return "attn2" in block_name
+    if method == "selfattn":
+        return "attn1" not in block_name
+    if method == "xattn":
+        return "attn2" not in block_name
+    raise NotImplementedError(f"train_method: {method} is not implemented.")
+
+
+class LoRAModule(nn.Module):
+    """One adapter: y = org(x) + up(down(x)) * multiplier * scale, scale = alpha / rank."""
+
+    def __init__(self, lora_name: str, org_module: nn.Module, multiplier=1.0, lora_dim=4, alpha=1):
+        super().__init__()
+        self.lora_name = lora_name
+        self.lora_dim = lora_dim
+        kind = org_module.__class__.__name__
+        if kind == "Linear":
+            self.lora_down = nn.Linear(org_module.in_features, lora_dim, bias=False)
+            self.lora_up = nn.Linear(lora_dim, org_module.out_features, bias=False)
+        elif kind == "Conv2d":
+            cin, cout = org_module.in_channels, org_module.out_channels
+            self.lora_dim = min(lora_dim, cin, cout)
+            if self.lora_dim != lora_dim:
+                print(f"{lora_name} dim (rank) is changed to: {self.lora_dim}")
+            self.lora_down = nn.Conv2d(cin, self.lora_dim, org_module.kernel_size, org_module.stride,
+                                       org_module.padding, bias=False)
+            self.lora_up = nn.Conv2d(self.lora_dim, cout, (1, 1), (1, 1), bias=False)
+        else:
+            raise TypeError(f"cannot adapt a {kind}")
+        if isinstance(alpha, torch.Tensor):
+            alpha = alpha.detach().numpy()
+        alpha = lora_dim if (alpha is None or alpha == 0) else alpha
+        self.scale = alpha / self.lora_dim
+        self.register_buffer("alpha", torch.tensor(alpha))
+        nn.init.kaiming_uniform_(self.lora_down.weight, a=math.sqrt(5))
+        nn.init.zeros_(self.lora_up.weight)
+        self.multiplier = multiplier
+        self._pending_org = [org_module]
+
+    def apply_to(self):
+        org = self._pending_org.pop()
+        self.org_forward = org.forward
+        org.forward = self.forward  # the engine recognises this patch (unet.find_adapter)
+
+    def forward(self, x):
+        # only reached when the adapted module is a real torch layer (not an engine holder)
+        return self.org_forward(x) + self.lora_up(self.lora_down(x)) * self.multiplier * self.scale
+
+
+class LoRANetwork(nn.Module):
+    def __init__(self, unet, rank: int = 4, multiplier: float = 1.0, alpha: float = 1.0,
+                 train_method: str = "full") -> None:
+        super().__init__()
+        self.multiplier, self.lora_dim, self.alpha = multiplier, rank, alpha
+        targets = list(DEFAULT_TARGET_REPLACE)  # read at call time (c3lier aliasing)
+        self.unet_loras: List[LoRAModule] = []
+        for name, module in unet.named_modules():
+            if _skip_block(train_method, name):
+                continue
+            if module.__class__.__name__ not in targets:
+                continue
+            for child_name, child in module.named_modules():
+                if child.__class__.__name__ in ("Linear", "Conv2d"):
+                    lora_name = f"{PREFIX}.{name}.{child_name}".replace(".", "_")
+                    print(lora_name)
+                    self.unet_loras.append(LoRAModule(lora_name, child, multiplier, rank, alpha))
+        print(f"create LoRA for U-Net: {len(self.unet_loras)} modules.")
+        seen = set()
+        for lora in self.unet_loras:
+            assert lora.lora_name not in seen, f"duplicated lora name: {lora.lora_name}. {seen}"
+            seen.add(lora.lora_name)
+        for lora in self.unet_loras:
+            lora.apply_to()
+            self.add_module(lora.lora_name, lora)
+        self._engine = [unet] if hasattr(unet, "lora_sites") else []
+        self.flat = None  # FlatState once bound
+
+    # ---- reference surface ----------------------------------------------------------------
+    def prepare_optimizer_params(self):
+        if not self.unet_loras:
+            return []
+        return [{"params": [p for lora in self.unet_loras for p in lora.parameters()]}]
+
+    def save_weights(self, file, dtype=None, metadata: Optional[dict] = None):
+        sd = {}
+        for key, v in self.state_dict().items():
+            if not key.startswith("lora"):
+                continue
+            v = v.detach()
+            if dtype is not None:
+                v = v.to("cpu").to(dtype)
+            sd[key] = v.contiguous()
+        if os.path.splitext(file)[1] == ".safetensors":
+            from safetensors.torch import save_file
+            save_file(sd, file, metadata)
+        else:
+            torch.save(sd, file)
+
+    def __enter__(self):
+        for lora in self.unet_loras:
+            lora.multiplier = 1.0
+
+    def __exit__(self, exc_type, exc_value, tb):
+        for lora in self.unet_loras:
+            lora.multiplier = 0
+
+    # ---- flat storage ---------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self.flat = None
+        p = next(iter(self.parameters()), None)
+        if p is not None and p.is_cuda and self._engine:
+            self.bind_flat()
+        return out
+
+    def bind_flat(self):
+        """Re-home every adapter weight as a view of one flat buffer in engine-site layout."""
+        eng = self._engine[0]
+        p0 = next(self.parameters())
+        eng._ensure_packed(p0.device)
+        sites = [s for s in eng.lora_sites() if s.adapters() is not None]
+        mine = {id(l) for l in self.unet_loras}
+        offsets, total = [], 0
+        for s in sites:
+            ads = s.adapters()
+            if any(id(a) not in mine for a in ads):
+                raise RuntimeError("leco_b200: UNet is adapted by another network")
+            if any(a.lora_down.__class__.__name__ != "Linear" and a.lora_down.kernel_size != (1, 1) for a in ads):
+                raise NotImplementedError("leco_b200: 3x3 conv adapters are not in the flat layout yet")
+            kl = (sum(a.lora_down.weight.shape[0] for a in ads) + 15) // 16 * 16
+            offsets.append((total, kl))
+            total += kl * s.k_in + s.n_total * kl
+        covered = sum(len(s.adapters()) for s in sites)
+        if covered != len(self.unet_loras):
+            raise NotImplementedError(
+                f"leco_b200: {len(self.unet_loras) - covered} adapters sit on layers without a fused engine site")
+        dev, dt = p0.device, p0.dtype
+        st = FlatState(torch.zeros(total, device=dev, dtype=dt), torch.zeros(total, device=dev, dtype=torch.float32),
+                       torch.zeros(total, device=dev, dtype=torch.uint8))
+        for s, (off, kl) in zip(sites, offsets):
+            na, nb = kl * s.k_in, s.n_total * kl
+            ad, bup = st.params[off:off + na].view(kl, s.k_in), st.params[off + na:off + na + nb].view(s.n_total, kl)
+            g_ad, g_bup = st.grads[off:off + na].view(kl, s.k_in), st.grads[off + na:off + na + nb].view(s.n_total, kl)
+            m_ad, m_bup = st.mask[off:off + na].view(kl, s.k_in), st.mask[off + na:off + na + nb].view(s.n_total, kl)
+            k0 = 0
+            for a, n0 in zip(s.adapters(), s.n_offsets):
+                wd, wu = a.lora_down.weight, a.lora_up.weight
+                r, n = wd.shape[0], wu.shape[0]
+                ad[k0:k0 + r].copy_(wd.detach().reshape(r, -1))
+                bup[n0:n0 + n, k0:k0 + r].copy_(wu.detach().reshape(n, r))
+                wd.data = ad[k0:k0 + r].view(wd.shape)
+                wu.data = bup[n0:n0 + n, k0:k0 + r].view(n, r, *wu.shape[2:]) if wu.dim() == 2 else \
+                    bup[n0:n0 + n, k0:k0 + r].unsqueeze(-1).unsqueeze(-1)
+                m_ad[k0:k0 + r] = 1
+                m_bup[n0:n0 + n, k0:k0 + r] = 1
+                k0 += r
+            s.bind_native(ad, bup, g_ad, g_bup)
+        st.n_real = int(st.mask.sum().item())
+        self.flat = st
+        return st
+
+
+class FlatState:
+    """Flat adapter storage: bf16 params, fp32 grads, uint8 mask (1 = a real LoRA element, 0 = operand
+    padding / off-block zero that must never be updated)."""
+
+    def __init__(self, params, grads, mask):
+        self.params, self.grads, self.mask = params, grads, mask
+        self.n_real = 0
+
+
+class FlatAdamW:
+    """torch.optim.AdamW semantics (train_lora.py:89, train_util.py:357-360) as ONE fused kernel over
+    the flat LoRA buffer; optimizer state lives in the parameter dtype like the reference's
+    (`network.to(dtype)` before the optimizer is built, train_lora.py:78-89) unless state_fp32."""
+
+    def __init__(self, flat: FlatState, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+                 state_fp32: bool = False):
+        self.flat = flat
+        sd = torch.float32 if state_fp32 else flat.params.dtype
+        self.exp_avg = torch.zeros_like(flat.params, dtype=sd)
+        self.exp_avg_sq = torch.zeros_like(flat.params, dtype=sd)
+        self.step_count = 0
+        self.lr = lr
+        self.defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self.hyper = torch.zeros(8, device=flat.params.device, dtype=torch.float32)
+
+    def step(self, grad_scale: float = 1.0):
+        from . import ops
+        self.step_count += 1
+        d = self.defaults
+        # pageable source: the copy is staged before this call returns, so the host values can change
+        self.hyper.copy_(torch.tensor([self.lr, d["betas"][0], d["betas"][1], d["eps"], d["weight_decay"],
+                                       float(self.step_count), grad_scale, 0.0], dtype=torch.float32))
+        ops.adamw_flat(self.flat.params, self.flat.grads, self.exp_avg, self.exp_avg_sq, self.flat.mask, self.hyper,
+                       zero_grad=True)
+
+    def zero_grad(self):
+        self.flat.grads.zero_()

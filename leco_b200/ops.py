@@ -353,6 +353,14 @@ def leco_loss(target, positive, neutral, uncond, sign_times_guidance: float, wan
     return loss, dt
 
 
+def axpby(x, y, a: float, b: float):
+    assert x.dtype == y.dtype and x.dtype in (torch.float32, BF16) and x.is_contiguous() and y.is_contiguous()
+    out = torch.empty_like(x)
+    capi.check(_lib().leco_axpby(_ptr(x), _ptr(y), _ptr(out), a, b, x.numel(), int(x.dtype == torch.float32),
+                                 _stream()), "leco_axpby")
+    return out
+
+
 def cast_f32_to_bf16(x):
     y = torch.empty(x.shape, device=x.device, dtype=BF16)
     capi.check(_lib().leco_cast_f32_to_bf16(_ptr(x), _ptr(y), x.numel(), _stream()), "leco_cast")
@@ -426,15 +434,16 @@ def attention_bwd(go, qt, kt, vt, saved, nb, sq, skv, heads, d, scale, dq_out, d
     gemm_batched(go4, v4, dP, n_pad=pad)                         # dP = dO V^T
     dS = softmax_bwd_rows(P, dP, skv, scale)                     # scale * P o (dP - rowsum(P o dP))
     del dP
+    sq_pad = (sq + 15) // 16 * 16        # K of the two "reduce over queries" GEMMs (zero padded)
     if dv_out is not None:
-        Pt = transpose_batched(P)                                # [.., skv_pad, sq]
-        goT = transpose_batched(go4)                             # [.., d, sq]
+        Pt = transpose_batched(P, cols_pad=sq_pad)               # [.., skv_pad, sq_pad]
+        goT = transpose_batched(go4, cols_pad=sq_pad)            # [.., d, sq_pad]
         gemm_batched(Pt[:, :, :skv], goT, _heads_view(dv_out, nb, skv, heads, d))
         del Pt, goT
     if dq_out is not None:
         Kt = transpose_batched(k4, cols_pad=skv_pad)             # [.., d, skv_pad]
         gemm_batched(dS, Kt, _heads_view(dq_out, nb, sq, heads, d))
     if dk_out is not None:
-        dSt = transpose_batched(dS)                              # [.., skv_pad, sq]
-        Qt = transpose_batched(q4)                               # [.., d, sq]
+        dSt = transpose_batched(dS, cols_pad=sq_pad)             # [.., skv_pad, sq_pad]
+        Qt = transpose_batched(q4, cols_pad=sq_pad)              # [.., d, sq_pad]
         gemm_batched(dSt[:, :, :skv], Qt, _heads_view(dk_out, nb, skv, heads, d))

@@ -1,0 +1,82 @@
+"""Step primitives with the reference's names and argument meaning (train_util.py), running on
+the engine.  `predict_noise` / `diffusion` are what a drop-in user calls; they accept the
+reference's own scheduler/unet duck types, so `train_lora.py`'s loop body works unchanged
+when handed an `EngineUNet` + `leco_b200.scheduler.DDIMScheduler`.
+"""
+from __future__ import annotations
+
+import torch
+
+UNET_IN_CHANNELS = 4
+VAE_SCALE_FACTOR = 8
+
+
+def get_random_noise(batch_size: int, height: int, width: int, generator: torch.Generator = None) -> torch.Tensor:
+    """train_util.py:20-32: CPU noise from the (global) generator."""
+    return torch.randn((batch_size, UNET_IN_CHANNELS, height // VAE_SCALE_FACTOR, width // VAE_SCALE_FACTOR),
+                       generator=generator, device="cpu")
+
+
+def get_initial_latents(scheduler, n_imgs: int, height: int, width: int, n_prompts: int, generator=None):
+    """train_util.py:43-57."""
+    noise = get_random_noise(n_imgs, height, width, generator=generator).repeat(n_prompts, 1, 1, 1)
+    return noise * scheduler.init_noise_sigma
+
+
+def concat_embeddings(unconditional: torch.Tensor, conditional: torch.Tensor, n_imgs: int):
+    """train_util.py:133-138: [uncond x n, cond x n]."""
+    return torch.cat([unconditional, conditional]).repeat_interleave(n_imgs, dim=0)
+
+
+def predict_noise(unet, scheduler, timestep, latents, text_embeddings, guidance_scale=7.5):
+    """train_util.py:142-168: CFG-batched UNet call + guidance combine."""
+    x2 = scheduler.scale_model_input(torch.cat([latents] * 2), timestep)
+    eps = unet(x2, timestep, encoder_hidden_states=text_embeddings).sample
+    eps_u, eps_c = eps.chunk(2)
+    return eps_u + guidance_scale * (eps_c - eps_u)
+
+
+@torch.no_grad()
+def diffusion(unet, scheduler, latents, text_embeddings, total_timesteps: int = 1000, start_timesteps=0, **kwargs):
+    """train_util.py:172-193."""
+    for timestep in scheduler.timesteps[start_timesteps:total_timesteps]:
+        eps = predict_noise(unet, scheduler, timestep, latents, text_embeddings, **kwargs)
+        latents = scheduler.step(eps, timestep, latents).prev_sample
+    return latents
+
+
+def predict_noise_xl(unet, scheduler, timestep, latents, text_embeddings, add_text_embeddings, add_time_ids,
+                     guidance_scale=7.5, guidance_rescale=0.7):
+    """train_util.py:217-257.  The reference computes a guidance rescale and then returns the
+    un-rescaled guided value: so does this."""
+    x2 = scheduler.scale_model_input(torch.cat([latents] * 2), timestep)
+    eps = unet(x2, timestep, encoder_hidden_states=text_embeddings,
+               added_cond_kwargs={"text_embeds": add_text_embeddings, "time_ids": add_time_ids}).sample
+    eps_u, eps_c = eps.chunk(2)
+    return eps_u + guidance_scale * (eps_c - eps_u)
+
+
+@torch.no_grad()
+def diffusion_xl(unet, scheduler, latents, text_embeddings, add_text_embeddings, add_time_ids,
+                 guidance_scale: float = 1.0, total_timesteps: int = 1000, start_timesteps=0):
+    """train_util.py:260-291."""
+    for timestep in scheduler.timesteps[start_timesteps:total_timesteps]:
+        eps = predict_noise_xl(unet, scheduler, timestep, latents, text_embeddings, add_text_embeddings,
+                               add_time_ids, guidance_scale=guidance_scale, guidance_rescale=0.7)
+        latents = scheduler.step(eps, timestep, latents).prev_sample
+    return latents
+
+
+def get_add_time_ids(height: int, width: int, dynamic_crops: bool = False, dtype: torch.dtype = torch.float32):
+    """train_util.py:295-330."""
+    if dynamic_crops:
+        scale = torch.rand(1).item() * 2 + 1
+        original = (int(height * scale), int(width * scale))
+        crop = (torch.randint(0, original[0] - height, (1,)).item(),
+                torch.randint(0, original[1] - width, (1,)).item())
+    else:
+        original, crop = (height, width), (0, 0)
+    ids = list(original + crop + (height, width))
+    if 256 * len(ids) + 1280 != 2816:
+        raise ValueError("Model expects an added time embedding vector of length 2816")
+    return torch.tensor([ids], dtype=dtype)

@@ -1,0 +1,306 @@
+"""The LECO training iteration (train_lora.py:141-302) as a fused, graph-captured GPU step.
+
+`LecoTrainer.iteration()` performs exactly one pass of the reference's loop body:
+
+  RNG draws in the reference's order          train_lora.py:149-156, 175-177
+  k-step DDIM denoise under CFG 3 with LoRA on            train_lora.py:179-193, train_util.py:172-193
+  timestep remap t* = timesteps_1000[int(k*1000/max)]     train_lora.py:195-199
+  positive / neutral / unconditional predictions, LoRA off  train_lora.py:202-237
+  target prediction, LoRA on, with gradient               train_lora.py:244-256
+  erase / enhance MSE objective                           prompt_util.py:107-135, train_lora.py:265-270
+  backward into the LoRA matrices only, AdamW step        train_lora.py:279-281
+
+What it does NOT repeat is work the reference executes redundantly (SURVEY §8a notes):
+  * all four predict_noise calls use guidance_scale=1, i.e. e_u + 1*(e_c - e_u) == e_c up to
+    rounding, and d/d(e_u) = 0: only the conditional half is evaluated / differentiated;
+  * identical prompts among positive / neutral / unconditional are evaluated once;
+  * the three LoRA-off passes share (latents, t) and run as one batched forward.
+Every kernel launch of a denoise step (UNet forward + CFG/DDIM update) is captured in one CUDA
+graph that is replayed k times; the tail (both passes, loss, backward) is a second graph.  The
+loss never leaves the device unless the caller reads it.
+
+Data parallel: every rank draws the SAME global noise / prompt / k from an
+identically seeded CPU generator and keeps its slice of the batch; one all-reduce of the
+flat fp32 LoRA gradient buffer per iteration, then the same fused AdamW on every rank.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import capi, ops
+from .lora import FlatAdamW, LoRANetwork
+from .scheduler import DDIMScheduler
+from .unet import EngineUNet, Tape
+
+UNET_IN_CHANNELS = 4      # train_util.py:12
+VAE_SCALE_FACTOR = 8      # train_util.py:13
+
+
+@dataclass
+class PromptPair:
+    """prompt_util.PromptEmbedsPair (prompt_util.py:70-105): four [1,77,D] embeddings + settings."""
+    target: torch.Tensor
+    positive: torch.Tensor
+    unconditional: torch.Tensor
+    neutral: torch.Tensor
+    guidance_scale: float = 1.0
+    resolution: int = 512
+    dynamic_resolution: bool = False
+    batch_size: int = 1
+    action: str = "erase"
+
+    def signed_guidance(self) -> float:
+        if self.action == "erase":      # neutral - g (positive - unconditional)
+            return -float(self.guidance_scale)
+        if self.action == "enhance":    # neutral + g (positive - unconditional)
+            return float(self.guidance_scale)
+        raise ValueError("action must be erase or enhance")
+
+
+def get_random_resolution_in_bucket(bucket_resolution: int = 512):
+    """train_util.py:404-416 (randint upper bound is exclusive)."""
+    lo, hi = (bucket_resolution // 2) // 64, bucket_resolution // 64
+    h = torch.randint(lo, hi, (1,)).item() * 64
+    w = torch.randint(lo, hi, (1,)).item() * 64
+    return h, w
+
+
+class _Graphed:
+    """A captured CUDA graph plus the static tensors it reads/writes."""
+
+    def __init__(self):
+        self.graph = None
+        self.launches = 0  # kernels inside one replay
+        self.static: Dict[str, torch.Tensor] = {}
+
+
+class LecoTrainer:
+    def __init__(self, unet: EngineUNet, network: LoRANetwork, scheduler: DDIMScheduler,
+                 prompt_pairs: Sequence[PromptPair], *, lr: float = 1e-4, optimizer_kwargs: Optional[dict] = None,
+                 max_denoising_steps: int = 50, denoise_guidance: float = 3.0, device="cuda",
+                 rank: int = 0, world_size: int = 1, use_cuda_graphs: bool = True, state_fp32: bool = False):
+        if network.flat is None:
+            raise RuntimeError("LecoTrainer needs the flat LoRA layout: move the network to CUDA first "
+                               "(network.to('cuda', dtype=torch.bfloat16))")
+        self.unet, self.network, self.scheduler = unet, network, scheduler
+        self.pairs = list(prompt_pairs)
+        self.max_steps = max_denoising_steps
+        self.denoise_guidance = float(denoise_guidance)
+        self.device = torch.device(device)
+        self.rank, self.world = rank, world_size
+        self.use_graphs = use_cuda_graphs
+        self.optimizer = FlatAdamW(network.flat, lr=lr, state_fp32=state_fp32, **(optimizer_kwargs or {}))
+        self.act_dtype = unet._act_dtype
+        for p in self.pairs:
+            if p.batch_size % world_size != 0:
+                raise ValueError(f"batch_size {p.batch_size} must be divisible by world_size {world_size}")
+        self._emb_cache: Dict[int, torch.Tensor] = {}
+        self._den: Dict[tuple, _Graphed] = {}
+        self._tail: Dict[tuple, _Graphed] = {}
+        self._tables = None
+        self.h2d_bytes = 0
+        self._pinned: Dict[tuple, torch.Tensor] = {}
+        self._iter = 0
+        self.launches = 0
+        self.last = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _emb(self, e: torch.Tensor) -> torch.Tensor:
+        k = id(e)
+        if k not in self._emb_cache:
+            self._emb_cache[k] = e.to(self.device, dtype=self.act_dtype).reshape(-1, e.shape[-1]).contiguous()
+        return self._emb_cache[k]
+
+    def _ctx(self, embs: Sequence[torch.Tensor], bl: int) -> torch.Tensor:
+        """train_util.concat_embeddings order: each embedding repeated bl times, blocks concatenated."""
+        return torch.cat([self._emb(e).unsqueeze(0).expand(bl, -1, -1) for e in embs], 0).reshape(
+            -1, embs[0].shape[-1]).contiguous()
+
+    def _sched_tables(self):
+        """Device tables for the 50-step grid: timestep and (guidance, cx, ce) per step."""
+        s = self.scheduler
+        s.set_timesteps(self.max_steps)
+        ts = [int(t) for t in s.timesteps]
+        coef = [[self.denoise_guidance, *s.coefficients(t)] for t in ts]
+        self._tables = (torch.tensor(ts, dtype=torch.float32, device=self.device),
+                        torch.tensor(coef, dtype=torch.float32, device=self.device))
+        return self._tables
+
+    # ------------------------------------------------------------------ one denoise step
+    def _denoise_body(self, st):
+        x2 = st["x"].repeat(2, 1, 1, 1)
+        eps = self.unet.run(x2, st["t"], st["ctx"], None, None)
+        x_new, _ = ops.guided_step(eps, st["x"], st["coef"], True, False)
+        st["x"].copy_(x_new)
+
+    def _denoise_graph(self, bl, h, w, D):
+        key = (bl, h, w, D)
+        g = self._den.get(key)
+        if g is not None:
+            return g
+        g = _Graphed()
+        dev = self.device
+        g.static = {"x": torch.zeros((bl, UNET_IN_CHANNELS, h, w), device=dev, dtype=torch.float32),
+                    "t": torch.zeros((2 * bl,), device=dev, dtype=torch.float32),
+                    "coef": torch.zeros((3,), device=dev, dtype=torch.float32),
+                    "ctx": torch.zeros((2 * bl * 77, D), device=dev, dtype=self.act_dtype)}
+        if self.use_graphs:
+            self.network.__enter__()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._denoise_body(g.static)  # warm-up (lazy inits, allocator)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g.graph = torch.cuda.CUDAGraph()
+            c0 = capi.launch_count()
+            with torch.cuda.graph(g.graph):
+                self._denoise_body(g.static)
+            g.launches = capi.launch_count() - c0
+            self.network.__exit__(None, None, None)
+        self._den[key] = g
+        return g
+
+    # ------------------------------------------------------------------ tail: 4 predictions + loss + backward
+    def _tail_body(self, st, groups, slots, bl, sgn_g):
+        """groups = number of distinct LoRA-off prompts, slots = (i_pos, i_neu, i_unc) into them."""
+        net = self.network
+        net.__exit__(None, None, None)                           # multiplier 0: LoRA-off passes
+        xr = st["x"].repeat(groups, 1, 1, 1)
+        eps_ng = self.unet.run(xr, st["t"][: groups * bl], st["ctx_ng"], None, None)
+        pos, neu, unc = (eps_ng[i * bl:(i + 1) * bl] for i in slots)
+        net.__enter__()                                          # multiplier 1: target pass with tape
+        tape = Tape(ops)
+        eps_t = self.unet.run(st["x"], st["t"][:bl], st["ctx_t"], None, tape)
+        loss, dt = ops.leco_loss(eps_t, pos, neu, unc, sgn_g, True)
+        tape.grads["eps"] = dt
+        tape.backward()
+        net.__exit__(None, None, None)
+        st["loss"].copy_(loss)
+
+    def _tail_graph(self, bl, h, w, D, groups, slots, sgn_g):
+        key = (bl, h, w, D, groups, slots, sgn_g)
+        g = self._tail.get(key)
+        if g is not None:
+            return g
+        g = _Graphed()
+        dev = self.device
+        g.static = {"x": torch.zeros((bl, UNET_IN_CHANNELS, h, w), device=dev, dtype=torch.float32),
+                    "t": torch.zeros((groups * bl,), device=dev, dtype=torch.float32),
+                    "ctx_ng": torch.zeros((groups * bl * 77, D), device=dev, dtype=self.act_dtype),
+                    "ctx_t": torch.zeros((bl * 77, D), device=dev, dtype=self.act_dtype),
+                    "loss": torch.zeros((1,), device=dev, dtype=torch.float32)}
+        if self.use_graphs:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._tail_body(g.static, groups, slots, bl, sgn_g)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.network.flat.grads.zero_()                      # the warm-up accumulated a gradient
+            g.graph = torch.cuda.CUDAGraph()
+            c0 = capi.launch_count()
+            with torch.cuda.graph(g.graph):
+                self._tail_body(g.static, groups, slots, bl, sgn_g)
+            g.launches = capi.launch_count() - c0
+        self._tail[key] = g
+        return g
+
+    # ------------------------------------------------------------------ the iteration
+    @torch.no_grad()
+    def iteration(self, fixed_k: Optional[int] = None, step_optimizer: bool = True,
+                  device_noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One LECO iteration; returns the (device) loss.  `device_noise` [B_local,4,h,w] fp32 skips the
+        host draw + H2D copy of the latent noise (inputs already resident in HBM)."""
+        sched = self.scheduler
+        launches0 = capi.launch_count()
+        tbl_t, tbl_coef = self._tables or self._sched_tables()
+        sched.set_timesteps(self.max_steps)
+        # ---- RNG draws: same generator, same order as train_lora.py:149-177
+        pair = self.pairs[torch.randint(0, len(self.pairs), (1,)).item()]
+        k = torch.randint(1, self.max_steps, (1,)).item()
+        if fixed_k is not None:
+            k = int(fixed_k)
+        height = width = pair.resolution
+        if pair.dynamic_resolution:
+            height, width = get_random_resolution_in_bucket(pair.resolution)
+        h, w = height // VAE_SCALE_FACTOR, width // VAE_SCALE_FACTOR
+        bl = pair.batch_size // self.world
+        D = pair.target.shape[-1]
+        dg = self._denoise_graph(bl, h, w, D)
+        st = dg.static
+        if device_noise is not None:
+            st["x"].copy_(device_noise)
+            self.h2d_bytes = 0
+        else:
+            noise = torch.randn((pair.batch_size, UNET_IN_CHANNELS, h, w), device="cpu") * sched.init_noise_sigma
+            self._stage_noise(noise, bl, h, w, st["x"])
+        st["ctx"].copy_(self._ctx([pair.unconditional, pair.target], bl))
+        if dg.graph is None:
+            self.network.__enter__()
+        for i in range(k):
+            st["t"].copy_(tbl_t[i].expand(2 * bl))
+            st["coef"].copy_(tbl_coef[i])
+            if dg.graph is not None:
+                dg.graph.replay()
+                self.launches += dg.launches
+            else:
+                self._denoise_body(st)
+        if dg.graph is None:
+            self.network.__exit__(None, None, None)
+
+        # ---- tail at t* = timesteps_1000[int(k*1000/max)] = 999 - int(k*1000/max)
+        t_star = float(999 - int(k * 1000 / self.max_steps))
+        distinct: List[torch.Tensor] = []
+        slots = []
+        for e in (pair.positive, pair.neutral, pair.unconditional):
+            for j, d in enumerate(distinct):
+                if d is e or (d.shape == e.shape and torch.equal(d, e)):
+                    slots.append(j)
+                    break
+            else:
+                distinct.append(e)
+                slots.append(len(distinct) - 1)
+        tg = self._tail_graph(bl, h, w, D, len(distinct), tuple(slots), pair.signed_guidance())
+        ts = tg.static
+        ts["x"].copy_(st["x"])
+        ts["t"].fill_(t_star)
+        ts["ctx_ng"].copy_(self._ctx(distinct, bl))
+        ts["ctx_t"].copy_(self._ctx([pair.target], bl))
+        if tg.graph is not None:
+            tg.graph.replay()
+            self.launches += tg.launches
+        else:
+            self._tail_body(ts, len(distinct), tuple(slots), bl, pair.signed_guidance())
+        loss = ts["loss"]
+
+        # ---- data-parallel exchange: one all-reduce of the flat LoRA gradient (+ the scalar loss)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.network.flat.grads)
+            dist.all_reduce(loss)
+            loss.mul_(1.0 / self.world)
+        if step_optimizer:
+            self.optimizer.step(grad_scale=1.0 / self.world)
+        self.launches += capi.launch_count() - launches0     # eager launches (graph replays were added above)
+        self.last = {"k": k, "timestep": t_star, "denoised": st["x"], "pair": pair}
+        return loss
+
+    def _stage_noise(self, noise, bl, h, w, dst):
+        """Host noise slice of this rank -> pinned staging -> device (the only per-step H2D traffic)."""
+        ring = self._pinned.get((bl, h, w))
+        if ring is None:  # two pinned staging buffers: the host may run one iteration ahead of the GPU
+            ring = self._pinned[(bl, h, w)] = [
+                [torch.empty((bl, UNET_IN_CHANNELS, h, w), dtype=torch.float32).pin_memory(), None] for _ in range(2)]
+        slot = ring[self._iter & 1]
+        if slot[1] is not None:
+            slot[1].synchronize()
+        slot[0].copy_(noise[self.rank * bl:(self.rank + 1) * bl])
+        dst.copy_(slot[0], non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record()
+        self._iter += 1
+        self.h2d_bytes = slot[0].numel() * 4

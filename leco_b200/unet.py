@@ -276,8 +276,17 @@ class LoraSite:
     def __init__(self, members: List[nn.Module], n_offsets: List[int], n_total: int, k_in: int):
         self.members, self.n_offsets, self.n_total, self.k_in = members, n_offsets, n_total, k_in
         self.ad = self.bup = None
+        self.g_ad = self.g_bup = None
         self._versions = None
-        self._adapters = None
+        self._native = False
+        self.ranks = None
+
+    def bind_native(self, ad, bup, g_ad, g_bup):
+        """The adapter Parameters are views of `ad`/`bup` (leco_b200.lora flat layout): no packing,
+        gradients accumulate straight into the flat fp32 buffer."""
+        self.ad, self.bup, self.g_ad, self.g_bup = ad, bup, g_ad, g_bup
+        self.ranks = [a.lora_down.weight.shape[0] for a in self.adapters()]
+        self._native = True
 
     def adapters(self):
         ads = [find_adapter(m) for m in self.members]
@@ -301,6 +310,11 @@ class LoraSite:
         return ads, mult
 
     def refresh(self, ads, device, dtype):
+        if self._native:
+            if ads[0].lora_down.weight.data_ptr() == self.ad.data_ptr():
+                return self.ad, self.bup
+            self._native = False  # parameters were re-homed (e.g. .to()): fall back to packing
+            self.ad = self.bup = self.g_ad = self.g_bup = None
         ranks = [a.lora_down.weight.shape[0] for a in ads]
         kl = (sum(ranks) + 15) // 16 * 16
         if kl > 64:
@@ -326,7 +340,8 @@ class LoraSite:
 
     # fp32 gradient accumulators in operand layout (zeroed per backward)
     def begin_grad(self, be):
-        self.g_ad = self.g_bup = None
+        if not self._native:
+            self.g_ad = self.g_bup = None
 
     def grad_ad(self, be):
         if self.g_ad is None:
@@ -345,11 +360,15 @@ class LoraSite:
         for a, n0, r in zip(ads, self.n_offsets, self.ranks):
             wd, wu = a.lora_down.weight, a.lora_up.weight
             n = wu.shape[0]
-            gd = None if self.g_ad is None else self.g_ad[k0:k0 + r].reshape(wd.shape).to(wd.dtype)
-            gu = None if self.g_bup is None else self.g_bup[n0:n0 + n, k0:k0 + r].reshape(wu.shape).to(wu.dtype)
+            gd = None if self.g_ad is None else self.g_ad[k0:k0 + r].reshape(wd.shape).to(wd.dtype, copy=True)
+            gu = None if self.g_bup is None else self.g_bup[n0:n0 + n, k0:k0 + r].reshape(wu.shape).to(wu.dtype, copy=True)
             out += [gd, gu]
             k0 += r
-        self.g_ad = self.g_bup = None
+        if self._native:  # handed to autograd as copies: reset the flat accumulators
+            self.g_ad.zero_()
+            self.g_bup.zero_()
+        else:
+            self.g_ad = self.g_bup = None
         return out
 
 

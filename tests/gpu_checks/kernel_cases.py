@@ -1,0 +1,362 @@
+"""GPU checks of every non-GEMM kernel and of the engine end to end (run through gpurun).
+
+Each case runs in a subprocess under a timeout.  References: tests/torch_backend.py (plain
+PyTorch fp32 of the same op) and the oracle (fp32 CPU UNet + autograd).
+Results -> gpurun_out/kernel_cases.json
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+
+def _rand(shape, scale=1.0, seed=0, dtype=None):
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(shape, generator=g) * scale
+    return x.to(dtype or torch.bfloat16).cuda()
+
+
+def _cmp(out, ref, tol=2e-2):
+    import torch
+    out, ref = out.float().cpu(), ref.float().cpu()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    return {"max_abs_err": err, "ref_absmax": scale, "rel": err / scale,
+            "ok": bool(torch.isfinite(out).all().item()) and err / scale < tol}
+
+
+def _merge(results):
+    ok = all(r["ok"] for r in results.values())
+    return {"ok": ok, "rel": max(r["rel"] for r in results.values()), "parts": results}
+
+
+def case_norms():
+    import torch
+    from leco_b200 import ops
+    from tests import torch_backend as tb
+    res = {}
+    for (n, hw, c) in ((2, 4096, 320), (3, 256, 1280), (2, 64, 2560), (4, 4, 64), (2, 1024, 960)):
+        x = _rand((n * hw, c), seed=1) * 1.5 + 0.3
+        gm, bt = _rand((c,), 0.2, 2) + 1.0, _rand((c,), 0.2, 3)
+        for silu in (True, False):
+            y, st = ops.group_norm(x, n, hw, gm, bt, 32, 1e-5, silu)
+            yr, str_ = tb.group_norm(x.cpu(), n, hw, gm.cpu(), bt.cpu(), 32, 1e-5, silu)
+            res[f"gn_{n}_{hw}_{c}_{int(silu)}"] = _cmp(y, yr)
+            res[f"gn_stats_{n}_{hw}_{c}_{int(silu)}"] = _cmp(st, str_, 1e-2)
+            dz = _rand((n * hw, c), seed=4)
+            dx = ops.group_norm_bwd(x, dz, st, gm, bt, n, hw, 32, silu)
+            dxr = tb.group_norm_bwd(x.cpu(), dz.cpu(), str_, gm.cpu(), bt.cpu(), n, hw, 32, silu)
+            res[f"gn_bwd_{n}_{hw}_{c}_{int(silu)}"] = _cmp(dx, dxr, 3e-2)
+    for (m, c) in ((16384, 320), (1024, 1280), (77, 64), (300, 640)):
+        x = _rand((m, c), seed=5) * 2 - 0.5
+        gm, bt = _rand((c,), 0.2, 6) + 1.0, _rand((c,), 0.2, 7)
+        y, st = ops.layer_norm(x, gm, bt, 1e-5, True)
+        yr, str_ = tb.layer_norm(x.cpu(), gm.cpu(), bt.cpu(), 1e-5, True)
+        res[f"ln_{m}_{c}"] = _cmp(y, yr)
+        dy = _rand((m, c), seed=8)
+        dx = ops.layer_norm_bwd(x, dy, st, gm)
+        res[f"ln_bwd_{m}_{c}"] = _cmp(dx, tb.layer_norm_bwd(x.cpu(), dy.cpu(), str_, gm.cpu()), 3e-2)
+    return _merge(res)
+
+
+def case_elementwise():
+    import torch
+    from leco_b200 import ops
+    from tests import torch_backend as tb
+    tb.ACT_DTYPE = torch.bfloat16
+    res = {}
+    x = _rand((3, 4, 16, 24), seed=1, dtype=torch.float32)
+    w, b = _rand((64, 4, 3, 3), 0.3, 2), _rand((64,), 0.1, 3)
+    res["conv_in_f32"] = _cmp(ops.conv_in(x, w, b), tb.conv_in(x.cpu(), w.cpu(), b.cpu()))
+    res["conv_in_bf16"] = _cmp(ops.conv_in(x.bfloat16(), w, b), tb.conv_in(x.bfloat16().cpu(), w.cpu(), b.cpu()))
+    xa = _rand((3 * 16 * 24, 64), seed=4)
+    wo, bo = _rand((4, 9, 64), 0.05, 5), _rand((4,), 0.1, 6)
+    res["conv_out"] = _cmp(ops.conv_out(xa, wo, bo, 3, 16, 24), tb.conv_out(xa.cpu(), wo.cpu(), bo.cpu(), 3, 16, 24))
+    dy = _rand((3, 4, 16, 24), seed=7, dtype=torch.float32)
+    res["conv_out_bwd"] = _cmp(ops.conv_out_bwd(dy, wo, 64), tb.conv_out_bwd(dy.cpu(), wo.cpu(), 64))
+    t = torch.tensor([999.0, 481.0, 1.0, 20.0], device="cuda")
+    res["temb"] = _cmp(ops.timestep_embedding(t, 320), tb.timestep_embedding(t.cpu(), 320))
+    v = _rand((1000, 64), seed=8)
+    res["silu"] = _cmp(ops.silu(v), tb.silu(v.cpu()))
+    y = v.clone()
+    res["add"] = _cmp(ops.add_(y, v), tb.add_(v.cpu().clone(), v.cpu()))
+    pre = _rand((300, 512), seed=9)
+    res["geglu"] = _cmp(ops.geglu_fwd(pre), tb.geglu_fwd(pre.cpu()))
+    do = _rand((300, 256), seed=10)
+    res["geglu_bwd"] = _cmp(ops.geglu_bwd(pre, do), tb.geglu_bwd(pre.cpu(), do.cpu()))
+    a, b2 = _rand((500, 64), seed=11), _rand((500, 192), seed=12)
+    cat = ops.concat2(a, b2)
+    res["concat"] = _cmp(cat, tb.concat2(a.cpu(), b2.cpu()), 1e-6)
+    sa, sb = ops.split2(cat, 64)
+    res["split_a"] = _cmp(sa, a, 1e-6)
+    res["split_b"] = _cmp(sb, b2, 1e-6)
+    xi = _rand((2 * 8 * 12, 64), seed=13)
+    res["upsample"] = _cmp(ops.upsample2x(xi, 2, 8, 12), tb.upsample2x(xi.cpu(), 2, 8, 12), 1e-6)
+    dyu = _rand((2 * 16 * 24, 64), seed=14)
+    res["upsample_bwd"] = _cmp(ops.upsample2x_bwd(dyu, 2, 8, 12), tb.upsample2x_bwd(dyu.cpu(), 2, 8, 12))
+    xs = _rand((2 * 8 * 12, 64), seed=15)
+    res["im2col_s2"] = _cmp(ops.im2col_s2(xs, 2, 8, 12), tb.im2col_s2(xs.cpu(), 2, 8, 12), 1e-6)
+    dc = _rand((2 * 4 * 6, 9 * 64), seed=16)
+    res["col2im_s2"] = _cmp(ops.col2im_s2(dc, 2, 8, 12), tb.col2im_s2(dc.cpu(), 2, 8, 12))
+    src = _rand((2, 3, 77, 64), seed=17)
+    res["transpose_pad"] = _cmp(ops.transpose_batched(src, cols_pad=80), tb.transpose_batched(src.cpu(), 80), 1e-6)
+    wide = _rand((2 * 100, 3 * 128), seed=18)
+    view = wide[:, 128:256].unflatten(0, (2, 100)).unflatten(2, (2, 64)).permute(0, 2, 1, 3)
+    res["transpose_strided"] = _cmp(ops.transpose_batched(view), tb.transpose_batched(view.cpu()), 1e-6)
+    s = _rand((2, 2, 50, 80), 3.0, 19, torch.float32)
+    res["softmax"] = _cmp(ops.softmax_rows(s, 77, 80),
+                          torch.nn.functional.pad(torch.softmax(s.cpu()[..., :77], -1), (0, 3)))
+    p = ops.softmax_rows(s, 77, 80)
+    dp = _rand((2, 2, 50, 80), 1.0, 20, torch.float32)
+    pf = p.float().cpu()[..., :77]
+    dref = pf * (dp.cpu()[..., :77] - (pf * dp.cpu()[..., :77]).sum(-1, keepdim=True)) * 0.125
+    res["softmax_bwd"] = _cmp(ops.softmax_bwd_rows(p, dp, 77, 0.125), torch.nn.functional.pad(dref, (0, 3)))
+    return _merge(res)
+
+
+def case_training_kernels():
+    import torch
+    from leco_b200 import ops
+    res = {}
+    for (M, N1, N2, tr) in ((16384, 960, 16, False), (1000, 320, 16, True), (4096, 2560, 32, False), (308, 1024, 16, True)):
+        a, b = _rand((M, N1), seed=1), _rand((M, N2), seed=2)
+        out = torch.zeros((N2, N1) if tr else (N1, N2), device="cuda")
+        ops.tn_reduce(a, b, out, 0.5, transpose_out=tr)
+        ref = 0.5 * a.float().t() @ b.float()
+        res[f"tn_{M}_{N1}_{N2}_{int(tr)}"] = _cmp(out, ref.t() if tr else ref, 2e-3)
+    # fused AdamW vs torch.optim.AdamW on fp32 (bf16 rounding of params bounds the difference)
+    n = 100000
+    p0 = _rand((n,), 0.1, 3)
+    g = _rand((n,), 0.01, 4, torch.float32)
+    p = p0.clone()
+    m = torch.zeros(n, device="cuda")
+    v = torch.zeros(n, device="cuda")
+    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.01, 1.0, 1.0, 0.0], device="cuda")
+    pt = torch.nn.Parameter(p0.float().clone())
+    opt = torch.optim.AdamW([pt], lr=1e-3)
+    for step in range(1, 4):
+        hyper[5] = float(step)
+        gg = g.clone() * step
+        ops.adamw_flat(p, gg, m, v, None, hyper, zero_grad=True)
+        pt.grad = (g * step).bfloat16().float()
+        opt.step()
+    res["adamw_3steps"] = _cmp(p, pt.data, 1e-2)
+    # parameters are STORED in bf16 (like the reference's): the result may differ from fp32 AdamW by
+    # about one bf16 ulp of the parameter, and must move in the same direction
+    ulp = pt.data.abs().clamp_min(1e-3) * 2.0 ** -7
+    worst = ((p.float() - pt.data).abs() / ulp).max().item()
+    res["adamw_within_ulps"] = {"rel": worst, "ok": worst < 3.0, "max_abs_err": worst, "ref_absmax": 1.0}
+    cos = torch.nn.functional.cosine_similarity((p.float() - p0.float()).flatten(), (pt.data - p0.float()).flatten(), dim=0).item()
+    res["adamw_update_cos"] = {"rel": 1 - cos, "ok": cos > 0.9, "max_abs_err": 1 - cos, "ref_absmax": 1.0}
+    # guided step + loss
+    eps = _rand((4, 4, 8, 8), seed=5, dtype=torch.float32)
+    x = _rand((2, 4, 8, 8), seed=6, dtype=torch.float32)
+    coef = torch.tensor([3.0, 1.01, -0.07], device="cuda")
+    xo, gd = ops.guided_step(eps, x, coef, True, True)
+    gref = eps[:2] + 3.0 * (eps[2:] - eps[:2])
+    res["guided"] = _cmp(gd, gref, 1e-5)
+    res["ddim"] = _cmp(xo, 1.01 * x - 0.07 * gref, 1e-5)
+    t_, p_, n_, u_ = (_rand((2, 4, 8, 8), seed=s, dtype=torch.float32) for s in (7, 8, 9, 10))
+    loss, dt = ops.leco_loss(t_, p_, n_, u_, -1.5)
+    goal = n_ - 1.5 * (p_ - u_)
+    res["loss"] = _cmp(loss, ((t_ - goal) ** 2).mean().reshape(1), 1e-5)
+    res["dloss"] = _cmp(dt, 2 * (t_ - goal) / t_.numel(), 1e-5)
+    return _merge(res)
+
+
+def case_attention(nb, sq, skv, heads, d, cross=False):
+    import torch
+    from leco_b200 import ops
+    from tests import torch_backend as tb
+    C = heads * d
+    if cross:
+        qbuf, kvbuf = _rand((nb * sq, C), seed=1), _rand((nb * skv, 2 * C), seed=2)
+        qt, kt, vt = qbuf, kvbuf[:, :C], kvbuf[:, C:]
+    else:
+        qkv = _rand((nb * sq, 3 * C), seed=1)
+        qt, kt, vt = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    scale = d ** -0.5
+    o, saved = ops.attention(qt, kt, vt, nb, sq, skv, heads, d, scale, True)
+    oref, _ = tb.attention(qt.cpu(), kt.cpu(), vt.cpu(), nb, sq, skv, heads, d, scale, False)
+    res = {"fwd": _cmp(o, oref)}
+    go = _rand((nb * sq, C), seed=3)
+    dq, dk, dv = (torch.empty((nb * s, C), device="cuda", dtype=torch.bfloat16) for s in (sq, skv, skv))
+    ops.attention_bwd(go, qt, kt, vt, saved, nb, sq, skv, heads, d, scale, dq, dk, dv)
+    rq, rk, rv = (torch.empty((nb * s, C)) for s in (sq, skv, skv))
+    tb.attention_bwd(go.cpu(), qt.cpu(), kt.cpu(), vt.cpu(), None, nb, sq, skv, heads, d, scale, rq, rk, rv)
+    res["dq"], res["dk"], res["dv"] = _cmp(dq, rq, 3e-2), _cmp(dk, rk, 3e-2), _cmp(dv, rv, 3e-2)
+    return _merge(res)
+
+
+def _engine_pair(arch, dtype=None):
+    import torch
+    from leco_b200.unet import SPECS, EngineUNet
+    from oracle.unet_ref import build_unet
+    oracle = build_unet(arch)
+    eng = EngineUNet(SPECS[arch])
+    eng.load_state_dict(oracle.state_dict())
+    eng.requires_grad_(False)
+    eng.to("cuda")
+    return oracle, eng
+
+
+def _inputs(arch, n, hw, seed=3):
+    import torch
+    from oracle.unet_ref import CONFIGS
+    cfg = CONFIGS[arch]
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((n, 4, hw, hw), generator=g)
+    ctx = torch.randn((n, 77, cfg.cross_attention_dim), generator=g)
+    added = None
+    if cfg.addition_embed_type:
+        pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
+        added = {"text_embeds": torch.randn((n, pooled), generator=g),
+                 "time_ids": torch.tensor([[hw * 8., hw * 8, 0, 0, hw * 8, hw * 8]] * n)}
+    return x, ctx, added
+
+
+def case_engine_forward(arch, n=2, hw=16, time_it=False):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 8)
+    oracle, eng = _engine_pair(arch)
+    x, ctx, added = _inputs(arch, n, hw)
+    t = torch.tensor(481)
+    # the oracle sees the same bf16-rounded weights/inputs the engine uses
+    oracle = oracle.to(torch.bfloat16).float()
+    with torch.no_grad():
+        t0 = time.time()
+        ref = oracle(x.bfloat16().float(), t, ctx.bfloat16().float(),
+                     None if added is None else {k: v.bfloat16().float() for k, v in added.items()}).sample
+        cpu_s = time.time() - t0
+        cu_added = None if added is None else {k: v.cuda() for k, v in added.items()}
+        out = eng(x.cuda(), t, encoder_hidden_states=ctx.cuda().bfloat16(), added_cond_kwargs=cu_added).sample
+        torch.cuda.synchronize()
+        res = _cmp(out, ref, 3e-2)
+        res["rel_rms"] = ((out.float().cpu() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+        res["oracle_cpu_s"] = cpu_s
+        if time_it:
+            xc, cc = x.cuda(), ctx.cuda().bfloat16()
+            for _ in range(2):
+                eng(xc, t, encoder_hidden_states=cc, added_cond_kwargs=cu_added)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.time()
+            e0.record()
+            for _ in range(3):
+                eng(xc, t, encoder_hidden_states=cc, added_cond_kwargs=cu_added)
+            e1.record()
+            torch.cuda.synchronize()
+            res["eager_ms_per_fwd_gpu"] = e0.elapsed_time(e1) / 3
+            res["eager_ms_per_fwd_wall"] = (time.time() - t0) * 1000 / 3
+    return res
+
+
+def case_engine_grads(arch, n=2, hw=8):
+    import torch
+    from oracle import leco_ref
+    oracle, eng = _engine_pair(arch)
+    oracle = oracle.to(torch.bfloat16).float()
+    x, ctx, added = _inputs(arch, n, hw)
+    t = torch.tensor(261)
+
+    def make(unet, dev):
+        torch.manual_seed(11)
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = leco_ref.LoRANetworkRef(unet, rank=4, multiplier=1.0, alpha=1.0)
+        g = torch.Generator().manual_seed(5)
+        for l in net.unet_loras:
+            l.lora_up.weight.data = (0.05 * torch.randn(l.lora_up.weight.shape, generator=g))
+            l.lora_down.weight.data = l.lora_down.weight.data.bfloat16().float()
+            l.lora_up.weight.data = l.lora_up.weight.data.bfloat16().float()
+        return net.to(dev)
+
+    net_o = make(oracle, "cpu")
+    net_e = make(eng, "cuda").to(torch.bfloat16)
+    goal = torch.randn((n, 4, hw, hw), generator=torch.Generator().manual_seed(9))
+    with net_o:
+        yo = oracle(x.bfloat16().float(), t, encoder_hidden_states=ctx.bfloat16().float()).sample
+    lo = torch.nn.functional.mse_loss(yo, goal)
+    lo.backward()
+    with net_e:
+        ye = eng(x.cuda().bfloat16(), t, encoder_hidden_states=ctx.cuda().bfloat16()).sample
+    le = torch.nn.functional.mse_loss(ye.float().cpu(), goal)  # loss on the CPU like train_lora.py:265-270
+    le.backward()
+    res = {"fwd": _cmp(ye, yo, 3e-2)}
+    num = den = 0.0
+    worst = 0.0
+    for a, b in zip(net_o.unet_loras, net_e.unet_loras):
+        for pa, pb in ((a.lora_down.weight, b.lora_down.weight), (a.lora_up.weight, b.lora_up.weight)):
+            ga, gb = pa.grad.float(), pb.grad.float().cpu()
+            num += (ga - gb).pow(2).sum().item()
+            den += ga.pow(2).sum().item()
+            worst = max(worst, (ga - gb).abs().max().item() / (ga.abs().max().item() + 1e-12))
+    rel = (num / den) ** 0.5
+    res["grads"] = {"rel": rel, "worst_tensor_rel": worst, "ok": rel < 5e-2, "max_abs_err": 0, "ref_absmax": den ** 0.5}
+    res["loss"] = {"rel": abs(lo.item() - le.item()) / lo.item(), "ok": abs(lo.item() - le.item()) / lo.item() < 2e-2,
+                   "max_abs_err": 0, "ref_absmax": lo.item()}
+    return _merge(res)
+
+
+CASES = [
+    ("norms", case_norms, {}),
+    ("elementwise", case_elementwise, {}),
+    ("training_kernels", case_training_kernels, {}),
+    ("attn_self_1024_d64", case_attention, dict(nb=2, sq=1024, skv=1024, heads=5, d=64)),
+    ("attn_cross_77", case_attention, dict(nb=2, sq=256, skv=77, heads=2, d=64, cross=True)),
+    ("attn_self_d40", case_attention, dict(nb=2, sq=256, skv=256, heads=8, d=40)),
+    ("attn_self_64_d8", case_attention, dict(nb=2, sq=64, skv=64, heads=8, d=8)),
+    ("attn_self_tiny_sq4", case_attention, dict(nb=2, sq=4, skv=4, heads=4, d=64)),
+    ("engine_fwd_tiny21", case_engine_forward, dict(arch="tiny21")),
+    ("engine_fwd_tiny15", case_engine_forward, dict(arch="tiny15")),
+    ("engine_fwd_tinyxl", case_engine_forward, dict(arch="tinyxl")),
+    ("engine_grads_tiny21", case_engine_grads, dict(arch="tiny21")),
+    ("engine_grads_tiny15", case_engine_grads, dict(arch="tiny15")),
+    ("engine_fwd_sd21_64", case_engine_forward, dict(arch="sd21", n=2, hw=64, time_it=True)),
+]
+
+
+def main():
+    if len(sys.argv) >= 3 and sys.argv[1] == "--case":
+        for n, fn, kw in CASES:
+            if n == sys.argv[2]:
+                print("RESULT " + json.dumps(fn(**kw)))
+                return
+        raise SystemExit("unknown case")
+    only = sys.argv[1:] or None
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    results = {}
+    for name, _, kw in CASES:
+        if only and not any(name.startswith(o) for o in only):
+            continue
+        t0 = time.time()
+        try:
+            pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", name], capture_output=True,
+                                text=True, timeout=600)
+            line = [l for l in pr.stdout.splitlines() if l.startswith("RESULT ")]
+            res = json.loads(line[-1][7:]) if pr.returncode == 0 and line else {
+                "ok": False, "rc": pr.returncode, "stderr": pr.stderr[-2500:], "stdout": pr.stdout[-800:]}
+        except subprocess.TimeoutExpired:
+            res = {"ok": False, "timeout": True}
+        res["secs"] = round(time.time() - t0, 1)
+        results[name] = res
+        brief = {k: v for k, v in res.items() if k != "parts"}
+        if not res.get("ok") and "parts" in res:
+            brief["failed_parts"] = {k: v for k, v in res["parts"].items() if not v.get("ok")}
+        print(name, json.dumps(brief)[:1500], flush=True)
+        with open(os.path.join(out_dir, "kernel_cases.json"), "w") as f:
+            json.dump(results, f, indent=1)
+    print(f"SUMMARY {sum(1 for r in results.values() if r.get('ok'))}/{len(results)} ok")
+
+
+if __name__ == "__main__":
+    main()

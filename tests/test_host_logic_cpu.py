@@ -1,0 +1,111 @@
+"""CPU: host-side mirrors of the reference interface (scheduler, LoRANetwork discovery / naming /
+init / export) against the oracle, and against the live reference when it is present."""
+import contextlib
+import io
+import os
+
+import pytest
+import torch
+
+from leco_b200 import lora as plora
+from leco_b200.scheduler import DDIMScheduler, create_noise_scheduler
+from leco_b200.unet import SPECS, EngineUNet
+from oracle import leco_ref
+from oracle.ref_loader import reference_available
+from oracle.sched_ref import create_noise_scheduler as oracle_sched
+from oracle.unet_ref import build_unet
+from tests import torch_backend
+
+
+@pytest.mark.parametrize("ptype", ["epsilon", "v_prediction"])
+def test_ddim_matches_oracle(ptype):
+    a, b = DDIMScheduler(ptype), oracle_sched("ddim", ptype)
+    for n in (50, 30, 1000):
+        a.set_timesteps(n)
+        b.set_timesteps(n)
+        assert a.timesteps.tolist() == b.timesteps.tolist()
+    a.set_timesteps(50)
+    b.set_timesteps(50)
+    g = torch.Generator().manual_seed(0)
+    x, e = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+    for t in (980, 500, 20, 0):
+        pa = a.step(e, t, x).prev_sample
+        pb = b.step(e, t, x).prev_sample
+        assert (pa - pb).abs().max().item() < 2e-6
+    assert a.init_noise_sigma == 1.0 and a.scale_model_input(x, 3) is x
+    with pytest.raises(ValueError):
+        create_noise_scheduler("nope")
+
+
+def _nets(arch="tiny21"):
+    eng = EngineUNet(SPECS[arch], backend=torch_backend)
+    ora = build_unet(arch)
+    torch.manual_seed(21)
+    with contextlib.redirect_stdout(io.StringIO()):
+        a = plora.LoRANetwork(eng, rank=4, multiplier=1.0, alpha=1.0)
+    torch.manual_seed(21)
+    with contextlib.redirect_stdout(io.StringIO()):
+        b = leco_ref.LoRANetworkRef(ora, rank=4, multiplier=1.0, alpha=1.0)
+    return a, b
+
+
+def test_lora_network_mirror_matches_oracle():
+    a, b = _nets()
+    assert len(a.unet_loras) == 192
+    assert list(a.state_dict().keys()) == list(b.state_dict().keys())
+    for (k, va), vb in zip(a.state_dict().items(), b.state_dict().values()):
+        assert torch.equal(va, vb), k            # same RNG draws in the same order
+    assert a.unet_loras[0].scale == 0.25 and float(a.unet_loras[0].alpha) == 1.0
+    pa, pb = a.prepare_optimizer_params(), b.prepare_optimizer_params()
+    assert len(pa) == 1 and len(pa[0]["params"]) == len(pb[0]["params"]) == 384
+    assert all(l.multiplier == 1.0 for l in a.unet_loras)
+    with a:
+        pass
+    assert all(l.multiplier == 0 for l in a.unet_loras)
+    with pytest.raises(NotImplementedError):
+        plora.LoRANetwork(EngineUNet(SPECS["tiny21"], backend=torch_backend), train_method="bogus")
+
+
+def test_save_weights_format(tmp_path):
+    from safetensors.torch import load_file
+    a, b = _nets()
+    f = str(tmp_path / "x_last.safetensors")
+    a.save_weights(f, dtype=torch.bfloat16)
+    sd = load_file(f)
+    want = b.lora_state_dict(torch.bfloat16)
+    assert sorted(sd.keys()) == sorted(want.keys())
+    for k in sd:
+        assert sd[k].dtype == torch.bfloat16 and torch.equal(sd[k], want[k]), k
+    assert "lora_unet_down_blocks_0_attentions_0_proj_in.alpha" in sd
+    assert sd["lora_unet_mid_block_attentions_0_transformer_blocks_0_attn2_to_k.lora_down.weight"].shape == (4, 128)
+
+
+def test_c3lier_aliasing_contract():
+    """extending DEFAULT_TARGET_REPLACE in place (train_lora.py:44-46) adds the conv blocks."""
+    eng = EngineUNet(SPECS["tiny15"], backend=torch_backend)
+    saved = list(plora.DEFAULT_TARGET_REPLACE)
+    try:
+        plora.DEFAULT_TARGET_REPLACE += plora.UNET_TARGET_REPLACE_MODULE_CONV
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = plora.LoRANetwork(eng, rank=8, alpha=1.0)
+        assert len(net.unet_loras) == 278
+    finally:
+        del plora.DEFAULT_TARGET_REPLACE[len(saved):]
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference sources only exist in the build container")
+def test_reference_lora_network_patches_engine_tree():
+    """The reference's OWN LoRANetwork must find the same targets on the engine's holder tree."""
+    from oracle.ref_loader import load_reference
+    ref = load_reference()
+    for arch, n in (("tiny21", 192), ("tiny15", 192), ("tinyxl", 302)):
+        eng = EngineUNet(SPECS[arch], backend=torch_backend)
+        ora = build_unet(arch)
+        with contextlib.redirect_stdout(io.StringIO()):
+            a = ref.lora.LoRANetwork(eng, rank=4, multiplier=1.0, alpha=1.0)
+            b = ref.lora.LoRANetwork(ora, rank=4, multiplier=1.0, alpha=1.0)
+        assert len(a.unet_loras) == n
+        assert [l.lora_name for l in a.unet_loras] == [l.lora_name for l in b.unet_loras]
+        from leco_b200.unet import find_adapter
+        sites = [s for s in (eng.pack("cpu", torch.float32) or eng).lora_sites() if s.adapters() is not None]
+        assert sum(len(s.members) for s in sites) == n
