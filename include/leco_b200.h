@@ -91,6 +91,8 @@ int leco_copy_cols(const void* src, int64_t lds, int scol0, void* dst, int64_t l
 int leco_upsample2x(const void* x, void* y, int n, int h, int w, int c, void* stream);
 int leco_upsample2x_bwd(const void* dy, void* dx, int n, int h, int w, int c, void* stream);
 int leco_im2col_s2(const void* x, void* col, int n, int h, int w, int c, void* stream);
+int leco_im2col_s1(const void* x, void* col, int n, int h, int w, int c, void* stream);
+int leco_rowgroup_sum(const void* x, void* out, int n, int hw, int c, void* stream);
 int leco_col2im_s2(const void* dcol, void* dx, int n, int h, int w, int c, void* stream);
 int leco_transpose(const void* in, void* out, int rows, int cols, int rows_pad, int64_t in_ld, int64_t in_bs0,
                    int64_t in_bs1, int64_t out_ld, int64_t out_bs0, int64_t out_bs1, int batch0, int batch1,
@@ -99,6 +101,15 @@ int leco_softmax_rows(const float* s, void* p, int64_t rows, int n_valid, int n_
                       void* stream);
 int leco_softmax_bwd_rows(const void* p, const float* dp, void* ds, int64_t rows, int n_valid, int n_pad,
                           int64_t ld_p, int64_t ld_dp, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * leco_flash_attn_fwd — fused softmax(scale Q K^T) V, head dim <= 64, S/P never leave the SM.
+ * Replaces xformers.memory_efficient_attention (enabled at train_lora.py:68).  q/k/v are [rows, ld]
+ * bf16 buffers (head h in columns [h*d, h*d+d)); v_t (optional) is V^T [batch][heads][d][skv_pad].
+ * ------------------------------------------------------------------------------- */
+int leco_flash_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                        const void* v_t, int64_t skv_pad, void* out, int64_t ldo, int batch, int heads, int sq,
+                        int skv, int d, float scale, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * GroupNorm(+SiLU) / LayerNorm (diffusers ResnetBlock2D.norm1/2, Transformer2DModel.norm,

@@ -79,9 +79,12 @@ _OPS: list[tuple[str, list]] = [
     ("leco_upsample2x_bwd", [P, P, I, I, I, I, P]),
     ("leco_im2col_s2", [P, P, I, I, I, I, P]),
     ("leco_col2im_s2", [P, P, I, I, I, I, P]),
+    ("leco_im2col_s1", [P, P, I, I, I, I, P]),
+    ("leco_rowgroup_sum", [P, P, I, I, I, P]),
     ("leco_transpose", [P, P, I, I, I, L, L, L, L, L, L, I, I, P]),
     ("leco_softmax_rows", [P, P, L, I, I, L, L, P]),
     ("leco_softmax_bwd_rows", [P, P, P, L, I, I, L, L, F, P]),
+    ("leco_flash_attn_fwd", [P, L, P, L, P, L, P, L, P, L, I, I, I, I, I, F, P]),
     ("leco_group_norm", [P, P, P, P, P, I, I, I, I, F, I, P, P]),
     ("leco_group_norm_bwd", [P, P, P, P, P, P, I, I, I, I, I, P, P]),
     ("leco_layer_norm", [P, P, P, P, P, L, I, F, P]),

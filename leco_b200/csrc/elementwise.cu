@@ -287,8 +287,8 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv
 
 // stride-2 3x3 pad-1 im2col: x NHWC [n,h,w,c] -> col [n*(h/2)*(w/2), 9*c] (k = tap*c + ch)
 __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, int n,
-                                 int h, int w, int c) {
-  const int vpp = c / 8, oh = h / 2, ow = w / 2;
+                                 int h, int w, int c, int stride) {
+  const int vpp = c / 8, oh = h / stride, ow = w / stride;
   const long long total = 1LL * n * oh * ow * 9 * vpp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -299,7 +299,7 @@ __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
     const int ox = (int)(p % ow);
     const int oy = (int)((p / ow) % oh);
     const int img = (int)(p / ((long long)ow * oh));
-    const int yy = 2 * oy + tap / 3 - 1, xx = 2 * ox + tap % 3 - 1;
+    const int yy = stride * oy + tap / 3 - 1, xx = stride * ox + tap % 3 - 1;
     bf16x8 q = {{0, 0, 0, 0}};
     if (yy >= 0 && yy < h && xx >= 0 && xx < w)
       q = *reinterpret_cast<const bf16x8*>(x + ((1LL * img * h + yy) * w + xx) * c + v * 8);
@@ -332,6 +332,35 @@ __global__ void col2im_s2_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bf
       for (int j = 0; j < 8; ++j) acc[j] += f[j];
     }
     *reinterpret_cast<bf16x8*>(dx + p * c + v * 8) = pack8(acc);
+  }
+}
+
+// out[n, c] = sum over the hw rows of sample n (the time-embedding bias gradient of a conv epilogue)
+__global__ void rowgroup_sum_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int hw,
+                                    int c) {
+  __shared__ float red[8][32][8];
+  const int n = blockIdx.x;
+  const int v = blockIdx.y * 32 + threadIdx.x;  // 8-channel vector column
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (v * 8 < c) {
+    for (int r = threadIdx.y; r < hw; r += 8) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + ((size_t)n * hw + r) * c + v * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.y == 0 && v * 8 < c) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+      for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x][j];
+      acc[j] = s;
+    }
+    *reinterpret_cast<bf16x8*>(out + (size_t)n * c + v * 8) = pack8(acc);
   }
 }
 
@@ -507,7 +536,22 @@ extern "C" int leco_im2col_s2(const void* x, void* col, int n, int h, int w, int
   LECO_REQUIRE(x && col && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "leco_im2col_s2: bad args");
   count_launch();
   im2col_s2_kernel<<<grid_for(1LL * n * (h / 2) * (w / 2) * 9 * (c / 8), 256), 256, 0, STREAM(stream)>>>(
-      BF(x), BFW(col), n, h, w, c);
+      BF(x), BFW(col), n, h, w, c, 2);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_im2col_s1(const void* x, void* col, int n, int h, int w, int c, void* stream) {
+  LECO_REQUIRE(x && col && c % 8 == 0, "leco_im2col_s1: bad args");
+  count_launch();
+  im2col_s2_kernel<<<grid_for(1LL * n * h * w * 9 * (c / 8), 256), 256, 0, STREAM(stream)>>>(BF(x), BFW(col), n, h, w,
+                                                                                          c, 1);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_rowgroup_sum(const void* x, void* out, int n, int hw, int c, void* stream) {
+  LECO_REQUIRE(x && out && c % 8 == 0, "leco_rowgroup_sum: bad args");
+  count_launch();
+  rowgroup_sum_kernel<<<dim3(n, (c / 8 + 31) / 32), dim3(32, 8), 0, STREAM(stream)>>>(BF(x), BFW(out), hw, c);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

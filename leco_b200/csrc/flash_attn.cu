@@ -1,0 +1,347 @@
+// Fused attention forward for sm_100a: O = softmax(scale * Q K^T) V per (sample, head), head dim <= 64.
+// Replaces xformers.memory_efficient_attention on the reference's path (train_lora.py:68).
+//
+// One CTA per (128-query tile, head, sample).  K/V tiles of 128 keys stream through TMA rings;
+//   S_j  = Q K_j^T      tcgen05.mma (M128 N128 K64)  -> TMEM, double buffered
+//   P_j  = exp2(S_j*c - m)  softmax warps read S from TMEM (tcgen05.ld), keep running max / sum in
+//                            registers, write P (bf16) into 128B-swizzled smem as the next A operand
+//   PV_j = P_j V_j      tcgen05.mma (M128 N64 K128)  -> TMEM, double buffered
+//   O    = O*alpha + PV_j   folded in registers by the softmax warps one tile late, so the tensor pipe
+//                            never waits for a TMEM rescale.
+// Nothing of S or P ever touches HBM: algorithmic traffic is Q, K, V, O once (K/V re-reads hit L2).
+// Roles: warp 0 lane 0 TMA, warp 1 lane 0 MMA issue, warp 2 TMEM alloc, warps 4-7 softmax (1 row/thread).
+//
+// V operand: v_mode 0 = V tile [keys, d] used directly as an MN-major B operand;
+//            v_mode 1 = a pre-transposed V^T [d, keys] (K-major B operand, like the GEMM kernel).
+#include "../../include/leco_b200.h"
+#include "common.cuh"
+
+namespace leco {
+void count_launch();
+
+constexpr int FA_BM = 128, FA_BN = 128, FA_D = 64;
+constexpr int FA_KS = 3, FA_VS = 3;                       // K / V ring depth
+constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;              // 16 KiB
+constexpr int FA_KV_BYTES = FA_BN * FA_D * 2;             // 16 KiB
+constexpr int FA_P_BYTES = FA_BM * FA_BN * 2;             // 32 KiB (two 64-key chunks)
+constexpr int FA_SMEM = FA_Q_BYTES + (FA_KS + FA_VS) * FA_KV_BYTES + 2 * FA_P_BYTES + 1024 + 512;
+constexpr int FA_TMEM_COLS = 512;                         // S: 2 x 128, PV: 2 x 64
+constexpr int FA_THREADS = 256;
+
+struct FlashParams {
+  CUtensorMap tm_q, tm_k, tm_v;
+  __nv_bfloat16* out;
+  long long ld_out;
+  int sq, skv, heads, d, n_kv_tiles, v_mode;
+  float scale_log2;  // softmax scale * log2(e)
+};
+
+// MN-major B operand (V tile as stored: keys x d), 128B swizzle: 8 key-rows of 128 B per atom.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((FA_KV_BYTES) >> 4) << 16;  // LBO: next 64-wide MN block (unused: N = 64)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;           // SBO: next group of 8 K rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t n, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __grid_constant__ FlashParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + FA_Q_BYTES;
+  uint8_t* sV = sK + FA_KS * FA_KV_BYTES;
+  uint8_t* sP = sV + FA_VS * FA_KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FA_P_BYTES);
+  uint64_t* q_full = bars;                 // [1]
+  uint64_t* k_full = bars + 1;             // [KS]
+  uint64_t* k_empty = k_full + FA_KS;      // [KS]
+  uint64_t* v_full = k_empty + FA_KS;      // [VS]
+  uint64_t* v_empty = v_full + FA_VS;      // [VS]
+  uint64_t* s_full = v_empty + FA_VS;      // [2]
+  uint64_t* s_empty = s_full + 2;          // [2]
+  uint64_t* p_full = s_empty + 2;          // [2]
+  uint64_t* p_empty = p_full + 2;          // [2]
+  uint64_t* pv_full = p_empty + 2;         // [2]
+  uint64_t* pv_empty = pv_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = p.n_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_q);
+    tma_prefetch_desc(&p.tm_k);
+    tma_prefetch_desc(&p.tm_v);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < FA_KS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < FA_VS; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_empty[i], 1);
+      mbar_init(&pv_full[i], 1);
+      mbar_init(&pv_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, FA_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;        // + buf * 128
+  const uint32_t tmem_pv = tmem_base + 256; // + buf * 64
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    mbar_arrive_expect_tx(q_full, FA_Q_BYTES);
+    tma_load_4d(sQ, &p.tm_q, q_full, 0, qt * FA_BM, head, b);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int ks = j % FA_KS, vs = j % FA_VS;
+      mbar_wait(&k_empty[ks], ((j / FA_KS) & 1) ^ 1);
+      mbar_arrive_expect_tx(&k_full[ks], FA_KV_BYTES);
+      tma_load_4d(sK + ks * FA_KV_BYTES, &p.tm_k, &k_full[ks], 0, j * FA_BN, head, b);
+      mbar_wait(&v_empty[vs], ((j / FA_VS) & 1) ^ 1);
+      mbar_arrive_expect_tx(&v_full[vs], FA_KV_BYTES);
+      if (p.v_mode == 0) {
+        tma_load_4d(sV + vs * FA_KV_BYTES, &p.tm_v, &v_full[vs], 0, j * FA_BN, head, b);
+      } else {  // V^T [d, keys]: two 64-key chunks, each [64 d-rows x 128 B]
+        tma_load_4d(sV + vs * FA_KV_BYTES, &p.tm_v, &v_full[vs], j * FA_BN, 0, head, b);
+        tma_load_4d(sV + vs * FA_KV_BYTES + FA_KV_BYTES / 2, &p.tm_v, &v_full[vs], j * FA_BN + 64, 0, head, b);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc_s = umma_idesc_bf16(FA_BN, false);
+    const uint32_t idesc_pv = umma_idesc_bf16(FA_D, p.v_mode == 0);
+    const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ));
+    auto issue_s = [&](int j) {
+      const int ks = j % FA_KS, sb = j & 1;
+      mbar_wait(&k_full[ks], (j / FA_KS) & 1);
+      mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint64_t dk = umma_desc_k_sw128(smem_u32(sK + ks * FA_KV_BYTES));
+#pragma unroll
+      for (int s = 0; s < FA_D / 16; ++s) umma_bf16(tmem_s + sb * FA_BN, dq + 2 * s, dk + 2 * s, idesc_s, s > 0 ? 1u : 0u);
+      umma_commit(&s_full[sb]);
+      umma_commit(&k_empty[ks]);
+    };
+    mbar_wait(q_full, 0);
+    issue_s(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j + 1 < n_tiles) issue_s(j + 1);
+      const int vs = j % FA_VS, pb = j & 1;
+      mbar_wait(&p_full[pb], (j >> 1) & 1);
+      mbar_wait(&v_full[vs], (j / FA_VS) & 1);
+      mbar_wait(&pv_empty[pb], ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t pbase = smem_u32(sP + pb * FA_P_BYTES);
+      const uint32_t vbase = smem_u32(sV + vs * FA_KV_BYTES);
+#pragma unroll
+      for (int s = 0; s < FA_BN / 16; ++s) {
+        // A = P: K-major, two 64-key chunks of [128 rows x 128 B]
+        const uint64_t da = umma_desc_k_sw128(pbase + (s >> 2) * (FA_P_BYTES / 2)) + 2 * (s & 3);
+        uint64_t db;
+        if (p.v_mode == 0)
+          db = umma_desc_mn_sw128(vbase + s * 16 * 128);                       // 16 key rows per k-step
+        else
+          db = umma_desc_k_sw128(vbase + (s >> 2) * (FA_KV_BYTES / 2)) + 2 * (s & 3);
+        umma_bf16(tmem_pv + pb * FA_D, da, db, idesc_pv, s > 0 ? 1u : 0u);
+      }
+      umma_commit(&pv_full[pb]);
+      umma_commit(&v_empty[vs]);
+      umma_commit(&p_empty[pb]);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax + output (1 row / thread)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+    float o[FA_D];
+#pragma unroll
+    for (int i = 0; i < FA_D; ++i) o[i] = 0.f;
+
+    auto fold_pv = [&](int j, float alpha) {  // o = o*alpha + PV_j
+      const int pb = j & 1;
+      mbar_wait(&pv_full[pb], (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < FA_D / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(tmem_pv + lane_off + pb * FA_D + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(raw[i]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pv_empty[pb]);
+    };
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int sb = j & 1;
+      const int kv0 = j * FA_BN;
+      const bool ragged = kv0 + FA_BN > p.skv;
+      mbar_wait(&s_full[sb], (j >> 1) & 1);
+      tc_fence_after();
+      // pass 1: row max
+      float mx = m_run;
+#pragma unroll 1
+      for (int c = 0; c < FA_BN / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_off + sb * FA_BN + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(raw[i]);
+          if (ragged && kv0 + c * 32 + i >= p.skv) s = -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_new = mx;
+      const float alpha = exp2f((m_run - m_new) * p.scale_log2);  // first tile: exp2(-inf) = 0
+      const float mb = m_new * p.scale_log2;
+      // pass 2: p = exp2(s*c - m*c); write P (bf16) into the swizzled A-operand tile
+      mbar_wait(&p_empty[sb], ((j >> 1) & 1) ^ 1);
+      uint8_t* prow = sP + sb * FA_P_BYTES + r * 128;
+      float rowsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < FA_BN / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_off + sb * FA_BN + c * 32, raw);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float s0 = __uint_as_float(raw[i]), s1 = __uint_as_float(raw[i + 1]);
+          float p0 = exp2f(fmaf(s0, p.scale_log2, -mb));
+          float p1 = exp2f(fmaf(s1, p.scale_log2, -mb));
+          if (ragged) {
+            if (kv0 + c * 32 + i >= p.skv) p0 = 0.f;
+            if (kv0 + c * 32 + i + 1 >= p.skv) p1 = 0.f;
+          }
+          rowsum += p0 + p1;
+          pk[i >> 1] = pack_bf16(p0, p1);
+        }
+        // 32 keys = 64 B = four 16-byte chunks; key chunk index within the 64-key half: (c&1)*4 + t
+        uint8_t* half = prow + (c >> 1) * (FA_P_BYTES / 2);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int chunk = (c & 1) * 4 + t;
+          *reinterpret_cast<uint4*>(half + ((chunk ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s_empty[sb]);
+        mbar_arrive(&p_full[sb]);
+      }
+      l_run = l_run * alpha + rowsum;
+      m_run = m_new;
+      if (j > 0) fold_pv(j - 1, alpha_prev);
+      alpha_prev = alpha;
+    }
+    fold_pv(n_tiles - 1, alpha_prev);
+    const int row = qt * FA_BM + r;
+    if (row < p.sq) {
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.sq + row) * p.ld_out + head * p.d;
+#pragma unroll
+      for (int c8 = 0; c8 < FA_D / 8; ++c8) {
+        if (c8 * 8 < p.d) {
+          uint4 v;
+          v.x = pack_bf16(o[c8 * 8 + 0] * inv, o[c8 * 8 + 1] * inv);
+          v.y = pack_bf16(o[c8 * 8 + 2] * inv, o[c8 * 8 + 3] * inv);
+          v.z = pack_bf16(o[c8 * 8 + 4] * inv, o[c8 * 8 + 5] * inv);
+          v.w = pack_bf16(o[c8 * 8 + 6] * inv, o[c8 * 8 + 7] * inv);
+          *reinterpret_cast<uint4*>(dst + c8 * 8) = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, FA_TMEM_COLS);
+}
+
+}  // namespace leco
+
+using namespace leco;
+
+// q/k/v: [rows, ld] bf16 buffers whose columns [head*d, head*d+d) hold that head (strides in elements).
+// v_t != NULL selects v_mode 1: v_t is V^T laid out [batch][heads][d][skv_pad] (skv_pad multiple of 8).
+extern "C" int leco_flash_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                   const void* v_t, int64_t skv_pad, void* out, int64_t ldo, int batch, int heads,
+                                   int sq, int skv, int d, float scale, void* stream) {
+  LECO_REQUIRE(q && k && out && (v || v_t), "leco_flash_attn_fwd: null pointer");
+  LECO_REQUIRE(d % 8 == 0 && d <= FA_D, "leco_flash_attn_fwd: head dim %d unsupported (<=64, multiple of 8)", d);
+  LECO_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldo % 8 == 0, "leco_flash_attn_fwd: strides must be multiples of 8");
+  FlashParams p;
+  memset(&p, 0, sizeof(p));
+  const uint32_t box_q[4] = {FA_D, FA_BM, 1, 1};
+  {
+    const uint64_t dims[4] = {(uint64_t)d, (uint64_t)sq, (uint64_t)heads, (uint64_t)batch};
+    const uint64_t str[3] = {(uint64_t)ldq * 2, (uint64_t)d * 2, (uint64_t)ldq * sq * 2};
+    if (make_tmap_bf16_4d(&p.tm_q, q, dims, str, box_q)) return -3;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)d, (uint64_t)skv, (uint64_t)heads, (uint64_t)batch};
+    const uint64_t str[3] = {(uint64_t)ldk * 2, (uint64_t)d * 2, (uint64_t)ldk * skv * 2};
+    if (make_tmap_bf16_4d(&p.tm_k, k, dims, str, box_q)) return -3;
+  }
+  if (v_t) {
+    LECO_REQUIRE(skv_pad % 8 == 0 && skv_pad >= skv, "leco_flash_attn_fwd: bad skv_pad");
+    const uint64_t dims[4] = {(uint64_t)skv_pad, (uint64_t)d, (uint64_t)heads, (uint64_t)batch};
+    const uint64_t str[3] = {(uint64_t)skv_pad * 2, (uint64_t)skv_pad * d * 2, (uint64_t)skv_pad * d * heads * 2};
+    const uint32_t box_v[4] = {64, FA_D, 1, 1};
+    if (make_tmap_bf16_4d(&p.tm_v, v_t, dims, str, box_v)) return -3;
+    p.v_mode = 1;
+  } else {
+    LECO_REQUIRE(ldv % 8 == 0, "leco_flash_attn_fwd: ldv must be a multiple of 8");
+    const uint64_t dims[4] = {(uint64_t)d, (uint64_t)skv, (uint64_t)heads, (uint64_t)batch};
+    const uint64_t str[3] = {(uint64_t)ldv * 2, (uint64_t)d * 2, (uint64_t)ldv * skv * 2};
+    if (make_tmap_bf16_4d(&p.tm_v, v, dims, str, box_q)) return -3;
+    p.v_mode = 0;
+  }
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ld_out = ldo;
+  p.sq = sq;
+  p.skv = skv;
+  p.heads = heads;
+  p.d = d;
+  p.n_kv_tiles = (skv + FA_BN - 1) / FA_BN;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((sq + FA_BM - 1) / FA_BM, heads, batch);
+  count_launch();
+  flash_attn_fwd_kernel<<<grid, FA_THREADS, FA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -29,6 +29,8 @@ from typing import List, Optional
 import torch
 import torch.nn as nn
 
+from .unet import down_as_rows, rows_as_down
+
 PREFIX = "lora_unet"
 # The reference keeps these as module-level lists and EXTENDS THE FIRST IN PLACE for c3lier
 # (train_lora.py:44-46): callers that do the same to `DEFAULT_TARGET_REPLACE` here get the
@@ -172,8 +174,6 @@ class LoRANetwork(nn.Module):
             ads = s.adapters()
             if any(id(a) not in mine for a in ads):
                 raise RuntimeError("leco_b200: UNet is adapted by another network")
-            if any(a.lora_down.__class__.__name__ != "Linear" and a.lora_down.kernel_size != (1, 1) for a in ads):
-                raise NotImplementedError("leco_b200: 3x3 conv adapters are not in the flat layout yet")
             kl = (sum(a.lora_down.weight.shape[0] for a in ads) + 15) // 16 * 16
             offsets.append((total, kl))
             total += kl * s.k_in + s.n_total * kl
@@ -193,9 +193,9 @@ class LoRANetwork(nn.Module):
             for a, n0 in zip(s.adapters(), s.n_offsets):
                 wd, wu = a.lora_down.weight, a.lora_up.weight
                 r, n = wd.shape[0], wu.shape[0]
-                ad[k0:k0 + r].copy_(wd.detach().reshape(r, -1))
+                ad[k0:k0 + r].copy_(down_as_rows(wd.detach()))
                 bup[n0:n0 + n, k0:k0 + r].copy_(wu.detach().reshape(n, r))
-                wd.data = ad[k0:k0 + r].view(wd.shape)
+                wd.data = rows_as_down(ad[k0:k0 + r], wd.shape)   # 3x3 adapters: a permuted (OHWI-stored) view
                 wu.data = bup[n0:n0 + n, k0:k0 + r].view(n, r, *wu.shape[2:]) if wu.dim() == 2 else \
                     bup[n0:n0 + n, k0:k0 + r].unsqueeze(-1).unsqueeze(-1)
                 m_ad[k0:k0 + r] = 1

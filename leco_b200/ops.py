@@ -231,6 +231,20 @@ def im2col_s2(x: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
     return col
 
 
+def im2col_s1(x: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
+    c = x.shape[1]
+    col = torch.empty((n * h * w, 9 * c), device=x.device, dtype=BF16)
+    capi.check(_lib().leco_im2col_s1(_ptr(x), _ptr(col), n, h, w, c, _stream()), "leco_im2col_s1")
+    return col
+
+
+def rowgroup_sum(x: torch.Tensor, n: int, hw: int) -> torch.Tensor:
+    c = x.shape[1]
+    out = torch.empty((n, c), device=x.device, dtype=BF16)
+    capi.check(_lib().leco_rowgroup_sum(_ptr(x), _ptr(out), n, hw, c, _stream()), "leco_rowgroup_sum")
+    return out
+
+
 def col2im_s2(dcol: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
     c = dcol.shape[1] // 9
     dx = torch.empty((n * h * w, c), device=dcol.device, dtype=BF16)
@@ -410,7 +424,31 @@ def _heads_view(t2d: torch.Tensor, nb: int, s: int, heads: int, d: int) -> torch
     return t2d.unflatten(0, (nb, s)).unflatten(2, (heads, d)).permute(0, 2, 1, 3)
 
 
+FLASH_V_MODE = 0        # 0: V used in place (MN-major B operand); 1: transposed copy of V first
+ATTENTION_IMPL = "flash"  # "flash" (fused, no-grad path) or "v0" (materialised P, also the grad path)
+
+
+def flash_attention(qt, kt, vt, nb, sq, skv, heads, d, scale, v_mode=None):
+    """Fused tcgen05 attention forward (head dim <= 64).  Views [rows, heads*d] with free row stride."""
+    v_mode = FLASH_V_MODE if v_mode is None else v_mode
+    o = torch.empty((nb * sq, heads * d), device=qt.device, dtype=BF16)
+    v_t, skv_pad = None, 0
+    if v_mode == 1:
+        skv_pad = (skv + 7) // 8 * 8
+        v_t = transpose_batched(_heads_view(vt, nb, skv, heads, d), cols_pad=skv_pad)   # [nb, heads, d, skv_pad]
+    capi.check(_lib().leco_flash_attn_fwd(_ptr(qt), qt.stride(0), _ptr(kt), kt.stride(0), _ptr(vt), vt.stride(0),
+                                          _ptr(v_t), skv_pad, _ptr(o), o.stride(0), nb, heads, sq, skv, d, scale,
+                                          _stream()), "leco_flash_attn_fwd")
+    return o
+
+
 def attention(qt, kt, vt, nb, sq, skv, heads, d, scale, save_for_bwd=False):
+    if not save_for_bwd and ATTENTION_IMPL == "flash" and d <= 64 and d % 8 == 0:
+        return flash_attention(qt, kt, vt, nb, sq, skv, heads, d, scale), None
+    return attention_v0(qt, kt, vt, nb, sq, skv, heads, d, scale, save_for_bwd)
+
+
+def attention_v0(qt, kt, vt, nb, sq, skv, heads, d, scale, save_for_bwd=False):
     skv_pad = (skv + 15) // 16 * 16
     q4, k4, v4 = _heads_view(qt, nb, sq, heads, d), _heads_view(kt, nb, skv, heads, d), _heads_view(vt, nb, skv, heads, d)
     S = torch.empty((nb, heads, sq, skv_pad), device=qt.device, dtype=torch.float32)

@@ -249,6 +249,14 @@ class Tape:
         self.grads[k] = g
         self._keep.append(t)
 
+    def accum_cols(self, t, col0, g):
+        """grads[t][:, col0:col0+g.shape[1]] = g   (disjoint column slices written once each)."""
+        k = id(t)
+        if k not in self.grads:
+            self.grads[k] = self.be.zeros_like(t)
+            self._keep.append(t)
+        self.be.copy_cols(g, 0, self.grads[k], col0, g.shape[1])
+
     def backward(self):
         for fn in reversed(self.nodes):
             fn()
@@ -266,6 +274,21 @@ def find_adapter(child: nn.Module):
     return None
 
 
+def down_as_rows(wd: torch.Tensor) -> torch.Tensor:
+    """lora_down.weight -> [r, K] in the engine's k order (Linear: as is; Conv: (kh, kw, cin))."""
+    if wd.dim() == 4:
+        return wd.permute(0, 2, 3, 1).reshape(wd.shape[0], -1)
+    return wd.reshape(wd.shape[0], -1)
+
+
+def rows_as_down(rows: torch.Tensor, shape) -> torch.Tensor:
+    """inverse of down_as_rows (a view when `rows` is contiguous)."""
+    if len(shape) == 4:
+        r, cin, kh, kw = shape
+        return rows.reshape(r, kh, kw, cin).permute(0, 3, 1, 2)
+    return rows.reshape(shape)
+
+
 class LoraSite:
     """One fused GEMM site with up to three adapted nn.Linear / 1x1-conv members sharing an
     input (q,k,v / k,v) or a single member.  Holds the padded tensor-core operands:
@@ -275,6 +298,8 @@ class LoraSite:
 
     def __init__(self, members: List[nn.Module], n_offsets: List[int], n_total: int, k_in: int):
         self.members, self.n_offsets, self.n_total, self.k_in = members, n_offsets, n_total, k_in
+        # a 3x3 lora_down ([r, Cin, 3, 3], lora.py:76-81) is stored as [r, (kh, kw, Cin)]: the k order of
+        # the implicit-GEMM conv
         self.ad = self.bup = None
         self.g_ad = self.g_bup = None
         self._versions = None
@@ -330,7 +355,7 @@ class LoraSite:
             for a, n0, r in zip(ads, self.n_offsets, ranks):
                 wd = a.lora_down.weight.detach()
                 wu = a.lora_up.weight.detach()
-                self.ad[k0:k0 + r].copy_(wd.reshape(r, -1))
+                self.ad[k0:k0 + r].copy_(down_as_rows(wd))
                 n = wu.shape[0]
                 self.bup[n0:n0 + n, k0:k0 + r].copy_(wu.reshape(n, r))
                 k0 += r
@@ -360,7 +385,7 @@ class LoraSite:
         for a, n0, r in zip(ads, self.n_offsets, self.ranks):
             wd, wu = a.lora_down.weight, a.lora_up.weight
             n = wu.shape[0]
-            gd = None if self.g_ad is None else self.g_ad[k0:k0 + r].reshape(wd.shape).to(wd.dtype, copy=True)
+            gd = None if self.g_ad is None else rows_as_down(self.g_ad[k0:k0 + r], wd.shape).to(wd.dtype, copy=True)
             gu = None if self.g_bup is None else self.g_bup[n0:n0 + n, k0:k0 + r].reshape(wu.shape).to(wu.dtype, copy=True)
             out += [gd, gu]
             k0 += r
@@ -409,6 +434,8 @@ class ConvPack:
         self.stride = m.stride[0]
         self.cin, self.cout = I, O
         self.module = m
+        self.site = LoraSite([m], [0], O, 9 * I)
+        self.n, self.k = O, 9 * I
 
 
 class NormPack:
@@ -417,6 +444,9 @@ class NormPack:
         self.beta = m.bias.detach().to(device=device, dtype=dtype).contiguous()
         self.eps = m.eps
         self.groups = getattr(m, "num_groups", None)
+
+
+TEMB_GROUP = 4
 
 
 # --------------------------------------------------------------------------- the engine
@@ -464,16 +494,21 @@ class EngineUNet(nn.Module):
             P.add1 = LinearPack([self.add_embedding.linear_1], device, dtype, need_wt=False)
             P.add2 = LinearPack([self.add_embedding.linear_2], device, dtype, need_wt=False)
         resnets: List[ResnetBlock2D] = [m for m in self.modules() if isinstance(m, ResnetBlock2D)]
-        P.temb_all = LinearPack([r.time_emb_proj for r in resnets], device, dtype, need_wt=False)
+        # all time_emb_proj layers share the input silu(emb): batched into GEMMs of TEMB_GROUP layers each
+        # (a group's stacked adapter rank must fit one 64-wide K-segment: 4 layers x rank <= 16)
+        P.temb = []
         P.res = {}
-        off = 0
-        for r in resnets:
-            rp = SimpleNamespace(norm1=NormPack(r.norm1, device, dtype), conv1=ConvPack(r.conv1, device, dtype),
-                                 norm2=NormPack(r.norm2, device, dtype), conv2=ConvPack(r.conv2, device, dtype),
-                                 shortcut=LinearPack([r.conv_shortcut], device, dtype) if r.conv_shortcut is not None else None,
-                                 temb_off=off, cout=r.conv1.out_channels)
-            off += r.conv1.out_channels
-            P.res[id(r)] = rp
+        for g0 in range(0, len(resnets), TEMB_GROUP):
+            grp = resnets[g0:g0 + TEMB_GROUP]
+            P.temb.append(LinearPack([r.time_emb_proj for r in grp], device, dtype, need_wt=False))
+            off = 0
+            for r in grp:
+                P.res[id(r)] = SimpleNamespace(
+                    norm1=NormPack(r.norm1, device, dtype), conv1=ConvPack(r.conv1, device, dtype),
+                    norm2=NormPack(r.norm2, device, dtype), conv2=ConvPack(r.conv2, device, dtype),
+                    shortcut=LinearPack([r.conv_shortcut], device, dtype) if r.conv_shortcut is not None else None,
+                    temb_group=g0 // TEMB_GROUP, temb_off=off, cout=r.conv1.out_channels)
+                off += r.conv1.out_channels
         P.tr = {}
         for t in (m for m in self.modules() if isinstance(m, Transformer2DModel)):
             tp = SimpleNamespace(norm=NormPack(t.norm, device, dtype),
@@ -552,12 +587,26 @@ class EngineUNet(nn.Module):
             tape.record(bwd)
         return out
 
-    def _conv3x3(self, be, tape, x: Act, pk: ConvPack, n, h, w, rowbias=None, residual: Optional[Act] = None):
-        if find_adapter(pk.module) is not None:
-            raise NotImplementedError("leco_b200: conv (c3lier) LoRA sites are not wired yet")
-        y = be.gemm(x.t, pk.w, bias=pk.bias, rowbias=rowbias, rows_per_group=h * w,
-                    residual=None if residual is None else residual.t, conv_nhw=(n, h, w))
-        out = Act(y, (x.rg or (residual is not None and residual.rg)) and tape is not None)
+    def _conv3x3(self, be, tape, x: Act, pk: ConvPack, n, h, w, rowbias: Optional[Act] = None, rb_col0: int = 0,
+                 residual: Optional[Act] = None):
+        """3x3 / stride 1 / pad 1 conv as implicit GEMM (+ per-sample bias slice `rowbias[:, rb_col0:...]`,
+        + residual).  A conv adapter (lora.py:68-82: 3x3 lora_down to r channels, 1x1 lora_up) adds
+        T = s*m*conv3x3(x, A) as the extra K-segment."""
+        act = pk.site.active()
+        kw = {}
+        T = ad = bup = None
+        sm = 1.0
+        if act is not None:
+            ads, mult = act
+            ad, bup = pk.site.refresh(ads, x.t.device, x.t.dtype)
+            sm = float(ads[0].scale) * mult
+            T = be.gemm(x.t, ad, alpha=sm, conv_nhw=(n, h, w))       # [M, Kl]
+            kw.update(lora_t=T, lora_up=bup)
+        rb = None if rowbias is None else rowbias.t[:, rb_col0:rb_col0 + pk.cout]
+        y = be.gemm(x.t, pk.w, bias=pk.bias, rowbias=rb, rows_per_group=h * w,
+                    residual=None if residual is None else residual.t, conv_nhw=(n, h, w), **kw)
+        rg = x.rg or (residual is not None and residual.rg) or (rowbias is not None and rowbias.rg) or act is not None
+        out = Act(y, rg and tape is not None)
         if out.rg:
             def bwd():
                 gy = tape.grad(y)
@@ -565,23 +614,41 @@ class EngineUNet(nn.Module):
                     return
                 if residual is not None and residual.rg:
                     tape.accum(residual.t, gy, owned=False)
+                if rowbias is not None and rowbias.rg:
+                    tape.accum_cols(rowbias.t, rb_col0, be.rowgroup_sum(gy, n, h * w))
+                dx_lora = None
+                if act is not None:
+                    dT = be.gemm(gy, be.transpose2d(bup), alpha=sm)              # s*m * dY B   [M, Kl]
+                    be.tn_reduce(gy, T, pk.site.grad_bup(be))
+                    be.tn_reduce(be.im2col_s1(x.t, n, h, w), dT, pk.site.grad_ad(be), transpose_out=True)
+                    if x.rg:
+                        kl = ad.shape[0]
+                        # dx[p,c] += sum_{tap',kl} dT[p+off(tap'), kl] * A[kl, flip(tap'), c]
+                        bmat = ad.reshape(kl, 9, pk.cin).flip(1).permute(2, 1, 0).reshape(pk.cin, 9 * kl).contiguous()
+                        dx_lora = (be.im2col_s1(dT, n, h, w), bmat)
                 if x.rg:
-                    tape.accum(x.t, be.gemm(gy, pk.wt_flip, conv_nhw=(n, h, w)), owned=True)
+                    dx = be.gemm(gy, pk.wt_flip, conv_nhw=(n, h, w))
+                    if dx_lora is not None:
+                        dx = be.gemm(dx_lora[0], dx_lora[1], residual=dx)
+                    tape.accum(x.t, dx, owned=True)
             tape.record(bwd)
         return out
 
     def _conv_s2(self, be, tape, x: Act, pk: ConvPack, n, h, w):
-        if find_adapter(pk.module) is not None:
-            raise NotImplementedError("leco_b200: conv (c3lier) LoRA sites are not wired yet")
-        col = be.im2col_s2(x.t, n, h, w)
-        y = be.gemm(col, pk.w, bias=pk.bias)
-        out = Act(y, x.rg and tape is not None)
-        if out.rg:
+        """3x3 / stride 2 / pad 1 (Downsample2D): explicit im2col (3 small layers) + the linear site."""
+        col_t = be.im2col_s2(x.t, n, h, w)
+        col = Act(col_t, x.rg and tape is not None)
+        out = self._linear(be, tape, col, pk)
+        if tape is not None and x.rg:
             def bwd():
-                gy = tape.grad(y)
-                if gy is not None:
-                    tape.accum(x.t, be.col2im_s2(be.gemm(gy, pk.wt), n, h, w), owned=True)
+                g = tape.grad(col_t)
+                if g is not None:
+                    tape.accum(x.t, be.col2im_s2(g, n, h, w), owned=True)
+            # recorded AFTER the linear node, so it runs BEFORE it in the reverse walk: re-order
+            lin = tape.nodes.pop() if out.rg else None
             tape.record(bwd)
+            if lin is not None:
+                tape.record(lin)
         return out
 
     def _group_norm(self, be, tape, x: Act, pk: NormPack, n, hw, silu):
@@ -640,11 +707,10 @@ class EngineUNet(nn.Module):
         return out
 
     # ---- network pieces ---------------------------------------------------------------
-    def _resnet(self, be, tape, x: Act, rp, temb_all, n, h, w):
+    def _resnet(self, be, tape, x: Act, rp, temb_groups, n, h, w):
         hw = h * w
         hdn = self._group_norm(be, tape, x, rp.norm1, n, hw, True)
-        rb = temb_all[:, rp.temb_off:rp.temb_off + rp.cout]
-        hdn = self._conv3x3(be, tape, hdn, rp.conv1, n, h, w, rowbias=rb)
+        hdn = self._conv3x3(be, tape, hdn, rp.conv1, n, h, w, rowbias=temb_groups[rp.temb_group], rb_col0=rp.temb_off)
         hdn = self._group_norm(be, tape, hdn, rp.norm2, n, hw, True)
         sc = x if rp.shortcut is None else self._linear(be, tape, x, rp.shortcut)
         return self._conv3x3(be, tape, hdn, rp.conv2, n, h, w, residual=sc)
@@ -730,9 +796,8 @@ class EngineUNet(nn.Module):
             add_in = be.cat_cols(added["text_embeds"].to(tid.dtype), tid)
             aug = be.gemm(be.silu(be.gemm(add_in, P.add1.w, bias=P.add1.bias)), P.add2.w, bias=P.add2.bias)
             emb = be.add_(emb, aug)
-        if any(find_adapter(m) is not None for m in P.temb_all.site.members):
-            raise NotImplementedError("leco_b200: time_emb_proj (c3lier) LoRA sites are not wired yet")
-        temb_all = be.gemm(be.silu(emb), P.temb_all.w, bias=P.temb_all.bias)
+        semb = Act(be.silu(emb), False)
+        temb_all = [self._linear(be, tape, semb, pk) for pk in P.temb]   # per-group [N, sum Cout]; c3lier adapts these
 
         ctx = Act(ctx2d, False)
         x = Act(be.conv_in(sample, P.conv_in_w, P.conv_in_b), False)
@@ -778,12 +843,20 @@ class EngineUNet(nn.Module):
 
     # ---- reference call surface -----------------------------------------------------------
     def lora_sites(self) -> List[LoraSite]:
+        """Every GEMM site an adapter can attach to (lierla: the transformer projections; c3lier adds the
+        resnet convs / time_emb_proj / shortcuts and the down/up-sampler convs)."""
         out = []
         P = self._P
         for tp in P.tr.values():
             out += [tp.proj_in.site, tp.proj_out.site]
             for bp in tp.blocks:
                 out += [bp.qkv.site, bp.out1.site, bp.q2.site, bp.kv2.site, bp.out2.site, bp.ff1.site, bp.ff2.site]
+        out += [pk.site for pk in P.temb]
+        for rp in P.res.values():
+            out += [rp.conv1.site, rp.conv2.site]
+            if rp.shortcut is not None:
+                out.append(rp.shortcut.site)
+        out += [pk.site for pk in P.samp.values()]
         return out
 
     def forward(self, sample, timestep, encoder_hidden_states=None, added_cond_kwargs=None, **_):

@@ -197,6 +197,48 @@ def case_attention(nb, sq, skv, heads, d, cross=False):
     return _merge(res)
 
 
+def case_flash(nb, sq, skv, heads, d, cross=False, v_mode=0, perf=False):
+    import torch
+    from leco_b200 import ops
+    from tests import torch_backend as tb
+    C = heads * d
+    if cross:
+        qbuf, kvbuf = _rand((nb * sq, C), seed=1), _rand((nb * skv, 2 * C), seed=2)
+        qt, kt, vt = qbuf, kvbuf[:, :C], kvbuf[:, C:]
+    else:
+        qkv = _rand((nb * sq, 3 * C), seed=1)
+        qt, kt, vt = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    scale = d ** -0.5
+    o = ops.flash_attention(qt, kt, vt, nb, sq, skv, heads, d, scale, v_mode=v_mode)
+    torch.cuda.synchronize()
+    if nb * heads * sq * skv <= 2 * 8 * 1024 * 1024 * 4:
+        oref, _ = tb.attention(qt.cpu(), kt.cpu(), vt.cpu(), nb, sq, skv, heads, d, scale, False)
+    else:  # big case: the (separately verified) materialised path is the reference
+        oref, _ = ops.attention_v0(qt, kt, vt, nb, sq, skv, heads, d, scale, False)
+    res = _cmp(o, oref)
+    if perf:
+        def timeit(fn, iters=10):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters
+        flops = 4.0 * nb * heads * sq * skv * d
+        ms = timeit(lambda: ops.flash_attention(qt, kt, vt, nb, sq, skv, heads, d, scale, v_mode=v_mode))
+        ms0 = timeit(lambda: ops.attention_v0(qt, kt, vt, nb, sq, skv, heads, d, scale, False), 3)
+        q4 = qt.unflatten(0, (nb, sq)).unflatten(2, (heads, d)).permute(0, 2, 1, 3)
+        k4 = kt.unflatten(0, (nb, skv)).unflatten(2, (heads, d)).permute(0, 2, 1, 3)
+        v4 = vt.unflatten(0, (nb, skv)).unflatten(2, (heads, d)).permute(0, 2, 1, 3)
+        ms_sdpa = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q4, k4, v4))
+        res.update(flash_ms=ms, flash_tflops=flops / ms / 1e9, v0_ms=ms0, torch_sdpa_ms=ms_sdpa)
+    return res
+
+
 def _engine_pair(arch, dtype=None):
     import torch
     from leco_b200.unet import SPECS, EngineUNet
@@ -315,6 +357,17 @@ CASES = [
     ("attn_self_d40", case_attention, dict(nb=2, sq=256, skv=256, heads=8, d=40)),
     ("attn_self_64_d8", case_attention, dict(nb=2, sq=64, skv=64, heads=8, d=8)),
     ("attn_self_tiny_sq4", case_attention, dict(nb=2, sq=4, skv=4, heads=4, d=64)),
+    ("flash_self_1024_m0", case_flash, dict(nb=2, sq=1024, skv=1024, heads=5, d=64, v_mode=0)),
+    ("flash_self_1024_m1", case_flash, dict(nb=2, sq=1024, skv=1024, heads=5, d=64, v_mode=1)),
+    ("flash_cross_77_m0", case_flash, dict(nb=2, sq=256, skv=77, heads=2, d=64, cross=True, v_mode=0)),
+    ("flash_cross_77_m1", case_flash, dict(nb=2, sq=256, skv=77, heads=2, d=64, cross=True, v_mode=1)),
+    ("flash_d40_m0", case_flash, dict(nb=2, sq=256, skv=256, heads=8, d=40, v_mode=0)),
+    ("flash_d40_m1", case_flash, dict(nb=2, sq=256, skv=256, heads=8, d=40, v_mode=1)),
+    ("flash_sq64_m0", case_flash, dict(nb=3, sq=64, skv=64, heads=4, d=64, v_mode=0)),
+    ("flash_sq200_skv300_m1", case_flash, dict(nb=1, sq=200, skv=300, heads=2, d=64, cross=True, v_mode=1)),
+    ("flash_sq200_skv300_m0", case_flash, dict(nb=1, sq=200, skv=300, heads=2, d=64, cross=True, v_mode=0)),
+    ("flash_perf_4096_m0", case_flash, dict(nb=4, sq=4096, skv=4096, heads=5, d=64, v_mode=0, perf=True)),
+    ("flash_perf_4096_m1", case_flash, dict(nb=4, sq=4096, skv=4096, heads=5, d=64, v_mode=1, perf=True)),
     ("engine_fwd_tiny21", case_engine_forward, dict(arch="tiny21")),
     ("engine_fwd_tiny15", case_engine_forward, dict(arch="tiny15")),
     ("engine_fwd_tinyxl", case_engine_forward, dict(arch="tinyxl")),

@@ -92,3 +92,42 @@ def test_lora_forward_and_grads_match_oracle_autograd(arch):
         base = _engine(arch, build_unet(arch))(x, t, encoder_hidden_states=ctx).sample
         off = eng(x, t, encoder_hidden_states=ctx).sample
     assert torch.equal(base, off)
+
+
+def test_c3lier_conv_adapters_match_oracle_autograd():
+    """BASELINE config 3 topology (attention + conv adapters, rank 8): 278 modules incl. 3x3
+    conv, stride-2 conv, 1x1 shortcut and time_emb_proj adapters — forward and all gradients vs autograd."""
+    arch = "tiny15"
+    oracle = build_unet(arch)
+    eng = _engine(arch, oracle)
+    x, ctx, _ = _inputs(arch, n=2, hw=8)
+    t = torch.tensor(261)
+    targets = leco_ref.ATTN_TARGETS + leco_ref.CONV_TARGETS
+
+    def make(unet):
+        torch.manual_seed(11)
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = leco_ref.LoRANetworkRef(unet, rank=8, multiplier=1.0, alpha=4.0, targets=targets)
+        g = torch.Generator().manual_seed(5)
+        for l in net.unet_loras:
+            l.lora_up.weight.data = 0.05 * torch.randn(l.lora_up.weight.shape, generator=g)
+        return net
+
+    net_o, net_e = make(oracle), make(eng)
+    assert len(net_o.unet_loras) == len(net_e.unet_loras) == 278
+    goal = torch.randn((2, 4, 8, 8), generator=torch.Generator().manual_seed(9))
+    outs = []
+    for unet, net in ((oracle, net_o), (eng, net_e)):
+        with net:
+            y = unet(x, t, encoder_hidden_states=ctx).sample
+        torch.nn.functional.mse_loss(y.float(), goal).backward()
+        outs.append(y.detach())
+    assert (outs[0] - outs[1]).abs().max().item() < 2e-4 * outs[0].abs().max().item() + 1e-5
+    worst, worst_name = 0.0, None
+    for a, b in zip(net_o.unet_loras, net_e.unet_loras):
+        for pa, pb in ((a.lora_down.weight, b.lora_down.weight), (a.lora_up.weight, b.lora_up.weight)):
+            assert pb.grad is not None, b.lora_name
+            rel = (pa.grad - pb.grad).abs().max().item() / (pa.grad.abs().max().item() + 1e-8)
+            if rel > worst:
+                worst, worst_name = rel, b.lora_name
+    assert worst < 5e-3, (worst, worst_name)

@@ -145,6 +145,22 @@ def im2col_s2(x, n, h, w):
     return cols.to(x.dtype)
 
 
+def im2col_s1(x, n, h, w):
+    c = x.shape[1]
+    xi = _f(x).reshape(n, h, w, c).permute(0, 3, 1, 2)
+    cols = F.unfold(xi, 3, padding=1, stride=1)
+    L = cols.shape[-1]
+    return cols.reshape(n, c, 9, L).permute(0, 3, 2, 1).reshape(n * L, 9 * c).to(x.dtype)
+
+
+def rowgroup_sum(x, n, hw):
+    return _f(x).reshape(n, hw, -1).sum(1).to(x.dtype)
+
+
+def copy_cols(src, scol0, dst, dcol0, ncols):
+    dst[:, dcol0:dcol0 + ncols] = src[:, scol0:scol0 + ncols]
+
+
 def col2im_s2(dcol, n, h, w):
     c = dcol.shape[1] // 9
     L = (h // 2) * (w // 2)
