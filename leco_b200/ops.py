@@ -424,8 +424,12 @@ def _heads_view(t2d: torch.Tensor, nb: int, s: int, heads: int, d: int) -> torch
     return t2d.unflatten(0, (nb, s)).unflatten(2, (heads, d)).permute(0, 2, 1, 3)
 
 
-FLASH_V_MODE = 0        # 0: V used in place (MN-major B operand); 1: transposed copy of V first
-ATTENTION_IMPL = "flash"  # "flash" (fused, no-grad path) or "v0" (materialised P, also the grad path)
+import os as _os
+
+# 0: V used in place (MN-major B operand); 1: transposed copy of V first
+FLASH_V_MODE = int(_os.environ.get("LECO_FLASH_V_MODE", "0"))
+# "flash" (fused, no-grad path) or "v0" (materialised P; always used on the grad path)
+ATTENTION_IMPL = _os.environ.get("LECO_ATTENTION", "flash")
 
 
 def flash_attention(qt, kt, vt, nb, sq, skv, heads, d, scale, v_mode=None):

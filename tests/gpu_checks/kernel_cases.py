@@ -243,7 +243,8 @@ def _engine_pair(arch, dtype=None):
     import torch
     from leco_b200.unet import SPECS, EngineUNet
     from oracle.unet_ref import build_unet
-    oracle = build_unet(arch)
+    torch.set_num_threads(min(8, os.cpu_count() or 8))
+    oracle = build_unet(arch)       # only the seeded weights are needed on the box
     eng = EngineUNet(SPECS[arch])
     eng.load_state_dict(oracle.state_dict())
     eng.requires_grad_(False)
@@ -266,25 +267,61 @@ def _inputs(arch, n, hw, seed=3):
     return x, ctx, added
 
 
+def oracle_forward(arch, n, hw):
+    """fp32 CPU oracle UNet output on bf16-rounded weights / inputs (what the engine is given)."""
+    import torch
+    from oracle.unet_ref import build_unet
+    oracle = build_unet(arch).to(torch.bfloat16).float()
+    x, ctx, added = _inputs(arch, n, hw)
+    with torch.no_grad():
+        return oracle(x.bfloat16().float(), torch.tensor(481), ctx.bfloat16().float(),
+                      None if added is None else {k: v.bfloat16().float() for k, v in added.items()}).sample
+
+
+def _make_net(unet, dev, mode=None):
+    import torch
+    from oracle import leco_ref
+    torch.manual_seed(11)
+    kw = dict(rank=4, alpha=1.0) if mode is None else dict(
+        rank=8, alpha=4.0, targets=leco_ref.ATTN_TARGETS + leco_ref.CONV_TARGETS)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = leco_ref.LoRANetworkRef(unet, multiplier=1.0, **kw)
+    g = torch.Generator().manual_seed(5)
+    for l in net.unet_loras:
+        l.lora_up.weight.data = (0.05 * torch.randn(l.lora_up.weight.shape, generator=g)).bfloat16().float()
+        l.lora_down.weight.data = l.lora_down.weight.data.bfloat16().float()
+    return net.to(dev)
+
+
+def oracle_grads(arch, n, hw, mode):
+    """oracle forward + autograd LoRA gradients of an MSE against a seeded goal (fp32 CPU)."""
+    import torch
+    from oracle.unet_ref import build_unet
+    oracle = build_unet(arch).to(torch.bfloat16).float()
+    x, ctx, _ = _inputs(arch, n, hw)
+    net = _make_net(oracle, "cpu", mode)
+    goal = torch.randn((n, 4, hw, hw), generator=torch.Generator().manual_seed(9))
+    with net:
+        yo = oracle(x.bfloat16().float(), torch.tensor(261), encoder_hidden_states=ctx.bfloat16().float()).sample
+    lo = torch.nn.functional.mse_loss(yo, goal)
+    lo.backward()
+    grads = [p.grad.clone() for l in net.unet_loras for p in (l.lora_down.weight, l.lora_up.weight)]
+    return {"y": yo.detach(), "loss": lo.item(), "grads": grads, "goal": goal}
+
+
 def case_engine_forward(arch, n=2, hw=16, time_it=False):
     import torch
-    torch.set_num_threads(os.cpu_count() or 8)
-    oracle, eng = _engine_pair(arch)
+    from tests.oracle_cache import cached
+    ref = cached(f"fwd_{arch}_{n}_{hw}", lambda: oracle_forward(arch, n, hw))
+    _, eng = _engine_pair(arch)
     x, ctx, added = _inputs(arch, n, hw)
     t = torch.tensor(481)
-    # the oracle sees the same bf16-rounded weights/inputs the engine uses
-    oracle = oracle.to(torch.bfloat16).float()
     with torch.no_grad():
-        t0 = time.time()
-        ref = oracle(x.bfloat16().float(), t, ctx.bfloat16().float(),
-                     None if added is None else {k: v.bfloat16().float() for k, v in added.items()}).sample
-        cpu_s = time.time() - t0
         cu_added = None if added is None else {k: v.cuda() for k, v in added.items()}
         out = eng(x.cuda(), t, encoder_hidden_states=ctx.cuda().bfloat16(), added_cond_kwargs=cu_added).sample
         torch.cuda.synchronize()
         res = _cmp(out, ref, 3e-2)
         res["rel_rms"] = ((out.float().cpu() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
-        res["oracle_cpu_s"] = cpu_s
         if time_it:
             xc, cc = x.cuda(), ctx.cuda().bfloat16()
             for _ in range(2):
@@ -302,49 +339,29 @@ def case_engine_forward(arch, n=2, hw=16, time_it=False):
     return res
 
 
-def case_engine_grads(arch, n=2, hw=8):
+def case_engine_grads(arch, n=2, hw=8, mode=None):
     import torch
-    from oracle import leco_ref
-    oracle, eng = _engine_pair(arch)
-    oracle = oracle.to(torch.bfloat16).float()
-    x, ctx, added = _inputs(arch, n, hw)
-    t = torch.tensor(261)
-
-    def make(unet, dev):
-        torch.manual_seed(11)
-        with contextlib.redirect_stdout(io.StringIO()):
-            net = leco_ref.LoRANetworkRef(unet, rank=4, multiplier=1.0, alpha=1.0)
-        g = torch.Generator().manual_seed(5)
-        for l in net.unet_loras:
-            l.lora_up.weight.data = (0.05 * torch.randn(l.lora_up.weight.shape, generator=g))
-            l.lora_down.weight.data = l.lora_down.weight.data.bfloat16().float()
-            l.lora_up.weight.data = l.lora_up.weight.data.bfloat16().float()
-        return net.to(dev)
-
-    net_o = make(oracle, "cpu")
-    net_e = make(eng, "cuda").to(torch.bfloat16)
-    goal = torch.randn((n, 4, hw, hw), generator=torch.Generator().manual_seed(9))
-    with net_o:
-        yo = oracle(x.bfloat16().float(), t, encoder_hidden_states=ctx.bfloat16().float()).sample
-    lo = torch.nn.functional.mse_loss(yo, goal)
-    lo.backward()
+    from tests.oracle_cache import cached
+    ora = cached(f"grads_{arch}" if mode is None else f"grads_{mode}_{arch}", lambda: oracle_grads(arch, n, hw, mode))
+    _, eng = _engine_pair(arch)
+    x, ctx, _ = _inputs(arch, n, hw)
+    net_e = _make_net(eng, "cuda", mode).to(torch.bfloat16)
     with net_e:
-        ye = eng(x.cuda().bfloat16(), t, encoder_hidden_states=ctx.cuda().bfloat16()).sample
-    le = torch.nn.functional.mse_loss(ye.float().cpu(), goal)  # loss on the CPU like train_lora.py:265-270
+        ye = eng(x.cuda().bfloat16(), torch.tensor(261), encoder_hidden_states=ctx.cuda().bfloat16()).sample
+    le = torch.nn.functional.mse_loss(ye.float().cpu(), ora["goal"])  # loss on the CPU like train_lora.py:265-270
     le.backward()
-    res = {"fwd": _cmp(ye, yo, 3e-2)}
-    num = den = 0.0
-    worst = 0.0
-    for a, b in zip(net_o.unet_loras, net_e.unet_loras):
-        for pa, pb in ((a.lora_down.weight, b.lora_down.weight), (a.lora_up.weight, b.lora_up.weight)):
-            ga, gb = pa.grad.float(), pb.grad.float().cpu()
-            num += (ga - gb).pow(2).sum().item()
-            den += ga.pow(2).sum().item()
-            worst = max(worst, (ga - gb).abs().max().item() / (ga.abs().max().item() + 1e-12))
+    res = {"fwd": _cmp(ye, ora["y"], 3e-2)}
+    num = den = worst = 0.0
+    got = [p.grad for l in net_e.unet_loras for p in (l.lora_down.weight, l.lora_up.weight)]
+    for ga, gb in zip(ora["grads"], got):
+        ga, gb = ga.float(), gb.float().cpu()
+        num += (ga - gb).pow(2).sum().item()
+        den += ga.pow(2).sum().item()
+        worst = max(worst, (ga - gb).abs().max().item() / (ga.abs().max().item() + 1e-12))
     rel = (num / den) ** 0.5
     res["grads"] = {"rel": rel, "worst_tensor_rel": worst, "ok": rel < 5e-2, "max_abs_err": 0, "ref_absmax": den ** 0.5}
-    res["loss"] = {"rel": abs(lo.item() - le.item()) / lo.item(), "ok": abs(lo.item() - le.item()) / lo.item() < 2e-2,
-                   "max_abs_err": 0, "ref_absmax": lo.item()}
+    dl = abs(ora["loss"] - le.item()) / ora["loss"]
+    res["loss"] = {"rel": dl, "ok": dl < 2e-2, "max_abs_err": 0, "ref_absmax": ora["loss"]}
     return _merge(res)
 
 
@@ -373,6 +390,7 @@ CASES = [
     ("engine_fwd_tinyxl", case_engine_forward, dict(arch="tinyxl")),
     ("engine_grads_tiny21", case_engine_grads, dict(arch="tiny21")),
     ("engine_grads_tiny15", case_engine_grads, dict(arch="tiny15")),
+    ("engine_grads_c3lier_tiny15", case_engine_grads, dict(arch="tiny15", mode="c3lier")),
     ("engine_fwd_sd21_64", case_engine_forward, dict(arch="sd21", n=2, hw=64, time_it=True)),
 ]
 

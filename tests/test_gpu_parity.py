@@ -27,7 +27,7 @@ def test_kernels_and_engine(name, fn, kw):
 
 def test_engine_forward_full_size_sd21():
     """BASELINE config size: SD2.1 architecture, 64x64 latents, CFG batch of 2 samples, vs the fp32 oracle."""
-    res = kernel_cases.case_engine_forward("sd21", n=2, hw=64)
+    res = kernel_cases.case_engine_forward("sd21", n=2, hw=64)   # oracle output: tests/golden/cache (fp32 CPU, ~1 min)
     assert res["ok"] and res["rel_rms"] < 2e-2, res
 
 
@@ -36,17 +36,13 @@ def test_engine_not_worse_than_reference_numerics():
     execution of the oracle network is from the fp32 oracle and require the engine to be at least as
     close (within 1.5x): the engine's fused fp32-accumulate epilogues may not lose accuracy."""
     import torch
-    from leco_b200.unet import SPECS, EngineUNet
-    from oracle.unet_ref import build_unet
+    from tests.oracle_cache import cached
     arch = "tiny21"
-    oracle = build_unet(arch).to(torch.bfloat16).float()
-    eng = EngineUNet(SPECS[arch])
-    eng.load_state_dict(oracle.state_dict())
-    eng.to("cuda")
+    ref = cached("fwd_tiny21_2_32", lambda: kernel_cases.oracle_forward(arch, 2, 32))
+    oracle, eng = kernel_cases._engine_pair(arch)
     x, ctx, _ = kernel_cases._inputs(arch, 2, 32)
     t = torch.tensor(481)
     with torch.no_grad():
-        ref = oracle(x.bfloat16().float(), t, ctx.bfloat16().float()).sample
         out = eng(x.cuda(), t, encoder_hidden_states=ctx.cuda().bfloat16()).sample.float().cpu()
         ref_bf16 = oracle.to("cuda", torch.bfloat16)(x.cuda().bfloat16(), t.cuda(), ctx.cuda().bfloat16()).sample.float().cpu()
     rms = lambda a: (a - ref).pow(2).mean().sqrt().item() / ref.pow(2).mean().sqrt().item()  # noqa: E731
@@ -60,19 +56,22 @@ def test_leco_iteration_matches_oracle(graphs):
     vs oracle/leco_ref.leco_iteration (fp32 CPU, pinned against the reference's train loop) on the same
     seeds.  Tolerance: 5% of the loss (bf16 network vs fp32 oracle)."""
     import torch
-    from __graft_entry__ import smoke_setup
-    trainer, oracle_iter, net, net_o = smoke_setup(use_graphs=graphs)
+    from __graft_entry__ import engine_trainer, oracle_iterations
+    from tests.oracle_cache import cached
+    ref = cached("iters_tiny21", lambda: oracle_iterations(3))
+    trainer, net = engine_trainer(use_graphs=graphs)
     torch.manual_seed(7)
-    got = [trainer.iteration().item() for _ in range(3)]
-    torch.manual_seed(7)
-    recs = [{} for _ in range(3)]
-    want = [oracle_iter(r) for r in recs]
-    for a, b in zip(got, want):
-        assert abs(a - b) <= 0.05 * abs(b) + 1e-7, (got, want)
+    got, ks = [], []
+    for _ in range(3):
+        got.append(trainer.iteration().item())
+        ks.append(trainer.last["k"])
+    assert ks == ref["k"]
+    for a, b in zip(got, ref["losses"]):
+        assert abs(a - b) <= 0.05 * abs(b) + 1e-7, (got, ref["losses"])
     # adapter weights after 3 steps: same direction, same size
     num = den = 0.0
-    for a, b in zip(net.unet_loras, net_o.unet_loras):
-        wa, wb = a.lora_up.weight.detach().float().cpu().reshape(-1), b.lora_up.weight.detach().reshape(-1)
+    for a, wb in zip(net.unet_loras, ref["lora_up"]):
+        wa, wb = a.lora_up.weight.detach().float().cpu().reshape(-1), wb.reshape(-1)
         num += torch.dot(wa, wb).item()
         den += (wa.norm() * wb.norm()).item()
     assert num / den > 0.9, num / den
