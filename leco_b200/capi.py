@@ -34,7 +34,7 @@ class GemmArgs(Structure):
         ("ld_rowbias", c_int64),
         ("residual", c_void_p), ("ldr", c_int64),
         ("epilogue", c_int32), ("alpha", c_float), ("out_fp32", c_int32), ("block_n", c_int32),
-        ("b_rows", c_int32),
+        ("b_rows", c_int32), ("cta_pair", c_int32),
     ]
 
 

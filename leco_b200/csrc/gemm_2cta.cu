@@ -1,0 +1,271 @@
+// 2-CTA (cta_group::2) variant of the tcgen05 GEMM: a cluster of two CTAs on one TPC computes a
+// 256 x BN output tile.  Each CTA stages ITS OWN 128 A rows and HALF of the B rows (N split); one
+// `tcgen05.mma.cta_group::2` issued by the leader CTA reads both CTAs' shared memory, so per-SM smem
+// fill per K-chunk drops from (128 + BN) to (128 + BN/2) rows — the 1-CTA kernel is bound by per-SM
+// operand ingest (~50 B/clk measured: 1250 TF at 8k^3, BN=256), not by the tensor pipe.
+//
+// Protocol (per smem stage s, accumulator stage a):
+//   both CTAs' TMA  --complete_tx-->  leader.full[s]   (leader arrive.expect_tx of BOTH CTAs' bytes)
+//   leader MMA      --tcgen05.commit multicast 0b11--> empty[s] in both CTAs, tmem_full[a] in both CTAs
+//   both epilogues  --(remote) arrive-->               leader.tmem_empty[a]   (count 8 = 4 warps x 2 CTAs)
+#include "gemm_common.cuh"
+
+namespace leco {
+void count_launch();
+
+// ---- cluster / cta_group::2 PTX ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();  // .aligned barrier: the warp must be converged (role branches diverge lane 0)
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit cleared).
+__device__ __forceinline__ void tma_load_4d_2cta(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                 int c2, int c3) {
+  const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (count 1) on the barrier at the same smem offset in every CTA of `mask` once prior MMAs retire
+__device__ __forceinline__ void umma_commit_2cta_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      :
+      : "r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
+__device__ __host__ __forceinline__ uint32_t umma_idesc_bf16_m256(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
+}
+
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int B_STAGE_BYTES = (BN / 2) * BLOCK_K * 2;  // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 6 : (BN >= 160 ? 7 : 8);
+  static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                     // [STAGES]  used in the leader only
+  uint64_t* empty_bar = bars + STAGES;           // [STAGES]  per CTA
+  uint64_t* tmem_full = bars + 2 * STAGES;       // [2]       per CTA
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]       used in the leader only (count 8)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_a);
+    tma_prefetch_desc(&p.tm_b);
+    if (p.has_seg2) {
+      tma_prefetch_desc(&p.tm_a2);
+      tma_prefetch_desc(&p.tm_b2);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();  // barriers of both CTAs exist before any remote signal / allocation handshake
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m2 = (p.tiles_m + 1) / 2;  // pairs of M tiles
+  const int tiles_mn = tiles_m2 * p.tiles_n;
+  const int total_tiles = tiles_mn * p.batch0 * p.batch1;
+  const int total_chunks = p.chunks1 + p.has_seg2;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const bool geglu = p.epilogue == 1;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+      const int bidx = tile / tiles_mn;
+      const int rem = tile - bidx * tiles_mn;
+      const int nt = rem / tiles_m2;
+      const int mt = (rem - nt * tiles_m2) * 2 + (int)rank;  // may be == tiles_m (dummy tile: all rows OOB)
+      const int b1 = bidx / p.batch0;
+      const int b0 = bidx - b1 * p.batch0;
+      // B rows held by this CTA: its half of the BN-wide N tile (GEGLU: rank 0 = hidden rows, rank 1 = gate rows)
+      const int nb_row = geglu ? (int)rank * (p.N / 2) + nt * (BN / 2) : nt * BN + (int)rank * (BN / 2);
+      int m0, img_n0, img_h0;
+      gemm_tile_origin(p, mt, m0, img_n0, img_h0);
+      for (int c = 0; c < total_chunks; ++c) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+        uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+        if (c < p.chunks1) {
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (p.a_tx_bytes + Cfg::B_STAGE_BYTES));
+          if (p.mode == 0) {
+            tma_load_4d_2cta(sa, &p.tm_a, &full_bar[stage], c * BLOCK_K, m0, b0, b1);
+          } else {
+            const int tap = c / p.cin_chunks;
+            const int cc = c - tap * p.cin_chunks;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            tma_load_4d_2cta(sa, &p.tm_a, &full_bar[stage], cc * BLOCK_K, kw - 1, img_h0 + kh - 1, img_n0);
+          }
+          tma_load_4d_2cta(sb, &p.tm_b, &full_bar[stage], c * BLOCK_K, nb_row, b0, b1);
+        } else {
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
+          tma_load_4d_2cta(sa, &p.tm_a2, &full_bar[stage], 0, m0, 0, 0);
+          tma_load_4d_2cta(sb, &p.tm_b2, &full_bar[stage], 0, nb_row, 0, 0);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // -------------------------------------------------------------- MMA issuer (leader CTA only)
+    const uint32_t idesc = umma_idesc_bf16_m256(BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
+      for (int c = 0; c < total_chunks; ++c) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const int ksteps = (c < p.chunks1 - 1) ? 4 : (c == p.chunks1 - 1 ? p.ksteps_last1 : p.ksteps2);
+        const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
+        const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
+        for (int j = 0; j < ksteps; ++j) umma_bf16_2cta(tmem_d, da + 2 * j, db + 2 * j, idesc, (c | j) != 0 ? 1u : 0u);
+        umma_commit_2cta_mc(&empty_bar[stage], 0b11);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit_2cta_mc(&tmem_full[as], 0b11);
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue (both CTAs, own 128 rows)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int it = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int bidx = tile / tiles_mn;
+      const int rem = tile - bidx * tiles_mn;
+      const int nt = rem / tiles_m2;
+      const int mt = (rem - nt * tiles_m2) * 2 + (int)rank;
+      const int b1 = bidx / p.batch0;
+      const int b0 = bidx - b1 * p.batch0;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
+      if (mt < p.tiles_m) {
+        gemm_epilogue_tile<BN>(p, trow, r, mt, nt, b0, b1);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tmem_empty[as], 0);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still be reading this CTA's smem / signalling its barriers
+  if (warp == 2) tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN>
+static int launch_2cta(const GemmParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LECO_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const long long pair_tiles = 1LL * ((p.tiles_m + 1) / 2) * p.tiles_n * p.batch0 * p.batch1;
+  const int max_clusters = sm_count() / 2;
+  const int clusters = (int)(pair_tiles < max_clusters ? pair_tiles : max_clusters);
+  gemm_tcgen05_2cta_kernel<BN><<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_gemm_2cta(const GemmParams& p, int bn, cudaStream_t stream) {
+  count_launch();
+  switch (bn) {
+    case 64: return launch_2cta<64>(p, stream);
+    case 128: return launch_2cta<128>(p, stream);
+    case 160: return launch_2cta<160>(p, stream);
+    default: return launch_2cta<256>(p, stream);
+  }
+}
+
+}  // namespace leco

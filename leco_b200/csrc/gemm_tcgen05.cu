@@ -20,88 +20,9 @@
 // allocator, warps 4-7 = epilogue (TMEM lane quadrant = warp % 4).
 #include <stdio.h>
 
-#include "../../include/leco_b200.h"
-#include "common.cuh"
+#include "gemm_common.cuh"
 
 namespace leco {
-
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;               // 64 bf16 = 128 B = one swizzle row
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int GEMM_THREADS = 256;
-
-struct GemmParams {
-  CUtensorMap tm_a, tm_b, tm_a2, tm_b2;
-  int mode, M, N;
-  int chunks1, ksteps_last1, cin_chunks;
-  int has_seg2, ksteps2;
-  int tiles_m, tiles_n, batch0, batch1;
-  int cn, ch, cw, hb, nb, tiles_per_img, rows_per_tile;
-  void* d;
-  long long ldd, d_bs0, d_bs1;
-  const __nv_bfloat16* bias;
-  const __nv_bfloat16* rowbias;
-  int rows_per_group;
-  long long ld_rowbias;
-  const __nv_bfloat16* residual;
-  long long ldr;
-  int epilogue;
-  float alpha;
-  int out_fp32;
-  unsigned a_tx_bytes;
-};
-
-template <int BN>
-struct GemmCfg {
-  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 160 ? 5 : 6);
-  // accumulator stage stride in TMEM columns (power of two so a stage never straddles an
-  // alignment boundary): 64 / 128 / 256
-  static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
-  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-};
-
-__device__ __forceinline__ void epi_store_bf16(__nv_bfloat16* dst, const float (&v)[32], int ncols_valid) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if (g * 8 < ncols_valid) {
-      uint4 o;
-      o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-      o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-      o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-      o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-      *reinterpret_cast<uint4*>(dst + g * 8) = o;
-    }
-  }
-}
-__device__ __forceinline__ void epi_store_f32(float* dst, const float (&v)[32], int ncols_valid) {
-#pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    if (g * 4 < ncols_valid) {
-      *reinterpret_cast<float4*>(dst + g * 4) =
-          make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-    }
-  }
-}
-// v[j] += src[j] for 32 bf16 (16-byte vector loads), guarded in groups of 8 columns
-__device__ __forceinline__ void epi_add_bf16(float (&v)[32], const __nv_bfloat16* src, int ncols_valid) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if (g * 8 < ncols_valid) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + g * 8));
-      v[g * 8 + 0] += bf16_lo(q.x);
-      v[g * 8 + 1] += bf16_hi(q.x);
-      v[g * 8 + 2] += bf16_lo(q.y);
-      v[g * 8 + 3] += bf16_hi(q.y);
-      v[g * 8 + 4] += bf16_lo(q.z);
-      v[g * 8 + 5] += bf16_hi(q.z);
-      v[g * 8 + 6] += bf16_lo(q.w);
-      v[g * 8 + 7] += bf16_hi(q.w);
-    }
-  }
-}
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -251,7 +172,6 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;                  // TMEM lane quadrant of this warp
     const int r = q * 32 + lane;             // row inside the tile
-    const bool geglu = (p.epilogue == 1);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -262,85 +182,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       const int mt = rem - nt * p.tiles_m;
       const int b1 = bidx / p.batch0;
       const int b0 = bidx - b1 * p.batch0;
-      const int n0 = nt * BN;
-      long long m;
-      bool row_ok;
-      if (p.mode == 0) {
-        m = static_cast<long long>(mt) * BLOCK_M + r;
-        row_ok = m < p.M;
-      } else {
-        int img_n0 = 0, img_h0 = 0;
-        if (p.nb > 1) {
-          img_n0 = mt * p.nb;
-          row_ok = (r < p.rows_per_tile) && (img_n0 + r / (p.ch * p.cw) < p.cn);
-        } else {
-          img_n0 = mt / p.tiles_per_img;
-          img_h0 = (mt - img_n0 * p.tiles_per_img) * p.hb;
-          row_ok = (r < p.rows_per_tile) && (img_h0 + r / p.cw < p.ch);
-        }
-        m = static_cast<long long>(img_n0 * p.ch + img_h0) * p.cw + r;
-      }
-      const long long boff = b0 * p.d_bs0 + b1 * p.d_bs1;
-
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
-
-      if (!geglu) {
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t raw[32];
-          tmem_ld_32x32b_x32(trow + c * 32, raw);
-          tmem_ld_wait();
-          const int col0 = n0 + c * 32;
-          const int nvalid = p.N - col0;  // may be <= 0 or > 32
-          if (row_ok && nvalid > 0) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
-            if (p.bias) epi_add_bf16(v, p.bias + col0, nvalid);
-            if (p.rowbias)
-              epi_add_bf16(v, p.rowbias + (m / p.rows_per_group) * p.ld_rowbias + col0, nvalid);
-            if (p.residual) epi_add_bf16(v, p.residual + boff + m * p.ldr + col0, nvalid);
-            if (p.out_fp32)
-              epi_store_f32(reinterpret_cast<float*>(p.d) + boff + m * p.ldd + col0, v, nvalid);
-            else
-              epi_store_bf16(reinterpret_cast<__nv_bfloat16*>(p.d) + boff + m * p.ldd + col0, v, nvalid);
-          }
-        }
-      } else {
-        // tile columns [0,BN/2) = hidden block, [BN/2,BN) = matching gate block
-#pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
-          uint32_t rh[32], rg[32];
-          tmem_ld_32x32b_x32(trow + c * 32, rh);
-          tmem_ld_32x32b_x32(trow + BN / 2 + c * 32, rg);
-          tmem_ld_wait();
-          const int ocol0 = nt * (BN / 2) + c * 32;
-          const int nvalid = p.N / 2 - ocol0;
-          if (row_ok && nvalid > 0) {
-            float h[32], g[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              h[j] = __uint_as_float(rh[j]) * p.alpha;
-              g[j] = __uint_as_float(rg[j]) * p.alpha;
-            }
-            if (p.bias) {
-              epi_add_bf16(h, p.bias + ocol0, 32);
-              epi_add_bf16(g, p.bias + p.N / 2 + ocol0, 32);
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) h[j] = h[j] * gelu_erf_f(g[j]);
-            epi_store_bf16(reinterpret_cast<__nv_bfloat16*>(p.d) + boff + m * p.ldd + ocol0, h, nvalid);
-          }
-        }
-      }
+      gemm_epilogue_tile<BN>(p, trow, r, mt, nt, b0, b1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
     }
   }
-
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -459,7 +309,7 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
     const uint64_t bs0 = batch0 > 1 ? (uint64_t)a->b_bs0 : (uint64_t)a->ldb * a->N;
     const uint64_t bs1 = batch1 > 1 ? (uint64_t)a->b_bs1 : bs0 * batch0;
     const uint64_t str[3] = {(uint64_t)a->ldb * 2, bs0 * 2, bs1 * 2};
-    const uint32_t box_b[4] = {BLOCK_K, (uint32_t)(a->epilogue == 1 ? bn / 2 : bn), 1, 1};
+    const uint32_t box_b[4] = {BLOCK_K, (uint32_t)((a->epilogue == 1 || a->cta_pair) ? bn / 2 : bn), 1, 1};
     if (make_tmap_bf16_4d(&p.tm_b, a->b, dims, str, box_b)) return -3;
   }
   if (a->a2) {
@@ -473,7 +323,7 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
     if (make_tmap_bf16_4d(&p.tm_a2, a->a2, dims_a, str_a, box2)) return -3;
     const uint64_t dims_b[4] = {(uint64_t)a->K2, (uint64_t)a->N, 1, 1};
     const uint64_t str_b[3] = {(uint64_t)a->ldb2 * 2, (uint64_t)a->ldb2 * a->N * 2, (uint64_t)a->ldb2 * a->N * 2};
-    const uint32_t box_b2[4] = {BLOCK_K, (uint32_t)(a->epilogue == 1 ? bn / 2 : bn), 1, 1};
+    const uint32_t box_b2[4] = {BLOCK_K, (uint32_t)((a->epilogue == 1 || a->cta_pair) ? bn / 2 : bn), 1, 1};
     if (make_tmap_bf16_4d(&p.tm_b2, a->b2, dims_b, str_b, box_b2)) return -3;
   }
   p.d = a->d;
@@ -492,6 +342,7 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
   p.alpha = a->alpha == 0.0f ? 1.0f : a->alpha;
   p.out_fp32 = a->out_fp32;
 
+  if (a->cta_pair) return launch_gemm_2cta(p, bn, stream);
   const long long total_tiles = 1LL * p.tiles_m * p.tiles_n * batch0 * batch1;
   const int grid = (int)(total_tiles < nsm ? total_tiles : nsm);
   count_launch();

@@ -14,6 +14,7 @@ from . import capi
 from .capi import GemmArgs
 
 BF16 = torch.bfloat16
+GEMM_2CTA = int(__import__('os').environ.get('LECO_GEMM_2CTA', '0'))  # 1: cta_group::2 kernel for plain/conv GEMMs
 
 
 def _stream() -> int:
@@ -39,7 +40,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
          residual: Optional[torch.Tensor] = None,
          lora_t: Optional[torch.Tensor] = None, lora_up: Optional[torch.Tensor] = None,
          geglu: bool = False, alpha: float = 1.0, out_fp32: bool = False,
-         conv_nhw: Optional[tuple] = None, block_n: int = 0) -> torch.Tensor:
+         conv_nhw: Optional[tuple] = None, block_n: int = 0, cta_pair: Optional[int] = None) -> torch.Tensor:
     """out[M,N] = epi(alpha * (a @ b.T + lora_t @ lora_up.T)).
 
     a: [M,K] bf16 (row stride free, inner stride 1), or with conv_nhw=(n,h,w) a contiguous NHWC
@@ -88,6 +89,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
     g.alpha = alpha
     g.out_fp32 = 1 if out_fp32 else 0
     g.block_n = block_n
+    g.cta_pair = GEMM_2CTA if cta_pair is None else int(cta_pair)
     capi.check(lib.leco_gemm_bf16(ctypes.byref(g), _stream()), "leco_gemm_bf16")
     return out
 

@@ -32,7 +32,7 @@ def _cmp(out, ref, tol=2e-2):
 
 
 def case_matrix(M, N, K, block_n=0, bias=False, rowbias=0, residual=False, lora=0, geglu=False,
-                alpha=1.0, out_fp32=False, strided=False):
+                alpha=1.0, out_fp32=False, strided=False, cta_pair=0):
     import torch
     from leco_b200 import ops
     a = _rand((M, K), seed=1)
@@ -64,7 +64,7 @@ def case_matrix(M, N, K, block_n=0, bias=False, rowbias=0, residual=False, lora=
         r = _rand(ref.shape, seed=7)
         ref = ref + r.float()
         kw["residual"] = r
-    out = ops.gemm(a, b, geglu=geglu, alpha=alpha, out_fp32=out_fp32, block_n=block_n, **kw)
+    out = ops.gemm(a, b, geglu=geglu, alpha=alpha, out_fp32=out_fp32, block_n=block_n, cta_pair=cta_pair, **kw)
     torch.cuda.synchronize()
     return _cmp(out, ref)
 
@@ -84,7 +84,7 @@ def case_batched(B1, B0, M, N, K, out_fp32=True, alpha=0.125):
     return _cmp(out, ref)
 
 
-def case_conv(n, h, w, cin, cout, block_n=0, bias=True, rowbias=True, residual=True, lora=0):
+def case_conv(n, h, w, cin, cout, block_n=0, bias=True, rowbias=True, residual=True, lora=0, cta_pair=0):
     import torch
     import torch.nn.functional as F
     from leco_b200 import ops
@@ -110,12 +110,12 @@ def case_conv(n, h, w, cin, cout, block_n=0, bias=True, rowbias=True, residual=T
         r = _rand(ref.shape, seed=27)
         ref = ref + r.float()
         kw["residual"] = r
-    out = ops.gemm(x.reshape(n * h * w, cin), wk, conv_nhw=(n, h, w), block_n=block_n, **kw)
+    out = ops.gemm(x.reshape(n * h * w, cin), wk, conv_nhw=(n, h, w), block_n=block_n, cta_pair=cta_pair, **kw)
     torch.cuda.synchronize()
     return _cmp(out, ref)
 
 
-def case_perf(M, N, K, block_n=0, conv=None, iters=20):
+def case_perf(M, N, K, block_n=0, conv=None, iters=20, cta_pair=0):
     import torch
     from leco_b200 import ops
     if conv:
@@ -128,6 +128,7 @@ def case_perf(M, N, K, block_n=0, conv=None, iters=20):
     b = _rand((N, K), scale=K ** -0.5, seed=32)
     out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
     kw = dict(conv_nhw=conv[:3]) if conv else {}
+    kw['cta_pair'] = cta_pair
     for _ in range(3):
         ops.gemm(a, b, out, block_n=block_n, **kw)
     torch.cuda.synchronize()
@@ -187,6 +188,31 @@ CASES = [
     ("conv_24x40_rect", case_conv, dict(n=1, h=24, w=40, cin=64, cout=64)),
     ("conv_lora16", case_conv, dict(n=2, h=32, w=32, cin=128, cout=128, lora=16)),
     ("conv_plain", case_conv, dict(n=2, h=32, w=32, cin=64, cout=64, bias=False, rowbias=False, residual=False)),
+    ("2cta_basic_bn128", case_matrix, dict(M=512, N=256, K=256, block_n=128, cta_pair=1)),
+    ("2cta_basic_bn256", case_matrix, dict(M=512, N=512, K=512, block_n=256, cta_pair=1)),
+    ("2cta_basic_bn160", case_matrix, dict(M=256, N=320, K=256, block_n=160, cta_pair=1)),
+    ("2cta_basic_bn64", case_matrix, dict(M=256, N=128, K=128, block_n=64, cta_pair=1)),
+    ("2cta_odd_tiles_m384", case_matrix, dict(M=384, N=256, K=320, cta_pair=1)),
+    ("2cta_ragged_m308", case_matrix, dict(M=308, N=320, K=1024, cta_pair=1)),
+    ("2cta_tiny_m4", case_matrix, dict(M=4, N=1280, K=320, bias=True, cta_pair=1)),
+    ("2cta_persist", case_matrix, dict(M=16384, N=2560, K=320, cta_pair=1)),
+    ("2cta_bias_rowbias_res", case_matrix, dict(M=512, N=320, K=320, bias=True, rowbias=128, residual=True, cta_pair=1)),
+    ("2cta_lora16", case_matrix, dict(M=1024, N=960, K=320, lora=16, cta_pair=1)),
+    ("2cta_geglu_lora", case_matrix, dict(M=300, N=1024, K=128, geglu=True, bias=True, lora=16, cta_pair=1)),
+    ("2cta_k80", case_matrix, dict(M=256, N=128, K=80, cta_pair=1)),
+    ("2cta_conv_64x64", case_conv, dict(n=2, h=64, w=64, cin=64, cout=64, cta_pair=1)),
+    ("2cta_conv_32_c128_n320", case_conv, dict(n=2, h=32, w=32, cin=128, cout=320, cta_pair=1)),
+    ("2cta_conv_8x8_n3", case_conv, dict(n=3, h=8, w=8, cin=128, cout=256, cta_pair=1)),
+    ("2cta_conv_2x2", case_conv, dict(n=4, h=2, w=2, cin=64, cout=64, cta_pair=1)),
+    ("2cta_conv_40x40", case_conv, dict(n=2, h=40, w=40, cin=64, cout=64, cta_pair=1)),
+    ("2cta_conv_lora16", case_conv, dict(n=2, h=32, w=32, cin=128, cout=128, lora=16, cta_pair=1)),
+    ("perf2_ff1", case_perf, dict(M=16384, N=2560, K=320, cta_pair=1)),
+    ("perf2_ff2", case_perf, dict(M=16384, N=320, K=1280, cta_pair=1)),
+    ("perf2_8k", case_perf, dict(M=8192, N=8192, K=8192, iters=5, cta_pair=1)),
+    ("perf2_conv_64_320", case_perf, dict(M=0, N=320, K=0, conv=(4, 64, 64, 320), cta_pair=1)),
+    ("perf2_conv_32_640", case_perf, dict(M=0, N=640, K=0, conv=(4, 32, 32, 640), cta_pair=1)),
+    ("perf2_conv_16_1280", case_perf, dict(M=0, N=1280, K=0, conv=(4, 16, 16, 1280), cta_pair=1)),
+    ("perf_conv_32_640", case_perf, dict(M=0, N=640, K=0, conv=(4, 32, 32, 640))),
     ("perf_ff1", case_perf, dict(M=16384, N=2560, K=320)),
     ("perf_ff2", case_perf, dict(M=16384, N=320, K=1280)),
     ("perf_8k", case_perf, dict(M=8192, N=8192, K=8192, iters=5)),

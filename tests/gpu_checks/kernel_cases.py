@@ -283,7 +283,7 @@ def _make_net(unet, dev, mode=None):
     from oracle import leco_ref
     torch.manual_seed(11)
     kw = dict(rank=4, alpha=1.0) if mode is None else dict(
-        rank=8, alpha=4.0, targets=leco_ref.ATTN_TARGETS + leco_ref.CONV_TARGETS)
+        rank=4, alpha=2.0, targets=leco_ref.ATTN_TARGETS + leco_ref.CONV_TARGETS)
     with contextlib.redirect_stdout(io.StringIO()):
         net = leco_ref.LoRANetworkRef(unet, multiplier=1.0, **kw)
     g = torch.Generator().manual_seed(5)
@@ -305,7 +305,7 @@ def oracle_grads(arch, n, hw, mode):
         yo = oracle(x.bfloat16().float(), torch.tensor(261), encoder_hidden_states=ctx.bfloat16().float()).sample
     lo = torch.nn.functional.mse_loss(yo, goal)
     lo.backward()
-    grads = [p.grad.clone() for l in net.unet_loras for p in (l.lora_down.weight, l.lora_up.weight)]
+    grads = [p.grad.to(torch.bfloat16) for l in net.unet_loras for p in (l.lora_down.weight, l.lora_up.weight)]  # bf16: small fixture
     return {"y": yo.detach(), "loss": lo.item(), "grads": grads, "goal": goal}
 
 

@@ -71,7 +71,7 @@ def test_leco_iteration_matches_oracle(graphs):
     # adapter weights after 3 steps: same direction, same size
     num = den = 0.0
     for a, wb in zip(net.unet_loras, ref["lora_up"]):
-        wa, wb = a.lora_up.weight.detach().float().cpu().reshape(-1), wb.reshape(-1)
+        wa, wb = a.lora_up.weight.detach().float().cpu().reshape(-1), wb.float().reshape(-1)
         num += torch.dot(wa, wb).item()
         den += (wa.norm() * wb.norm()).item()
     assert num / den > 0.9, num / den

@@ -23,7 +23,7 @@ def _f(x):
 
 # ------------------------------------------------------------------ GEMM family
 def gemm(a, b, out=None, *, bias=None, rowbias=None, rows_per_group=1, residual=None, lora_t=None, lora_up=None,
-         geglu=False, alpha=1.0, out_fp32=False, conv_nhw=None, block_n=0):
+         geglu=False, alpha=1.0, out_fp32=False, conv_nhw=None, block_n=0, cta_pair=None):
     dt = torch.float32 if out_fp32 else a.dtype
     if conv_nhw is not None:
         n, h, w = conv_nhw
