@@ -65,6 +65,8 @@ typedef struct leco_gemm_args {
   int32_t block_n; /* 0 = heuristic; else 64 / 128 / 160 / 256 */
   int32_t b_rows;  /* rows of B that exist per batch entry (0 = N); rows in [b_rows,N) read as 0 */
   int32_t cta_pair; /* 1 = 2-CTA (cta_group::2) kernel: 256 x block_n tiles per CTA pair */
+  void* splitk_ws;  /* optional ZEROED fp32 workspace (left zeroed): enables split-K for small-M, long-K problems */
+  int64_t splitk_ws_bytes;
 } leco_gemm_args;
 int leco_gemm_bf16(const leco_gemm_args* args, void* stream);
 

@@ -35,6 +35,7 @@ class GemmArgs(Structure):
         ("residual", c_void_p), ("ldr", c_int64),
         ("epilogue", c_int32), ("alpha", c_float), ("out_fp32", c_int32), ("block_n", c_int32),
         ("b_rows", c_int32), ("cta_pair", c_int32),
+        ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_int64),
     ]
 
 

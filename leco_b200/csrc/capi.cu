@@ -1,6 +1,7 @@
 // Error plumbing, device info and the driver-API tensor-map encoder for the C ABI.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -22,6 +23,14 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LECO_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 int sm_count() {
   static int n = 0;

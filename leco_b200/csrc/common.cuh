@@ -35,6 +35,13 @@ int sm_count();
     }                                                                                  \
   } while (0)
 
+// Programmatic dependent launch (PDL): every leco kernel is launched with the programmatic-stream-
+// serialization attribute, signals `griddepcontrol.launch_dependents` at entry and executes
+// `griddepcontrol.wait` before its first global-memory access, so the prologue of kernel N+1 (barrier init,
+// TMEM allocation, descriptor prefetch, block scheduling) overlaps the tail of kernel N — also inside captured
+// CUDA graphs.  LECO_PDL=0 in the environment turns the attribute off (the device instructions become no-ops).
+bool pdl_enabled();
+
 // 4-D bf16 tensor map, dims/strides innermost first; stride[0] is implied (2 bytes).
 // box[i] elements per dim; swizzle 128B; OOB reads fill with zeros.
 int make_tmap_bf16_4d(CUtensorMap* out, const void* base, const uint64_t dims[4],
@@ -42,6 +49,32 @@ int make_tmap_bf16_4d(CUtensorMap* out, const void* base, const uint64_t dims[4]
 
 // ---------------------------------------------------------------- device ----
 #ifdef __CUDACC__
+
+template <typename... KP, typename... A>
+inline cudaError_t launch_kernel_pdl(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KP>(args)...);
+}
+#define LECO_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (void)leco::launch_kernel_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream), __VA_ARGS__)
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// simple kernels: let the successor start launching, then wait for every predecessor's memory to be visible
+__device__ __forceinline__ void pdl_entry() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

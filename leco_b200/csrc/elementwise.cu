@@ -37,6 +37,15 @@ template <typename TIn>
 __global__ void conv_in_kernel(const TIn* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                                int n, int h, int wd, int cout) {
+  pdl_entry();
+  extern __shared__ float s_w[];  // [36][cout] (k-major so a thread's 8 channels are contiguous) + bias[cout]
+  float* s_b = s_w + 36 * cout;
+  for (int i = threadIdx.x; i < 36 * cout; i += blockDim.x) {
+    const int o = i / 36, k = i - o * 36;
+    s_w[k * cout + o] = __bfloat162float(w[i]);
+  }
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) s_b[i] = bias ? __bfloat162float(bias[i]) : 0.f;
+  __syncthreads();
   const int groups = cout / 8;
   const long long total = 1LL * n * h * wd * groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -46,7 +55,9 @@ __global__ void conv_in_kernel(const TIn* __restrict__ x, const __nv_bfloat16* _
     const int px = (int)(pix % wd);
     const int py = (int)((pix / wd) % h);
     const int img = (int)(pix / ((long long)wd * h));
-    float patch[36];
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = s_b[g * 8 + j];
 #pragma unroll
     for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -54,20 +65,20 @@ __global__ void conv_in_kernel(const TIn* __restrict__ x, const __nv_bfloat16* _
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const int yy = py + ky - 1, xx = px + kx - 1;
-          float v = 0.f;
-          if (yy >= 0 && yy < h && xx >= 0 && xx < wd)
-            v = static_cast<float>(x[((1LL * img * 4 + c) * h + yy) * wd + xx]);
-          patch[c * 9 + ky * 3 + kx] = v;
+          if (yy >= 0 && yy < h && xx >= 0 && xx < wd) {
+            const float v = static_cast<float>(x[((1LL * img * 4 + c) * h + yy) * wd + xx]);
+            const float4* wr = reinterpret_cast<const float4*>(s_w + (c * 9 + ky * 3 + kx) * cout + g * 8);
+            const float4 w0 = wr[0], w1 = wr[1];
+            acc[0] = fmaf(v, w0.x, acc[0]);
+            acc[1] = fmaf(v, w0.y, acc[1]);
+            acc[2] = fmaf(v, w0.z, acc[2]);
+            acc[3] = fmaf(v, w0.w, acc[3]);
+            acc[4] = fmaf(v, w1.x, acc[4]);
+            acc[5] = fmaf(v, w1.y, acc[5]);
+            acc[6] = fmaf(v, w1.z, acc[6]);
+            acc[7] = fmaf(v, w1.w, acc[7]);
+          }
         }
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const __nv_bfloat16* wr = w + (size_t)(g * 8 + j) * 36;
-      float a = bias ? __bfloat162float(bias[g * 8 + j]) : 0.f;
-#pragma unroll
-      for (int k = 0; k < 36; ++k) a = fmaf(patch[k], __bfloat162float(__ldg(wr + k)), a);
-      acc[j] = a;
-    }
     *reinterpret_cast<bf16x8*>(y + pix * cout + g * 8) = pack8(acc);
   }
 }
@@ -77,6 +88,7 @@ __global__ void conv_in_kernel(const TIn* __restrict__ x, const __nv_bfloat16* _
 __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                 const __nv_bfloat16* __restrict__ bias, float* __restrict__ y, int n,
                                 int h, int wd, int c, int cout) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -118,6 +130,7 @@ __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, const __nv_
 // dx[p, ci] = sum_{o,tap} dy[o, p - off(tap)] * w[o][tap][ci]
 __global__ void conv_out_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ w,
                                     __nv_bfloat16* __restrict__ dx, int n, int h, int wd, int c, int cout) {
+  pdl_entry();
   const int vpp = c / 8;
   const long long total = 1LL * n * h * wd * vpp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -150,6 +163,7 @@ __global__ void conv_out_bwd_kernel(const float* __restrict__ dy, const __nv_bfl
 // diffusers get_timestep_embedding(flip_sin_to_cos=True, freq_shift=0): [cos | sin]
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out,
                                           int n, int dim) {
+  pdl_entry();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * half) return;
@@ -162,6 +176,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, __nv_bflo
 
 // ------------------------------------------------------------------ elementwise
 __global__ void silu_kernel(const bf16x8* __restrict__ x, bf16x8* __restrict__ y, long long nvec) {
+  pdl_entry();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     float f[8];
@@ -173,6 +188,7 @@ __global__ void silu_kernel(const bf16x8* __restrict__ x, bf16x8* __restrict__ y
 }
 // y += x   (gradient accumulation)
 __global__ void add_inplace_kernel(bf16x8* __restrict__ y, const bf16x8* __restrict__ x, long long nvec) {
+  pdl_entry();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     float a[8], b[8];
@@ -186,6 +202,7 @@ __global__ void add_inplace_kernel(bf16x8* __restrict__ y, const bf16x8* __restr
 // GEGLU: pre [M, 2H] = [hidden | gate] -> out [M,H] = hidden * gelu(gate)
 __global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfloat16* __restrict__ out,
                                  long long M, int H) {
+  pdl_entry();
   const int vpr = H / 8;
   const long long total = M * vpr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -202,6 +219,7 @@ __global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfl
 }
 __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dout,
                                  __nv_bfloat16* __restrict__ dpre, long long M, int H) {
+  pdl_entry();
   const int vpr = H / 8;
   const long long total = M * vpr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -228,6 +246,7 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __
 __global__ void copy_cols_kernel(const __nv_bfloat16* __restrict__ src, long long lds, int scol0,
                                  __nv_bfloat16* __restrict__ dst, long long ldd, int dcol0, long long M,
                                  int ncols) {
+  pdl_entry();
   const int vpr = ncols / 8;
   const long long total = M * vpr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -242,6 +261,7 @@ __global__ void copy_cols_kernel(const __nv_bfloat16* __restrict__ src, long lon
 // nearest 2x upsample NHWC: y[n, 2h, 2w, c]
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n,
                                   int h, int w, int c) {
+  pdl_entry();
   const int vpp = c / 8;
   const long long total = 1LL * n * 2 * h * 2 * w * vpp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -259,6 +279,7 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
 // backward: dx[n,h,w,c] = sum of the 2x2 block of dy[n,2h,2w,c]
 __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
                                       int n, int h, int w, int c) {
+  pdl_entry();
   const int vpp = c / 8;
   const long long total = 1LL * n * h * w * vpp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -288,6 +309,7 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv
 // stride-2 3x3 pad-1 im2col: x NHWC [n,h,w,c] -> col [n*(h/2)*(w/2), 9*c] (k = tap*c + ch)
 __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, int n,
                                  int h, int w, int c, int stride) {
+  pdl_entry();
   const int vpp = c / 8, oh = h / stride, ow = w / stride;
   const long long total = 1LL * n * oh * ow * 9 * vpp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -309,6 +331,7 @@ __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
 // col2im (gather form): dx[n,h,w,c] = sum over (out pixel, tap) that read this input pixel
 __global__ void col2im_s2_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx, int n,
                                  int h, int w, int c) {
+  pdl_entry();
   const int vpp = c / 8, oh = h / 2, ow = w / 2;
   const long long total = 1LL * n * h * w * vpp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -338,6 +361,7 @@ __global__ void col2im_s2_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bf
 // out[n, c] = sum over the hw rows of sample n (the time-embedding bias gradient of a conv epilogue)
 __global__ void rowgroup_sum_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int hw,
                                     int c) {
+  pdl_entry();
   __shared__ float red[8][32][8];
   const int n = blockIdx.x;
   const int v = blockIdx.y * 32 + threadIdx.x;  // 8-channel vector column
@@ -370,6 +394,7 @@ __global__ void transpose_kernel(const __nv_bfloat16* __restrict__ in, __nv_bflo
                                  int rows, int cols, int rows_pad, long long in_ld, long long in_bs0,
                                  long long in_bs1, long long out_ld, long long out_bs0, long long out_bs1,
                                  int batch0) {
+  pdl_entry();
   __shared__ __nv_bfloat16 tile[32][34];
   const int b = blockIdx.z;
   const int b1 = b / batch0, b0 = b % batch0;
@@ -391,6 +416,7 @@ __global__ void transpose_kernel(const __nv_bfloat16* __restrict__ in, __nv_bflo
 // [n_valid, n_pad) written as 0.  One warp per row.
 __global__ void softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, long long rows,
                                     int n_valid, int n_pad, long long ld_s, long long ld_p) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -414,6 +440,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* 
 __global__ void softmax_bwd_rows_kernel(const __nv_bfloat16* __restrict__ p, const float* __restrict__ dp,
                                         __nv_bfloat16* __restrict__ ds, long long rows, int n_valid, int n_pad,
                                         long long ld_p, long long ld_dp, float scale) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -441,13 +468,17 @@ extern "C" int leco_conv_in(const void* x, int x_is_fp32, const void* w, const v
                             int wd, int cout, void* stream) {
   LECO_REQUIRE(x && w && y && cout % 8 == 0, "leco_conv_in: bad args");
   const long long work = 1LL * n * h * wd * (cout / 8);
+  const size_t smem = (size_t)37 * cout * sizeof(float);
+  LECO_REQUIRE(smem <= 48 * 1024, "leco_conv_in: cout=%d too wide", cout);
+  int grid = grid_for(work, 256);
+  if (grid > 148 * 4) grid = 148 * 4;  // each block re-stages the weights: keep the grid modest
   count_launch();
   if (x_is_fp32)
-    conv_in_kernel<float><<<grid_for(work, 128), 128, 0, STREAM(stream)>>>(
-        reinterpret_cast<const float*>(x), BF(w), BF(bias), BFW(y), n, h, wd, cout);
+    LECO_LAUNCH(conv_in_kernel<float>, grid, 256, smem, STREAM(stream), reinterpret_cast<const float*>(x), BF(w), BF(bias),
+                                                              BFW(y), n, h, wd, cout);
   else
-    conv_in_kernel<__nv_bfloat16><<<grid_for(work, 128), 128, 0, STREAM(stream)>>>(BF(x), BF(w), BF(bias),
-                                                                                   BFW(y), n, h, wd, cout);
+    LECO_LAUNCH(conv_in_kernel<__nv_bfloat16>, grid, 256, smem, STREAM(stream), BF(x), BF(w), BF(bias), BFW(y), n, h, wd,
+                                                                      cout);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -455,7 +486,7 @@ extern "C" int leco_conv_out(const void* x, const void* w, const void* bias, flo
                              int cout, void* stream) {
   LECO_REQUIRE(x && w && y && c % 8 == 0 && cout >= 1 && cout <= 8, "leco_conv_out: bad args");
   count_launch();
-  conv_out_kernel<<<grid_for(1LL * n * h * wd * 32, 256), 256, 0, STREAM(stream)>>>(BF(x), BF(w), BF(bias), y, n,
+  LECO_LAUNCH(conv_out_kernel, grid_for(1LL * n * h * wd * 32, 256), 256, 0, STREAM(stream), BF(x), BF(w), BF(bias), y, n,
                                                                                    h, wd, c, cout);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -464,7 +495,7 @@ extern "C" int leco_conv_out_bwd(const float* dy, const void* w, void* dx, int n
                                  void* stream) {
   LECO_REQUIRE(dy && w && dx && c % 8 == 0 && cout >= 1 && cout <= 8, "leco_conv_out_bwd: bad args");
   count_launch();
-  conv_out_bwd_kernel<<<grid_for(1LL * n * h * wd * (c / 8), 256), 256, 0, STREAM(stream)>>>(dy, BF(w), BFW(dx),
+  LECO_LAUNCH(conv_out_bwd_kernel, grid_for(1LL * n * h * wd * (c / 8), 256), 256, 0, STREAM(stream), dy, BF(w), BFW(dx),
                                                                                            n, h, wd, c, cout);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -472,14 +503,14 @@ extern "C" int leco_conv_out_bwd(const float* dy, const void* w, void* dx, int n
 extern "C" int leco_timestep_embedding(const float* t, void* out, int n, int dim, void* stream) {
   LECO_REQUIRE(t && out && dim % 2 == 0, "leco_timestep_embedding: bad args");
   count_launch();
-  timestep_embedding_kernel<<<(n * dim / 2 + 127) / 128, 128, 0, STREAM(stream)>>>(t, BFW(out), n, dim);
+  LECO_LAUNCH(timestep_embedding_kernel, (n * dim / 2 + 127) / 128, 128, 0, STREAM(stream), t, BFW(out), n, dim);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 extern "C" int leco_silu(const void* x, void* y, int64_t numel, void* stream) {
   LECO_REQUIRE(x && y && numel % 8 == 0, "leco_silu: numel must be a multiple of 8");
   count_launch();
-  silu_kernel<<<grid_for(numel / 8, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const bf16x8*>(x),
+  LECO_LAUNCH(silu_kernel, grid_for(numel / 8, 256), 256, 0, STREAM(stream), reinterpret_cast<const bf16x8*>(x),
                                                                    reinterpret_cast<bf16x8*>(y), numel / 8);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -487,7 +518,7 @@ extern "C" int leco_silu(const void* x, void* y, int64_t numel, void* stream) {
 extern "C" int leco_add_inplace(void* y, const void* x, int64_t numel, void* stream) {
   LECO_REQUIRE(x && y && numel % 8 == 0, "leco_add_inplace: numel must be a multiple of 8");
   count_launch();
-  add_inplace_kernel<<<grid_for(numel / 8, 256), 256, 0, STREAM(stream)>>>(
+  LECO_LAUNCH(add_inplace_kernel, grid_for(numel / 8, 256), 256, 0, STREAM(stream), 
       reinterpret_cast<bf16x8*>(y), reinterpret_cast<const bf16x8*>(x), numel / 8);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -495,14 +526,14 @@ extern "C" int leco_add_inplace(void* y, const void* x, int64_t numel, void* str
 extern "C" int leco_geglu_fwd(const void* pre, void* out, int64_t M, int H, void* stream) {
   LECO_REQUIRE(pre && out && H % 8 == 0, "leco_geglu_fwd: bad args");
   count_launch();
-  geglu_fwd_kernel<<<grid_for(M * (H / 8), 256), 256, 0, STREAM(stream)>>>(BF(pre), BFW(out), M, H);
+  LECO_LAUNCH(geglu_fwd_kernel, grid_for(M * (H / 8), 256), 256, 0, STREAM(stream), BF(pre), BFW(out), M, H);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 extern "C" int leco_geglu_bwd(const void* pre, const void* dout, void* dpre, int64_t M, int H, void* stream) {
   LECO_REQUIRE(pre && dout && dpre && H % 8 == 0, "leco_geglu_bwd: bad args");
   count_launch();
-  geglu_bwd_kernel<<<grid_for(M * (H / 8), 256), 256, 0, STREAM(stream)>>>(BF(pre), BF(dout), BFW(dpre), M, H);
+  LECO_LAUNCH(geglu_bwd_kernel, grid_for(M * (H / 8), 256), 256, 0, STREAM(stream), BF(pre), BF(dout), BFW(dpre), M, H);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -511,7 +542,7 @@ extern "C" int leco_copy_cols(const void* src, int64_t lds, int scol0, void* dst
   LECO_REQUIRE(src && dst && ncols % 8 == 0 && scol0 % 8 == 0 && dcol0 % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0,
                "leco_copy_cols: columns / strides must be multiples of 8");
   count_launch();
-  copy_cols_kernel<<<grid_for(M * (ncols / 8), 256), 256, 0, STREAM(stream)>>>(BF(src), lds, scol0, BFW(dst),
+  LECO_LAUNCH(copy_cols_kernel, grid_for(M * (ncols / 8), 256), 256, 0, STREAM(stream), BF(src), lds, scol0, BFW(dst),
                                                                                ldd, dcol0, M, ncols);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -519,7 +550,7 @@ extern "C" int leco_copy_cols(const void* src, int64_t lds, int scol0, void* dst
 extern "C" int leco_upsample2x(const void* x, void* y, int n, int h, int w, int c, void* stream) {
   LECO_REQUIRE(x && y && c % 8 == 0, "leco_upsample2x: bad args");
   count_launch();
-  upsample2x_kernel<<<grid_for(4LL * n * h * w * (c / 8), 256), 256, 0, STREAM(stream)>>>(BF(x), BFW(y), n, h, w,
+  LECO_LAUNCH(upsample2x_kernel, grid_for(4LL * n * h * w * (c / 8), 256), 256, 0, STREAM(stream), BF(x), BFW(y), n, h, w,
                                                                                         c);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -527,7 +558,7 @@ extern "C" int leco_upsample2x(const void* x, void* y, int n, int h, int w, int 
 extern "C" int leco_upsample2x_bwd(const void* dy, void* dx, int n, int h, int w, int c, void* stream) {
   LECO_REQUIRE(dy && dx && c % 8 == 0, "leco_upsample2x_bwd: bad args");
   count_launch();
-  upsample2x_bwd_kernel<<<grid_for(1LL * n * h * w * (c / 8), 256), 256, 0, STREAM(stream)>>>(BF(dy), BFW(dx), n,
+  LECO_LAUNCH(upsample2x_bwd_kernel, grid_for(1LL * n * h * w * (c / 8), 256), 256, 0, STREAM(stream), BF(dy), BFW(dx), n,
                                                                                             h, w, c);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -535,7 +566,7 @@ extern "C" int leco_upsample2x_bwd(const void* dy, void* dx, int n, int h, int w
 extern "C" int leco_im2col_s2(const void* x, void* col, int n, int h, int w, int c, void* stream) {
   LECO_REQUIRE(x && col && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "leco_im2col_s2: bad args");
   count_launch();
-  im2col_s2_kernel<<<grid_for(1LL * n * (h / 2) * (w / 2) * 9 * (c / 8), 256), 256, 0, STREAM(stream)>>>(
+  LECO_LAUNCH(im2col_s2_kernel, grid_for(1LL * n * (h / 2) * (w / 2) * 9 * (c / 8), 256), 256, 0, STREAM(stream), 
       BF(x), BFW(col), n, h, w, c, 2);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -543,7 +574,7 @@ extern "C" int leco_im2col_s2(const void* x, void* col, int n, int h, int w, int
 extern "C" int leco_im2col_s1(const void* x, void* col, int n, int h, int w, int c, void* stream) {
   LECO_REQUIRE(x && col && c % 8 == 0, "leco_im2col_s1: bad args");
   count_launch();
-  im2col_s2_kernel<<<grid_for(1LL * n * h * w * 9 * (c / 8), 256), 256, 0, STREAM(stream)>>>(BF(x), BFW(col), n, h, w,
+  LECO_LAUNCH(im2col_s2_kernel, grid_for(1LL * n * h * w * 9 * (c / 8), 256), 256, 0, STREAM(stream), BF(x), BFW(col), n, h, w,
                                                                                           c, 1);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -551,14 +582,14 @@ extern "C" int leco_im2col_s1(const void* x, void* col, int n, int h, int w, int
 extern "C" int leco_rowgroup_sum(const void* x, void* out, int n, int hw, int c, void* stream) {
   LECO_REQUIRE(x && out && c % 8 == 0, "leco_rowgroup_sum: bad args");
   count_launch();
-  rowgroup_sum_kernel<<<dim3(n, (c / 8 + 31) / 32), dim3(32, 8), 0, STREAM(stream)>>>(BF(x), BFW(out), hw, c);
+  LECO_LAUNCH(rowgroup_sum_kernel, dim3(n, (c / 8 + 31) / 32), dim3(32, 8), 0, STREAM(stream), BF(x), BFW(out), hw, c);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 extern "C" int leco_col2im_s2(const void* dcol, void* dx, int n, int h, int w, int c, void* stream) {
   LECO_REQUIRE(dcol && dx && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "leco_col2im_s2: bad args");
   count_launch();
-  col2im_s2_kernel<<<grid_for(1LL * n * h * w * (c / 8), 256), 256, 0, STREAM(stream)>>>(BF(dcol), BFW(dx), n, h,
+  LECO_LAUNCH(col2im_s2_kernel, grid_for(1LL * n * h * w * (c / 8), 256), 256, 0, STREAM(stream), BF(dcol), BFW(dx), n, h,
                                                                                        w, c);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -571,7 +602,7 @@ extern "C" int leco_transpose(const void* in, void* out, int rows, int cols, int
   LECO_REQUIRE(1LL * batch0 * batch1 <= 65535, "leco_transpose: too many batches");
   dim3 grid((cols + 31) / 32, (rows_pad + 31) / 32, batch0 * batch1), block(32, 8);
   count_launch();
-  transpose_kernel<<<grid, block, 0, STREAM(stream)>>>(BF(in), BFW(out), rows, cols, rows_pad, in_ld, in_bs0,
+  LECO_LAUNCH(transpose_kernel, grid, block, 0, STREAM(stream), BF(in), BFW(out), rows, cols, rows_pad, in_ld, in_bs0,
                                                        in_bs1, out_ld, out_bs0, out_bs1, batch0);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -580,7 +611,7 @@ extern "C" int leco_softmax_rows(const float* s, void* p, int64_t rows, int n_va
                                  int64_t ld_p, void* stream) {
   LECO_REQUIRE(s && p && n_valid > 0 && n_pad >= n_valid, "leco_softmax_rows: bad args");
   count_launch();
-  softmax_rows_kernel<<<grid_for(rows * 32, 256), 256, 0, STREAM(stream)>>>(s, BFW(p), rows, n_valid, n_pad, ld_s,
+  LECO_LAUNCH(softmax_rows_kernel, grid_for(rows * 32, 256), 256, 0, STREAM(stream), s, BFW(p), rows, n_valid, n_pad, ld_s,
                                                                            ld_p);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -589,7 +620,7 @@ extern "C" int leco_softmax_bwd_rows(const void* p, const float* dp, void* ds, i
                                      int n_pad, int64_t ld_p, int64_t ld_dp, float scale, void* stream) {
   LECO_REQUIRE(p && dp && ds && n_valid > 0 && n_pad >= n_valid, "leco_softmax_bwd_rows: bad args");
   count_launch();
-  softmax_bwd_rows_kernel<<<grid_for(rows * 32, 256), 256, 0, STREAM(stream)>>>(BF(p), dp, BFW(ds), rows, n_valid,
+  LECO_LAUNCH(softmax_bwd_rows_kernel, grid_for(rows * 32, 256), 256, 0, STREAM(stream), BF(p), dp, BFW(ds), rows, n_valid,
                                                                                n_pad, ld_p, ld_dp, scale);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -51,6 +51,7 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t n, bool b_mn_major)
 }
 
 __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __grid_constant__ FlashParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   const uint32_t tmem_s = tmem_base;        // + buf * 128
   const uint32_t tmem_pv = tmem_base + 256; // + buf * 64
 
@@ -341,7 +343,7 @@ extern "C" int leco_flash_attn_fwd(const void* q, int64_t ldq, const void* k, in
   }
   dim3 grid((sq + FA_BM - 1) / FA_BM, heads, batch);
   count_launch();
-  flash_attn_fwd_kernel<<<grid, FA_THREADS, FA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  LECO_LAUNCH(flash_attn_fwd_kernel, grid, FA_THREADS, FA_SMEM, reinterpret_cast<cudaStream_t>(stream), p);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -91,6 +91,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
@@ -134,6 +135,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   const int tiles_m2 = (p.tiles_m + 1) / 2;  // pairs of M tiles
   const int tiles_mn = tiles_m2 * p.tiles_n;
@@ -253,7 +255,7 @@ static int launch_2cta(const GemmParams& p, cudaStream_t stream) {
   const long long pair_tiles = 1LL * ((p.tiles_m + 1) / 2) * p.tiles_n * p.batch0 * p.batch1;
   const int max_clusters = sm_count() / 2;
   const int clusters = (int)(pair_tiles < max_clusters ? pair_tiles : max_clusters);
-  gemm_tcgen05_2cta_kernel<BN><<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  LECO_LAUNCH(gemm_tcgen05_2cta_kernel<BN>, 2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream, p);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

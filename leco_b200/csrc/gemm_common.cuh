@@ -30,6 +30,10 @@ struct GemmParams {
   float alpha;
   int out_fp32;
   unsigned a_tx_bytes;
+  // split-K: tile index carries a K-slice id; partial sums are red.add'ed (fp32) into `ws` [M][ldws]
+  int k_splits;
+  float* ws;
+  long long ldws;
 };
 
 template <int BN>
@@ -110,7 +114,28 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   }
   const long long boff = b0 * p.d_bs0 + b1 * p.d_bs1;
 
-  if (!geglu) {
+  if (p.k_splits > 1) {
+    // partial accumulator of one K-slice -> fp32 workspace (bias / residual are applied by the finalize kernel)
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(trow + c * 32, raw);
+      tmem_ld_wait();
+      const int col0 = n0 + c * 32;
+      const int nvalid = p.N - col0;
+      if (row_ok && nvalid > 0) {
+        float* dst = p.ws + m * p.ldws + col0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (g * 4 < nvalid)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
+                         "f"(__uint_as_float(raw[g * 4 + 0]) * p.alpha), "f"(__uint_as_float(raw[g * 4 + 1]) * p.alpha),
+                         "f"(__uint_as_float(raw[g * 4 + 2]) * p.alpha), "f"(__uint_as_float(raw[g * 4 + 3]) * p.alpha)
+                         : "memory");
+        }
+      }
+    }
+  } else if (!geglu) {
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t raw[32];

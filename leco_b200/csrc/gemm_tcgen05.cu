@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  pdl_launch_dependents();  // the next kernel may start its prologue while this one runs
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -72,34 +73,32 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel; from here on global memory is touched
 
   const int tiles_mn = p.tiles_m * p.tiles_n;
-  const int total_tiles = tiles_mn * p.batch0 * p.batch1;
-  const int total_chunks = p.chunks1 + p.has_seg2;
+  const int splits = p.k_splits;
+  const int total_tiles = tiles_mn * p.batch0 * p.batch1 * splits;
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int bidx = tile / tiles_mn;
-      const int rem = tile - bidx * tiles_mn;
+      const int ks = tile % splits;
+      const int t2 = tile / splits;
+      const int bidx = t2 / tiles_mn;
+      const int rem = t2 - bidx * tiles_mn;
       const int nt = rem / p.tiles_m;
       const int mt = rem - nt * p.tiles_m;
       const int b1 = bidx / p.batch0;
       const int b0 = bidx - b1 * p.batch0;
       const int n0 = nt * BN;
-      int m0 = mt * BLOCK_M, img_n0 = 0, img_h0 = 0;
-      if (p.mode == 1) {
-        if (p.nb > 1) {
-          img_n0 = mt * p.nb;
-        } else {
-          img_n0 = mt / p.tiles_per_img;
-          img_h0 = (mt - img_n0 * p.tiles_per_img) * p.hb;
-        }
-        m0 = (img_n0 * p.ch + img_h0) * p.cw;
-      }
-      for (int c = 0; c < total_chunks; ++c) {
+      int m0, img_n0, img_h0;
+      gemm_tile_origin(p, mt, m0, img_n0, img_h0);
+      // this tile's K-slice: segment-1 chunks [c_begin, c_end) (+ the LoRA segment on the last slice)
+      const int c_begin = (int)((long long)ks * p.chunks1 / splits);
+      const int c_end = (int)((long long)(ks + 1) * p.chunks1 / splits) + ((ks == splits - 1) ? p.has_seg2 : 0);
+      for (int c = c_begin; c < c_end; ++c) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
         uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
@@ -150,7 +149,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       mbar_wait(&tmem_empty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
-      for (int c = 0; c < total_chunks; ++c) {
+      const int ks = tile % splits;
+      const int c_begin = (int)((long long)ks * p.chunks1 / splits);
+      const int c_end = (int)((long long)(ks + 1) * p.chunks1 / splits) + ((ks == splits - 1) ? p.has_seg2 : 0);
+      uint32_t acc = 0;
+      for (int c = c_begin; c < c_end; ++c) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const int ksteps = (c < p.chunks1 - 1) ? 4 : (c == p.chunks1 - 1 ? p.ksteps_last1 : p.ksteps2);
@@ -158,7 +161,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
         for (int j = 0; j < ksteps; ++j) {
           // +32 bytes (16 bf16) along K inside the 128B swizzle row: +2 in the >>4 address field
-          umma_bf16(tmem_d, da + 2 * j, db + 2 * j, idesc, (c | j) != 0 ? 1u : 0u);
+          umma_bf16(tmem_d, da + 2 * j, db + 2 * j, idesc, acc);
+          acc = 1;
         }
         umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
         if (++stage == STAGES) {
@@ -176,8 +180,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int bidx = tile / tiles_mn;
-      const int rem = tile - bidx * tiles_mn;
+      const int t2 = tile / splits;
+      const int bidx = t2 / tiles_mn;
+      const int rem = t2 - bidx * tiles_mn;
       const int nt = rem / p.tiles_m;
       const int mt = rem - nt * p.tiles_m;
       const int b1 = bidx / p.batch0;
@@ -196,25 +201,77 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+// split-K finalize: out = bf16(ws + bias + rowbias + residual); the workspace is zeroed again on the way
+__global__ void splitk_finalize_kernel(const GemmParams p) {
+  pdl_entry();
+  const int vpr = p.N / 4;
+  const long long total = (long long)p.M * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / vpr;
+    const int col = (int)(i % vpr) * 4;
+    float4* w = reinterpret_cast<float4*>(p.ws + m * p.ldws + col);
+    float4 v = *w;
+    *w = make_float4(0.f, 0.f, 0.f, 0.f);
+    float f[4] = {v.x, v.y, v.z, v.w};
+    auto add4 = [&](const __nv_bfloat16* src) {
+      const uint2 q = *reinterpret_cast<const uint2*>(src);
+      f[0] += bf16_lo(q.x);
+      f[1] += bf16_hi(q.x);
+      f[2] += bf16_lo(q.y);
+      f[3] += bf16_hi(q.y);
+    };
+    if (p.bias) add4(p.bias + col);
+    if (p.rowbias) add4(p.rowbias + (m / p.rows_per_group) * p.ld_rowbias + col);
+    if (p.residual) add4(p.residual + m * p.ldr + col);
+    uint2 o;
+    o.x = pack_bf16(f[0], f[1]);
+    o.y = pack_bf16(f[2], f[3]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.d) + m * p.ldd + col) = o;
+  }
+}
+void count_launch();
+static int launch_splitk_finalize(const GemmParams& p, cudaStream_t stream) {
+  const long long total = (long long)p.M * (p.N / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  count_launch();
+  LECO_LAUNCH(splitk_finalize_kernel, (int)blocks, 256, 0, stream, p);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------ host side
-static int pick_block_n(const leco_gemm_args& a, int tiles_m, int batches, int nsm) {
+// Chooses the N tile and the K split together: score = tensor efficiency of the tile shape x how much of the
+// machine the (tiles x splits) grid fills.  `max_split` = 1 disables split-K.
+static int pick_block_n(const leco_gemm_args& a, int tiles_m, int batches, int nsm, int chunks, int max_split,
+                        int* split_out) {
+  *split_out = 1;
   if (a.epilogue == 1) return 128;
-  if (a.block_n) return a.block_n;
   const int cand[4] = {256, 160, 128, 64};
   const double rate[4] = {1.0, 0.95, 0.9, 0.6};
   double best = -1;
   int best_bn = 128;
   for (int i = 0; i < 4; ++i) {
     const int bn = cand[i];
+    if (a.block_n && a.block_n != bn) continue;
     const int tn = (a.N + bn - 1) / bn;
     const double util_n = double(a.N) / double(tn * bn);  // ragged last tile wastes MMA
     const long long tiles = 1LL * tiles_m * tn * batches;
-    const long long waves = (tiles + nsm - 1) / nsm;
-    const double eff = double(tiles) / double(waves * nsm);
-    const double score = rate[i] * util_n * eff;
+    int sp = 1;
+    if (max_split > 1 && tiles * 2 <= nsm) {
+      sp = (int)(nsm / tiles);
+      if (sp > max_split) sp = max_split;
+      while (sp > 1 && chunks / sp < 4) --sp;
+    }
+    const long long ctas = tiles * sp;
+    const long long waves = (ctas + nsm - 1) / nsm;
+    const double eff = double(ctas) / double(waves * nsm);
+    const double score = rate[i] * util_n * eff * (sp > 1 ? 0.97 : 1.0);  // split-K pays a finalize pass
     if (score > best + 1e-9) {
       best = score;
       best_bn = bn;
+      *split_out = sp;
     }
   }
   return best_bn;
@@ -229,12 +286,10 @@ static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  LECO_LAUNCH(gemm_tcgen05_kernel<BN>, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, p);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
-
-void count_launch();
 
 }  // namespace leco
 
@@ -300,7 +355,10 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
   }
 
   const int nsm = sm_count();
-  const int bn = pick_block_n(*a, p.tiles_m, batch0 * batch1, nsm);
+  const bool splitk_ok = a->splitk_ws && !a->cta_pair && !a->out_fp32 && a->epilogue == 0 && batch0 * batch1 == 1 &&
+                         (size_t)a->M * a->N * 4 <= (size_t)a->splitk_ws_bytes && a->N % 4 == 0;
+  int k_split = 1;
+  const int bn = pick_block_n(*a, p.tiles_m, batch0 * batch1, nsm, p.chunks1, splitk_ok ? 8 : 1, &k_split);
   LECO_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "leco_gemm_bf16: unsupported block_n %d", bn);
   if (a->epilogue == 1) LECO_REQUIRE(a->N % 128 == 0 && !a->out_fp32 && !a->residual && !a->rowbias, "leco_gemm_bf16: GEGLU needs N%%128==0, bf16 out, no residual/rowbias");
   p.tiles_n = (a->N + bn - 1) / bn;
@@ -342,14 +400,26 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
   p.alpha = a->alpha == 0.0f ? 1.0f : a->alpha;
   p.out_fp32 = a->out_fp32;
 
+  p.k_splits = 1;
   if (a->cta_pair) return launch_gemm_2cta(p, bn, stream);
-  const long long total_tiles = 1LL * p.tiles_m * p.tiles_n * batch0 * batch1;
+  long long total_tiles = 1LL * p.tiles_m * p.tiles_n * batch0 * batch1;
+  // split-K: few output tiles but a long K (the 16x16 / 8x8 UNet levels at small batch): spread the K range
+  // over idle SMs; partial sums meet in an fp32 workspace, splitk_finalize_kernel applies the epilogue
+  if (k_split > 1) {
+    p.k_splits = k_split;
+    p.ws = reinterpret_cast<float*>(a->splitk_ws);
+    p.ldws = a->N;
+    total_tiles *= k_split;
+  }
   const int grid = (int)(total_tiles < nsm ? total_tiles : nsm);
   count_launch();
+  int rc;
   switch (bn) {
-    case 64: return launch_gemm<64>(p, grid, stream);
-    case 128: return launch_gemm<128>(p, grid, stream);
-    case 160: return launch_gemm<160>(p, grid, stream);
-    default: return launch_gemm<256>(p, grid, stream);
+    case 64: rc = launch_gemm<64>(p, grid, stream); break;
+    case 128: rc = launch_gemm<128>(p, grid, stream); break;
+    case 160: rc = launch_gemm<160>(p, grid, stream); break;
+    default: rc = launch_gemm<256>(p, grid, stream); break;
   }
+  if (rc == 0 && p.k_splits > 1) rc = launch_splitk_finalize(p, stream);
+  return rc;
 }

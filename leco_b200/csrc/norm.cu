@@ -26,11 +26,13 @@ __device__ __forceinline__ float dsilu_f(float y) {
 }
 
 constexpr int GN_MAX_GROUPS = 64;
+constexpr int GN_MAX_SPLITS = 64;
 
 // ---- pass 1 (forward): partial[n][split][g] = (sum x, sum x^2)
 // blockDim.x = vpp * R (vpp = C/8 vector columns, R row lanes); each thread owns one vector column.
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ partial, int hw, int C,
                                 int G, int vpp, int splits) {
+  pdl_entry();
   __shared__ float sm[GN_MAX_GROUPS][2];
   const int n = blockIdx.x, sp = blockIdx.y;
   for (int i = threadIdx.x; i < G * 2; i += blockDim.x) (&sm[0][0])[i] = 0.f;
@@ -44,7 +46,20 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __r
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   if (rl < R) {
     const __nv_bfloat16* base = x + ((size_t)n * hw) * C + v * 8;
-    for (int r = r0 + rl; r < r1; r += R) {
+    int r = r0 + rl;
+    for (; r + R < r1; r += 2 * R) {  // two independent 16-byte loads in flight
+      float f[8], g[8];
+      const v8 qa = *reinterpret_cast<const v8*>(base + (size_t)r * C);
+      const v8 qb = *reinterpret_cast<const v8*>(base + (size_t)(r + R) * C);
+      up8(qa, f);
+      up8(qb, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += f[j] + g[j];
+        s2[j] = fmaf(f[j], f[j], fmaf(g[j], g[j], s2[j]));
+      }
+    }
+    for (; r < r1; r += R) {
       float f[8];
       up8(*reinterpret_cast<const v8*>(base + (size_t)r * C), f);
 #pragma unroll
@@ -71,6 +86,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
                                 const float2* __restrict__ partial, float2* __restrict__ stats,
                                 const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                                 int hw, int C, int G, int splits, float eps, int silu) {
+  pdl_entry();
   __shared__ float2 ms[GN_MAX_GROUPS];
   const int n = blockIdx.x;
   const int cpg = C / G;
@@ -116,6 +132,7 @@ __global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const _
                                     const float2* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
                                     const __nv_bfloat16* __restrict__ beta, float2* __restrict__ partial, int hw,
                                     int C, int G, int vpp, int splits, int silu) {
+  pdl_entry();
   __shared__ float sm[GN_MAX_GROUPS][2];
   __shared__ float2 ms[GN_MAX_GROUPS];
   const int n = blockIdx.x, sp = blockIdx.y;
@@ -168,6 +185,7 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
                                     const float2* __restrict__ partial, const __nv_bfloat16* __restrict__ gamma,
                                     const __nv_bfloat16* __restrict__ beta, int hw, int C, int G, int splits,
                                     int silu) {
+  pdl_entry();
   __shared__ float2 ms[GN_MAX_GROUPS];
   __shared__ float2 gs[GN_MAX_GROUPS];
   const int n = blockIdx.x;
@@ -215,6 +233,7 @@ constexpr int LN_MAX_VEC = 8;  // per lane -> C <= 2048
 __global__ void ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                               float2* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
                               const __nv_bfloat16* __restrict__ beta, long long M, int C, float eps) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -268,6 +287,7 @@ __global__ void ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16
 __global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                               __nv_bfloat16* __restrict__ dx, const float2* __restrict__ stats,
                               const __nv_bfloat16* __restrict__ gamma, long long M, int C) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -318,9 +338,9 @@ static int gn_launch_cfg(int hw, int C, int* vpp, int* threads, int* splits) {
   int R = 256 / *vpp;
   if (R < 1) R = 1;
   *threads = *vpp * R;
-  int s = hw / 64;
+  int s = hw / 16;   // >= 16 pixel rows per block; many small blocks keep enough loads in flight
   if (s < 1) s = 1;
-  if (s > 32) s = 32;
+  if (s > GN_MAX_SPLITS) s = GN_MAX_SPLITS;
   *splits = s;
   return 0;
 }
@@ -332,8 +352,8 @@ using namespace leco;
 #define BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 #define BFW(p) reinterpret_cast<__nv_bfloat16*>(p)
 
-// workspace: float2[n * 32 splits * G]  (leco_group_norm_workspace_bytes)
-extern "C" int64_t leco_group_norm_workspace_bytes(int n, int G) { return (int64_t)n * 32 * G * 8; }
+// workspace: float2[n * GN_MAX_SPLITS * G]  (leco_group_norm_workspace_bytes)
+extern "C" int64_t leco_group_norm_workspace_bytes(int n, int G) { return (int64_t)n * GN_MAX_SPLITS * G * 8; }
 
 extern "C" int leco_group_norm(const void* x, void* y, void* stats /*float2[n*G]*/, const void* gamma,
                                const void* beta, int n, int hw, int C, int G, float eps, int silu,
@@ -343,7 +363,7 @@ extern "C" int leco_group_norm(const void* x, void* y, void* stats /*float2[n*G]
   int vpp, threads, splits;
   LECO_REQUIRE(gn_launch_cfg(hw, C, &vpp, &threads, &splits) == 0, "leco_group_norm: C=%d too wide", C);
   count_launch();
-  gn_stats_kernel<<<dim3(n, splits), threads, 0, STREAM(stream)>>>(BF(x), reinterpret_cast<float2*>(workspace), hw,
+  LECO_LAUNCH(gn_stats_kernel, dim3(n, splits), threads, 0, STREAM(stream), BF(x), reinterpret_cast<float2*>(workspace), hw,
                                                                   C, G, vpp, splits);
   LECO_CHECK_CUDA(cudaGetLastError());
   long long work = (long long)hw * vpp;
@@ -351,7 +371,7 @@ extern "C" int leco_group_norm(const void* x, void* y, void* stats /*float2[n*G]
   if (gy > 592) gy = 592;
   if (gy < 1) gy = 1;
   count_launch();
-  gn_apply_kernel<<<dim3(n, gy), 256, 0, STREAM(stream)>>>(BF(x), BFW(y), reinterpret_cast<const float2*>(workspace),
+  LECO_LAUNCH(gn_apply_kernel, dim3(n, gy), 256, 0, STREAM(stream), BF(x), BFW(y), reinterpret_cast<const float2*>(workspace),
                                                           reinterpret_cast<float2*>(stats), BF(gamma), BF(beta), hw,
                                                           C, G, splits, eps, silu);
   LECO_CHECK_CUDA(cudaGetLastError());
@@ -366,7 +386,7 @@ extern "C" int leco_group_norm_bwd(const void* x, const void* dz, void* dx, cons
   int vpp, threads, splits;
   LECO_REQUIRE(gn_launch_cfg(hw, C, &vpp, &threads, &splits) == 0, "leco_group_norm_bwd: C=%d too wide", C);
   count_launch();
-  gn_bwd_stats_kernel<<<dim3(n, splits), threads, 0, STREAM(stream)>>>(
+  LECO_LAUNCH(gn_bwd_stats_kernel, dim3(n, splits), threads, 0, STREAM(stream), 
       BF(x), BF(dz), reinterpret_cast<const float2*>(stats), BF(gamma), BF(beta),
       reinterpret_cast<float2*>(workspace), hw, C, G, vpp, splits, silu);
   LECO_CHECK_CUDA(cudaGetLastError());
@@ -375,7 +395,7 @@ extern "C" int leco_group_norm_bwd(const void* x, const void* dz, void* dx, cons
   if (gy > 592) gy = 592;
   if (gy < 1) gy = 1;
   count_launch();
-  gn_bwd_apply_kernel<<<dim3(n, gy), 256, 0, STREAM(stream)>>>(
+  LECO_LAUNCH(gn_bwd_apply_kernel, dim3(n, gy), 256, 0, STREAM(stream), 
       BF(x), BF(dz), BFW(dx), reinterpret_cast<const float2*>(stats), reinterpret_cast<const float2*>(workspace),
       BF(gamma), BF(beta), hw, C, G, splits, silu);
   LECO_CHECK_CUDA(cudaGetLastError());
@@ -389,7 +409,7 @@ extern "C" int leco_layer_norm(const void* x, void* y, void* stats /*float2[M] o
   long long blocks = (M + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
   count_launch();
-  ln_fwd_kernel<<<(int)blocks, 256, 0, STREAM(stream)>>>(BF(x), BFW(y), reinterpret_cast<float2*>(stats), BF(gamma),
+  LECO_LAUNCH(ln_fwd_kernel, (int)blocks, 256, 0, STREAM(stream), BF(x), BFW(y), reinterpret_cast<float2*>(stats), BF(gamma),
                                                        BF(beta), M, C, eps);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -401,7 +421,7 @@ extern "C" int leco_layer_norm_bwd(const void* x, const void* dy, void* dx, cons
   long long blocks = (M + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
   count_launch();
-  ln_bwd_kernel<<<(int)blocks, 256, 0, STREAM(stream)>>>(BF(x), BF(dy), BFW(dx), reinterpret_cast<const float2*>(stats),
+  LECO_LAUNCH(ln_bwd_kernel, (int)blocks, 256, 0, STREAM(stream), BF(x), BF(dy), BFW(dx), reinterpret_cast<const float2*>(stats),
                                                        BF(gamma), M, C);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;

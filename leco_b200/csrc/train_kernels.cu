@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256)
 tn_reduce_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __nv_bfloat16* __restrict__ B,
                  long long ldb, float* __restrict__ out, long long ldo, long long M, int N1, int N2, float scale,
                  int rows_per_split, int transpose_out) {
+  pdl_entry();
   __shared__ __align__(16) __nv_bfloat16 sA[TN_ROWS][TN_TILE_N1];
   __shared__ __align__(16) __nv_bfloat16 sB[TN_ROWS][64];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -87,6 +88,7 @@ template <typename TState>
 __global__ void adamw_flat_kernel(__nv_bfloat16* __restrict__ p, float* __restrict__ g, TState* __restrict__ m,
                                   TState* __restrict__ v, const uint8_t* __restrict__ mask,
                                   const float* __restrict__ hyper, long long n, int zero_grad) {
+  pdl_entry();
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], step = hyper[5],
               gs = hyper[6];
   const float bc1 = 1.0f - powf(b1, step), bc2 = 1.0f - powf(b2, step);
@@ -119,6 +121,7 @@ __global__ void adamw_flat_kernel(__nv_bfloat16* __restrict__ p, float* __restri
 __global__ void guided_step_kernel(const float* __restrict__ eps, const float* __restrict__ x,
                                    float* __restrict__ x_out, float* __restrict__ guided_out,
                                    const float* __restrict__ coef, long long half) {
+  pdl_entry();
   const float g = coef[0], cx = coef[1], ce = coef[2];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < half;
        i += (long long)gridDim.x * blockDim.x) {
@@ -133,6 +136,7 @@ __global__ void guided_step_kernel(const float* __restrict__ eps, const float* _
 __global__ void leco_loss_kernel(const float* __restrict__ t, const float* __restrict__ pp,
                                  const float* __restrict__ nn, const float* __restrict__ uu, float sgn_gs,
                                  float* __restrict__ loss, float* __restrict__ dt, long long numel) {
+  pdl_entry();
   __shared__ float red[32];
   float s = 0.f;
   const float inv = 1.0f / (float)numel;
@@ -156,11 +160,13 @@ __global__ void leco_loss_kernel(const float* __restrict__ t, const float* __res
 
 // fp32 -> bf16 / bf16 -> fp32 flat casts, and scaled fp32 fill (graph-friendly helpers)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  pdl_entry();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16(x[i]);
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
+  pdl_entry();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     y[i] = __bfloat162float(x[i]);
@@ -169,6 +175,7 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float*
 template <typename T>
 __global__ void axpby_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ out, float a, float b,
                              long long n) {
+  pdl_entry();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     out[i] = static_cast<T>(a * static_cast<float>(x[i]) + b * static_cast<float>(y[i]));
@@ -186,14 +193,18 @@ extern "C" int leco_tn_reduce(const void* a, int64_t lda, const void* b, int64_t
   LECO_REQUIRE(a && b && out && M > 0, "leco_tn_reduce: null / empty");
   LECO_REQUIRE(N1 % 8 == 0 && N2 % 8 == 0 && N2 <= 64 && lda % 8 == 0 && ldb % 8 == 0,
                "leco_tn_reduce: N1%%8, N2%%8, N2<=64, strides%%8 required (N1=%d N2=%d)", N1, N2);
-  int splits = (int)((M + 511) / 512);
-  if (splits > 64) splits = 64;
+  // enough blocks to fill the machine: (N1/128) column blocks x M splits of >= 64 rows
+  const int col_blocks = (N1 + TN_TILE_N1 - 1) / TN_TILE_N1;
+  int splits = (int)((M + 63) / 64);
+  const int want = (148 * 4 + col_blocks - 1) / col_blocks;
+  if (splits > want) splits = want;
+  if (splits < 1) splits = 1;
   int rows_per = (int)((M + splits - 1) / splits);
   rows_per = (rows_per + TN_ROWS - 1) / TN_ROWS * TN_ROWS;
   splits = (int)((M + rows_per - 1) / rows_per);
   dim3 grid((N1 + TN_TILE_N1 - 1) / TN_TILE_N1, splits);
   count_launch();
-  tn_reduce_kernel<<<grid, 256, 0, STREAM(stream)>>>(BF(a), lda, BF(b), ldb, out, ldo, M, N1, N2, scale, rows_per, transpose_out);
+  LECO_LAUNCH(tn_reduce_kernel, grid, 256, 0, STREAM(stream), BF(a), lda, BF(b), ldb, out, ldo, M, N1, N2, scale, rows_per, transpose_out);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -205,11 +216,11 @@ extern "C" int leco_adamw_flat(void* params_bf16, float* grads, void* exp_avg, v
   if (blocks > 148 * 8) blocks = 148 * 8;
   count_launch();
   if (state_is_fp32)
-    adamw_flat_kernel<float><<<(int)blocks, 256, 0, STREAM(stream)>>>(
+    LECO_LAUNCH(adamw_flat_kernel<float>, (int)blocks, 256, 0, STREAM(stream), 
         BFW(params_bf16), grads, reinterpret_cast<float*>(exp_avg), reinterpret_cast<float*>(exp_avg_sq),
         reinterpret_cast<const uint8_t*>(mask_u8), hyper_dev, n, zero_grad);
   else
-    adamw_flat_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, STREAM(stream)>>>(
+    LECO_LAUNCH(adamw_flat_kernel<__nv_bfloat16>, (int)blocks, 256, 0, STREAM(stream), 
         BFW(params_bf16), grads, BFW(exp_avg), BFW(exp_avg_sq), reinterpret_cast<const uint8_t*>(mask_u8),
         hyper_dev, n, zero_grad);
   LECO_CHECK_CUDA(cudaGetLastError());
@@ -222,7 +233,7 @@ extern "C" int leco_guided_step(const float* eps_pair, const float* x, float* x_
   long long blocks = (half_numel + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   count_launch();
-  guided_step_kernel<<<(int)blocks, 256, 0, STREAM(stream)>>>(eps_pair, x, x_out, guided_out, coef_dev, half_numel);
+  LECO_LAUNCH(guided_step_kernel, (int)blocks, 256, 0, STREAM(stream), eps_pair, x, x_out, guided_out, coef_dev, half_numel);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -231,7 +242,7 @@ extern "C" int leco_loss(const float* target, const float* positive, const float
                          float sign_times_guidance, float* loss_out, float* dtarget, int64_t numel, void* stream) {
   LECO_REQUIRE(target && positive && neutral && uncond && loss_out && numel > 0, "leco_loss: null / empty");
   count_launch();
-  leco_loss_kernel<<<1, 1024, 0, STREAM(stream)>>>(target, positive, neutral, uncond, sign_times_guidance, loss_out,
+  LECO_LAUNCH(leco_loss_kernel, 1, 1024, 0, STREAM(stream), target, positive, neutral, uncond, sign_times_guidance, loss_out,
                                                   dtarget, numel);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -242,7 +253,7 @@ extern "C" int leco_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* s
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   count_launch();
-  cast_f32_bf16_kernel<<<(int)blocks, 256, 0, STREAM(stream)>>>(x, BFW(y), n);
+  LECO_LAUNCH(cast_f32_bf16_kernel, (int)blocks, 256, 0, STREAM(stream), x, BFW(y), n);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -251,7 +262,7 @@ extern "C" int leco_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* s
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   count_launch();
-  cast_bf16_f32_kernel<<<(int)blocks, 256, 0, STREAM(stream)>>>(BF(x), y, n);
+  LECO_LAUNCH(cast_bf16_f32_kernel, (int)blocks, 256, 0, STREAM(stream), BF(x), y, n);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -263,11 +274,11 @@ extern "C" int leco_axpby(const void* x, const void* y, void* out, float a, floa
   if (blocks > 148 * 8) blocks = 148 * 8;
   count_launch();
   if (is_fp32)
-    axpby_kernel<float><<<(int)blocks, 256, 0, STREAM(stream)>>>(reinterpret_cast<const float*>(x),
+    LECO_LAUNCH(axpby_kernel<float>, (int)blocks, 256, 0, STREAM(stream), reinterpret_cast<const float*>(x),
                                                                 reinterpret_cast<const float*>(y),
                                                                 reinterpret_cast<float*>(out), a, b, n);
   else
-    axpby_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, STREAM(stream)>>>(BF(x), BF(y), BFW(out), a, b, n);
+    LECO_LAUNCH(axpby_kernel<__nv_bfloat16>, (int)blocks, 256, 0, STREAM(stream), BF(x), BF(y), BFW(out), a, b, n);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -17,6 +17,19 @@ BF16 = torch.bfloat16
 GEMM_2CTA = int(__import__('os').environ.get('LECO_GEMM_2CTA', '0'))  # 1: cta_group::2 kernel for plain/conv GEMMs
 
 
+SPLIT_K = int(__import__('os').environ.get('LECO_SPLIT_K', '1'))
+_SPLITK_WS = {}
+
+
+def _splitk_workspace(device) -> torch.Tensor:
+    """Zeroed fp32 scratch for split-K partial sums (the finalize kernel leaves it zeroed).  One per device:
+    GEMMs on a stream are ordered, so it can be shared."""
+    ws = _SPLITK_WS.get(device)
+    if ws is None:
+        ws = _SPLITK_WS[device] = torch.zeros(8 << 20, device=device, dtype=torch.float32)  # 32 MiB
+    return ws
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -90,6 +103,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
     g.out_fp32 = 1 if out_fp32 else 0
     g.block_n = block_n
     g.cta_pair = GEMM_2CTA if cta_pair is None else int(cta_pair)
+    if SPLIT_K and not g.cta_pair:
+        ws = _splitk_workspace(a.device)
+        g.splitk_ws, g.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4
     capi.check(lib.leco_gemm_bf16(ctypes.byref(g), _stream()), "leco_gemm_bf16")
     return out
 

@@ -188,6 +188,11 @@ CASES = [
     ("conv_24x40_rect", case_conv, dict(n=1, h=24, w=40, cin=64, cout=64)),
     ("conv_lora16", case_conv, dict(n=2, h=32, w=32, cin=128, cout=128, lora=16)),
     ("conv_plain", case_conv, dict(n=2, h=32, w=32, cin=64, cout=64, bias=False, rowbias=False, residual=False)),
+    ("splitk_conv16_1280", case_conv, dict(n=4, h=16, w=16, cin=1280, cout=1280)),
+    ("splitk_conv8_lora", case_conv, dict(n=4, h=8, w=8, cin=1280, cout=1280, lora=16)),
+    ("splitk_linear_m308", case_matrix, dict(M=308, N=2560, K=1024, bias=True)),
+    ("splitk_linear_m256_res", case_matrix, dict(M=256, N=1280, K=5120, bias=True, residual=True, lora=16)),
+    ("perf_conv_8_1280", case_perf, dict(M=0, N=1280, K=0, conv=(4, 8, 8, 1280))),
     ("2cta_basic_bn128", case_matrix, dict(M=512, N=256, K=256, block_n=128, cta_pair=1)),
     ("2cta_basic_bn256", case_matrix, dict(M=512, N=512, K=512, block_n=256, cta_pair=1)),
     ("2cta_basic_bn160", case_matrix, dict(M=256, N=320, K=256, block_n=160, cta_pair=1)),
