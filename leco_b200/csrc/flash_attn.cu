@@ -9,7 +9,10 @@
 //   O    = O*alpha + PV_j   folded in registers by the softmax warps one tile late, so the tensor pipe
 //                            never waits for a TMEM rescale.
 // Nothing of S or P ever touches HBM: algorithmic traffic is Q, K, V, O once (K/V re-reads hit L2).
-// Roles: warp 0 lane 0 TMA, warp 1 lane 0 MMA issue, warp 2 TMEM alloc, warps 4-7 softmax (1 row/thread).
+// Roles: warp 0 lane 0 TMA, warp 1 lane 0 MMA issue, warp 2 TMEM alloc, warps 4-7 and 8-11 = two softmax
+// warpgroups: thread (wg, row) owns keys [64*wg, 64*wg+64) of S row `row` and output columns [32*wg, 32*wg+32);
+// only the running row max crosses warpgroups (one smem exchange + named barrier per tile), the two partial
+// row sums are added once at the end.  exp2 is the MUFU-bound part: splitting the keys halves it per thread.
 //
 // V operand: v_mode 0 = V tile [keys, d] used directly as an MN-major B operand;
 //            v_mode 1 = a pre-transposed V^T [d, keys] (K-major B operand, like the GEMM kernel).
@@ -24,9 +27,9 @@ constexpr int FA_KS = 3, FA_VS = 3;                       // K / V ring depth
 constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;              // 16 KiB
 constexpr int FA_KV_BYTES = FA_BN * FA_D * 2;             // 16 KiB
 constexpr int FA_P_BYTES = FA_BM * FA_BN * 2;             // 32 KiB (two 64-key chunks)
-constexpr int FA_SMEM = FA_Q_BYTES + (FA_KS + FA_VS) * FA_KV_BYTES + 2 * FA_P_BYTES + 1024 + 512;
+constexpr int FA_SMEM = FA_Q_BYTES + (FA_KS + FA_VS) * FA_KV_BYTES + 2 * FA_P_BYTES + 1024 + 512 + (2 * 2 + 2) * 128 * 4;
 constexpr int FA_TMEM_COLS = 512;                         // S: 2 x 128, PV: 2 x 64
-constexpr int FA_THREADS = 256;
+constexpr int FA_THREADS = 384;                          // 4 control warps + 2 softmax warpgroups
 
 struct FlashParams {
   CUtensorMap tm_q, tm_k, tm_v;
@@ -50,6 +53,12 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t n, bool b_mn_major)
   return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __grid_constant__ FlashParams p) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
@@ -71,6 +80,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
   uint64_t* pv_full = p_empty + 2;         // [2]
   uint64_t* pv_empty = pv_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_empty + 2);
+  float* mx_buf = reinterpret_cast<float*>(tmem_slot + 2);  // [2 tiles][2 warpgroups][128 rows] maxima + [2][128] sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
@@ -93,11 +103,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&s_empty[i], 8);
+      mbar_init(&p_full[i], 8);
       mbar_init(&p_empty[i], 1);
       mbar_init(&pv_full[i], 1);
-      mbar_init(&pv_empty[i], 4);
+      mbar_init(&pv_empty[i], 8);
     }
     fence_barrier_init();
   }
@@ -174,27 +184,25 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
       umma_commit(&p_empty[pb]);
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ softmax + output (1 row / thread)
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
+    // ------------------------------------------------------------------ softmax + output
+    const int wg = (warp - 4) >> 2;          // 0: keys 0-63 / out cols 0-31, 1: keys 64-127 / out cols 32-63
+    const int q = warp & 3;                  // TMEM lane quadrant
+    const int r = q * 32 + lane;             // row of the query tile
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
-    float o[FA_D];
+    float m_run = -INFINITY, l_part = 0.f, alpha_prev = 1.f;
+    float o[FA_D / 2];
 #pragma unroll
-    for (int i = 0; i < FA_D; ++i) o[i] = 0.f;
+    for (int i = 0; i < FA_D / 2; ++i) o[i] = 0.f;
 
-    auto fold_pv = [&](int j, float alpha) {  // o = o*alpha + PV_j
+    auto fold_pv = [&](int j, float alpha) {  // o = o*alpha + PV_j[:, 32*wg : 32*wg+32]
       const int pb = j & 1;
       mbar_wait(&pv_full[pb], (j >> 1) & 1);
       tc_fence_after();
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(tmem_pv + lane_off + pb * FA_D + wg * 32, raw);
+      tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < FA_D / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(tmem_pv + lane_off + pb * FA_D + c * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(raw[i]));
-      }
+      for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(raw[i]));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pv_empty[pb]);
@@ -202,42 +210,44 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
 
     for (int j = 0; j < n_tiles; ++j) {
       const int sb = j & 1;
-      const int kv0 = j * FA_BN;
-      const bool ragged = kv0 + FA_BN > p.skv;
+      const int kv0 = j * FA_BN + wg * 64;     // first key of this thread's half
+      const bool ragged = kv0 + 64 > p.skv;
       mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
-      // pass 1: row max
-      float mx = m_run;
+      const uint32_t s_addr = tmem_s + lane_off + sb * FA_BN + wg * 64;
+      // pass 1: max over this half, then exchange with the other warpgroup
+      float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < FA_BN / 32; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t raw[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_off + sb * FA_BN + c * 32, raw);
+        tmem_ld_32x32b_x32(s_addr + c * 32, raw);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(raw[i]);
-          if (ragged && kv0 + c * 32 + i >= p.skv) s = -INFINITY;
-          mx = fmaxf(mx, s);
+          float sv = __uint_as_float(raw[i]);
+          if (ragged && kv0 + c * 32 + i >= p.skv) sv = -INFINITY;
+          mx = fmaxf(mx, sv);
         }
       }
-      const float m_new = mx;
-      const float alpha = exp2f((m_run - m_new) * p.scale_log2);  // first tile: exp2(-inf) = 0
+      mx_buf[(sb * 2 + wg) * 128 + r] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the two softmax warpgroups only
+      const float m_new = fmaxf(m_run, fmaxf(mx, mx_buf[(sb * 2 + (wg ^ 1)) * 128 + r]));
+      const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);  // first tile: ex2(-inf) = 0
       const float mb = m_new * p.scale_log2;
-      // pass 2: p = exp2(s*c - m*c); write P (bf16) into the swizzled A-operand tile
+      // pass 2: p = 2^(s*c - m*c) -> bf16 -> swizzled A-operand tile (this half = 64 keys = one 128-byte row)
       mbar_wait(&p_empty[sb], ((j >> 1) & 1) ^ 1);
-      uint8_t* prow = sP + sb * FA_P_BYTES + r * 128;
+      uint8_t* prow = sP + sb * FA_P_BYTES + wg * (FA_P_BYTES / 2) + r * 128;
       float rowsum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < FA_BN / 32; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t raw[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_off + sb * FA_BN + c * 32, raw);
+        tmem_ld_32x32b_x32(s_addr + c * 32, raw);
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float s0 = __uint_as_float(raw[i]), s1 = __uint_as_float(raw[i + 1]);
-          float p0 = exp2f(fmaf(s0, p.scale_log2, -mb));
-          float p1 = exp2f(fmaf(s1, p.scale_log2, -mb));
+          float p0 = ex2_approx(fmaf(__uint_as_float(raw[i]), p.scale_log2, -mb));
+          float p1 = ex2_approx(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2, -mb));
           if (ragged) {
             if (kv0 + c * 32 + i >= p.skv) p0 = 0.f;
             if (kv0 + c * 32 + i + 1 >= p.skv) p1 = 0.f;
@@ -245,12 +255,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
           rowsum += p0 + p1;
           pk[i >> 1] = pack_bf16(p0, p1);
         }
-        // 32 keys = 64 B = four 16-byte chunks; key chunk index within the 64-key half: (c&1)*4 + t
-        uint8_t* half = prow + (c >> 1) * (FA_P_BYTES / 2);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const int chunk = (c & 1) * 4 + t;
-          *reinterpret_cast<uint4*>(half + ((chunk ^ (r & 7)) << 4)) =
+          const int chunk = c * 4 + t;  // 16-byte chunk (8 keys) inside the 128-byte row
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) =
               make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
         }
       }
@@ -261,19 +269,23 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
         mbar_arrive(&s_empty[sb]);
         mbar_arrive(&p_full[sb]);
       }
-      l_run = l_run * alpha + rowsum;
+      l_part = l_part * alpha + rowsum;
       m_run = m_new;
       if (j > 0) fold_pv(j - 1, alpha_prev);
       alpha_prev = alpha;
     }
     fold_pv(n_tiles - 1, alpha_prev);
+    // total row sum = sum of the two warpgroups' partial sums (same running max in both)
+    mx_buf[512 + wg * 128 + r] = l_part;  // separate slots: the max slots may still be read by the partner
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l_tot = l_part + mx_buf[512 + (wg ^ 1) * 128 + r];
     const int row = qt * FA_BM + r;
     if (row < p.sq) {
-      const float inv = 1.0f / l_run;
-      __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.sq + row) * p.ld_out + head * p.d;
+      const float inv = 1.0f / l_tot;
+      __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.sq + row) * p.ld_out + head * p.d + wg * 32;
 #pragma unroll
-      for (int c8 = 0; c8 < FA_D / 8; ++c8) {
-        if (c8 * 8 < p.d) {
+      for (int c8 = 0; c8 < 4; ++c8) {
+        if (wg * 32 + c8 * 8 < p.d) {
           uint4 v;
           v.x = pack_bf16(o[c8 * 8 + 0] * inv, o[c8 * 8 + 1] * inv);
           v.y = pack_bf16(o[c8 * 8 + 2] * inv, o[c8 * 8 + 3] * inv);

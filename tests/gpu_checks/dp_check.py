@@ -1,0 +1,81 @@
+"""Data-parallel parity on real GPUs: an R-GPU iteration at global batch B must equal the
+1-GPU iteration at batch B on the same seeds (loss to fp32-reduction tolerance, LoRA weights after the
+step within bf16 rounding).  Launch:
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+      tests/gpu_checks/dp_check.py
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+
+def build(arch, dev, rank, world, batch, graphs):
+    import torch
+    from leco_b200.lora import LoRANetwork
+    from leco_b200.scheduler import DDIMScheduler
+    from leco_b200.synthetic import build_engine, prompt_embedding
+    from leco_b200.trainer import LecoTrainer, PromptPair
+    from leco_b200.unet import SPECS
+    unet = build_engine(arch, dev, seed=0)
+    torch.manual_seed(1234)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = LoRANetwork(unet, rank=4, multiplier=1.0, alpha=1.0)
+    net.to(dev, dtype=torch.bfloat16)
+    D = SPECS[arch].cross_attention_dim
+    emb = {p: prompt_embedding(p, D) for p in ("van gogh", "", "painting")}
+    pair = PromptPair(target=emb["van gogh"], positive=emb["van gogh"], unconditional=emb[""], neutral=emb["painting"],
+                      guidance_scale=1.0, resolution=128, batch_size=batch, action="erase")
+    tr = LecoTrainer(unet, net, DDIMScheduler("v_prediction"), [pair], lr=1e-3, max_denoising_steps=8, device=dev,
+                     rank=rank, world_size=world, use_cuda_graphs=graphs, state_fp32=True)
+    return tr, net
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    arch, batch, iters = "tiny21", 4, 3
+    tr, net = build(arch, dev, rank, world, batch, graphs=True)
+    torch.manual_seed(7)
+    losses = [tr.iteration().item() for _ in range(iters)]
+    flat = net.flat.params.float().clone()
+    # all ranks must hold identical weights after identical updates
+    ref = flat.clone()
+    dist.broadcast(ref, 0)
+    same = bool(torch.equal(ref, flat))
+    ok_all = torch.tensor([int(same)], device=dev)
+    dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+    result = None
+    if rank == 0:
+        tr1, net1 = build(arch, dev, 0, 1, batch, graphs=False)
+        torch.manual_seed(7)
+        losses1 = [tr1.iteration().item() for _ in range(iters)]
+        flat1 = net1.flat.params.float()
+        mask = net1.flat.mask.bool()
+        dw = (flat - flat1)[mask]
+        ulp = flat1[mask].abs().clamp_min(1e-4) * 2.0 ** -7
+        result = {"world": world, "losses_dp": losses, "losses_single": losses1,
+                  "loss_rel_err": max(abs(a - b) / abs(b) for a, b in zip(losses, losses1)),
+                  "weights_max_ulps": float((dw.abs() / ulp).max()), "weights_frac_differing": float((dw != 0).float().mean()),
+                  "ranks_identical": bool(ok_all.item())}
+        result["ok"] = result["loss_rel_err"] < 2e-3 and result["ranks_identical"] and result["weights_max_ulps"] <= 4.0
+        print("DP_RESULT " + json.dumps(result))
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(result, open(os.path.join(ROOT, "gpurun_out", f"dp_check_w{world}.json"), "w"), indent=1)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
