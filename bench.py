@@ -94,14 +94,33 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference arm
+def _pick_threads(cores: int) -> int:
+    """Host thread count for the CPU arm: all cores unless a quick conv probe says oversubscription hurts
+    (it does on 100+-thread boxes)."""
+    import torch
+    best, best_t = cores, None
+    x = torch.randn(2, 320, 64, 64)
+    w = torch.randn(320, 320, 3, 3)
+    for n in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
+        torch.set_num_threads(n)
+        torch.nn.functional.conv2d(x, w, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.nn.functional.conv2d(x, w, padding=1)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < 0.9 * best_t:
+            best, best_t = n, dt
+    return best
+
+
 def cpu_reference_forward_seconds(n_fwd: int, warm: int, b: int = 1):
-    """Times `predict_noise` of the oracle port (LECO arithmetic + restated UNet, fp32, all host
-    threads) for a CFG batch of 2*b samples at the bench architecture/resolution."""
+    """Times `predict_noise` of the oracle port (LECO arithmetic + restated UNet, fp32, host threads) for a CFG
+    batch of 2*b samples at the bench architecture/resolution.  n_fwd is capped so a run stays within minutes."""
     import torch
     from oracle import leco_ref
     from oracle.sched_ref import create_noise_scheduler
     from oracle.unet_ref import CONFIGS, build_unet
-    cores = os.cpu_count() or 1
+    cores = _pick_threads(os.cpu_count() or 1)
     torch.set_num_threads(cores)
     unet = build_unet(ARCH)
     sched = create_noise_scheduler("ddim", "v_prediction")
@@ -132,10 +151,11 @@ def run_reference(args):
     if rank != 0:
         return
     k = args.k
-    sec, cores = cpu_reference_forward_seconds(max(1, args.steps), max(0, min(args.warmup, 1)))
+    n_timed = max(1, min(args.steps, 2))  # one CFG forward is ~1 min of CPU: bound the run to a few minutes
+    sec, cores = cpu_reference_forward_seconds(n_timed, 0)
     b_global = B_PER_GPU * args.gpus
     val = cpu_latents_per_s(sec, B_PER_GPU, k)  # CPU path does not shard: whole-job value on the host
-    sample = (f"{max(1, args.steps)} timed predict_noise call(s) (1 CFG UNet forward, 2 samples, fp32) of the same "
+    sample = (f"{n_timed} timed predict_noise call(s) (1 CFG UNet forward, 2 samples, fp32) of the same "
               f"arch/resolution = {sec:.1f} s each; iteration extrapolated as 2B(k+4) fwd + 2B*1.23 fwd, B={B_PER_GPU}, k={k}")
     line = {"impl": "reference", "metric": "leco_train_latents_per_sec", "value": val, "unit": "latents/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * B_PER_GPU / val,

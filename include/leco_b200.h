@@ -67,6 +67,16 @@ typedef struct leco_gemm_args {
   int32_t cta_pair; /* 1 = 2-CTA (cta_group::2) kernel: 256 x block_n tiles per CTA pair */
   void* splitk_ws;  /* optional ZEROED fp32 workspace (left zeroed): enables split-K for small-M, long-K problems */
   int64_t splitk_ws_bytes;
+  /* in-kernel LoRA (alternative to a2/b2): fl_ad = stacked lora_down [fl_kl][K] (row stride fl_ld_ad), fl_bup =
+   * stacked lora_up [N][fl_kl]; D += fl_scale * (A.fl_ad^T).fl_bup^T computed inside the same kernel;
+   * fl_t_out (optional) receives fl_scale * A.fl_ad^T as bf16 [M][fl_ld_t] */
+  const void* fl_ad;
+  const void* fl_bup;
+  int32_t fl_kl, fl_rank;
+  int64_t fl_ld_ad, fl_ld_bup;
+  float fl_scale;
+  void* fl_t_out;
+  int64_t fl_ld_t;
 } leco_gemm_args;
 int leco_gemm_bf16(const leco_gemm_args* args, void* stream);
 

@@ -36,6 +36,9 @@ class GemmArgs(Structure):
         ("epilogue", c_int32), ("alpha", c_float), ("out_fp32", c_int32), ("block_n", c_int32),
         ("b_rows", c_int32), ("cta_pair", c_int32),
         ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_int64),
+        ("fl_ad", c_void_p), ("fl_bup", c_void_p), ("fl_kl", c_int32), ("fl_rank", c_int32),
+        ("fl_ld_ad", c_int64), ("fl_ld_bup", c_int64), ("fl_scale", c_float), ("fl_t_out", c_void_p),
+        ("fl_ld_t", c_int64),
     ]
 
 

@@ -34,16 +34,28 @@ struct GemmParams {
   int k_splits;
   float* ws;
   long long ldws;
+  // in-kernel LoRA (lora.py:102-106 in ONE kernel): the stacked lora_down rows `Ad` ride along as fl_kl extra
+  // B rows, so accumulator columns [BN, BN+fl_kl) hold T_raw = x.Ad^T; the epilogue adds fl_scale*T_raw.Bup^T
+  CUtensorMap tm_ad;
+  int fl_kl;                      // 0 = off; else 16/32/48/64 padded stacked rank
+  int fl_rank;                    // real stacked rank (columns >= fl_rank of T are zero)
+  float fl_scale;                 // alpha/rank * multiplier
+  const __nv_bfloat16* fl_bup;    // [N][fl_ld_bup] stacked lora_up (block structure)
+  long long fl_ld_bup;
+  __nv_bfloat16* fl_t_out;        // optional [M][fl_ld_t]: fl_scale*T (saved for the backward)
+  long long fl_ld_t;
 };
+constexpr int FL_MAX_KL = 64;
 
-template <int BN>
+template <int BN, bool FL = false>
 struct GemmCfg {
-  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_ROWS = BN + (FL ? FL_MAX_KL : 0);  // W rows (+ room for the stacked lora_down rows)
+  static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 160 ? 5 : 6);
+  static constexpr int STAGES = FL ? (BN >= 160 ? 4 : (BN >= 128 ? 5 : 6)) : ((BN >= 256) ? 4 : (BN >= 160 ? 5 : 6));
   // accumulator stage stride in TMEM columns (power of two so a stage never straddles an
   // alignment boundary): 64 / 128 / 256
-  static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
+  static constexpr int ACC_STRIDE = FL ? 256 : ((BN <= 64) ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -88,6 +100,38 @@ __device__ __forceinline__ void epi_add_bf16(float (&v)[32], const __nv_bfloat16
   }
 }
 
+// v[j] += fl_scale * sum_k T_raw[k] * Bup[n0 + j][k] for the 32 output columns of one chunk.  T_raw is re-read
+// from TMEM in groups of 8 columns (cheap) so no large register array is live.
+__device__ __forceinline__ void epi_lora_add(float (&v)[32], const GemmParams& p, uint32_t t_addr, long long ncol0,
+                                             int nvalid) {
+  const int groups = (p.fl_rank + 7) >> 3;
+  for (int g = 0; g < groups; ++g) {
+    uint32_t traw[8];
+    tmem_ld_32x32b_x8(t_addr + g * 8, traw);
+    tmem_ld_wait();
+    float t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = __uint_as_float(traw[k]) * p.fl_scale;
+    const __nv_bfloat16* bp = p.fl_bup + ncol0 * p.fl_ld_bup + g * 8;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < nvalid) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(bp + j * p.fl_ld_bup));
+        float a = v[j];
+        a = fmaf(t[0], bf16_lo(q.x), a);
+        a = fmaf(t[1], bf16_hi(q.x), a);
+        a = fmaf(t[2], bf16_lo(q.y), a);
+        a = fmaf(t[3], bf16_hi(q.y), a);
+        a = fmaf(t[4], bf16_lo(q.z), a);
+        a = fmaf(t[5], bf16_hi(q.z), a);
+        a = fmaf(t[6], bf16_lo(q.w), a);
+        a = fmaf(t[7], bf16_hi(q.w), a);
+        v[j] = a;
+      }
+    }
+  }
+}
+
 // One output tile: TMEM accumulator (this thread's row r of lane quadrant q) -> epilogue -> global.
 // `trow` = TMEM address of the row's first accumulator column; (mt, nt, b0, b1) identify the tile.
 template <int BN>
@@ -113,6 +157,21 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
     m = static_cast<long long>(img_n0 * p.ch + img_h0) * p.cw + r;
   }
   const long long boff = b0 * p.d_bs0 + b1 * p.d_bs1;
+  if (p.fl_kl && p.fl_t_out && nt == 0) {  // save fl_scale*T for the backward (dB = dY^T T)
+    for (int g = 0; g < p.fl_kl / 8; ++g) {
+      uint32_t traw[8];
+      tmem_ld_32x32b_x8(trow + BN + g * 8, traw);
+      tmem_ld_wait();
+      if (row_ok) {
+        uint4 o;
+        o.x = pack_bf16(__uint_as_float(traw[0]) * p.fl_scale, __uint_as_float(traw[1]) * p.fl_scale);
+        o.y = pack_bf16(__uint_as_float(traw[2]) * p.fl_scale, __uint_as_float(traw[3]) * p.fl_scale);
+        o.z = pack_bf16(__uint_as_float(traw[4]) * p.fl_scale, __uint_as_float(traw[5]) * p.fl_scale);
+        o.w = pack_bf16(__uint_as_float(traw[6]) * p.fl_scale, __uint_as_float(traw[7]) * p.fl_scale);
+        *reinterpret_cast<uint4*>(p.fl_t_out + m * p.fl_ld_t + g * 8) = o;
+      }
+    }
+  }
 
   if (p.k_splits > 1) {
     // partial accumulator of one K-slice -> fp32 workspace (bias / residual are applied by the finalize kernel)
@@ -124,13 +183,16 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       const int col0 = n0 + c * 32;
       const int nvalid = p.N - col0;
       if (row_ok && nvalid > 0) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+        if (p.fl_kl) epi_lora_add(v, p, trow + BN, col0, nvalid);  // linear in T: each K-slice adds its part
         float* dst = p.ws + m * p.ldws + col0;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           if (g * 4 < nvalid)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
-                         "f"(__uint_as_float(raw[g * 4 + 0]) * p.alpha), "f"(__uint_as_float(raw[g * 4 + 1]) * p.alpha),
-                         "f"(__uint_as_float(raw[g * 4 + 2]) * p.alpha), "f"(__uint_as_float(raw[g * 4 + 3]) * p.alpha)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4), "f"(v[g * 4 + 0]),
+                         "f"(v[g * 4 + 1]), "f"(v[g * 4 + 2]), "f"(v[g * 4 + 3])
                          : "memory");
         }
       }
@@ -147,6 +209,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+        if (p.fl_kl) epi_lora_add(v, p, trow + BN, col0, nvalid);
         if (p.bias) epi_add_bf16(v, p.bias + col0, nvalid);
         if (p.rowbias)
           epi_add_bf16(v, p.rowbias + (m / p.rows_per_group) * p.ld_rowbias + col0, nvalid);
@@ -173,6 +236,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
         for (int j = 0; j < 32; ++j) {
           h[j] = __uint_as_float(rh[j]) * p.alpha;
           g[j] = __uint_as_float(rg[j]) * p.alpha;
+        }
+        if (p.fl_kl) {
+          epi_lora_add(h, p, trow + BN, ocol0, 32);
+          epi_lora_add(g, p, trow + BN, p.N / 2 + ocol0, 32);
         }
         if (p.bias) {
           epi_add_bf16(h, p.bias + ocol0, 32);

@@ -24,10 +24,10 @@
 
 namespace leco {
 
-template <int BN>
+template <int BN, bool FL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, FL>;
   constexpr int STAGES = Cfg::STAGES;
   pdl_launch_dependents();  // the next kernel may start its prologue while this one runs
   extern __shared__ uint8_t smem_raw[];
@@ -49,6 +49,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_a);
     tma_prefetch_desc(&p.tm_b);
+    if (FL) tma_prefetch_desc(&p.tm_ad);
     if (p.has_seg2) {
       tma_prefetch_desc(&p.tm_a2);
       tma_prefetch_desc(&p.tm_b2);
@@ -103,7 +104,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
         uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
         if (c < p.chunks1) {
-          mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes + Cfg::B_STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes + BN * BLOCK_K * 2 + (FL ? p.fl_kl * BLOCK_K * 2 : 0));
+          if (FL)  // stacked lora_down rows for this K chunk land right behind the W rows of the B tile
+            tma_load_4d(sb + BN * BLOCK_K * 2, &p.tm_ad, &full_bar[stage], c * BLOCK_K, 0, 0, 0);
           if (p.mode == 0) {
             tma_load_4d(sa, &p.tm_a, &full_bar[stage], c * BLOCK_K, m0, b0, b1);
           } else {
@@ -121,7 +124,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             tma_load_4d(sb, &p.tm_b, &full_bar[stage], c * BLOCK_K, n0, b0, b1);
           }
         } else {
-          mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + BN * BLOCK_K * 2);
           tma_load_4d(sa, &p.tm_a2, &full_bar[stage], 0, m0, 0, 0);
           if (p.epilogue == 1) {
             tma_load_4d(sb, &p.tm_b2, &full_bar[stage], 0, nt * (BN / 2), 0, 0);
@@ -139,7 +142,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     }
   } else if (warp == 1 && lane == 0) {
     // -------------------------------------------------------------- MMA issuer
-    const uint32_t idesc = umma_idesc_bf16_m128(BN);
+    const uint32_t idesc = umma_idesc_bf16_m128(BN + (FL ? p.fl_kl : 0));  // FL: extra columns = x.Ad^T
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -255,14 +258,15 @@ static int pick_block_n(const leco_gemm_args& a, int tiles_m, int batches, int n
   for (int i = 0; i < 4; ++i) {
     const int bn = cand[i];
     if (a.block_n && a.block_n != bn) continue;
+    if (a.fl_ad && bn == 256) continue;  // BN + stacked rank must fit one UMMA (N <= 256)
     const int tn = (a.N + bn - 1) / bn;
     const double util_n = double(a.N) / double(tn * bn);  // ragged last tile wastes MMA
     const long long tiles = 1LL * tiles_m * tn * batches;
     int sp = 1;
-    if (max_split > 1 && tiles * 2 <= nsm) {
+    if (max_split > 1 && tiles * 2 <= nsm && chunks >= 36) {  // only long-K problems repay the finalize pass
       sp = (int)(nsm / tiles);
       if (sp > max_split) sp = max_split;
-      while (sp > 1 && chunks / sp < 4) --sp;
+      while (sp > 1 && chunks / sp < 8) --sp;
     }
     const long long ctas = tiles * sp;
     const long long waves = (ctas + nsm - 1) / nsm;
@@ -277,16 +281,16 @@ static int pick_block_n(const leco_gemm_args& a, int tiles_m, int batches, int n
   return best_bn;
 }
 
-template <int BN>
+template <int BN, bool FL>
 static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, FL>;
   static bool attr_set = false;
   if (!attr_set) {
-    LECO_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>,
+    LECO_CHECK_CUDA(cudaFuncSetAttribute((gemm_tcgen05_kernel<BN, FL>),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  LECO_LAUNCH(gemm_tcgen05_kernel<BN>, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, p);
+  LECO_LAUNCH((gemm_tcgen05_kernel<BN, FL>), grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, p);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -356,7 +360,7 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
 
   const int nsm = sm_count();
   const bool splitk_ok = a->splitk_ws && !a->cta_pair && !a->out_fp32 && a->epilogue == 0 && batch0 * batch1 == 1 &&
-                         (size_t)a->M * a->N * 4 <= (size_t)a->splitk_ws_bytes && a->N % 4 == 0;
+                         (size_t)a->M * a->N * 4 <= (size_t)a->splitk_ws_bytes && a->N % 4 == 0 && !a->fl_t_out;
   int k_split = 1;
   const int bn = pick_block_n(*a, p.tiles_m, batch0 * batch1, nsm, p.chunks1, splitk_ok ? 8 : 1, &k_split);
   LECO_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "leco_gemm_bf16: unsupported block_n %d", bn);
@@ -383,6 +387,26 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
     const uint64_t str_b[3] = {(uint64_t)a->ldb2 * 2, (uint64_t)a->ldb2 * a->N * 2, (uint64_t)a->ldb2 * a->N * 2};
     const uint32_t box_b2[4] = {BLOCK_K, (uint32_t)((a->epilogue == 1 || a->cta_pair) ? bn / 2 : bn), 1, 1};
     if (make_tmap_bf16_4d(&p.tm_b2, a->b2, dims_b, str_b, box_b2)) return -3;
+  }
+  if (a->fl_ad) {
+    LECO_REQUIRE(a->fl_bup && a->fl_kl >= 16 && a->fl_kl <= FL_MAX_KL && a->fl_kl % 16 == 0 && a->fl_rank >= 1 &&
+                     a->fl_rank <= a->fl_kl,
+                 "leco_gemm_bf16: fused LoRA needs kl in {16..64} and 1 <= rank <= kl (kl=%d rank=%d)", a->fl_kl, a->fl_rank);
+    LECO_REQUIRE(!a->a2 && !a->cta_pair && !a->out_fp32 && batch0 * batch1 == 1 && a->fl_ld_ad % 8 == 0 &&
+                     a->fl_ld_bup % 8 == 0,
+                 "leco_gemm_bf16: fused LoRA excludes the T segment / 2-CTA / fp32 out / batching");
+    const uint64_t dims[4] = {(uint64_t)a->K, (uint64_t)a->fl_kl, 1, 1};
+    const uint64_t str[3] = {(uint64_t)a->fl_ld_ad * 2, (uint64_t)a->fl_ld_ad * a->fl_kl * 2, (uint64_t)a->fl_ld_ad * a->fl_kl * 2};
+    const uint32_t box[4] = {BLOCK_K, (uint32_t)a->fl_kl, 1, 1};
+    if (make_tmap_bf16_4d(&p.tm_ad, a->fl_ad, dims, str, box)) return -3;
+    p.fl_kl = a->fl_kl;
+    p.fl_rank = a->fl_rank;
+    p.fl_scale = a->fl_scale;
+    p.fl_bup = reinterpret_cast<const __nv_bfloat16*>(a->fl_bup);
+    p.fl_ld_bup = a->fl_ld_bup;
+    p.fl_t_out = reinterpret_cast<__nv_bfloat16*>(a->fl_t_out);
+    p.fl_ld_t = a->fl_ld_t;
+    if (a->fl_t_out) LECO_REQUIRE(a->fl_ld_t % 8 == 0, "leco_gemm_bf16: fl_ld_t must be a multiple of 8");
   }
   p.d = a->d;
   p.ldd = a->ldd;
@@ -414,11 +438,19 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
   const int grid = (int)(total_tiles < nsm ? total_tiles : nsm);
   count_launch();
   int rc;
-  switch (bn) {
-    case 64: rc = launch_gemm<64>(p, grid, stream); break;
-    case 128: rc = launch_gemm<128>(p, grid, stream); break;
-    case 160: rc = launch_gemm<160>(p, grid, stream); break;
-    default: rc = launch_gemm<256>(p, grid, stream); break;
+  if (p.fl_kl) {
+    switch (bn) {
+      case 64: rc = launch_gemm<64, true>(p, grid, stream); break;
+      case 128: rc = launch_gemm<128, true>(p, grid, stream); break;
+      default: rc = launch_gemm<160, true>(p, grid, stream); break;
+    }
+  } else {
+    switch (bn) {
+      case 64: rc = launch_gemm<64, false>(p, grid, stream); break;
+      case 128: rc = launch_gemm<128, false>(p, grid, stream); break;
+      case 160: rc = launch_gemm<160, false>(p, grid, stream); break;
+      default: rc = launch_gemm<256, false>(p, grid, stream); break;
+    }
   }
   if (rc == 0 && p.k_splits > 1) rc = launch_splitk_finalize(p, stream);
   return rc;

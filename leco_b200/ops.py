@@ -53,12 +53,16 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
          residual: Optional[torch.Tensor] = None,
          lora_t: Optional[torch.Tensor] = None, lora_up: Optional[torch.Tensor] = None,
          geglu: bool = False, alpha: float = 1.0, out_fp32: bool = False,
-         conv_nhw: Optional[tuple] = None, block_n: int = 0, cta_pair: Optional[int] = None) -> torch.Tensor:
+         conv_nhw: Optional[tuple] = None, block_n: int = 0, cta_pair: Optional[int] = None,
+         fl_ad: Optional[torch.Tensor] = None, fl_bup: Optional[torch.Tensor] = None, fl_scale: float = 1.0,
+         fl_rank: int = 0, fl_t_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = epi(alpha * (a @ b.T + lora_t @ lora_up.T)).
 
     a: [M,K] bf16 (row stride free, inner stride 1), or with conv_nhw=(n,h,w) a contiguous NHWC
        image [n*h*w, C] convolved 3x3/s1/p1 with b = [N, 9*C] (k = tap*C + c).
     b: [N,K] bf16 K-major.  lora_t: [M,K2], lora_up: [N,K2] (K2 in 16..64, multiple of 16).
+    In-kernel LoRA (instead of lora_t/lora_up): fl_ad [Kl,K] stacked lora_down, fl_bup [N,Kl] stacked lora_up:
+    out += fl_scale * (a @ fl_ad.T) @ fl_bup.T inside the same kernel; fl_t_out [M,Kl] receives fl_scale*a@fl_ad.T.
     """
     lib = capi.load()
     _req_bf16(a, "a"), _req_bf16(b, "b")
@@ -103,6 +107,17 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
     g.out_fp32 = 1 if out_fp32 else 0
     g.block_n = block_n
     g.cta_pair = GEMM_2CTA if cta_pair is None else int(cta_pair)
+    if fl_ad is not None:
+        _req_bf16(fl_ad, "fl_ad"), _req_bf16(fl_bup, "fl_bup")
+        kl = fl_ad.shape[0]
+        assert fl_ad.shape[1] == K and fl_bup.shape == (N, kl) and fl_ad.stride(1) == 1 and fl_bup.stride(1) == 1
+        g.fl_ad, g.fl_bup, g.fl_kl, g.fl_rank = _ptr(fl_ad), _ptr(fl_bup), kl, (fl_rank or kl)
+        g.fl_ld_ad, g.fl_ld_bup, g.fl_scale = fl_ad.stride(0), fl_bup.stride(0), fl_scale
+        g.cta_pair = 0
+        if fl_t_out is not None:
+            _req_bf16(fl_t_out, "fl_t_out")
+            assert fl_t_out.shape == (M, kl) and fl_t_out.stride(1) == 1
+            g.fl_t_out, g.fl_ld_t = _ptr(fl_t_out), fl_t_out.stride(0)
     if SPLIT_K and not g.cta_pair:
         ws = _splitk_workspace(a.device)
         g.splitk_ws, g.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4

@@ -466,6 +466,7 @@ class EngineUNet(nn.Module):
         self._act_dtype = torch.bfloat16
         self._last_tape: Optional[Tape] = None
         self.attention_impl = "auto"
+        self.fused_lora = True   # LoRA branch computed inside the GEMM kernel (False: separate T GEMM + K-segment)
 
     # ---- reference-facing no-ops -------------------------------------------------------
     def enable_xformers_memory_efficient_attention(self, *a, **k):  # train_lora.py:68
@@ -551,17 +552,24 @@ class EngineUNet(nn.Module):
         act = pk.site.active()
         kw = {}
         T = ad = bup = None
-        scale = mult = 1.0
+        sm = 1.0
+        rg_out = x.rg or (residual is not None and residual.rg) or act is not None
+        need_grad = tape is not None and rg_out
         if act is not None:
             ads, mult = act
             ad, bup = pk.site.refresh(ads, x.t.device, x.t.dtype)
-            scale = float(ads[0].scale)
-            T = be.gemm(x.t, ad, alpha=scale * mult)          # T = s*m * x A^T   [M, Kl]
-            kw.update(lora_t=T, lora_up=bup)
-        rg_out = x.rg or (residual is not None and residual.rg) or act is not None
+            sm = float(ads[0].scale) * mult
+            if self.fused_lora:   # T = s*m x A^T is formed inside the GEMM kernel (extra accumulator columns)
+                kw.update(fl_ad=ad, fl_bup=bup, fl_scale=sm, fl_rank=sum(pk.site.ranks))
+                if need_grad:
+                    T = be.zeros((x.t.shape[0], ad.shape[0]), x.t)
+                    kw["fl_t_out"] = T
+            else:
+                T = be.gemm(x.t, ad, alpha=sm)                  # T = s*m * x A^T   [M, Kl]
+                kw.update(lora_t=T, lora_up=bup)
         y = be.gemm(x.t, pk.w, bias=pk.bias, residual=None if residual is None else residual.t, geglu=geglu, **kw)
-        out = Act(y, rg_out and tape is not None)
-        if tape is not None and out.rg:
+        out = Act(y, need_grad)
+        if need_grad:
             assert not geglu, "GEGLU epilogue is used on the no-grad path only"
 
             def bwd():
@@ -571,19 +579,26 @@ class EngineUNet(nn.Module):
                 if residual is not None and residual.rg:
                     tape.accum(residual.t, gy, owned=False)
                 kw2 = {}
+                dT = None
                 if act is not None:
-                    sm = scale * mult
                     bupT = be.transpose2d(bup)                       # [Kl, N]
-                    dT = be.gemm(gy, bupT, alpha=sm)                 # s*m * dY B      [M, Kl]
+                    if self.fused_lora and x.rg:
+                        # one kernel: dT = s*m dY B (saved) and dx = dY W + dT A
+                        dT = be.zeros((gy.shape[0], bupT.shape[0]), gy)
+                        kw2.update(fl_ad=bupT, fl_bup=be.transpose2d(ad), fl_scale=sm, fl_rank=sum(pk.site.ranks),
+                                   fl_t_out=dT)
+                    else:
+                        dT = be.gemm(gy, bupT, alpha=sm)             # s*m * dY B      [M, Kl]
+                        if x.rg:
+                            kw2.update(lora_t=dT, lora_up=be.transpose2d(ad))   # + dT A
                     # dB[n,k] += sum_m dY[m,n] T[m,k]   (T already carries s*m)
                     be.tn_reduce(gy, T, pk.site.grad_bup(be))
-                    # dA[k,j] += sum_m dT[m,k] x[m,j]   -> accumulated transposed-in-place
-                    be.tn_reduce(x.t, dT, pk.site.grad_ad(be), transpose_out=True)
-                    if x.rg:
-                        kw2.update(lora_t=dT, lora_up=be.transpose2d(ad))   # + dT A
                 if x.rg:
                     dx = be.gemm(gy, pk.wt, **kw2)
                     tape.accum(x.t, dx, owned=True)
+                if act is not None:
+                    # dA[k,j] += sum_m dT[m,k] x[m,j]   -> accumulated transposed-in-place
+                    be.tn_reduce(x.t, dT, pk.site.grad_ad(be), transpose_out=True)
             tape.record(bwd)
         return out
 
@@ -600,8 +615,14 @@ class EngineUNet(nn.Module):
             ads, mult = act
             ad, bup = pk.site.refresh(ads, x.t.device, x.t.dtype)
             sm = float(ads[0].scale) * mult
-            T = be.gemm(x.t, ad, alpha=sm, conv_nhw=(n, h, w))       # [M, Kl]
-            kw.update(lora_t=T, lora_up=bup)
+            if self.fused_lora:
+                kw.update(fl_ad=ad, fl_bup=bup, fl_scale=sm, fl_rank=sum(pk.site.ranks))
+                if tape is not None:
+                    T = be.zeros((x.t.shape[0], ad.shape[0]), x.t)
+                    kw["fl_t_out"] = T
+            else:
+                T = be.gemm(x.t, ad, alpha=sm, conv_nhw=(n, h, w))       # [M, Kl]
+                kw.update(lora_t=T, lora_up=bup)
         rb = None if rowbias is None else rowbias.t[:, rb_col0:rb_col0 + pk.cout]
         y = be.gemm(x.t, pk.w, bias=pk.bias, rowbias=rb, rows_per_group=h * w,
                     residual=None if residual is None else residual.t, conv_nhw=(n, h, w), **kw)

@@ -115,6 +115,61 @@ def case_conv(n, h, w, cin, cout, block_n=0, bias=True, rowbias=True, residual=T
     return _cmp(out, ref)
 
 
+def case_fl(M, N, K, kl=16, rank=4, geglu=False, conv=None, bias=True, residual=True, t_out=False, block_n=0):
+    """In-kernel LoRA: out = a W^T + s (a Ad^T) Bup^T (+ epilogue), optional saved T."""
+    import torch
+    import torch.nn.functional as F
+    from leco_b200 import ops
+    sc = 0.25
+    if conv:
+        n, h, w, cin = conv
+        M, K = n * h * w, 9 * cin
+        x = _rand((n, h, w, cin), seed=21)
+        wt = _rand((N, cin, 3, 3), scale=(9 * cin) ** -0.5, seed=22)
+        a = x.reshape(M, cin)
+        wk = wt.permute(0, 2, 3, 1).reshape(N, K).contiguous()
+        adw = torch.zeros((kl, cin, 3, 3))
+        adw[:rank] = torch.randn((rank, cin, 3, 3), generator=torch.Generator().manual_seed(5)) * (9 * cin) ** -0.5
+        adw = adw.to(torch.bfloat16).cuda()
+        ad = adw.permute(0, 2, 3, 1).reshape(kl, K).contiguous()
+        base = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1).permute(0, 2, 3, 1).reshape(M, N)
+        t = sc * F.conv2d(x.float().permute(0, 3, 1, 2), adw.float(), padding=1).permute(0, 2, 3, 1).reshape(M, kl)
+        kw = dict(conv_nhw=(n, h, w))
+    else:
+        a = _rand((M, K), seed=1)
+        wk = _rand((N, K), scale=K ** -0.5, seed=2)
+        ad = torch.zeros((kl, K))
+        ad[:rank] = torch.randn((rank, K), generator=torch.Generator().manual_seed(5)) * K ** -0.5
+        ad = ad.to(torch.bfloat16).cuda()
+        base = a.float() @ wk.float().t()
+        t = sc * (a.float() @ ad.float().t())
+        kw = {}
+    bup = torch.zeros((N, kl))
+    bup[:, :rank] = torch.randn((N, rank), generator=torch.Generator().manual_seed(6)) * 0.3
+    bup = bup.to(torch.bfloat16).cuda()
+    ref = base + t @ bup.float().t()
+    if bias:
+        bv = _rand((N,), seed=7)
+        ref = ref + bv.float()[None]
+        kw["bias"] = bv
+    if geglu:
+        hh, gg = ref[:, :N // 2], ref[:, N // 2:]
+        ref = hh * F.gelu(gg)
+    if residual and not geglu:
+        r = _rand(ref.shape, seed=8)
+        ref = ref + r.float()
+        kw["residual"] = r
+    tbuf = torch.zeros((M, kl), device="cuda", dtype=torch.bfloat16) if t_out else None
+    out = ops.gemm(a, wk, geglu=geglu, fl_ad=ad, fl_bup=bup, fl_scale=sc, fl_rank=rank, fl_t_out=tbuf, block_n=block_n, **kw)
+    torch.cuda.synchronize()
+    res = _cmp(out, ref)
+    if t_out:
+        rt = _cmp(tbuf, t)
+        res["t_rel"] = rt["rel"]
+        res["ok"] = res["ok"] and rt["ok"]
+    return res
+
+
 def case_perf(M, N, K, block_n=0, conv=None, iters=20, cta_pair=0):
     import torch
     from leco_b200 import ops
@@ -188,6 +243,15 @@ CASES = [
     ("conv_24x40_rect", case_conv, dict(n=1, h=24, w=40, cin=64, cout=64)),
     ("conv_lora16", case_conv, dict(n=2, h=32, w=32, cin=128, cout=128, lora=16)),
     ("conv_plain", case_conv, dict(n=2, h=32, w=32, cin=64, cout=64, bias=False, rowbias=False, residual=False)),
+    ("fl_linear_r4", case_fl, dict(M=1024, N=320, K=320)),
+    ("fl_linear_qkv_r12_tout", case_fl, dict(M=4096, N=960, K=320, rank=12, t_out=True)),
+    ("fl_linear_kl32_bn128", case_fl, dict(M=512, N=640, K=640, kl=32, rank=24, block_n=128, t_out=True)),
+    ("fl_linear_bn64_ragged", case_fl, dict(M=300, N=72, K=128, block_n=64)),
+    ("fl_geglu", case_fl, dict(M=512, N=2560, K=320, geglu=True)),
+    ("fl_splitk_m256", case_fl, dict(M=256, N=1280, K=5120)),
+    ("fl_ctx_m308", case_fl, dict(M=308, N=640, K=1024, rank=8)),
+    ("fl_conv_32", case_fl, dict(M=0, N=128, K=0, conv=(2, 32, 32, 128), t_out=True)),
+    ("fl_conv_8_splitk", case_fl, dict(M=0, N=1280, K=0, conv=(4, 8, 8, 1280), rank=8)),
     ("splitk_conv16_1280", case_conv, dict(n=4, h=16, w=16, cin=1280, cout=1280)),
     ("splitk_conv8_lora", case_conv, dict(n=4, h=8, w=8, cin=1280, cout=1280, lora=16)),
     ("splitk_linear_m308", case_matrix, dict(M=308, N=2560, K=1024, bias=True)),

@@ -23,7 +23,8 @@ def _f(x):
 
 # ------------------------------------------------------------------ GEMM family
 def gemm(a, b, out=None, *, bias=None, rowbias=None, rows_per_group=1, residual=None, lora_t=None, lora_up=None,
-         geglu=False, alpha=1.0, out_fp32=False, conv_nhw=None, block_n=0, cta_pair=None):
+         geglu=False, alpha=1.0, out_fp32=False, conv_nhw=None, block_n=0, cta_pair=None,
+         fl_ad=None, fl_bup=None, fl_scale=1.0, fl_rank=0, fl_t_out=None):
     dt = torch.float32 if out_fp32 else a.dtype
     if conv_nhw is not None:
         n, h, w = conv_nhw
@@ -36,6 +37,15 @@ def gemm(a, b, out=None, *, bias=None, rowbias=None, rows_per_group=1, residual=
     if lora_t is not None:
         y = y + _f(lora_t) @ _f(lora_up).t()
     y = y * alpha
+    if fl_ad is not None:
+        if conv_nhw is not None:
+            wa = _f(fl_ad).reshape(fl_ad.shape[0], 3, 3, c).permute(0, 3, 1, 2)
+            t = F.conv2d(x, wa, padding=1).permute(0, 2, 3, 1).reshape(n * h * w, -1) * fl_scale
+        else:
+            t = fl_scale * (_f(a) @ _f(fl_ad).t())
+        y = y + t @ _f(fl_bup).t()
+        if fl_t_out is not None:
+            fl_t_out.copy_(t.to(fl_t_out.dtype))
     if bias is not None:
         y = y + _f(bias)[None]
     if rowbias is not None:
