@@ -77,6 +77,7 @@ typedef struct leco_gemm_args {
   float fl_scale;
   void* fl_t_out;
   int64_t fl_ld_t;
+  int32_t debug_mode; /* perf triage: 1 = no MMAs, 2 = no TMA loads (results are garbage) */
 } leco_gemm_args;
 int leco_gemm_bf16(const leco_gemm_args* args, void* stream);
 

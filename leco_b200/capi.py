@@ -38,7 +38,7 @@ class GemmArgs(Structure):
         ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_int64),
         ("fl_ad", c_void_p), ("fl_bup", c_void_p), ("fl_kl", c_int32), ("fl_rank", c_int32),
         ("fl_ld_ad", c_int64), ("fl_ld_bup", c_int64), ("fl_scale", c_float), ("fl_t_out", c_void_p),
-        ("fl_ld_t", c_int64),
+        ("fl_ld_t", c_int64), ("debug_mode", c_int32),
     ]
 
 

@@ -215,60 +215,55 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
       mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t s_addr = tmem_s + lane_off + sb * FA_BN + wg * 64;
-      // pass 1: max over this half, then exchange with the other warpgroup
+      // this thread's 64 scores: both TMEM loads in flight, one wait; S is then free for the next QK^T
+      uint32_t s0[32], s1[32];
+      tmem_ld_32x32b_x32(s_addr, s0);
+      tmem_ld_32x32b_x32(s_addr + 32, s1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sb]);
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(s_addr + c * 32, raw);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float sv = __uint_as_float(raw[i]);
-          if (ragged && kv0 + c * 32 + i >= p.skv) sv = -INFINITY;
-          mx = fmaxf(mx, sv);
+      for (int i = 0; i < 32; ++i) {
+        float a = __uint_as_float(s0[i]), b2 = __uint_as_float(s1[i]);
+        if (ragged) {
+          if (kv0 + i >= p.skv) a = -INFINITY;
+          if (kv0 + 32 + i >= p.skv) b2 = -INFINITY;
         }
+        mx = fmaxf(mx, fmaxf(a, b2));
       }
       mx_buf[(sb * 2 + wg) * 128 + r] = mx;
       asm volatile("bar.sync 1, 256;" ::: "memory");   // the two softmax warpgroups only
       const float m_new = fmaxf(m_run, fmaxf(mx, mx_buf[(sb * 2 + (wg ^ 1)) * 128 + r]));
       const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);  // first tile: ex2(-inf) = 0
       const float mb = m_new * p.scale_log2;
-      // pass 2: p = 2^(s*c - m*c) -> bf16 -> swizzled A-operand tile (this half = 64 keys = one 128-byte row)
+      // p = 2^(s*c - m*c) -> bf16 -> swizzled A-operand tile (this half = 64 keys = one 128-byte row)
       mbar_wait(&p_empty[sb], ((j >> 1) & 1) ^ 1);
       uint8_t* prow = sP + sb * FA_P_BYTES + wg * (FA_P_BYTES / 2) + r * 128;
       float rowsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(s_addr + c * 32, raw);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(raw[i]), p.scale_log2, -mb));
-          float p1 = ex2_approx(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2, -mb));
-          if (ragged) {
-            if (kv0 + c * 32 + i >= p.skv) p0 = 0.f;
-            if (kv0 + c * 32 + i + 1 >= p.skv) p1 = 0.f;
-          }
-          rowsum += p0 + p1;
-          pk[i >> 1] = pack_bf16(p0, p1);
-        }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int chunk = c * 4 + t;  // 16-byte chunk (8 keys) inside the 128-byte row
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) =
-              make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-        }
-      }
-      tc_fence_before();
+#define FA_EXP_HALF(SRC, KOFF, CHUNK0)                                                        \
+  _Pragma("unroll") for (int t = 0; t < 4; ++t) {                                             \
+    uint32_t pk[4];                                                                           \
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                           \
+      const int i = t * 8 + u * 2;                                                            \
+      float p0 = ex2_approx(fmaf(__uint_as_float(SRC[i]), p.scale_log2, -mb));                \
+      float p1 = ex2_approx(fmaf(__uint_as_float(SRC[i + 1]), p.scale_log2, -mb));            \
+      if (ragged) {                                                                           \
+        if (kv0 + KOFF + i >= p.skv) p0 = 0.f;                                                \
+        if (kv0 + KOFF + i + 1 >= p.skv) p1 = 0.f;                                            \
+      }                                                                                       \
+      rowsum += p0 + p1;                                                                      \
+      pk[u] = pack_bf16(p0, p1);                                                              \
+    }                                                                                         \
+    *reinterpret_cast<uint4*>(prow + (((CHUNK0 + t) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]); \
+  }
+      FA_EXP_HALF(s0, 0, 0)
+      FA_EXP_HALF(s1, 32, 4)
+#undef FA_EXP_HALF
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_empty[sb]);
-        mbar_arrive(&p_full[sb]);
-      }
+      if (lane == 0) mbar_arrive(&p_full[sb]);
       l_part = l_part * alpha + rowsum;
       m_run = m_new;
       if (j > 0) fold_pv(j - 1, alpha_prev);

@@ -31,6 +31,7 @@ struct GemmParams {
   int out_fp32;
   unsigned a_tx_bytes;
   // split-K: tile index carries a K-slice id; partial sums are red.add'ed (fp32) into `ws` [M][ldws]
+  int dbg;  // perf triage only: 1 = skip the MMAs (TMA-only pipeline), 2 = skip the TMA loads (MMA-only)
   int k_splits;
   float* ws;
   long long ldws;
@@ -182,11 +183,14 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       tmem_ld_wait();
       const int col0 = n0 + c * 32;
       const int nvalid = p.N - col0;
-      if (row_ok && nvalid > 0) {
-        float v[32];
+      const bool ok = row_ok && nvalid > 0;
+      float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
-        if (p.fl_kl) epi_lora_add(v, p, trow + BN, col0, nvalid);  // linear in T: each K-slice adds its part
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+      // tcgen05.ld is warp-aligned: every lane runs it, invalid rows just add nothing (nvalid 0).
+      // Linear in T: each K-slice adds its own part.
+      if (p.fl_kl) epi_lora_add(v, p, trow + BN, col0, ok ? nvalid : 0);
+      if (ok) {
         float* dst = p.ws + m * p.ldws + col0;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -205,11 +209,12 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       tmem_ld_wait();
       const int col0 = n0 + c * 32;
       const int nvalid = p.N - col0;  // may be <= 0 or > 32
-      if (row_ok && nvalid > 0) {
-        float v[32];
+      const bool ok = row_ok && nvalid > 0;
+      float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
-        if (p.fl_kl) epi_lora_add(v, p, trow + BN, col0, nvalid);
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+      if (p.fl_kl) epi_lora_add(v, p, trow + BN, col0, ok ? nvalid : 0);  // all lanes (aligned TMEM loads inside)
+      if (ok) {
         if (p.bias) epi_add_bf16(v, p.bias + col0, nvalid);
         if (p.rowbias)
           epi_add_bf16(v, p.rowbias + (m / p.rows_per_group) * p.ld_rowbias + col0, nvalid);
@@ -230,17 +235,18 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       tmem_ld_wait();
       const int ocol0 = nt * (BN / 2) + c * 32;
       const int nvalid = p.N / 2 - ocol0;
-      if (row_ok && nvalid > 0) {
-        float h[32], g[32];
+      const bool ok = row_ok && nvalid > 0;
+      float h[32], g[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          h[j] = __uint_as_float(rh[j]) * p.alpha;
-          g[j] = __uint_as_float(rg[j]) * p.alpha;
-        }
-        if (p.fl_kl) {
-          epi_lora_add(h, p, trow + BN, ocol0, 32);
-          epi_lora_add(g, p, trow + BN, p.N / 2 + ocol0, 32);
-        }
+      for (int j = 0; j < 32; ++j) {
+        h[j] = __uint_as_float(rh[j]) * p.alpha;
+        g[j] = __uint_as_float(rg[j]) * p.alpha;
+      }
+      if (p.fl_kl) {  // all lanes (aligned TMEM loads inside)
+        epi_lora_add(h, p, trow + BN, ocol0, ok ? 32 : 0);
+        epi_lora_add(g, p, trow + BN, p.N / 2 + ocol0, ok ? 32 : 0);
+      }
+      if (ok) {
         if (p.bias) {
           epi_add_bf16(h, p.bias + ocol0, 32);
           epi_add_bf16(g, p.bias + p.N / 2 + ocol0, 32);

@@ -103,7 +103,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
         uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
-        if (c < p.chunks1) {
+        if (p.dbg == 2) {
+          mbar_arrive(&full_bar[stage]);
+        } else if (c < p.chunks1) {
           mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes + BN * BLOCK_K * 2 + (FL ? p.fl_kl * BLOCK_K * 2 : 0));
           if (FL)  // stacked lora_down rows for this K chunk land right behind the W rows of the B tile
             tma_load_4d(sb + BN * BLOCK_K * 2, &p.tm_ad, &full_bar[stage], c * BLOCK_K, 0, 0, 0);
@@ -162,12 +164,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         const int ksteps = (c < p.chunks1 - 1) ? 4 : (c == p.chunks1 - 1 ? p.ksteps_last1 : p.ksteps2);
         const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
         const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
-        for (int j = 0; j < ksteps; ++j) {
-          // +32 bytes (16 bf16) along K inside the 128B swizzle row: +2 in the >>4 address field
-          umma_bf16(tmem_d, da + 2 * j, db + 2 * j, idesc, acc);
-          acc = 1;
+        if (p.dbg == 1) {
+          mbar_arrive(&empty_bar[stage]);
+        } else {
+          for (int j = 0; j < ksteps; ++j) {
+            // +32 bytes (16 bf16) along K inside the 128B swizzle row: +2 in the >>4 address field
+            umma_bf16(tmem_d, da + 2 * j, db + 2 * j, idesc, acc);
+            acc = 1;
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
         }
-        umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -408,6 +414,7 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
     p.fl_ld_t = a->fl_ld_t;
     if (a->fl_t_out) LECO_REQUIRE(a->fl_ld_t % 8 == 0, "leco_gemm_bf16: fl_ld_t must be a multiple of 8");
   }
+  p.dbg = a->debug_mode;
   p.d = a->d;
   p.ldd = a->ldd;
   p.d_bs0 = batch0 > 1 ? a->d_bs0 : 0;

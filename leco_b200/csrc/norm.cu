@@ -88,18 +88,22 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
                                 int hw, int C, int G, int splits, float eps, int silu) {
   pdl_entry();
   __shared__ float2 ms[GN_MAX_GROUPS];
+  __shared__ float acc[GN_MAX_GROUPS][2];
   const int n = blockIdx.x;
   const int cpg = C / G;
+  for (int i = threadIdx.x; i < G * 2; i += blockDim.x) (&acc[0][0])[i] = 0.f;
+  __syncthreads();
+  // all threads fold the per-split partial sums (splits*G entries) instead of G threads walking them serially
+  for (int i = threadIdx.x; i < splits * G; i += blockDim.x) {
+    const float2 p = partial[(size_t)n * splits * G + i];
+    atomicAdd(&acc[i % G][0], p.x);
+    atomicAdd(&acc[i % G][1], p.y);
+  }
+  __syncthreads();
   if (threadIdx.x < G) {
-    float a = 0.f, b = 0.f;
-    for (int s = 0; s < splits; ++s) {
-      const float2 p = partial[((size_t)n * splits + s) * G + threadIdx.x];
-      a += p.x;
-      b += p.y;
-    }
     const float cnt = (float)hw * (float)cpg;
-    const float mean = a / cnt;
-    const float var = fmaxf(b / cnt - mean * mean, 0.f);
+    const float mean = acc[threadIdx.x][0] / cnt;
+    const float var = fmaxf(acc[threadIdx.x][1] / cnt - mean * mean, 0.f);
     const float2 r = make_float2(mean, rsqrtf(var + eps));
     ms[threadIdx.x] = r;
     if (blockIdx.y == 0) stats[(size_t)n * G + threadIdx.x] = r;
@@ -190,15 +194,18 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
   __shared__ float2 gs[GN_MAX_GROUPS];
   const int n = blockIdx.x;
   const int cpg = C / G;
+  __shared__ float acc[GN_MAX_GROUPS][2];
+  for (int i = threadIdx.x; i < G * 2; i += blockDim.x) (&acc[0][0])[i] = 0.f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < splits * G; i += blockDim.x) {
+    const float2 p = partial[(size_t)n * splits * G + i];
+    atomicAdd(&acc[i % G][0], p.x);
+    atomicAdd(&acc[i % G][1], p.y);
+  }
+  __syncthreads();
   if (threadIdx.x < G) {
-    float a = 0.f, b = 0.f;
-    for (int s = 0; s < splits; ++s) {
-      const float2 p = partial[((size_t)n * splits + s) * G + threadIdx.x];
-      a += p.x;
-      b += p.y;
-    }
     const float cnt = (float)hw * (float)cpg;
-    gs[threadIdx.x] = make_float2(a / cnt, b / cnt);
+    gs[threadIdx.x] = make_float2(acc[threadIdx.x][0] / cnt, acc[threadIdx.x][1] / cnt);
     ms[threadIdx.x] = stats[(size_t)n * G + threadIdx.x];
   }
   __syncthreads();
@@ -367,8 +374,8 @@ extern "C" int leco_group_norm(const void* x, void* y, void* stats /*float2[n*G]
                                                                   C, G, vpp, splits);
   LECO_CHECK_CUDA(cudaGetLastError());
   long long work = (long long)hw * vpp;
-  int gy = (int)((work + 255) / 256);
-  if (gy > 592) gy = 592;
+  int gy = (int)((work + 256 * 4 - 1) / (256 * 4));   // >= 4 vectors per thread: the per-block prologue amortises
+  if (gy > 296 / (n < 1 ? 1 : n) + 1) gy = 296 / (n < 1 ? 1 : n) + 1;
   if (gy < 1) gy = 1;
   count_launch();
   LECO_LAUNCH(gn_apply_kernel, dim3(n, gy), 256, 0, STREAM(stream), BF(x), BFW(y), reinterpret_cast<const float2*>(workspace),
@@ -391,8 +398,8 @@ extern "C" int leco_group_norm_bwd(const void* x, const void* dz, void* dx, cons
       reinterpret_cast<float2*>(workspace), hw, C, G, vpp, splits, silu);
   LECO_CHECK_CUDA(cudaGetLastError());
   long long work = (long long)hw * vpp;
-  int gy = (int)((work + 255) / 256);
-  if (gy > 592) gy = 592;
+  int gy = (int)((work + 256 * 4 - 1) / (256 * 4));
+  if (gy > 296 / (n < 1 ? 1 : n) + 1) gy = 296 / (n < 1 ? 1 : n) + 1;
   if (gy < 1) gy = 1;
   count_launch();
   LECO_LAUNCH(gn_bwd_apply_kernel, dim3(n, gy), 256, 0, STREAM(stream), 

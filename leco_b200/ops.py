@@ -17,6 +17,7 @@ BF16 = torch.bfloat16
 GEMM_2CTA = int(__import__('os').environ.get('LECO_GEMM_2CTA', '0'))  # 1: cta_group::2 kernel for plain/conv GEMMs
 
 
+_GEMM_DEBUG_MODE = int(__import__('os').environ.get('LECO_GEMM_DEBUG', '0'))
 SPLIT_K = int(__import__('os').environ.get('LECO_SPLIT_K', '1'))
 _SPLITK_WS = {}
 
@@ -106,6 +107,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
     g.alpha = alpha
     g.out_fp32 = 1 if out_fp32 else 0
     g.block_n = block_n
+    g.debug_mode = _GEMM_DEBUG_MODE
     g.cta_pair = GEMM_2CTA if cta_pair is None else int(cta_pair)
     if fl_ad is not None:
         _req_bf16(fl_ad, "fl_ad"), _req_bf16(fl_bup, "fl_bup")

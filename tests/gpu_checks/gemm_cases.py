@@ -310,7 +310,7 @@ def main():
         t0 = time.time()
         try:
             pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", name],
-                                capture_output=True, text=True, timeout=180)
+                                capture_output=True, text=True, timeout=60)
             line = [l for l in pr.stdout.splitlines() if l.startswith("RESULT ")]
             if pr.returncode == 0 and line:
                 res = json.loads(line[-1][7:])

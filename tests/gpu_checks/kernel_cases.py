@@ -412,7 +412,7 @@ def main():
         t0 = time.time()
         try:
             pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", name], capture_output=True,
-                                text=True, timeout=600)
+                                text=True, timeout=150)
             line = [l for l in pr.stdout.splitlines() if l.startswith("RESULT ")]
             res = json.loads(line[-1][7:]) if pr.returncode == 0 and line else {
                 "ok": False, "rc": pr.returncode, "stderr": pr.stderr[-2500:], "stdout": pr.stdout[-800:]}
