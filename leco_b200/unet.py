@@ -466,7 +466,8 @@ class EngineUNet(nn.Module):
         self._act_dtype = torch.bfloat16
         self._last_tape: Optional[Tape] = None
         self.attention_impl = "auto"
-        self.fused_lora = True   # LoRA branch computed inside the GEMM kernel (False: separate T GEMM + K-segment)
+        # LoRA branch computed inside the GEMM kernel (True) or as a separate T GEMM + extra K-segment (False)
+        self.fused_lora = bool(int(__import__('os').environ.get('LECO_FUSED_LORA', '0')))
 
     # ---- reference-facing no-ops -------------------------------------------------------
     def enable_xformers_memory_efficient_attention(self, *a, **k):  # train_lora.py:68

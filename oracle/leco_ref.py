@@ -180,6 +180,7 @@ class PromptPairRef:
     dynamic_resolution: bool = False
     batch_size: int = 1
     action: str = "erase"
+    dynamic_crops: bool = False      # XL only (prompt_util.py:53)
 
     def loss(self, target_latents, positive_latents, neutral_latents, unconditional_latents):
         if self.action == "erase":       # prompt_util.py:107-120
@@ -237,4 +238,59 @@ def leco_iteration(unet, scheduler, network, optimizer, lr_scheduler, prompt_pai
                       target=target.detach(), loss=float(loss.item()))
     optimizer.step()                                                         # :280
     lr_scheduler.step()                                                      # :281
+    return float(loss.item())
+
+
+class EmbedsXL:
+    """prompt_util.PromptEmbedsXL (prompt_util.py:17-23): (text_embeds [1,77,2048], pooled_embeds [1,1280])."""
+
+    def __init__(self, text_embeds, pooled_embeds):
+        self.text_embeds, self.pooled_embeds = text_embeds, pooled_embeds
+
+
+def leco_iteration_xl(unet, scheduler, network, optimizer, lr_scheduler, prompt_pairs, *, max_denoising_steps=50,
+                      device="cpu", weight_dtype=torch.float32, fixed_k: Optional[int] = None,
+                      record: Optional[dict] = None):
+    """One pass of the SDXL loop body train_lora_xl.py:160-366: as leco_iteration plus the pooled text embedding
+    and `add_time_ids` conditioning (train_util.py:217-291, :295-330).  PromptPairRef fields hold EmbedsXL."""
+    with torch.no_grad():
+        scheduler.set_timesteps(max_denoising_steps, device=device)           # :162-164
+        optimizer.zero_grad()
+        pair = prompt_pairs[torch.randint(0, len(prompt_pairs), (1,)).item()]   # :168-170
+        k = torch.randint(1, max_denoising_steps, (1,)).item()                # :173-175
+        if fixed_k is not None:
+            k = fixed_k
+        height = width = pair.resolution
+        if pair.dynamic_resolution:                                           # :178-181
+            height, width = get_random_resolution_in_bucket(pair.resolution)
+        latents = get_initial_latents(scheduler, pair.batch_size, height, width, 1).to(device, dtype=weight_dtype)
+        ids = get_add_time_ids(height, width, dynamic_crops=pair.dynamic_crops, dtype=weight_dtype).to(device)  # :196-201
+        ids2 = concat_embeddings(ids, ids, pair.batch_size)
+
+        def cond(c):
+            return dict(text_embeddings=concat_embeddings(pair.unconditional.text_embeds, c.text_embeds, pair.batch_size),
+                        added_cond_kwargs={"text_embeds": concat_embeddings(pair.unconditional.pooled_embeds,
+                                                                            c.pooled_embeds, pair.batch_size),
+                                           "time_ids": ids2})
+        with network:                                                         # :203-225 (diffusion_xl)
+            denoised = latents
+            for t in scheduler.timesteps[0:k]:
+                eps = predict_noise(unet, scheduler, t, denoised, guidance_scale=3, **cond(pair.target))
+                denoised = scheduler.step(eps, t, denoised).prev_sample
+        scheduler.set_timesteps(1000)
+        t_cur = scheduler.timesteps[int(k * 1000 / max_denoising_steps)]
+
+        def nograd_pass(c):
+            return predict_noise(unet, scheduler, t_cur, denoised, guidance_scale=1, **cond(c)).to("cpu", dtype=torch.float32)
+        positive, neutral, uncond = nograd_pass(pair.positive), nograd_pass(pair.neutral), nograd_pass(pair.unconditional)
+    with network:
+        target = predict_noise(unet, scheduler, t_cur, denoised, guidance_scale=1, **cond(pair.target)).to(
+            "cpu", dtype=torch.float32)
+    loss = pair.loss(target_latents=target, positive_latents=positive, neutral_latents=neutral,
+                     unconditional_latents=uncond)
+    loss.backward()
+    if record is not None:
+        record.update(k=k, timestep=int(t_cur), loss=float(loss.item()))
+    optimizer.step()
+    lr_scheduler.step()
     return float(loss.item())

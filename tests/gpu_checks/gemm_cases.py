@@ -170,6 +170,70 @@ def case_fl(M, N, K, kl=16, rank=4, geglu=False, conv=None, bias=True, residual=
     return res
 
 
+def case_mma_rate():
+    """Perf triage: one 128 x BN tile per SM, K = 16384 (256 chunks), for every BN and pipeline mode
+    (0 normal, 1 TMA only, 2 MMA only).  Reports microseconds per K-chunk."""
+    import torch
+    from leco_b200 import ops
+    out = {"ok": True}
+    K = 16384
+    for bn in (64, 128, 160, 256):
+        a = _rand((148 * 128, K), seed=1)
+        b = _rand((bn, K), scale=K ** -0.5, seed=2)
+        o = torch.empty((148 * 128, bn), device="cuda", dtype=torch.bfloat16)
+        for mode in (0, 1, 2):
+            ops._GEMM_DEBUG_MODE = mode
+            for _ in range(2):
+                ops.gemm(a, b, o, block_n=bn)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                ops.gemm(a, b, o, block_n=bn)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / 5 * 1e3
+            out[f"bn{bn}_mode{mode}_us_per_chunk"] = round(us / (K // 64), 4)
+        ops._GEMM_DEBUG_MODE = 0
+    return out
+
+
+def case_fl_perf():
+    """in-kernel LoRA vs separate T GEMM + K-segment on the UNet's level-0 shapes."""
+    import torch
+    from leco_b200 import ops
+    res = {"ok": True}
+    for (M, N, K, geglu) in ((16384, 320, 320, False), (16384, 960, 320, False), (16384, 2560, 320, True),
+                             (16384, 320, 1280, False), (4096, 640, 640, False)):
+        a = _rand((M, K), seed=1)
+        w = _rand((N, K), scale=K ** -0.5, seed=2)
+        ad = _rand((16, K), scale=K ** -0.5, seed=3)
+        bup = _rand((N, 16), scale=0.1, seed=4)
+        o = torch.empty((M, N // 2 if geglu else N), device="cuda", dtype=torch.bfloat16)
+
+        def t_plain():
+            ops.gemm(a, w, o, geglu=geglu)
+
+        def t_seg():
+            t = ops.gemm(a, ad, alpha=0.25)
+            ops.gemm(a, w, o, geglu=geglu, lora_t=t, lora_up=bup)
+
+        def t_fl():
+            ops.gemm(a, w, o, geglu=geglu, fl_ad=ad, fl_bup=bup, fl_scale=0.25, fl_rank=4)
+        for name, fn in (("plain", t_plain), ("seg2", t_seg), ("fused", t_fl)):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            res[f"M{M}_N{N}_K{K}_{name}_us"] = round(e0.elapsed_time(e1) / 20 * 1e3, 2)
+    return res
+
+
 def case_perf(M, N, K, block_n=0, conv=None, iters=20, cta_pair=0):
     import torch
     from leco_b200 import ops
@@ -243,6 +307,8 @@ CASES = [
     ("conv_24x40_rect", case_conv, dict(n=1, h=24, w=40, cin=64, cout=64)),
     ("conv_lora16", case_conv, dict(n=2, h=32, w=32, cin=128, cout=128, lora=16)),
     ("conv_plain", case_conv, dict(n=2, h=32, w=32, cin=64, cout=64, bias=False, rowbias=False, residual=False)),
+    ("triage_mma_rate", case_mma_rate, dict()),
+    ("triage_fl_perf", case_fl_perf, dict()),
     ("fl_linear_r4", case_fl, dict(M=1024, N=320, K=320)),
     ("fl_linear_qkv_r12_tout", case_fl, dict(M=4096, N=960, K=320, rank=12, t_out=True)),
     ("fl_linear_kl32_bn128", case_fl, dict(M=512, N=640, K=640, kl=32, rank=24, block_n=128, t_out=True)),
