@@ -123,25 +123,34 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
   const uint32_t tmem_s = tmem_base;        // + buf * 128
   const uint32_t tmem_pv = tmem_base + 256; // + buf * 64
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    mbar_arrive_expect_tx(q_full, FA_Q_BYTES);
-    tma_load_4d(sQ, &p.tm_q, q_full, 0, qt * FA_BM, head, b);
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, FA_Q_BYTES);
+      tma_load_4d(sQ, &p.tm_q, q_full, 0, qt * FA_BM, head, b);
+    }
+    __syncwarp();
     for (int j = 0; j < n_tiles; ++j) {
       const int ks = j % FA_KS, vs = j % FA_VS;
       mbar_wait(&k_empty[ks], ((j / FA_KS) & 1) ^ 1);
-      mbar_arrive_expect_tx(&k_full[ks], FA_KV_BYTES);
-      tma_load_4d(sK + ks * FA_KV_BYTES, &p.tm_k, &k_full[ks], 0, j * FA_BN, head, b);
-      mbar_wait(&v_empty[vs], ((j / FA_VS) & 1) ^ 1);
-      mbar_arrive_expect_tx(&v_full[vs], FA_KV_BYTES);
-      if (p.v_mode == 0) {
-        tma_load_4d(sV + vs * FA_KV_BYTES, &p.tm_v, &v_full[vs], 0, j * FA_BN, head, b);
-      } else {  // V^T [d, keys]: two 64-key chunks, each [64 d-rows x 128 B]
-        tma_load_4d(sV + vs * FA_KV_BYTES, &p.tm_v, &v_full[vs], j * FA_BN, 0, head, b);
-        tma_load_4d(sV + vs * FA_KV_BYTES + FA_KV_BYTES / 2, &p.tm_v, &v_full[vs], j * FA_BN + 64, 0, head, b);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&k_full[ks], FA_KV_BYTES);
+        tma_load_4d(sK + ks * FA_KV_BYTES, &p.tm_k, &k_full[ks], 0, j * FA_BN, head, b);
       }
+      __syncwarp();
+      mbar_wait(&v_empty[vs], ((j / FA_VS) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&v_full[vs], FA_KV_BYTES);
+        if (p.v_mode == 0) {
+          tma_load_4d(sV + vs * FA_KV_BYTES, &p.tm_v, &v_full[vs], 0, j * FA_BN, head, b);
+        } else {  // V^T [d, keys]: two 64-key chunks, each [64 d-rows x 128 B]
+          tma_load_4d(sV + vs * FA_KV_BYTES, &p.tm_v, &v_full[vs], j * FA_BN, 0, head, b);
+          tma_load_4d(sV + vs * FA_KV_BYTES + FA_KV_BYTES / 2, &p.tm_v, &v_full[vs], j * FA_BN + 64, 0, head, b);
+        }
+      }
+      __syncwarp();
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc_s = umma_idesc_bf16(FA_BN, false);
     const uint32_t idesc_pv = umma_idesc_bf16(FA_D, p.v_mode == 0);
@@ -152,10 +161,13 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
       mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint64_t dk = umma_desc_k_sw128(smem_u32(sK + ks * FA_KV_BYTES));
+      if (elect_one()) {
 #pragma unroll
-      for (int s = 0; s < FA_D / 16; ++s) umma_bf16(tmem_s + sb * FA_BN, dq + 2 * s, dk + 2 * s, idesc_s, s > 0 ? 1u : 0u);
-      umma_commit(&s_full[sb]);
-      umma_commit(&k_empty[ks]);
+        for (int s = 0; s < FA_D / 16; ++s) umma_bf16(tmem_s + sb * FA_BN, dq + 2 * s, dk + 2 * s, idesc_s, s > 0 ? 1u : 0u);
+        umma_commit(&s_full[sb]);
+        umma_commit(&k_empty[ks]);
+      }
+      __syncwarp();
     };
     mbar_wait(q_full, 0);
     issue_s(0);
@@ -168,6 +180,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
       tc_fence_after();
       const uint32_t pbase = smem_u32(sP + pb * FA_P_BYTES);
       const uint32_t vbase = smem_u32(sV + vs * FA_KV_BYTES);
+      if (elect_one()) {
 #pragma unroll
       for (int s = 0; s < FA_BN / 16; ++s) {
         // A = P: K-major, two 64-key chunks of [128 rows x 128 B]
@@ -182,6 +195,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
       umma_commit(&pv_full[pb]);
       umma_commit(&v_empty[vs]);
       umma_commit(&p_empty[pb]);
+      }
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax + output

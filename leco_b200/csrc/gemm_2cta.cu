@@ -144,8 +144,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const bool geglu = p.epilogue == 1;
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------ TMA producer (both CTAs)
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs; warp-uniform loop)
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
@@ -161,31 +161,34 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
       gemm_tile_origin(p, mt, m0, img_n0, img_h0);
       for (int c = 0; c < total_chunks; ++c) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
-        uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
-        if (c < p.chunks1) {
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (p.a_tx_bytes + Cfg::B_STAGE_BYTES));
-          if (p.mode == 0) {
-            tma_load_4d_2cta(sa, &p.tm_a, &full_bar[stage], c * BLOCK_K, m0, b0, b1);
+        if (elect_one()) {
+          uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+          uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+          if (c < p.chunks1) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (p.a_tx_bytes + Cfg::B_STAGE_BYTES));
+            if (p.mode == 0) {
+              tma_load_4d_2cta(sa, &p.tm_a, &full_bar[stage], c * BLOCK_K, m0, b0, b1);
+            } else {
+              const int tap = c / p.cin_chunks;
+              const int cc = c - tap * p.cin_chunks;
+              const int kh = tap / 3, kw = tap - kh * 3;
+              tma_load_4d_2cta(sa, &p.tm_a, &full_bar[stage], cc * BLOCK_K, kw - 1, img_h0 + kh - 1, img_n0);
+            }
+            tma_load_4d_2cta(sb, &p.tm_b, &full_bar[stage], c * BLOCK_K, nb_row, b0, b1);
           } else {
-            const int tap = c / p.cin_chunks;
-            const int cc = c - tap * p.cin_chunks;
-            const int kh = tap / 3, kw = tap - kh * 3;
-            tma_load_4d_2cta(sa, &p.tm_a, &full_bar[stage], cc * BLOCK_K, kw - 1, img_h0 + kh - 1, img_n0);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
+            tma_load_4d_2cta(sa, &p.tm_a2, &full_bar[stage], 0, m0, 0, 0);
+            tma_load_4d_2cta(sb, &p.tm_b2, &full_bar[stage], 0, nb_row, 0, 0);
           }
-          tma_load_4d_2cta(sb, &p.tm_b, &full_bar[stage], c * BLOCK_K, nb_row, b0, b1);
-        } else {
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
-          tma_load_4d_2cta(sa, &p.tm_a2, &full_bar[stage], 0, m0, 0, 0);
-          tma_load_4d_2cta(sb, &p.tm_b2, &full_bar[stage], 0, nb_row, 0, 0);
         }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && leader) {
+  } else if (warp == 1 && leader) {
     // -------------------------------------------------------------- MMA issuer (leader CTA only)
     const uint32_t idesc = umma_idesc_bf16_m256(BN);
     int stage = 0;
@@ -203,14 +206,18 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
         const int ksteps = (c < p.chunks1 - 1) ? 4 : (c == p.chunks1 - 1 ? p.ksteps_last1 : p.ksteps2);
         const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
         const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
-        for (int j = 0; j < ksteps; ++j) umma_bf16_2cta(tmem_d, da + 2 * j, db + 2 * j, idesc, (c | j) != 0 ? 1u : 0u);
-        umma_commit_2cta_mc(&empty_bar[stage], 0b11);
+        if (elect_one()) {
+          for (int j = 0; j < ksteps; ++j) umma_bf16_2cta(tmem_d, da + 2 * j, db + 2 * j, idesc, (c | j) != 0 ? 1u : 0u);
+          umma_commit_2cta_mc(&empty_bar[stage], 0b11);
+        }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit_2cta_mc(&tmem_full[as], 0b11);
+      if (elect_one()) umma_commit_2cta_mc(&tmem_full[as], 0b11);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue (both CTAs, own 128 rows)

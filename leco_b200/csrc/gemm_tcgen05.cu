@@ -80,8 +80,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   const int splits = p.k_splits;
   const int total_tiles = tiles_mn * p.batch0 * p.batch1 * splits;
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------ TMA producer
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (warp-uniform loop, one lane issues)
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -101,49 +101,52 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       const int c_end = (int)((long long)(ks + 1) * p.chunks1 / splits) + ((ks == splits - 1) ? p.has_seg2 : 0);
       for (int c = c_begin; c < c_end; ++c) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
-        uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
-        if (p.dbg == 2) {
-          mbar_arrive(&full_bar[stage]);
-        } else if (c < p.chunks1) {
-          mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes + BN * BLOCK_K * 2 + (FL ? p.fl_kl * BLOCK_K * 2 : 0));
-          if (FL)  // stacked lora_down rows for this K chunk land right behind the W rows of the B tile
-            tma_load_4d(sb + BN * BLOCK_K * 2, &p.tm_ad, &full_bar[stage], c * BLOCK_K, 0, 0, 0);
-          if (p.mode == 0) {
-            tma_load_4d(sa, &p.tm_a, &full_bar[stage], c * BLOCK_K, m0, b0, b1);
+        if (elect_one()) {
+          uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+          uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+          if (p.dbg == 2) {
+            mbar_arrive(&full_bar[stage]);
+          } else if (c < p.chunks1) {
+            mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes + BN * BLOCK_K * 2 + (FL ? p.fl_kl * BLOCK_K * 2 : 0));
+            if (FL)  // stacked lora_down rows for this K chunk land right behind the W rows of the B tile
+              tma_load_4d(sb + BN * BLOCK_K * 2, &p.tm_ad, &full_bar[stage], c * BLOCK_K, 0, 0, 0);
+            if (p.mode == 0) {
+              tma_load_4d(sa, &p.tm_a, &full_bar[stage], c * BLOCK_K, m0, b0, b1);
+            } else {
+              const int tap = c / p.cin_chunks;
+              const int cc = c - tap * p.cin_chunks;
+              const int kh = tap / 3, kw = tap - kh * 3;
+              tma_load_4d(sa, &p.tm_a, &full_bar[stage], cc * BLOCK_K, kw - 1, img_h0 + kh - 1, img_n0);
+            }
+            if (p.epilogue == 1) {
+              // GEGLU: tile columns [0,BN/2) <- hidden rows, [BN/2,BN) <- the matching gate rows
+              tma_load_4d(sb, &p.tm_b, &full_bar[stage], c * BLOCK_K, nt * (BN / 2), b0, b1);
+              tma_load_4d(sb + (BN / 2) * BLOCK_K * 2, &p.tm_b, &full_bar[stage], c * BLOCK_K,
+                          p.N / 2 + nt * (BN / 2), b0, b1);
+            } else {
+              tma_load_4d(sb, &p.tm_b, &full_bar[stage], c * BLOCK_K, n0, b0, b1);
+            }
           } else {
-            const int tap = c / p.cin_chunks;
-            const int cc = c - tap * p.cin_chunks;
-            const int kh = tap / 3, kw = tap - kh * 3;
-            tma_load_4d(sa, &p.tm_a, &full_bar[stage], cc * BLOCK_K, kw - 1, img_h0 + kh - 1, img_n0);
-          }
-          if (p.epilogue == 1) {
-            // GEGLU: tile columns [0,BN/2) <- hidden rows, [BN/2,BN) <- the matching gate rows
-            tma_load_4d(sb, &p.tm_b, &full_bar[stage], c * BLOCK_K, nt * (BN / 2), b0, b1);
-            tma_load_4d(sb + (BN / 2) * BLOCK_K * 2, &p.tm_b, &full_bar[stage], c * BLOCK_K,
-                        p.N / 2 + nt * (BN / 2), b0, b1);
-          } else {
-            tma_load_4d(sb, &p.tm_b, &full_bar[stage], c * BLOCK_K, n0, b0, b1);
-          }
-        } else {
-          mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + BN * BLOCK_K * 2);
-          tma_load_4d(sa, &p.tm_a2, &full_bar[stage], 0, m0, 0, 0);
-          if (p.epilogue == 1) {
-            tma_load_4d(sb, &p.tm_b2, &full_bar[stage], 0, nt * (BN / 2), 0, 0);
-            tma_load_4d(sb + (BN / 2) * BLOCK_K * 2, &p.tm_b2, &full_bar[stage], 0,
-                        p.N / 2 + nt * (BN / 2), 0, 0);
-          } else {
-            tma_load_4d(sb, &p.tm_b2, &full_bar[stage], 0, n0, 0, 0);
+            mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + BN * BLOCK_K * 2);
+            tma_load_4d(sa, &p.tm_a2, &full_bar[stage], 0, m0, 0, 0);
+            if (p.epilogue == 1) {
+              tma_load_4d(sb, &p.tm_b2, &full_bar[stage], 0, nt * (BN / 2), 0, 0);
+              tma_load_4d(sb + (BN / 2) * BLOCK_K * 2, &p.tm_b2, &full_bar[stage], 0,
+                          p.N / 2 + nt * (BN / 2), 0, 0);
+            } else {
+              tma_load_4d(sb, &p.tm_b2, &full_bar[stage], 0, n0, 0, 0);
+            }
           }
         }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // -------------------------------------------------------------- MMA issuer
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer (warp-uniform loop, one lane issues)
     const uint32_t idesc = umma_idesc_bf16_m128(BN + (FL ? p.fl_kl : 0));  // FL: extra columns = x.Ad^T
     int stage = 0;
     uint32_t phase = 0;
@@ -164,22 +167,31 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         const int ksteps = (c < p.chunks1 - 1) ? 4 : (c == p.chunks1 - 1 ? p.ksteps_last1 : p.ksteps2);
         const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
         const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
-        if (p.dbg == 1) {
-          mbar_arrive(&empty_bar[stage]);
-        } else {
-          for (int j = 0; j < ksteps; ++j) {
+        if (elect_one()) {
+          if (p.dbg == 1) {
+            mbar_arrive(&empty_bar[stage]);
+          } else {
             // +32 bytes (16 bf16) along K inside the 128B swizzle row: +2 in the >>4 address field
-            umma_bf16(tmem_d, da + 2 * j, db + 2 * j, idesc, acc);
-            acc = 1;
+            if (ksteps == 4) {
+              umma_bf16(tmem_d, da, db, idesc, acc);
+              umma_bf16(tmem_d, da + 2, db + 2, idesc, 1u);
+              umma_bf16(tmem_d, da + 4, db + 4, idesc, 1u);
+              umma_bf16(tmem_d, da + 6, db + 6, idesc, 1u);
+            } else {
+              for (int j = 0; j < ksteps; ++j) umma_bf16(tmem_d, da + 2 * j, db + 2 * j, idesc, (acc | j) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
         }
+        __syncwarp();
+        acc = 1;
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+      if (elect_one()) umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
