@@ -9,7 +9,8 @@ namespace leco {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;               // 64 bf16 = 128 B = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 256;      // 2-CTA variant: 4 role warps + 4 epilogue warps
+constexpr int GEMM_THREADS_1CTA = 384; // 1-CTA kernel: 4 role warps + 8 epilogue warps (two per TMEM lane quadrant)
 
 struct GemmParams {
   CUtensorMap tm_a, tm_b, tm_a2, tm_b2;
@@ -136,8 +137,10 @@ __device__ __forceinline__ void epi_lora_add(float (&v)[32], const GemmParams& p
 // One output tile: TMEM accumulator (this thread's row r of lane quadrant q) -> epilogue -> global.
 // `trow` = TMEM address of the row's first accumulator column; (mt, nt, b0, b1) identify the tile.
 template <int BN>
+// The tile's 32-column groups c = c_start, c_start + c_step, ... are this warp's share (two epilogue warps can
+// split one lane quadrant).
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t trow, int r, int mt, int nt, int b0,
-                                                   int b1) {
+                                                   int b1, int c_start = 0, int c_step = 1) {
   const bool geglu = (p.epilogue == 1);
   const int n0 = nt * BN;
   long long m;
@@ -158,7 +161,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
     m = static_cast<long long>(img_n0 * p.ch + img_h0) * p.cw + r;
   }
   const long long boff = b0 * p.d_bs0 + b1 * p.d_bs1;
-  if (p.fl_kl && p.fl_t_out && nt == 0) {  // save fl_scale*T for the backward (dB = dY^T T)
+  if (p.fl_kl && p.fl_t_out && nt == 0 && c_start == 0) {  // save fl_scale*T for the backward (dB = dY^T T)
     for (int g = 0; g < p.fl_kl / 8; ++g) {
       uint32_t traw[8];
       tmem_ld_32x32b_x8(trow + BN + g * 8, traw);
@@ -177,7 +180,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   if (p.k_splits > 1) {
     // partial accumulator of one K-slice -> fp32 workspace (bias / residual are applied by the finalize kernel)
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c_start; c < BN / 32; c += c_step) {
       uint32_t raw[32];
       tmem_ld_32x32b_x32(trow + c * 32, raw);
       tmem_ld_wait();
@@ -203,7 +206,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
     }
   } else if (!geglu) {
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c_start; c < BN / 32; c += c_step) {
       uint32_t raw[32];
       tmem_ld_32x32b_x32(trow + c * 32, raw);
       tmem_ld_wait();
@@ -228,7 +231,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   } else {
     // tile columns [0,BN/2) = hidden block, [BN/2,BN) = matching gate block
 #pragma unroll 1
-    for (int c = 0; c < BN / 64; ++c) {
+    for (int c = c_start; c < BN / 64; c += c_step) {
       uint32_t rh[32], rg[32];
       tmem_ld_32x32b_x32(trow + c * 32, rh);
       tmem_ld_32x32b_x32(trow + BN / 2 + c * 32, rg);

@@ -17,7 +17,8 @@
 //   add, GEGLU, bf16 or fp32 store.
 //
 // Roles: warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4-7 = epilogue (TMEM lane quadrant = warp % 4).
+// allocator, warps 4-11 = epilogue (TMEM lane quadrant = warp % 4; the two warps of a quadrant take
+// alternate 32-column groups).
 #include <stdio.h>
 
 #include "gemm_common.cuh"
@@ -25,7 +26,7 @@
 namespace leco {
 
 template <int BN, bool FL>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS_1CTA, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN, FL>;
   constexpr int STAGES = Cfg::STAGES;
@@ -62,7 +63,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
     fence_barrier_init();
   }
@@ -80,10 +81,17 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   const int splits = p.k_splits;
   const int total_tiles = tiles_mn * p.batch0 * p.batch1 * splits;
 
+  // Both role loops below are latency chains of ONE warp: every instruction per K chunk counts (the tensor
+  // pipe needs a 4-MMA chunk every ~220-550 cycles).  So: 32-bit shared addresses computed with one IMAD per
+  // stage, incremental filter-tap counters instead of divisions, and a fixed-shape fast path for full chunks.
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (warp-uniform loop, one lane issues)
     int stage = 0;
     uint32_t phase = 0;
+    const uint32_t tx1 = p.a_tx_bytes + BN * BLOCK_K * 2 + (FL ? p.fl_kl * BLOCK_K * 2 : 0);
+    const int dbg = p.dbg;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int ks = tile % splits;
       const int t2 = tile / splits;
@@ -96,49 +104,75 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       const int n0 = nt * BN;
       int m0, img_n0, img_h0;
       gemm_tile_origin(p, mt, m0, img_n0, img_h0);
-      // this tile's K-slice: segment-1 chunks [c_begin, c_end) (+ the LoRA segment on the last slice)
+      // this tile's K-slice: segment-1 chunks [c_begin, c_end1) (+ the LoRA segment on the last slice)
       const int c_begin = (int)((long long)ks * p.chunks1 / splits);
-      const int c_end = (int)((long long)(ks + 1) * p.chunks1 / splits) + ((ks == splits - 1) ? p.has_seg2 : 0);
-      for (int c = c_begin; c < c_end; ++c) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+      const int c_end1 = (int)((long long)(ks + 1) * p.chunks1 / splits);
+      const bool seg2 = p.has_seg2 && ks == splits - 1;
+      // filter-tap counters of the implicit conv (mode 1): chunk c = (tap, cc), tap = kh*3 + kw
+      int cc = 0, kw = 0, kh = 0;
+      if (p.mode != 0) {
+        const int tap = c_begin / p.cin_chunks;
+        cc = c_begin - tap * p.cin_chunks;
+        kh = tap / 3;
+        kw = tap - kh * 3;
+      }
+      for (int c = c_begin; c < c_end1; ++c) {
+        mbar_wait_u32(empty0 + stage * 8, phase ^ 1);
         if (elect_one()) {
-          uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
-          uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
-          if (p.dbg == 2) {
-            mbar_arrive(&full_bar[stage]);
-          } else if (c < p.chunks1) {
-            mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes + BN * BLOCK_K * 2 + (FL ? p.fl_kl * BLOCK_K * 2 : 0));
-            if (FL)  // stacked lora_down rows for this K chunk land right behind the W rows of the B tile
-              tma_load_4d(sb + BN * BLOCK_K * 2, &p.tm_ad, &full_bar[stage], c * BLOCK_K, 0, 0, 0);
+          const uint32_t fb = full0 + stage * 8;
+          const uint32_t sa = sa0 + stage * A_STAGE_BYTES;
+          const uint32_t sb = sb0 + stage * Cfg::B_STAGE_BYTES;
+          if (dbg == 2) {
+            mbar_arrive_u32(fb);
+          } else {
+            mbar_arrive_expect_tx_u32(fb, tx1);
             if (p.mode == 0) {
-              tma_load_4d(sa, &p.tm_a, &full_bar[stage], c * BLOCK_K, m0, b0, b1);
+              tma_load_4d_u32(sa, &p.tm_a, fb, c * BLOCK_K, m0, b0, b1);
             } else {
-              const int tap = c / p.cin_chunks;
-              const int cc = c - tap * p.cin_chunks;
-              const int kh = tap / 3, kw = tap - kh * 3;
-              tma_load_4d(sa, &p.tm_a, &full_bar[stage], cc * BLOCK_K, kw - 1, img_h0 + kh - 1, img_n0);
+              tma_load_4d_u32(sa, &p.tm_a, fb, cc * BLOCK_K, kw - 1, img_h0 + kh - 1, img_n0);
             }
             if (p.epilogue == 1) {
               // GEGLU: tile columns [0,BN/2) <- hidden rows, [BN/2,BN) <- the matching gate rows
-              tma_load_4d(sb, &p.tm_b, &full_bar[stage], c * BLOCK_K, nt * (BN / 2), b0, b1);
-              tma_load_4d(sb + (BN / 2) * BLOCK_K * 2, &p.tm_b, &full_bar[stage], c * BLOCK_K,
-                          p.N / 2 + nt * (BN / 2), b0, b1);
+              tma_load_4d_u32(sb, &p.tm_b, fb, c * BLOCK_K, nt * (BN / 2), b0, b1);
+              tma_load_4d_u32(sb + (BN / 2) * BLOCK_K * 2, &p.tm_b, fb, c * BLOCK_K, p.N / 2 + nt * (BN / 2), b0, b1);
             } else {
-              tma_load_4d(sb, &p.tm_b, &full_bar[stage], c * BLOCK_K, n0, b0, b1);
+              tma_load_4d_u32(sb, &p.tm_b, fb, c * BLOCK_K, n0, b0, b1);
             }
+            if (FL)  // stacked lora_down rows for this K chunk land right behind the W rows of the B tile
+              tma_load_4d_u32(sb + BN * BLOCK_K * 2, &p.tm_ad, fb, c * BLOCK_K, 0, 0, 0);
+          }
+        }
+        if (++cc == p.cin_chunks) {
+          cc = 0;
+          if (++kw == 3) {
+            kw = 0;
+            ++kh;
+          }
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (seg2) {
+        mbar_wait_u32(empty0 + stage * 8, phase ^ 1);
+        if (elect_one()) {
+          const uint32_t fb = full0 + stage * 8;
+          const uint32_t sa = sa0 + stage * A_STAGE_BYTES;
+          const uint32_t sb = sb0 + stage * Cfg::B_STAGE_BYTES;
+          if (dbg == 2) {
+            mbar_arrive_u32(fb);
           } else {
-            mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + BN * BLOCK_K * 2);
-            tma_load_4d(sa, &p.tm_a2, &full_bar[stage], 0, m0, 0, 0);
+            mbar_arrive_expect_tx_u32(fb, A_STAGE_BYTES + BN * BLOCK_K * 2);
+            tma_load_4d_u32(sa, &p.tm_a2, fb, 0, m0, 0, 0);
             if (p.epilogue == 1) {
-              tma_load_4d(sb, &p.tm_b2, &full_bar[stage], 0, nt * (BN / 2), 0, 0);
-              tma_load_4d(sb + (BN / 2) * BLOCK_K * 2, &p.tm_b2, &full_bar[stage], 0,
-                          p.N / 2 + nt * (BN / 2), 0, 0);
+              tma_load_4d_u32(sb, &p.tm_b2, fb, 0, nt * (BN / 2), 0, 0);
+              tma_load_4d_u32(sb + (BN / 2) * BLOCK_K * 2, &p.tm_b2, fb, 0, p.N / 2 + nt * (BN / 2), 0, 0);
             } else {
-              tma_load_4d(sb, &p.tm_b2, &full_bar[stage], 0, n0, 0, 0);
+              tma_load_4d_u32(sb, &p.tm_b2, fb, 0, n0, 0, 0);
             }
           }
         }
-        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -148,49 +182,66 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer (warp-uniform loop, one lane issues)
     const uint32_t idesc = umma_idesc_bf16_m128(BN + (FL ? p.fl_kl : 0));  // FL: extra columns = x.Ad^T
+    const uint32_t a_lo0 = umma_desc_lo(sa0), b_lo0 = umma_desc_lo(sb0);
+    const uint32_t tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
+    const int dbg = p.dbg;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tmem_empty[as], aphase ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
       const int ks = tile % splits;
       const int c_begin = (int)((long long)ks * p.chunks1 / splits);
-      const int c_end = (int)((long long)(ks + 1) * p.chunks1 / splits) + ((ks == splits - 1) ? p.has_seg2 : 0);
+      const int c_end1 = (int)((long long)(ks + 1) * p.chunks1 / splits);
+      const bool seg2 = p.has_seg2 && ks == splits - 1;
+      // chunks [c_begin, c_fast) are full 4-k-step chunks; the K tail and the LoRA segment take the generic path
+      const int c_fast = (dbg == 1) ? c_begin : ((c_end1 == p.chunks1 && p.ksteps_last1 != 4) ? c_end1 - 1 : c_end1);
+      const int c_end = c_end1 + (seg2 ? 1 : 0);
+      mbar_wait_u32(tempty0 + as * 8, aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
       uint32_t acc = 0;
-      for (int c = c_begin; c < c_end; ++c) {
-        mbar_wait(&full_bar[stage], phase);
+      for (int c = c_begin; c < c_fast; ++c) {
+        mbar_wait_u32(full0 + stage * 8, phase);
         tc_fence_after();
-        const int ksteps = (c < p.chunks1 - 1) ? 4 : (c == p.chunks1 - 1 ? p.ksteps_last1 : p.ksteps2);
-        const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
-        const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
         if (elect_one()) {
-          if (p.dbg == 1) {
-            mbar_arrive(&empty_bar[stage]);
-          } else {
-            // +32 bytes (16 bf16) along K inside the 128B swizzle row: +2 in the >>4 address field
-            if (ksteps == 4) {
-              umma_bf16(tmem_d, da, db, idesc, acc);
-              umma_bf16(tmem_d, da + 2, db + 2, idesc, 1u);
-              umma_bf16(tmem_d, da + 4, db + 4, idesc, 1u);
-              umma_bf16(tmem_d, da + 6, db + 6, idesc, 1u);
-            } else {
-              for (int j = 0; j < ksteps; ++j) umma_bf16(tmem_d, da + 2 * j, db + 2 * j, idesc, (acc | j) != 0 ? 1u : 0u);
-            }
-            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          }
+          // +32 bytes (16 bf16) along K inside the 128B swizzle row: +2 in the >>4 address field
+          const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (Cfg::B_STAGE_BYTES >> 4);
+          umma_bf16_lo(tmem_d, a_lo, b_lo, idesc, acc);
+          umma_bf16_lo(tmem_d, a_lo + 2, b_lo + 2, idesc, 1u);
+          umma_bf16_lo(tmem_d, a_lo + 4, b_lo + 4, idesc, 1u);
+          umma_bf16_lo(tmem_d, a_lo + 6, b_lo + 6, idesc, 1u);
+          umma_commit_u32(empty0 + stage * 8);  // smem slot reusable once these MMAs retire
         }
-        __syncwarp();
         acc = 1;
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      if (elect_one()) umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+      for (int c = c_fast; c < c_end; ++c) {
+        mbar_wait_u32(full0 + stage * 8, phase);
+        tc_fence_after();
+        const int ksteps = (c < p.chunks1 - 1) ? 4 : (c == p.chunks1 - 1 ? p.ksteps_last1 : p.ksteps2);
+        if (elect_one()) {
+          if (dbg == 1) {
+            mbar_arrive_u32(empty0 + stage * 8);
+          } else {
+            const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4);
+            const uint32_t b_lo = b_lo0 + stage * (Cfg::B_STAGE_BYTES >> 4);
+            for (int j = 0; j < ksteps; ++j) umma_bf16_lo(tmem_d, a_lo + 2 * j, b_lo + 2 * j, idesc, (acc | j) != 0 ? 1u : 0u);
+            umma_commit_u32(empty0 + stage * 8);
+          }
+        }
+        acc = 1;
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit_u32(tfull0 + as * 8);  // accumulator complete -> epilogue
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -208,10 +259,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       const int mt = rem - nt * p.tiles_m;
       const int b1 = bidx / p.batch0;
       const int b0 = bidx - b1 * p.batch0;
-      mbar_wait(&tmem_full[as], aphase);
+      mbar_wait_backoff(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
-      gemm_epilogue_tile<BN>(p, trow, r, mt, nt, b0, b1);
+      if (p.dbg != 3) gemm_epilogue_tile<BN>(p, trow, r, mt, nt, b0, b1, (warp - 4) >> 2, 2);  // dbg 3: perf triage without the epilogue
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -308,7 +359,7 @@ static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  LECO_LAUNCH((gemm_tcgen05_kernel<BN, FL>), grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, p);
+  LECO_LAUNCH((gemm_tcgen05_kernel<BN, FL>), grid, GEMM_THREADS_1CTA, Cfg::SMEM_BYTES, stream, p);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

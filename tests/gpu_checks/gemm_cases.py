@@ -275,6 +275,36 @@ def case_perf(M, N, K, block_n=0, conv=None, iters=20, cta_pair=0):
     return {"ok": True, "ms": ms, "tflops": tf, "cublas_ms": ms_ref}
 
 
+def case_shape_modes():
+    """The UNet's dominant GEMM shapes timed under the pipeline triage modes:
+    0 normal, 1 TMA only, 2 MMA only, 3 no epilogue.  Microseconds per launch."""
+    from leco_b200 import ops
+    res = {"ok": True}
+    shapes = {
+        "conv64_320": dict(M=0, N=320, K=0, conv=(4, 64, 64, 320)),
+        "conv32_640": dict(M=0, N=640, K=0, conv=(4, 32, 32, 640)),
+        "conv16_1280": dict(M=0, N=1280, K=0, conv=(4, 16, 16, 1280)),
+        "conv64_640to320": dict(M=0, N=320, K=0, conv=(4, 64, 64, 640)),
+        "ff1": dict(M=16384, N=2560, K=320),
+        "ff2": dict(M=16384, N=320, K=1280),
+        "qkv320": dict(M=16384, N=320, K=320),
+        "lin640": dict(M=4096, N=640, K=640),
+    }
+    for name, kw in shapes.items():
+        for mode in (0, 1, 2, 3):
+            ops._GEMM_DEBUG_MODE = mode
+            try:
+                r = case_perf(iters=20, **kw)
+            finally:
+                ops._GEMM_DEBUG_MODE = 0
+            res[f"{name}_mode{mode}_us"] = round(r["ms"] * 1e3, 2)
+            if mode == 0:
+                res[f"{name}_tflops"] = round(r["tflops"], 1)
+                if r["cublas_ms"]:
+                    res[f"{name}_cublas_us"] = round(r["cublas_ms"] * 1e3, 2)
+    return res
+
+
 CASES = [
     ("basic_bn128", case_matrix, dict(M=256, N=256, K=256, block_n=128)),
     ("basic_bn64", case_matrix, dict(M=256, N=256, K=256, block_n=64)),
@@ -309,6 +339,7 @@ CASES = [
     ("conv_plain", case_conv, dict(n=2, h=32, w=32, cin=64, cout=64, bias=False, rowbias=False, residual=False)),
     ("triage_mma_rate", case_mma_rate, dict()),
     ("triage_fl_perf", case_fl_perf, dict()),
+    ("triage_shape_modes", case_shape_modes, dict()),
     ("fl_linear_r4", case_fl, dict(M=1024, N=320, K=320)),
     ("fl_linear_qkv_r12_tout", case_fl, dict(M=4096, N=960, K=320, rank=12, t_out=True)),
     ("fl_linear_kl32_bn128", case_fl, dict(M=512, N=640, K=640, kl=32, rank=24, block_n=128, t_out=True)),
