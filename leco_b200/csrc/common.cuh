@@ -321,5 +321,20 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// Branch-free exact-GELU for GEMM epilogues (which are instruction-issue bound): erf by Abramowitz-Stegun 7.1.26,
+// |error| <= 1.5e-7 -- three orders below the bf16 rounding of the result.  ~15 instructions, 2 MUFU.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float ax = fabsf(x) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
 #endif  // __CUDACC__
 }  // namespace leco

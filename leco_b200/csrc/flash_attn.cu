@@ -123,23 +123,19 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
   const uint32_t tmem_s = tmem_base;        // + buf * 128
   const uint32_t tmem_pv = tmem_base + 256; // + buf * 64
 
+  // Each role below is ONE elected lane running its whole loop (tests/gpu_checks/mma_probe.cu: re-electing the warp
+  // every iteration costs ~700 cycles per round against ~60 for the single-lane loop).
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
+    // ------------------------------------------------------------------ TMA producer (one elected lane)
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, FA_Q_BYTES);
       tma_load_4d(sQ, &p.tm_q, q_full, 0, qt * FA_BM, head, b);
-    }
-    __syncwarp();
-    for (int j = 0; j < n_tiles; ++j) {
-      const int ks = j % FA_KS, vs = j % FA_VS;
-      mbar_wait(&k_empty[ks], ((j / FA_KS) & 1) ^ 1);
-      if (elect_one()) {
+      for (int j = 0; j < n_tiles; ++j) {
+        const int ks = j % FA_KS, vs = j % FA_VS;
+        mbar_wait(&k_empty[ks], ((j / FA_KS) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[ks], FA_KV_BYTES);
         tma_load_4d(sK + ks * FA_KV_BYTES, &p.tm_k, &k_full[ks], 0, j * FA_BN, head, b);
-      }
-      __syncwarp();
-      mbar_wait(&v_empty[vs], ((j / FA_VS) & 1) ^ 1);
-      if (elect_one()) {
+        mbar_wait(&v_empty[vs], ((j / FA_VS) & 1) ^ 1);
         mbar_arrive_expect_tx(&v_full[vs], FA_KV_BYTES);
         if (p.v_mode == 0) {
           tma_load_4d(sV + vs * FA_KV_BYTES, &p.tm_v, &v_full[vs], 0, j * FA_BN, head, b);
@@ -148,55 +144,50 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
           tma_load_4d(sV + vs * FA_KV_BYTES + FA_KV_BYTES / 2, &p.tm_v, &v_full[vs], j * FA_BN + 64, 0, head, b);
         }
       }
-      __syncwarp();
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc_s = umma_idesc_bf16(FA_BN, false);
-    const uint32_t idesc_pv = umma_idesc_bf16(FA_D, p.v_mode == 0);
-    const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ));
-    auto issue_s = [&](int j) {
-      const int ks = j % FA_KS, sb = j & 1;
-      mbar_wait(&k_full[ks], (j / FA_KS) & 1);
-      mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const uint64_t dk = umma_desc_k_sw128(smem_u32(sK + ks * FA_KV_BYTES));
-      if (elect_one()) {
+    // ------------------------------------------------------------------ MMA issuer (one elected lane)
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc_bf16(FA_BN, false);
+      const uint32_t idesc_pv = umma_idesc_bf16(FA_D, p.v_mode == 0);
+      const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ));
+      auto issue_s = [&](int j) {
+        const int ks = j % FA_KS, sb = j & 1;
+        mbar_wait(&k_full[ks], (j / FA_KS) & 1);
+        mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t dk = umma_desc_k_sw128(smem_u32(sK + ks * FA_KV_BYTES));
 #pragma unroll
         for (int s = 0; s < FA_D / 16; ++s) umma_bf16(tmem_s + sb * FA_BN, dq + 2 * s, dk + 2 * s, idesc_s, s > 0 ? 1u : 0u);
         umma_commit(&s_full[sb]);
         umma_commit(&k_empty[ks]);
-      }
-      __syncwarp();
-    };
-    mbar_wait(q_full, 0);
-    issue_s(0);
-    for (int j = 0; j < n_tiles; ++j) {
-      if (j + 1 < n_tiles) issue_s(j + 1);
-      const int vs = j % FA_VS, pb = j & 1;
-      mbar_wait(&p_full[pb], (j >> 1) & 1);
-      mbar_wait(&v_full[vs], (j / FA_VS) & 1);
-      mbar_wait(&pv_empty[pb], ((j >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t pbase = smem_u32(sP + pb * FA_P_BYTES);
-      const uint32_t vbase = smem_u32(sV + vs * FA_KV_BYTES);
-      if (elect_one()) {
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_s(j + 1);
+        const int vs = j % FA_VS, pb = j & 1;
+        mbar_wait(&p_full[pb], (j >> 1) & 1);
+        mbar_wait(&v_full[vs], (j / FA_VS) & 1);
+        mbar_wait(&pv_empty[pb], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t pbase = smem_u32(sP + pb * FA_P_BYTES);
+        const uint32_t vbase = smem_u32(sV + vs * FA_KV_BYTES);
 #pragma unroll
-      for (int s = 0; s < FA_BN / 16; ++s) {
-        // A = P: K-major, two 64-key chunks of [128 rows x 128 B]
-        const uint64_t da = umma_desc_k_sw128(pbase + (s >> 2) * (FA_P_BYTES / 2)) + 2 * (s & 3);
-        uint64_t db;
-        if (p.v_mode == 0)
-          db = umma_desc_mn_sw128(vbase + s * 16 * 128);                       // 16 key rows per k-step
-        else
-          db = umma_desc_k_sw128(vbase + (s >> 2) * (FA_KV_BYTES / 2)) + 2 * (s & 3);
-        umma_bf16(tmem_pv + pb * FA_D, da, db, idesc_pv, s > 0 ? 1u : 0u);
+        for (int s = 0; s < FA_BN / 16; ++s) {
+          // A = P: K-major, two 64-key chunks of [128 rows x 128 B]
+          const uint64_t da = umma_desc_k_sw128(pbase + (s >> 2) * (FA_P_BYTES / 2)) + 2 * (s & 3);
+          uint64_t db;
+          if (p.v_mode == 0)
+            db = umma_desc_mn_sw128(vbase + s * 16 * 128);                       // 16 key rows per k-step
+          else
+            db = umma_desc_k_sw128(vbase + (s >> 2) * (FA_KV_BYTES / 2)) + 2 * (s & 3);
+          umma_bf16(tmem_pv + pb * FA_D, da, db, idesc_pv, s > 0 ? 1u : 0u);
+        }
+        umma_commit(&pv_full[pb]);
+        umma_commit(&v_empty[vs]);
+        umma_commit(&p_empty[pb]);
       }
-      umma_commit(&pv_full[pb]);
-      umma_commit(&v_empty[vs]);
-      umma_commit(&p_empty[pb]);
-      }
-      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax + output

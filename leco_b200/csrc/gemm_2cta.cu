@@ -145,7 +145,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
   const bool geglu = p.epilogue == 1;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (both CTAs; warp-uniform loop)
+    // ------------------------------------------------------------ TMA producer (both CTAs; one elected lane each)
+    if (elect_one()) {
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
@@ -161,7 +162,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
       gemm_tile_origin(p, mt, m0, img_n0, img_h0);
       for (int c = 0; c < total_chunks; ++c) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (elect_one()) {
+        {
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
           if (c < p.chunks1) {
@@ -181,15 +182,16 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
             tma_load_4d_2cta(sb, &p.tm_b2, &full_bar[stage], 0, nb_row, 0, 0);
           }
         }
-        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
+    }
   } else if (warp == 1 && leader) {
-    // -------------------------------------------------------------- MMA issuer (leader CTA only)
+    // -------------------------------------------------------------- MMA issuer (leader CTA only; one elected lane)
+    if (elect_one()) {
     const uint32_t idesc = umma_idesc_bf16_m256(BN);
     int stage = 0;
     uint32_t phase = 0;
@@ -206,18 +208,15 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
         const int ksteps = (c < p.chunks1 - 1) ? 4 : (c == p.chunks1 - 1 ? p.ksteps_last1 : p.ksteps2);
         const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
         const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
-        if (elect_one()) {
-          for (int j = 0; j < ksteps; ++j) umma_bf16_2cta(tmem_d, da + 2 * j, db + 2 * j, idesc, (c | j) != 0 ? 1u : 0u);
-          umma_commit_2cta_mc(&empty_bar[stage], 0b11);
-        }
-        __syncwarp();
+        for (int j = 0; j < ksteps; ++j) umma_bf16_2cta(tmem_d, da + 2 * j, db + 2 * j, idesc, (c | j) != 0 ? 1u : 0u);
+        umma_commit_2cta_mc(&empty_bar[stage], 0b11);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      if (elect_one()) umma_commit_2cta_mc(&tmem_full[as], 0b11);
-      __syncwarp();
+      umma_commit_2cta_mc(&tmem_full[as], 0b11);
+    }
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue (both CTAs, own 128 rows)

@@ -9,8 +9,8 @@ namespace leco {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;               // 64 bf16 = 128 B = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int GEMM_THREADS = 256;      // 2-CTA variant: 4 role warps + 4 epilogue warps
-constexpr int GEMM_THREADS_1CTA = 384; // 1-CTA kernel: 4 role warps + 8 epilogue warps (two per TMEM lane quadrant)
+constexpr int GEMM_THREADS = 256;  // 4 role warps + 4 epilogue warps (8 epilogue warps measured no faster: the
+                                   // epilogue is instruction-issue bound per scheduler, not latency bound)
 
 struct GemmParams {
   CUtensorMap tm_a, tm_b, tm_a2, tm_b2;
@@ -54,7 +54,9 @@ struct GemmCfg {
   static constexpr int B_ROWS = BN + (FL ? FL_MAX_KL : 0);  // W rows (+ room for the stacked lora_down rows)
   static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = FL ? (BN >= 160 ? 4 : (BN >= 128 ? 5 : 6)) : ((BN >= 256) ? 4 : (BN >= 160 ? 5 : 6));
+  // as many stages as fit 227 KB: with the role loops at the tensor floor the main loop is bound by bytes in flight
+  static constexpr int STAGES = FL ? (BN >= 160 ? 4 : (BN >= 128 ? 5 : 6)) : ((BN >= 256) ? 4 : (BN >= 160 ? 6 : (BN >= 128 ? 7 : 9)));
+  static_assert(STAGES * STAGE_BYTES + 1024 + 256 <= 232448, "stage ring exceeds 227 KB");
   // accumulator stage stride in TMEM columns (power of two so a stage never straddles an
   // alignment boundary): 64 / 128 / 256
   static constexpr int ACC_STRIDE = FL ? 256 : ((BN <= 64) ? 64 : (BN <= 128 ? 128 : 256));
@@ -255,7 +257,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
           epi_add_bf16(g, p.bias + p.N / 2 + ocol0, 32);
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) h[j] = h[j] * gelu_erf_f(g[j]);
+        for (int j = 0; j < 32; ++j) h[j] = h[j] * gelu_erf_fast(g[j]);
         epi_store_bf16(reinterpret_cast<__nv_bfloat16*>(p.d) + boff + m * p.ldd + ocol0, h, nvalid);
       }
     }

@@ -17,8 +17,7 @@
 //   add, GEGLU, bf16 or fp32 store.
 //
 // Roles: warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4-11 = epilogue (TMEM lane quadrant = warp % 4; the two warps of a quadrant take
-// alternate 32-column groups).
+// allocator, warps 4-7 = epilogue (TMEM lane quadrant = warp % 4).
 #include <stdio.h>
 
 #include "gemm_common.cuh"
@@ -26,7 +25,7 @@
 namespace leco {
 
 template <int BN, bool FL>
-__global__ void __launch_bounds__(GEMM_THREADS_1CTA, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN, FL>;
   constexpr int STAGES = Cfg::STAGES;
@@ -63,7 +62,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], 4);
     }
     fence_barrier_init();
   }
@@ -79,34 +78,48 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
 
   const int tiles_mn = p.tiles_m * p.tiles_n;
   const int splits = p.k_splits;
-  const int total_tiles = tiles_mn * p.batch0 * p.batch1 * splits;
+  const int n_batches = p.batch0 * p.batch1;
+  const int total_tiles = tiles_mn * n_batches * splits;
 
   // Both role loops below are latency chains of ONE warp: every instruction per K chunk counts (the tensor
   // pipe needs a 4-MMA chunk every ~220-550 cycles).  So: 32-bit shared addresses computed with one IMAD per
   // stage, incremental filter-tap counters instead of divisions, and a fixed-shape fast path for full chunks.
   const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
   const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
+  // Measured with tests/gpu_checks/mma_probe.cu: a role loop that runs ENTIRELY inside one elect.sync region issues
+  // a 4-MMA chunk at the tensor floor (320 cycles at N=160); re-electing / re-converging the warp every chunk costs
+  // ~700 cycles per chunk.  So each role is one elected lane running its whole persistent loop.
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (warp-uniform loop, one lane issues)
+    // ------------------------------------------------------------ TMA producer (one elected lane)
+    if (elect_one()) {
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t tx1 = p.a_tx_bytes + BN * BLOCK_K * 2 + (FL ? p.fl_kl * BLOCK_K * 2 : 0);
     const int dbg = p.dbg;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int ks = tile % splits;
-      const int t2 = tile / splits;
-      const int bidx = t2 / tiles_mn;
+      // per-tile index math runs on ONE lane's latency chain: skip every division the common case does not need
+      int ks = 0, t2 = tile, bidx = 0, b0 = 0, b1 = 0;
+      if (splits > 1) {
+        t2 = tile / splits;
+        ks = tile - t2 * splits;
+      }
+      if (n_batches > 1) {
+        bidx = t2 / tiles_mn;
+        b1 = bidx / p.batch0;
+        b0 = bidx - b1 * p.batch0;
+      }
       const int rem = t2 - bidx * tiles_mn;
       const int nt = rem / p.tiles_m;
       const int mt = rem - nt * p.tiles_m;
-      const int b1 = bidx / p.batch0;
-      const int b0 = bidx - b1 * p.batch0;
       const int n0 = nt * BN;
       int m0, img_n0, img_h0;
       gemm_tile_origin(p, mt, m0, img_n0, img_h0);
       // this tile's K-slice: segment-1 chunks [c_begin, c_end1) (+ the LoRA segment on the last slice)
-      const int c_begin = (int)((long long)ks * p.chunks1 / splits);
-      const int c_end1 = (int)((long long)(ks + 1) * p.chunks1 / splits);
+      int c_begin = 0, c_end1 = p.chunks1;
+      if (splits > 1) {
+        c_begin = (int)((long long)ks * p.chunks1 / splits);
+        c_end1 = (int)((long long)(ks + 1) * p.chunks1 / splits);
+      }
       const bool seg2 = p.has_seg2 && ks == splits - 1;
       // filter-tap counters of the implicit conv (mode 1): chunk c = (tap, cc), tap = kh*3 + kw
       int cc = 0, kw = 0, kh = 0;
@@ -118,7 +131,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       }
       for (int c = c_begin; c < c_end1; ++c) {
         mbar_wait_u32(empty0 + stage * 8, phase ^ 1);
-        if (elect_one()) {
+        {
           const uint32_t fb = full0 + stage * 8;
           const uint32_t sa = sa0 + stage * A_STAGE_BYTES;
           const uint32_t sb = sb0 + stage * Cfg::B_STAGE_BYTES;
@@ -156,7 +169,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       }
       if (seg2) {
         mbar_wait_u32(empty0 + stage * 8, phase ^ 1);
-        if (elect_one()) {
+        {
           const uint32_t fb = full0 + stage * 8;
           const uint32_t sa = sa0 + stage * A_STAGE_BYTES;
           const uint32_t sb = sb0 + stage * Cfg::B_STAGE_BYTES;
@@ -179,8 +192,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         }
       }
     }
+    }
   } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer (warp-uniform loop, one lane issues)
+    // -------------------------------------------------------------- MMA issuer (one elected lane)
+    if (elect_one()) {
     const uint32_t idesc = umma_idesc_bf16_m128(BN + (FL ? p.fl_kl : 0));  // FL: extra columns = x.Ad^T
     const uint32_t a_lo0 = umma_desc_lo(sa0), b_lo0 = umma_desc_lo(sb0);
     const uint32_t tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
@@ -191,9 +206,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int ks = tile % splits;
-      const int c_begin = (int)((long long)ks * p.chunks1 / splits);
-      const int c_end1 = (int)((long long)(ks + 1) * p.chunks1 / splits);
+      int ks = 0, c_begin = 0, c_end1 = p.chunks1;
+      if (splits > 1) {
+        ks = tile % splits;
+        c_begin = (int)((long long)ks * p.chunks1 / splits);
+        c_end1 = (int)((long long)(ks + 1) * p.chunks1 / splits);
+      }
       const bool seg2 = p.has_seg2 && ks == splits - 1;
       // chunks [c_begin, c_fast) are full 4-k-step chunks; the K tail and the LoRA segment take the generic path
       const int c_fast = (dbg == 1) ? c_begin : ((c_end1 == p.chunks1 && p.ksteps_last1 != 4) ? c_end1 - 1 : c_end1);
@@ -205,7 +223,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       for (int c = c_begin; c < c_fast; ++c) {
         mbar_wait_u32(full0 + stage * 8, phase);
         tc_fence_after();
-        if (elect_one()) {
+        {
           // +32 bytes (16 bf16) along K inside the 128B swizzle row: +2 in the >>4 address field
           const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4);
           const uint32_t b_lo = b_lo0 + stage * (Cfg::B_STAGE_BYTES >> 4);
@@ -225,7 +243,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         mbar_wait_u32(full0 + stage * 8, phase);
         tc_fence_after();
         const int ksteps = (c < p.chunks1 - 1) ? 4 : (c == p.chunks1 - 1 ? p.ksteps_last1 : p.ksteps2);
-        if (elect_one()) {
+        {
           if (dbg == 1) {
             mbar_arrive_u32(empty0 + stage * 8);
           } else {
@@ -241,8 +259,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           phase ^= 1;
         }
       }
-      if (elect_one()) umma_commit_u32(tfull0 + as * 8);  // accumulator complete -> epilogue
-      __syncwarp();
+      umma_commit_u32(tfull0 + as * 8);  // accumulator complete -> epilogue
+    }
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
@@ -262,7 +280,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       mbar_wait_backoff(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
-      if (p.dbg != 3) gemm_epilogue_tile<BN>(p, trow, r, mt, nt, b0, b1, (warp - 4) >> 2, 2);  // dbg 3: perf triage without the epilogue
+      if (p.dbg != 3) gemm_epilogue_tile<BN>(p, trow, r, mt, nt, b0, b1);  // dbg 3: perf triage without the epilogue
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -359,7 +377,7 @@ static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  LECO_LAUNCH((gemm_tcgen05_kernel<BN, FL>), grid, GEMM_THREADS_1CTA, Cfg::SMEM_BYTES, stream, p);
+  LECO_LAUNCH((gemm_tcgen05_kernel<BN, FL>), grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, p);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -234,7 +234,7 @@ def case_fl_perf():
     return res
 
 
-def case_perf(M, N, K, block_n=0, conv=None, iters=20, cta_pair=0):
+def case_perf(M, N, K, block_n=0, conv=None, iters=20, cta_pair=0, graph=False):
     import torch
     from leco_b200 import ops
     if conv:
@@ -252,10 +252,27 @@ def case_perf(M, N, K, block_n=0, conv=None, iters=20, cta_pair=0):
         ops.gemm(a, b, out, block_n=block_n, **kw)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        ops.gemm(a, b, out, block_n=block_n, **kw)
-    e1.record()
+    if graph:
+        # device time without the host's per-launch cost: replay `iters` captured launches (as the trainer does)
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ops.gemm(a, b, out, block_n=block_n, **kw)
+        torch.cuda.current_stream().wait_stream(side)
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                ops.gemm(a, b, out, block_n=block_n, **kw)
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        g.replay()
+        e1.record()
+    else:
+        e0.record()
+        for _ in range(iters):
+            ops.gemm(a, b, out, block_n=block_n, **kw)
+        e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
@@ -294,10 +311,14 @@ def case_shape_modes():
         for mode in (0, 1, 2, 3):
             ops._GEMM_DEBUG_MODE = mode
             try:
-                r = case_perf(iters=20, **kw)
+                r = case_perf(iters=20, graph=True, **kw)
             finally:
                 ops._GEMM_DEBUG_MODE = 0
             res[f"{name}_mode{mode}_us"] = round(r["ms"] * 1e3, 2)
+            if mode == 0 and "conv" in kw or mode == 0 and kw.get("M", 0) >= 4096:
+                ops._GEMM_DEBUG_MODE = 0
+                r2 = case_perf(iters=20, graph=True, cta_pair=1, **kw)
+                res[f"{name}_2cta_us"] = round(r2["ms"] * 1e3, 2)
             if mode == 0:
                 res[f"{name}_tflops"] = round(r["tflops"], 1)
                 if r["cublas_ms"]:

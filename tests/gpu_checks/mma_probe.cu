@@ -138,10 +138,19 @@ __global__ void __launch_bounds__(256) probe_loop(int n, int flags, int chunks, 
         if (!ready) mbar_wait_u32(full0 + stage * 8, phase);
         const int ns = (stage + 1 == STAGES) ? 0 : stage + 1;
         ready = mbar_try_wait_u32(full0 + ns * 8, (stage + 1 == STAGES) ? phase ^ 1 : phase);
+      } else if (flags & 32) {
+        // no wait at all: free-running issue loop
+      } else if (flags & 64) {
+        mbar_wait_u32(smem_u32(done_bar), 1);  // a wait that always succeeds at once (fresh barrier, parity 1)
+      } else if (flags & 256) {
+        uint32_t ok = 0;
+        while (!ok)
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok) : "r"(full0 + stage * 8), "r"(phase) : "memory");
       } else {
         mbar_wait_u32(full0 + stage * 8, phase);
       }
-      tc_fence_after();
+      if (!(flags & 128)) tc_fence_after();
       const bool issuer = (flags & 8) ? (lane == 0) : elect_one();
       if (issuer) {
         const uint32_t a_lo = a_lo0 + (stage & 1) * (a_stage >> 4);
@@ -175,15 +184,147 @@ __global__ void __launch_bounds__(256) probe_loop(int n, int flags, int chunks, 
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
+// ---- probe 3: the whole MMA role loop inside ONE elect.sync region (single-thread loop) ----
+// variant 0: stage-indexed addresses (IMAD from the stage counter); 1: addresses carried incrementally;
+// 2: as 1 plus the stage loop unrolled by STAGES (compile-time stage inside the body)
+template <int STAGES, int VAR>
+__global__ void __launch_bounds__(256) probe_single(int n, int chunks, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t a_stage = 16384, b_stage = 256 * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * (a_stage + b_stage));
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* done_bar = bars + 2 * STAGES;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  for (int i = threadIdx.x; i < 2 * (a_stage + b_stage) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u + (i & 7);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 2) {
+    tmem_alloc(slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < chunks; ++c) {
+        mbar_wait_u32(empty0 + stage * 8, phase ^ 1);
+        mbar_arrive_u32(full0 + stage * 8);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16_m128(n);
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem)), b_lo0 = umma_desc_lo(smem_u32(smem + 2 * a_stage));
+    const long long t0 = clock64();
+    if (elect_one()) {
+      if (VAR == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int c = 0; c < chunks; ++c) {
+          mbar_wait_u32(full0 + stage * 8, phase);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + (stage & 1) * (a_stage >> 4);
+          const uint32_t b_lo = b_lo0 + (stage & 1) * (b_stage >> 4);
+          umma_bf16_lo(tmem, a_lo, b_lo, idesc, 1u);
+          umma_bf16_lo(tmem, a_lo + 2, b_lo + 2, idesc, 1u);
+          umma_bf16_lo(tmem, a_lo + 4, b_lo + 4, idesc, 1u);
+          umma_bf16_lo(tmem, a_lo + 6, b_lo + 6, idesc, 1u);
+          umma_commit_u32(empty0 + stage * 8);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      } else if (VAR == 1) {
+        int stage = 0;
+        uint32_t phase = 0, fb = full0, eb = empty0, a_lo = a_lo0, b_lo = b_lo0;
+        for (int c = 0; c < chunks; ++c) {
+          mbar_wait_u32(fb, phase);
+          tc_fence_after();
+          umma_bf16_lo(tmem, a_lo, b_lo, idesc, 1u);
+          umma_bf16_lo(tmem, a_lo + 2, b_lo + 2, idesc, 1u);
+          umma_bf16_lo(tmem, a_lo + 4, b_lo + 4, idesc, 1u);
+          umma_bf16_lo(tmem, a_lo + 6, b_lo + 6, idesc, 1u);
+          umma_commit_u32(eb);
+          fb += 8; eb += 8;
+          a_lo ^= (a_stage >> 4); b_lo ^= (b_stage >> 4);  // 2 operand buffers in this probe
+          if (++stage == STAGES) { stage = 0; phase ^= 1; fb = full0; eb = empty0; }
+        }
+      } else {
+        uint32_t phase = 0;
+        for (int c = 0; c < chunks; c += STAGES) {
+#pragma unroll
+          for (int s = 0; s < STAGES; ++s) {
+            mbar_wait_u32(full0 + s * 8, phase);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + (s & 1) * (a_stage >> 4);
+            const uint32_t b_lo = b_lo0 + (s & 1) * (b_stage >> 4);
+            umma_bf16_lo(tmem, a_lo, b_lo, idesc, 1u);
+            umma_bf16_lo(tmem, a_lo + 2, b_lo + 2, idesc, 1u);
+            umma_bf16_lo(tmem, a_lo + 4, b_lo + 4, idesc, 1u);
+            umma_bf16_lo(tmem, a_lo + 6, b_lo + 6, idesc, 1u);
+            umma_commit_u32(empty0 + s * 8);
+          }
+          phase ^= 1;
+        }
+      }
+      umma_commit(done_bar);
+    }
+    __syncwarp();
+    mbar_wait(done_bar, 0);
+    const long long t1 = clock64();
+    if (lane == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+template <int VAR>
+static void run_single(const char* name, long long* d_out) {
+  const int smem_bytes = 2 * (16384 + 32768) + 256 + 1024;
+  cudaFuncSetAttribute(probe_single<6, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  const int chunks = 8190;  // multiple of 6
+  for (int n : {64, 160, 256}) {
+    long long cyc = 0;
+    for (int rep = 0; rep < 2; ++rep) probe_single<6, VAR><<<148, 256, smem_bytes>>>(n, chunks, d_out);
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) {
+      printf("%s n %d: %s\n", name, n, cudaGetErrorString(err));
+      return;
+    }
+    cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
+    printf("%-26s N=%3d  %7.1f cyc/chunk (4 MMAs; tensor floor %5.1f)\n", name, n, (double)cyc / chunks, 4 * 128.0 * n / 256.0);
+  }
+}
+
 static void run_loop_probe(long long* d_out) {
+  run_single<0>("single-thread stage-indexed", d_out);
+  run_single<1>("single-thread incremental", d_out);
+  run_single<2>("single-thread unrolled", d_out);
   const int smem_bytes = 2 * (16384 + 32768) + 256 + 1024;
   cudaFuncSetAttribute(probe_loop<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   cudaFuncSetAttribute(probe_loop<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   const int chunks = 8192;
   struct V { const char* name; int flags; int stages; };
-  const V vs[] = {{"loop elect", 0, 6},          {"loop lane0", 8, 6},           {"loop elect +spinners", 2, 6},
-                  {"loop elect +sleepers", 6, 6}, {"loop elect prefetch-wait", 16, 6}, {"pair elect", 1, 3},
-                  {"pair elect +spinners", 3, 3}, {"pair elect +sleepers", 7, 3}, {"pair prefetch +sleepers", 23, 3}};
+  const V vs[] = {{"loop elect", 0, 6},        {"loop lane0", 8, 6},          {"no wait", 32, 6},
+                  {"no wait no fence", 32 + 128, 6}, {"always-true wait", 64, 6}, {"always-true, no fence", 64 + 128, 6},
+                  {"real wait, no fence", 128, 6}, {"test_wait spin", 256, 6},  {"test_wait, no fence", 256 + 128, 6},
+                  {"pair elect", 1, 3},         {"pair no fence", 1 + 128, 3},  {"pair test_wait no fence", 1 + 256 + 128, 3}};
   for (const V& v : vs) {
     for (int n : {64, 160, 256}) {
       long long cyc = 0;
