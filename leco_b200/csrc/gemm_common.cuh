@@ -104,6 +104,37 @@ __device__ __forceinline__ void epi_add_bf16(float (&v)[32], const __nv_bfloat16
   }
 }
 
+// The epilogue's global operands of one 32-column group (bias, per-row-group bias, residual), fetched one group
+// AHEAD of the TMEM data they are added to: an epilogue iteration is a latency chain (TMEM load -> global loads ->
+// math -> store), and the residual comes from L2/HBM; prefetching overlaps that latency with the previous group.
+struct EpiGlobals {
+  uint4 b[4], rb[4], rs[4];
+};
+__device__ __forceinline__ void epi_load_globals(EpiGlobals& G, const __nv_bfloat16* bias, const __nv_bfloat16* rb_row,
+                                                 const __nv_bfloat16* res_row, int col0, int nvalid, bool ok) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const bool on = ok && g * 8 < nvalid;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    G.b[g] = (on && bias) ? __ldg(reinterpret_cast<const uint4*>(bias + col0 + g * 8)) : z;
+    G.rb[g] = (on && rb_row) ? __ldg(reinterpret_cast<const uint4*>(rb_row + col0 + g * 8)) : z;
+    G.rs[g] = (on && res_row) ? __ldg(reinterpret_cast<const uint4*>(res_row + col0 + g * 8)) : z;
+  }
+}
+__device__ __forceinline__ void epi_add_q(float (&v)[32], const uint4 (&q)[4]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    v[g * 8 + 0] += bf16_lo(q[g].x);
+    v[g * 8 + 1] += bf16_hi(q[g].x);
+    v[g * 8 + 2] += bf16_lo(q[g].y);
+    v[g * 8 + 3] += bf16_hi(q[g].y);
+    v[g * 8 + 4] += bf16_lo(q[g].z);
+    v[g * 8 + 5] += bf16_hi(q[g].z);
+    v[g * 8 + 6] += bf16_lo(q[g].w);
+    v[g * 8 + 7] += bf16_hi(q[g].w);
+  }
+}
+
 // v[j] += fl_scale * sum_k T_raw[k] * Bup[n0 + j][k] for the 32 output columns of one chunk.  T_raw is re-read
 // from TMEM in groups of 8 columns (cheap) so no large register array is live.
 __device__ __forceinline__ void epi_lora_add(float (&v)[32], const GemmParams& p, uint32_t t_addr, long long ncol0,
@@ -139,10 +170,8 @@ __device__ __forceinline__ void epi_lora_add(float (&v)[32], const GemmParams& p
 // One output tile: TMEM accumulator (this thread's row r of lane quadrant q) -> epilogue -> global.
 // `trow` = TMEM address of the row's first accumulator column; (mt, nt, b0, b1) identify the tile.
 template <int BN>
-// The tile's 32-column groups c = c_start, c_start + c_step, ... are this warp's share (two epilogue warps can
-// split one lane quadrant).
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t trow, int r, int mt, int nt, int b0,
-                                                   int b1, int c_start = 0, int c_step = 1) {
+                                                   int b1) {
   const bool geglu = (p.epilogue == 1);
   const int n0 = nt * BN;
   long long m;
@@ -163,7 +192,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
     m = static_cast<long long>(img_n0 * p.ch + img_h0) * p.cw + r;
   }
   const long long boff = b0 * p.d_bs0 + b1 * p.d_bs1;
-  if (p.fl_kl && p.fl_t_out && nt == 0 && c_start == 0) {  // save fl_scale*T for the backward (dB = dY^T T)
+  if (p.fl_kl && p.fl_t_out && nt == 0) {  // save fl_scale*T for the backward (dB = dY^T T)
     for (int g = 0; g < p.fl_kl / 8; ++g) {
       uint32_t traw[8];
       tmem_ld_32x32b_x8(trow + BN + g * 8, traw);
@@ -182,7 +211,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   if (p.k_splits > 1) {
     // partial accumulator of one K-slice -> fp32 workspace (bias / residual are applied by the finalize kernel)
 #pragma unroll 1
-    for (int c = c_start; c < BN / 32; c += c_step) {
+    for (int c = 0; c < BN / 32; ++c) {
       uint32_t raw[32];
       tmem_ld_32x32b_x32(trow + c * 32, raw);
       tmem_ld_wait();
@@ -207,33 +236,38 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       }
     }
   } else if (!geglu) {
-#pragma unroll 1
-    for (int c = c_start; c < BN / 32; c += c_step) {
+    const __nv_bfloat16* rb_row = p.rowbias ? p.rowbias + (m / p.rows_per_group) * p.ld_rowbias : nullptr;
+    const __nv_bfloat16* res_row = p.residual ? p.residual + boff + m * p.ldr : nullptr;
+    EpiGlobals cur, nxt;
+    epi_load_globals(cur, p.bias, rb_row, res_row, n0, p.N - n0, row_ok);
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
       uint32_t raw[32];
       tmem_ld_32x32b_x32(trow + c * 32, raw);
-      tmem_ld_wait();
       const int col0 = n0 + c * 32;
       const int nvalid = p.N - col0;  // may be <= 0 or > 32
       const bool ok = row_ok && nvalid > 0;
+      if (c + 1 < BN / 32) epi_load_globals(nxt, p.bias, rb_row, res_row, col0 + 32, nvalid - 32, row_ok);
+      tmem_ld_wait();
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
       if (p.fl_kl) epi_lora_add(v, p, trow + BN, col0, ok ? nvalid : 0);  // all lanes (aligned TMEM loads inside)
       if (ok) {
-        if (p.bias) epi_add_bf16(v, p.bias + col0, nvalid);
-        if (p.rowbias)
-          epi_add_bf16(v, p.rowbias + (m / p.rows_per_group) * p.ld_rowbias + col0, nvalid);
-        if (p.residual) epi_add_bf16(v, p.residual + boff + m * p.ldr + col0, nvalid);
+        if (p.bias) epi_add_q(v, cur.b);
+        if (p.rowbias) epi_add_q(v, cur.rb);
+        if (p.residual) epi_add_q(v, cur.rs);
         if (p.out_fp32)
           epi_store_f32(reinterpret_cast<float*>(p.d) + boff + m * p.ldd + col0, v, nvalid);
         else
           epi_store_bf16(reinterpret_cast<__nv_bfloat16*>(p.d) + boff + m * p.ldd + col0, v, nvalid);
       }
+      if (c + 1 < BN / 32) cur = nxt;
     }
   } else {
     // tile columns [0,BN/2) = hidden block, [BN/2,BN) = matching gate block
 #pragma unroll 1
-    for (int c = c_start; c < BN / 64; c += c_step) {
+    for (int c = 0; c < BN / 64; ++c) {
       uint32_t rh[32], rg[32];
       tmem_ld_32x32b_x32(trow + c * 32, rh);
       tmem_ld_32x32b_x32(trow + BN / 2 + c * 32, rg);

@@ -47,12 +47,21 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __r
   if (rl < R) {
     const __nv_bfloat16* base = x + ((size_t)n * hw) * C + v * 8;
     int r = r0 + rl;
-    for (; r + R < r1; r += 2 * R) {  // two independent 16-byte loads in flight
-      float f[8], g[8];
+    for (; r + 3 * R < r1; r += 4 * R) {  // four independent 16-byte loads in flight
       const v8 qa = *reinterpret_cast<const v8*>(base + (size_t)r * C);
       const v8 qb = *reinterpret_cast<const v8*>(base + (size_t)(r + R) * C);
+      const v8 qc = *reinterpret_cast<const v8*>(base + (size_t)(r + 2 * R) * C);
+      const v8 qd = *reinterpret_cast<const v8*>(base + (size_t)(r + 3 * R) * C);
+      float f[8], g[8];
       up8(qa, f);
       up8(qb, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += f[j] + g[j];
+        s2[j] = fmaf(f[j], f[j], fmaf(g[j], g[j], s2[j]));
+      }
+      up8(qc, f);
+      up8(qd, g);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s1[j] += f[j] + g[j];
@@ -82,10 +91,13 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __r
 }
 
 // ---- pass 2 (forward): y = (x-mean)*rstd*gamma+beta [silu]; also writes stats[n][g] = (mean, rstd)
+// Same thread layout as pass 1 (blockDim.x = vpp * R, one 8-channel vector column per thread), so the per-channel
+// scale = rstd*gamma and shift = beta - mean*scale are loop invariants: the row loop is load, 8 FMA, SiLU, store.
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                 const float2* __restrict__ partial, float2* __restrict__ stats,
                                 const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
-                                int hw, int C, int G, int splits, float eps, int silu) {
+                                int hw, int C, int G, int splits, float eps, int silu, int vpp) {
   pdl_entry();
   __shared__ float2 ms[GN_MAX_GROUPS];
   __shared__ float acc[GN_MAX_GROUPS][2];
@@ -109,25 +121,53 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
     if (blockIdx.y == 0) stats[(size_t)n * G + threadIdx.x] = r;
   }
   __syncthreads();
-  const int vpp = C / 8;
-  const long long total = (long long)hw * vpp;
-  const __nv_bfloat16* xb = x + (size_t)n * hw * C;
-  __nv_bfloat16* yb = y + (size_t)n * hw * C;
-  for (long long i = blockIdx.y * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.y * blockDim.x) {
-    const int v = (int)(i % vpp);
-    float f[8], gm[8], bt[8];
-    up8(*reinterpret_cast<const v8*>(xb + i * 8), f);
+  const int R = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp, rl = threadIdx.x / vpp;
+  if (rl >= R) return;
+  float sc[8], sh[8];
+  {
+    float gm[8], bt[8];
     up8(__ldg(reinterpret_cast<const v8*>(gamma + v * 8)), gm);
     up8(__ldg(reinterpret_cast<const v8*>(beta + v * 8)), bt);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float2 m = ms[(v * 8 + j) / cpg];
-      float o = (f[j] - m.x) * m.y * gm[j] + bt[j];
-      if (silu) o = silu_f(o);
-      f[j] = o;
+      sc[j] = m.y * gm[j];
+      sh[j] = fmaf(-m.x, sc[j], bt[j]);
     }
-    *reinterpret_cast<v8*>(yb + i * 8) = pk8(f);
+  }
+  const int rows_per = (hw + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(hw, r0 + rows_per);
+  const __nv_bfloat16* xb = x + ((size_t)n * hw) * C + v * 8;
+  __nv_bfloat16* yb = y + ((size_t)n * hw) * C + v * 8;
+  int r = r0 + rl;
+  for (; r + R < r1; r += 2 * R) {  // two independent 16-byte loads in flight
+    float f[8], g[8];
+    const v8 qa = *reinterpret_cast<const v8*>(xb + (size_t)r * C);
+    const v8 qb = *reinterpret_cast<const v8*>(xb + (size_t)(r + R) * C);
+    up8(qa, f);
+    up8(qb, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sc[j], sh[j]);
+      g[j] = fmaf(g[j], sc[j], sh[j]);
+      if (silu) {
+        f[j] = silu_fast(f[j]);
+        g[j] = silu_fast(g[j]);
+      }
+    }
+    *reinterpret_cast<v8*>(yb + (size_t)r * C) = pk8(f);
+    *reinterpret_cast<v8*>(yb + (size_t)(r + R) * C) = pk8(g);
+  }
+  for (; r < r1; r += R) {
+    float f[8];
+    up8(*reinterpret_cast<const v8*>(xb + (size_t)r * C), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (silu) f[j] = silu_fast(f[j]);
+    }
+    *reinterpret_cast<v8*>(yb + (size_t)r * C) = pk8(f);
   }
 }
 
@@ -373,14 +413,15 @@ extern "C" int leco_group_norm(const void* x, void* y, void* stats /*float2[n*G]
   LECO_LAUNCH(gn_stats_kernel, dim3(n, splits), threads, 0, STREAM(stream), BF(x), reinterpret_cast<float2*>(workspace), hw,
                                                                   C, G, vpp, splits);
   LECO_CHECK_CUDA(cudaGetLastError());
-  long long work = (long long)hw * vpp;
-  int gy = (int)((work + 256 * 4 - 1) / (256 * 4));   // >= 4 vectors per thread: the per-block prologue amortises
-  if (gy > 296 / (n < 1 ? 1 : n) + 1) gy = 296 / (n < 1 ? 1 : n) + 1;
+  // pass 2: ~8 blocks per SM over the whole batch, but at least 4 pixel rows per thread so the prologue amortises
+  const int R = threads / vpp;
+  int gy = (8 * 148) / (n < 1 ? 1 : n);
+  if (gy > hw / (4 * R)) gy = hw / (4 * R);
   if (gy < 1) gy = 1;
   count_launch();
-  LECO_LAUNCH(gn_apply_kernel, dim3(n, gy), 256, 0, STREAM(stream), BF(x), BFW(y), reinterpret_cast<const float2*>(workspace),
+  LECO_LAUNCH(gn_apply_kernel, dim3(n, gy), threads, 0, STREAM(stream), BF(x), BFW(y), reinterpret_cast<const float2*>(workspace),
                                                           reinterpret_cast<float2*>(stats), BF(gamma), BF(beta), hw,
-                                                          C, G, splits, eps, silu);
+                                                          C, G, splits, eps, silu, vpp);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -5,7 +5,9 @@ import sys
 from collections import defaultdict
 
 
-def main(path, k=None):
+def main(path, until=None):
+    """until: kernel-name substring; only launches up to (and including) its first occurrence are summarised
+    (e.g. `guided_step` = the first CFG denoise step of the iteration, i.e. one no-grad UNet forward)."""
     rows = []
     with open(path, newline="") as f:
         lines = [l for l in f if not l.startswith("==")]
@@ -19,6 +21,11 @@ def main(path, k=None):
         name = re.sub(r"\(.*", "", r["Kernel Name"])
         name = re.sub(r"^void |leco::", "", name)
         rows.append((name, ns))
+    if until:
+        for i, (n, _) in enumerate(rows):
+            if until in n:
+                rows = rows[:i + 1]
+                break
     tot = sum(ns for _, ns in rows)
     agg = defaultdict(lambda: [0, 0.0])
     for n, ns in rows:
