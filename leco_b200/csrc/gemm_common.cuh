@@ -111,14 +111,18 @@ struct EpiGlobals {
   uint4 b[4], rb[4], rs[4];
 };
 __device__ __forceinline__ void epi_load_globals(EpiGlobals& G, const __nv_bfloat16* bias, const __nv_bfloat16* rb_row,
-                                                 const __nv_bfloat16* res_row, int col0, int nvalid, bool ok) {
+                                                 const __nv_bfloat16* res_row, int col0, int nvalid, bool ok,
+                                                 bool keep_rs = false) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const bool on = ok && g * 8 < nvalid;
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    G.b[g] = (on && bias) ? __ldg(reinterpret_cast<const uint4*>(bias + col0 + g * 8)) : z;
-    G.rb[g] = (on && rb_row) ? __ldg(reinterpret_cast<const uint4*>(rb_row + col0 + g * 8)) : z;
-    G.rs[g] = (on && res_row) ? __ldg(reinterpret_cast<const uint4*>(res_row + col0 + g * 8)) : z;
+    if (keep_rs) {  // this call refreshes bias / row bias only
+      G.b[g] = (on && bias) ? __ldg(reinterpret_cast<const uint4*>(bias + col0 + g * 8)) : z;
+      G.rb[g] = (on && rb_row) ? __ldg(reinterpret_cast<const uint4*>(rb_row + col0 + g * 8)) : z;
+    } else {        // this call fetches the residual only
+      G.rs[g] = (on && res_row) ? __ldg(reinterpret_cast<const uint4*>(res_row + col0 + g * 8)) : z;
+    }
   }
 }
 __device__ __forceinline__ void epi_add_q(float (&v)[32], const uint4 (&q)[4]) {
@@ -238,16 +242,19 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   } else if (!geglu) {
     const __nv_bfloat16* rb_row = p.rowbias ? p.rowbias + (m / p.rows_per_group) * p.ld_rowbias : nullptr;
     const __nv_bfloat16* res_row = p.residual ? p.residual + boff + m * p.ldr : nullptr;
+    // the residual (L2 / HBM latency) is fetched one group ahead; bias and row bias (L1-resident, shared by all
+    // rows) are fetched at the top of the iteration, before the wait on the TMEM load
     EpiGlobals cur, nxt;
-    epi_load_globals(cur, p.bias, rb_row, res_row, n0, p.N - n0, row_ok);
-#pragma unroll
+    epi_load_globals(cur, nullptr, nullptr, res_row, n0, p.N - n0, row_ok);
+#pragma unroll 1  // (fully unrolled this loop bloats the 11 kernel instantiations by 50% and measured slower)
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t raw[32];
       tmem_ld_32x32b_x32(trow + c * 32, raw);
       const int col0 = n0 + c * 32;
       const int nvalid = p.N - col0;  // may be <= 0 or > 32
       const bool ok = row_ok && nvalid > 0;
-      if (c + 1 < BN / 32) epi_load_globals(nxt, p.bias, rb_row, res_row, col0 + 32, nvalid - 32, row_ok);
+      epi_load_globals(cur, p.bias, rb_row, nullptr, col0, nvalid, row_ok, /*keep_rs=*/true);
+      if (c + 1 < BN / 32) epi_load_globals(nxt, nullptr, nullptr, res_row, col0 + 32, nvalid - 32, row_ok);
       tmem_ld_wait();
       float v[32];
 #pragma unroll
@@ -262,7 +269,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
         else
           epi_store_bf16(reinterpret_cast<__nv_bfloat16*>(p.d) + boff + m * p.ldd + col0, v, nvalid);
       }
-      if (c + 1 < BN / 32) cur = nxt;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) cur.rs[g] = nxt.rs[g];
     }
   } else {
     // tile columns [0,BN/2) = hidden block, [BN/2,BN) = matching gate block

@@ -19,6 +19,10 @@ Every kernel launch of a denoise step (UNet forward + CFG/DDIM update) is captur
 graph that is replayed k times; the tail (both passes, loss, backward) is a second graph.  The
 loss never leaves the device unless the caller reads it.
 
+SDXL (train_lora_xl.py:160-366, train_util.py:217-330): a prompt is an `EmbedsXL` (text [1,77,2048] + pooled
+[1,1280]); every UNet call additionally gets `added_cond_kwargs = {text_embeds, time_ids}` where
+time_ids = get_add_time_ids(height, width, dynamic_crops) is drawn AFTER the latent noise (:196-201).
+
 Data parallel: every rank draws the SAME global noise / prompt / k from an
 identically seeded CPU generator and keeps its slice of the batch; one all-reduce of the
 flat fp32 LoRA gradient buffer per iteration, then the same fused AdamW on every rank.
@@ -33,6 +37,7 @@ import torch
 from . import capi, ops
 from .lora import FlatAdamW, LoRANetwork
 from .scheduler import DDIMScheduler
+from .train_util import get_add_time_ids
 from .unet import EngineUNet, Tape
 
 UNET_IN_CHANNELS = 4      # train_util.py:12
@@ -40,17 +45,26 @@ VAE_SCALE_FACTOR = 8      # train_util.py:13
 
 
 @dataclass
+class EmbedsXL:
+    """prompt_util.PromptEmbedsXL (prompt_util.py:17-23): text_embeds [1,77,2048] + pooled_embeds [1,1280]."""
+    text_embeds: torch.Tensor
+    pooled_embeds: torch.Tensor
+
+
+@dataclass
 class PromptPair:
-    """prompt_util.PromptEmbedsPair (prompt_util.py:70-105): four [1,77,D] embeddings + settings."""
-    target: torch.Tensor
-    positive: torch.Tensor
-    unconditional: torch.Tensor
-    neutral: torch.Tensor
+    """prompt_util.PromptEmbedsPair (prompt_util.py:70-105): four prompt embeddings + settings.  SD1.x/2.x: each
+    is a [1,77,D] tensor; SDXL: each is an `EmbedsXL`."""
+    target: object
+    positive: object
+    unconditional: object
+    neutral: object
     guidance_scale: float = 1.0
     resolution: int = 512
     dynamic_resolution: bool = False
     batch_size: int = 1
     action: str = "erase"
+    dynamic_crops: bool = False     # SDXL only (prompt_util.py:42, train_util.py:301-310)
 
     def signed_guidance(self) -> float:
         if self.action == "erase":      # neutral - g (positive - unconditional)
@@ -94,6 +108,10 @@ class LecoTrainer:
         self.use_graphs = use_cuda_graphs
         self.optimizer = FlatAdamW(network.flat, lr=lr, state_fp32=state_fp32, **(optimizer_kwargs or {}))
         self.act_dtype = unet._act_dtype
+        self.xl = bool(unet.spec.text_time)
+        for p in self.pairs:
+            if self.xl != isinstance(p.target, EmbedsXL):
+                raise ValueError("SDXL UNets take EmbedsXL prompts (text + pooled); SD1.x/2.x take plain tensors")
         for p in self.pairs:
             if p.batch_size % world_size != 0:
                 raise ValueError(f"batch_size {p.batch_size} must be divisible by world_size {world_size}")
@@ -108,6 +126,32 @@ class LecoTrainer:
         self.last = {}
 
     # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _text(e) -> torch.Tensor:
+        return e.text_embeds if isinstance(e, EmbedsXL) else e
+
+    @staticmethod
+    def _same_prompt(a, b) -> bool:
+        if a is b:
+            return True
+        ta, tb = LecoTrainer._text(a), LecoTrainer._text(b)
+        if ta.shape != tb.shape or not torch.equal(ta, tb):
+            return False
+        if isinstance(a, EmbedsXL) != isinstance(b, EmbedsXL):
+            return False
+        return not isinstance(a, EmbedsXL) or torch.equal(a.pooled_embeds, b.pooled_embeds)
+
+    def _pooled(self, embs: Sequence[EmbedsXL], bl: int) -> torch.Tensor:
+        """concat_embeddings order for the pooled embeddings: [P] rows, each prompt repeated bl times."""
+        return torch.cat([e.pooled_embeds.to(self.device, dtype=self.act_dtype).reshape(1, -1).expand(bl, -1)
+                          for e in embs], 0).contiguous()
+
+    def _added(self, st, n_rows: int, key_pooled: str):
+        """added_cond_kwargs of one UNet call over the first n_rows samples (None for SD1.x/2.x)."""
+        if not self.xl:
+            return None
+        return {"text_embeds": st[key_pooled], "time_ids": st["ids"][:n_rows]}
+
     def _emb(self, e: torch.Tensor) -> torch.Tensor:
         k = id(e)
         if k not in self._emb_cache:
@@ -116,6 +160,7 @@ class LecoTrainer:
 
     def _ctx(self, embs: Sequence[torch.Tensor], bl: int) -> torch.Tensor:
         """train_util.concat_embeddings order: each embedding repeated bl times, blocks concatenated."""
+        embs = [self._text(e) for e in embs]
         return torch.cat([self._emb(e).unsqueeze(0).expand(bl, -1, -1) for e in embs], 0).reshape(
             -1, embs[0].shape[-1]).contiguous()
 
@@ -132,7 +177,7 @@ class LecoTrainer:
     # ------------------------------------------------------------------ one denoise step
     def _denoise_body(self, st):
         x2 = st["x"].repeat(2, 1, 1, 1)
-        eps = self.unet.run(x2, st["t"], st["ctx"], None, None)
+        eps = self.unet.run(x2, st["t"], st["ctx"], self._added(st, x2.shape[0], "pooled"), None)
         x_new, _ = ops.guided_step(eps, st["x"], st["coef"], True, False)
         st["x"].copy_(x_new)
 
@@ -147,6 +192,9 @@ class LecoTrainer:
                     "t": torch.zeros((2 * bl,), device=dev, dtype=torch.float32),
                     "coef": torch.zeros((3,), device=dev, dtype=torch.float32),
                     "ctx": torch.zeros((2 * bl * 77, D), device=dev, dtype=self.act_dtype)}
+        if self.xl:
+            g.static["pooled"] = torch.zeros((2 * bl, self.unet.spec.add_text_dim), device=dev, dtype=self.act_dtype)
+            g.static["ids"] = torch.zeros((2 * bl, 6), device=dev, dtype=torch.float32)
         if self.use_graphs:
             self.network.__enter__()
             side = torch.cuda.Stream()
@@ -170,11 +218,11 @@ class LecoTrainer:
         net = self.network
         net.__exit__(None, None, None)                           # multiplier 0: LoRA-off passes
         xr = st["x"].repeat(groups, 1, 1, 1)
-        eps_ng = self.unet.run(xr, st["t"][: groups * bl], st["ctx_ng"], None, None)
+        eps_ng = self.unet.run(xr, st["t"][: groups * bl], st["ctx_ng"], self._added(st, groups * bl, "pooled_ng"), None)
         pos, neu, unc = (eps_ng[i * bl:(i + 1) * bl] for i in slots)
         net.__enter__()                                          # multiplier 1: target pass with tape
         tape = Tape(ops)
-        eps_t = self.unet.run(st["x"], st["t"][:bl], st["ctx_t"], None, tape)
+        eps_t = self.unet.run(st["x"], st["t"][:bl], st["ctx_t"], self._added(st, bl, "pooled_t"), tape)
         loss, dt = ops.leco_loss(eps_t, pos, neu, unc, sgn_g, True)
         tape.grads["eps"] = dt
         tape.backward()
@@ -193,6 +241,11 @@ class LecoTrainer:
                     "ctx_ng": torch.zeros((groups * bl * 77, D), device=dev, dtype=self.act_dtype),
                     "ctx_t": torch.zeros((bl * 77, D), device=dev, dtype=self.act_dtype),
                     "loss": torch.zeros((1,), device=dev, dtype=torch.float32)}
+        if self.xl:
+            P = self.unet.spec.add_text_dim
+            g.static["pooled_ng"] = torch.zeros((groups * bl, P), device=dev, dtype=self.act_dtype)
+            g.static["pooled_t"] = torch.zeros((bl, P), device=dev, dtype=self.act_dtype)
+            g.static["ids"] = torch.zeros((groups * bl, 6), device=dev, dtype=torch.float32)
         if self.use_graphs:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -229,7 +282,7 @@ class LecoTrainer:
             height, width = get_random_resolution_in_bucket(pair.resolution)
         h, w = height // VAE_SCALE_FACTOR, width // VAE_SCALE_FACTOR
         bl = pair.batch_size // self.world
-        D = pair.target.shape[-1]
+        D = self._text(pair.target).shape[-1]
         dg = self._denoise_graph(bl, h, w, D)
         st = dg.static
         if device_noise is not None:
@@ -239,6 +292,11 @@ class LecoTrainer:
             noise = torch.randn((pair.batch_size, UNET_IN_CHANNELS, h, w), device="cpu") * sched.init_noise_sigma
             self._stage_noise(noise, bl, h, w, st["x"])
         st["ctx"].copy_(self._ctx([pair.unconditional, pair.target], bl))
+        ids = None
+        if self.xl:  # drawn after the latent noise (train_lora_xl.py:183-201); same row for every sample
+            ids = get_add_time_ids(height, width, dynamic_crops=pair.dynamic_crops).to(self.device, dtype=torch.float32)
+            st["ids"].copy_(ids.reshape(1, 6).expand(2 * bl, 6))
+            st["pooled"].copy_(self._pooled([pair.unconditional, pair.target], bl))
         if dg.graph is None:
             self.network.__enter__()
         for i in range(k):
@@ -258,7 +316,7 @@ class LecoTrainer:
         slots = []
         for e in (pair.positive, pair.neutral, pair.unconditional):
             for j, d in enumerate(distinct):
-                if d is e or (d.shape == e.shape and torch.equal(d, e)):
+                if self._same_prompt(d, e):
                     slots.append(j)
                     break
             else:
@@ -270,6 +328,10 @@ class LecoTrainer:
         ts["t"].fill_(t_star)
         ts["ctx_ng"].copy_(self._ctx(distinct, bl))
         ts["ctx_t"].copy_(self._ctx([pair.target], bl))
+        if self.xl:
+            ts["ids"].copy_(ids.reshape(1, 6).expand(ts["ids"].shape[0], 6))
+            ts["pooled_ng"].copy_(self._pooled(distinct, bl))
+            ts["pooled_t"].copy_(self._pooled([pair.target], bl))
         if tg.graph is not None:
             tg.graph.replay()
             self.launches += tg.launches

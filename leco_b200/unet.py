@@ -55,6 +55,11 @@ class UNetSpec:
     def temb_dim(self) -> int:
         return self.block_out_channels[0] * 4
 
+    @property
+    def add_text_dim(self) -> int:
+        """Width of the pooled text embedding of `added_cond_kwargs["text_embeds"]` (SDXL: 2816 - 6*256 = 1280)."""
+        return self.add_proj_in - 6 * self.add_time_dim
+
 
 SPECS: Dict[str, UNetSpec] = {
     "sd15": UNetSpec("sd15", cross_attention_dim=768, num_heads=(8, 8, 8, 8)),

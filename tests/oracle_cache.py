@@ -43,6 +43,9 @@ def main():
     from __graft_entry__ import oracle_iterations
     cached("iters_tiny21", lambda: oracle_iterations(3), write=True)
     print("iters", flush=True)
+    from __graft_entry__ import oracle_iterations_xl
+    cached("iters_tinyxl", lambda: oracle_iterations_xl(3), write=True)
+    print("iters xl", flush=True)
 
 
 if __name__ == "__main__":

@@ -49,7 +49,7 @@ def test_forward_matches_oracle(arch):
     assert err < 2e-4 * ref.abs().max().item() + 1e-5, err
 
 
-@pytest.mark.parametrize("arch", ["tiny21", "tiny15"])
+@pytest.mark.parametrize("arch", ["tiny21", "tiny15", "tinyxl"])
 def test_lora_forward_and_grads_match_oracle_autograd(arch):
     oracle = build_unet(arch)
     eng = _engine(arch, oracle)
@@ -66,13 +66,14 @@ def test_lora_forward_and_grads_match_oracle_autograd(arch):
         return net
 
     net_o, net_e = make(oracle), make(eng)
-    assert len(net_o.unet_loras) == len(net_e.unet_loras) == 192
+    # 16 Transformer2DModel x 12 adapted layers (SD1.x/2.x); tinyxl: 11 Transformer2DModel, 28 blocks: 11*2 + 28*10
+    assert len(net_o.unet_loras) == len(net_e.unet_loras) == (302 if arch == "tinyxl" else 192)
     assert [l.lora_name for l in net_o.unet_loras] == [l.lora_name for l in net_e.unet_loras]
     goal = torch.randn((2, 4, 8, 8), generator=torch.Generator().manual_seed(9))
 
     def loss_of(unet, net):
         with net:
-            y = unet(x, t, encoder_hidden_states=ctx).sample
+            y = unet(x, t, encoder_hidden_states=ctx, added_cond_kwargs=added).sample
         return torch.nn.functional.mse_loss(y.float(), goal), y
 
     lo, yo = loss_of(oracle, net_o)
@@ -89,8 +90,8 @@ def test_lora_forward_and_grads_match_oracle_autograd(arch):
     assert worst < 5e-3, worst
     # multiplier == 0 (outside `with network:`) must equal the frozen network exactly
     with torch.no_grad():
-        base = _engine(arch, build_unet(arch))(x, t, encoder_hidden_states=ctx).sample
-        off = eng(x, t, encoder_hidden_states=ctx).sample
+        base = _engine(arch, build_unet(arch))(x, t, encoder_hidden_states=ctx, added_cond_kwargs=added).sample
+        off = eng(x, t, encoder_hidden_states=ctx, added_cond_kwargs=added).sample
     assert torch.equal(base, off)
 
 

@@ -7,6 +7,7 @@ import pytest
 from tests.gpu_checks import gemm_cases, kernel_cases
 
 pytestmark = pytest.mark.gpu
+from __graft_entry__ import BF16_LOSS_FLOOR  # noqa: E402
 
 GEMM = [(n, f, kw) for n, f, kw in gemm_cases.CASES if not n.startswith("perf_")]
 KERN = [(n, f, kw) for n, f, kw in kernel_cases.CASES if n != "engine_fwd_sd21_64"]
@@ -67,8 +68,34 @@ def test_leco_iteration_matches_oracle(graphs):
         ks.append(trainer.last["k"])
     assert ks == ref["k"]
     for a, b in zip(got, ref["losses"]):
-        assert abs(a - b) <= 0.05 * abs(b) + 1e-7, (got, ref["losses"])
+        assert abs(a - b) <= 0.05 * abs(b) + BF16_LOSS_FLOOR, (got, ref["losses"])
     # adapter weights after 3 steps: same direction, same size
+    num = den = 0.0
+    for a, wb in zip(net.unet_loras, ref["lora_up"]):
+        wa, wb = a.lora_up.weight.detach().float().cpu().reshape(-1), wb.float().reshape(-1)
+        num += torch.dot(wa, wb).item()
+        den += (wa.norm() * wb.norm()).item()
+    assert num / den > 0.9, num / den
+
+
+@pytest.mark.parametrize("graphs", [False, True], ids=["eager", "cuda_graphs"])
+def test_leco_iteration_xl_matches_oracle(graphs):
+    """three SDXL-loop iterations (pooled text embedding + add_time_ids with dynamic crops drawn
+    after the noise, train_lora_xl.py:160-366) on the tinyxl topology vs oracle/leco_ref.leco_iteration_xl (pinned
+    against the reference's train_lora_xl.train()).  Same k draws; loss within 5% (bf16 engine vs fp32 oracle)."""
+    import torch
+    from __graft_entry__ import engine_trainer_xl, oracle_iterations_xl
+    from tests.oracle_cache import cached
+    ref = cached("iters_tinyxl", lambda: oracle_iterations_xl(3))
+    trainer, net = engine_trainer_xl(use_graphs=graphs)
+    torch.manual_seed(7)
+    got, ks = [], []
+    for _ in range(3):
+        got.append(trainer.iteration().item())
+        ks.append(trainer.last["k"])
+    assert ks == ref["k"]
+    for a, b in zip(got, ref["losses"]):
+        assert abs(a - b) <= 0.05 * abs(b) + BF16_LOSS_FLOOR, (got, ref["losses"])
     num = den = 0.0
     for a, wb in zip(net.unet_loras, ref["lora_up"]):
         wa, wb = a.lora_up.weight.detach().float().cpu().reshape(-1), wb.float().reshape(-1)
