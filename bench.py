@@ -265,6 +265,11 @@ def run_ours(args):
     kern_flop = 2.0 * n_s * 64 * 64 * 320 * 9 * 320
     burst, sustained, how = measured_peaks()
     kern_tf = kern_flop / (kern_ms * 1e-3) / 1e12
+    # DRAM traffic of one launch of this kernel from the committed `ncu --set full` capture (bytes, or None)
+    traffic = None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "conv_kernel_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
 
     if rank == 0:
         it_s = args.steps / sec
@@ -282,7 +287,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<160> implicit-GEMM conv3x3 320->320 @64x64, "
                          f"{n_s} samples (M=16384,N=320,K=2880)", "achieved": kern_tf, "peak": burst,
-                         "unit": "TFLOP/s", "frac": kern_tf / burst, "traffic": None, "peak_source": how,
+                         "unit": "TFLOP/s", "frac": kern_tf / burst, "traffic": traffic, "peak_source": how,
                          "ms": kern_ms},
             "step_roofline": {"bound": "tensor", "w_min_tflop_per_step": wmin, "w_ref_tflop_per_step":
                               w_ref_tflop(B_PER_GPU, k) * world, "achieved": wmin / (sec / args.steps),
