@@ -17,6 +17,8 @@
 // V operand: v_mode 0 = V tile [keys, d] used directly as an MN-major B operand;
 //            v_mode 1 = a pre-transposed V^T [d, keys] (K-major B operand, like the GEMM kernel).
 #include "../../include/leco_b200.h"
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace leco {
@@ -214,10 +216,13 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
       if (lane == 0) mbar_arrive(&pv_empty[pb]);
     };
 
-    for (int j = 0; j < n_tiles; ++j) {
+    // One KV tile of the online softmax.  RG (= this half tile runs past skv) is a compile-time flag: written as a
+    // run-time `if (ragged)` the per-score masks became ~400 predicated instructions per tile that take issue slots
+    // even when off (ncu: the kernel is issue-bound, ALU the busiest pipe), so the ragged tile gets its own copy.
+    auto softmax_tile = [&](int j, auto rg_tag) {
+      constexpr bool ragged = decltype(rg_tag)::value;
       const int sb = j & 1;
       const int kv0 = j * FA_BN + wg * 64;     // first key of this thread's half
-      const bool ragged = kv0 + 64 > p.skv;
       mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t s_addr = tmem_s + lane_off + sb * FA_BN + wg * 64;
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float a = __uint_as_float(s0[i]), b2 = __uint_as_float(s1[i]);
-        if (ragged) {
+        if constexpr (ragged) {
           if (kv0 + i >= p.skv) a = -INFINITY;
           if (kv0 + 32 + i >= p.skv) b2 = -INFINITY;
         }
@@ -247,7 +252,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
       // p = 2^(s*c - m*c) -> bf16 -> swizzled A-operand tile (this half = 64 keys = one 128-byte row)
       mbar_wait(&p_empty[sb], ((j >> 1) & 1) ^ 1);
       uint8_t* prow = sP + sb * FA_P_BYTES + wg * (FA_P_BYTES / 2) + r * 128;
-      float rowsum = 0.f;
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;  // four partial sums: no 64-long dependent FADD chain
 #define FA_EXP_HALF(SRC, KOFF, CHUNK0)                                                        \
   _Pragma("unroll") for (int t = 0; t < 4; ++t) {                                             \
     uint32_t pk[4];                                                                           \
@@ -255,11 +260,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
       const int i = t * 8 + u * 2;                                                            \
       float p0 = ex2_approx(fmaf(__uint_as_float(SRC[i]), p.scale_log2, -mb));                \
       float p1 = ex2_approx(fmaf(__uint_as_float(SRC[i + 1]), p.scale_log2, -mb));            \
-      if (ragged) {                                                                           \
+      if constexpr (ragged) {                                                                 \
         if (kv0 + KOFF + i >= p.skv) p0 = 0.f;                                                \
         if (kv0 + KOFF + i + 1 >= p.skv) p1 = 0.f;                                            \
       }                                                                                       \
-      rowsum += p0 + p1;                                                                      \
+      if (u == 0) rs0 += p0 + p1; else if (u == 1) rs1 += p0 + p1; else if (u == 2) rs2 += p0 + p1; else rs3 += p0 + p1; \
       pk[u] = pack_bf16(p0, p1);                                                              \
     }                                                                                         \
     *reinterpret_cast<uint4*>(prow + (((CHUNK0 + t) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]); \
@@ -270,10 +275,16 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[sb]);
-      l_part = l_part * alpha + rowsum;
+      l_part = l_part * alpha + ((rs0 + rs1) + (rs2 + rs3));
       m_run = m_new;
       if (j > 0) fold_pv(j - 1, alpha_prev);
       alpha_prev = alpha;
+    };
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j * FA_BN + wg * 64 + 64 > p.skv)
+        softmax_tile(j, std::true_type{});
+      else
+        softmax_tile(j, std::false_type{});
     }
     fold_pv(n_tiles - 1, alpha_prev);
     // total row sum = sum of the two warpgroups' partial sums (same running max in both)
