@@ -64,7 +64,8 @@ typedef struct leco_gemm_args {
   int32_t out_fp32;
   int32_t block_n; /* 0 = heuristic; else 64 / 128 / 160 / 256 */
   int32_t b_rows;  /* rows of B that exist per batch entry (0 = N); rows in [b_rows,N) read as 0 */
-  int32_t cta_pair; /* 1 = 2-CTA (cta_group::2) kernel: 256 x block_n tiles per CTA pair */
+  int32_t cta_pair; /* 0 = 1-CTA kernel, 1 = 2-CTA (cta_group::2) kernel: 256 x block_n tiles per CTA pair,
+                       2 = let the library choose per shape */
   void* splitk_ws;  /* optional ZEROED fp32 workspace (left zeroed): enables split-K for small-M, long-K problems */
   int64_t splitk_ws_bytes;
   /* in-kernel LoRA (alternative to a2/b2): fl_ad = stacked lora_down [fl_kl][K] (row stride fl_ld_ad), fl_bup =

@@ -44,6 +44,34 @@ __device__ __forceinline__ void tma_load_4d_2cta(void* smem_dst, const CUtensorM
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_2cta_u32(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                     int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// descriptors by their low words (see umma_bf16_lo in common.cuh)
+__device__ __forceinline__ void umma_bf16_2cta_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_SW128_HI)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta_mc_u32(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                                uint32_t accumulate) {
   asm volatile(
@@ -80,10 +108,11 @@ template <int BN>
 struct Gemm2Cfg {
   static constexpr int B_STAGE_BYTES = (BN / 2) * BLOCK_K * 2;  // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 6 : (BN >= 160 ? 7 : 8);
+  static constexpr int STAGES = (BN >= 256) ? 7 : (BN >= 160 ? 8 : (BN >= 128 ? 9 : 10));  // fill 227 KB
   static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static_assert(SMEM_BYTES <= 232448, "stage ring exceeds 227 KB");
 };
 
 template <int BN>
@@ -144,79 +173,113 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const bool geglu = p.epilogue == 1;
 
+  // role loops: same lean single-elected-lane structure as gemm_tcgen05.cu
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs; one elected lane each)
     if (elect_one()) {
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-      const int bidx = tile / tiles_mn;
-      const int rem = tile - bidx * tiles_mn;
-      const int nt = rem / tiles_m2;
-      const int mt = (rem - nt * tiles_m2) * 2 + (int)rank;  // may be == tiles_m (dummy tile: all rows OOB)
-      const int b1 = bidx / p.batch0;
-      const int b0 = bidx - b1 * p.batch0;
-      // B rows held by this CTA: its half of the BN-wide N tile (GEGLU: rank 0 = hidden rows, rank 1 = gate rows)
-      const int nb_row = geglu ? (int)rank * (p.N / 2) + nt * (BN / 2) : nt * BN + (int)rank * (BN / 2);
-      int m0, img_n0, img_h0;
-      gemm_tile_origin(p, mt, m0, img_n0, img_h0);
-      for (int c = 0; c < total_chunks; ++c) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        {
-          uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
-          uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
-          if (c < p.chunks1) {
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (p.a_tx_bytes + Cfg::B_STAGE_BYTES));
-            if (p.mode == 0) {
-              tma_load_4d_2cta(sa, &p.tm_a, &full_bar[stage], c * BLOCK_K, m0, b0, b1);
-            } else {
-              const int tap = c / p.cin_chunks;
-              const int cc = c - tap * p.cin_chunks;
-              const int kh = tap / 3, kw = tap - kh * 3;
-              tma_load_4d_2cta(sa, &p.tm_a, &full_bar[stage], cc * BLOCK_K, kw - 1, img_h0 + kh - 1, img_n0);
-            }
-            tma_load_4d_2cta(sb, &p.tm_b, &full_bar[stage], c * BLOCK_K, nb_row, b0, b1);
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx1 = 2 * (p.a_tx_bytes + Cfg::B_STAGE_BYTES);
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        const int bidx = tile / tiles_mn;
+        const int rem = tile - bidx * tiles_mn;
+        const int nt = rem / tiles_m2;
+        const int mt = (rem - nt * tiles_m2) * 2 + (int)rank;  // may be == tiles_m (dummy tile: all rows OOB)
+        const int b1 = bidx / p.batch0;
+        const int b0 = bidx - b1 * p.batch0;
+        // B rows held by this CTA: its half of the BN-wide N tile (GEGLU: rank 0 = hidden rows, rank 1 = gate rows)
+        const int nb_row = geglu ? (int)rank * (p.N / 2) + nt * (BN / 2) : nt * BN + (int)rank * (BN / 2);
+        int m0, img_n0, img_h0;
+        gemm_tile_origin(p, mt, m0, img_n0, img_h0);
+        int cc = 0, kw = 0, kh = 0;  // filter-tap counters of the implicit conv (chunk c = (tap, cc), tap = kh*3 + kw)
+        for (int c = 0; c < p.chunks1; ++c) {
+          mbar_wait_u32(empty0 + stage * 8, phase ^ 1);
+          const uint32_t fb = full0 + stage * 8;
+          const uint32_t sa = sa0 + stage * A_STAGE_BYTES;
+          const uint32_t sb = sb0 + stage * Cfg::B_STAGE_BYTES;
+          if (leader) mbar_arrive_expect_tx_u32(fb, tx1);
+          if (p.mode == 0) {
+            tma_load_4d_2cta_u32(sa, &p.tm_a, fb, c * BLOCK_K, m0, b0, b1);
           } else {
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
-            tma_load_4d_2cta(sa, &p.tm_a2, &full_bar[stage], 0, m0, 0, 0);
-            tma_load_4d_2cta(sb, &p.tm_b2, &full_bar[stage], 0, nb_row, 0, 0);
+            tma_load_4d_2cta_u32(sa, &p.tm_a, fb, cc * BLOCK_K, kw - 1, img_h0 + kh - 1, img_n0);
+          }
+          tma_load_4d_2cta_u32(sb, &p.tm_b, fb, c * BLOCK_K, nb_row, b0, b1);
+          if (++cc == p.cin_chunks) {
+            cc = 0;
+            if (++kw == 3) {
+              kw = 0;
+              ++kh;
+            }
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
           }
         }
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+        if (p.has_seg2) {
+          mbar_wait_u32(empty0 + stage * 8, phase ^ 1);
+          const uint32_t fb = full0 + stage * 8;
+          if (leader) mbar_arrive_expect_tx_u32(fb, 2 * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
+          tma_load_4d_2cta_u32(sa0 + stage * A_STAGE_BYTES, &p.tm_a2, fb, 0, m0, 0, 0);
+          tma_load_4d_2cta_u32(sb0 + stage * Cfg::B_STAGE_BYTES, &p.tm_b2, fb, 0, nb_row, 0, 0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
-    }
     }
   } else if (warp == 1 && leader) {
     // -------------------------------------------------------------- MMA issuer (leader CTA only; one elected lane)
     if (elect_one()) {
-    const uint32_t idesc = umma_idesc_bf16_m256(BN);
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tmem_empty[as], aphase ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
-      for (int c = 0; c < total_chunks; ++c) {
-        mbar_wait(&full_bar[stage], phase);
+      const uint32_t idesc = umma_idesc_bf16_m256(BN);
+      const uint32_t a_lo0 = umma_desc_lo(sa0), b_lo0 = umma_desc_lo(sb0);
+      const uint32_t tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
+      const int c_fast = (p.ksteps_last1 != 4) ? p.chunks1 - 1 : p.chunks1;  // full 4-k-step chunks
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait_u32(tempty0 + as * 8, aphase ^ 1);
         tc_fence_after();
-        const int ksteps = (c < p.chunks1 - 1) ? 4 : (c == p.chunks1 - 1 ? p.ksteps_last1 : p.ksteps2);
-        const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
-        const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
-        for (int j = 0; j < ksteps; ++j) umma_bf16_2cta(tmem_d, da + 2 * j, db + 2 * j, idesc, (c | j) != 0 ? 1u : 0u);
-        umma_commit_2cta_mc(&empty_bar[stage], 0b11);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+        const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
+        uint32_t acc = 0;
+        for (int c = 0; c < c_fast; ++c) {
+          mbar_wait_u32(full0 + stage * 8, phase);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (Cfg::B_STAGE_BYTES >> 4);
+          umma_bf16_2cta_lo(tmem_d, a_lo, b_lo, idesc, acc);
+          umma_bf16_2cta_lo(tmem_d, a_lo + 2, b_lo + 2, idesc, 1u);
+          umma_bf16_2cta_lo(tmem_d, a_lo + 4, b_lo + 4, idesc, 1u);
+          umma_bf16_2cta_lo(tmem_d, a_lo + 6, b_lo + 6, idesc, 1u);
+          umma_commit_2cta_mc_u32(empty0 + stage * 8, 0b11);
+          acc = 1;
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
+        for (int c = c_fast; c < total_chunks; ++c) {
+          mbar_wait_u32(full0 + stage * 8, phase);
+          tc_fence_after();
+          const int ksteps = (c < p.chunks1 - 1) ? 4 : (c == p.chunks1 - 1 ? p.ksteps_last1 : p.ksteps2);
+          const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (Cfg::B_STAGE_BYTES >> 4);
+          for (int j = 0; j < ksteps; ++j) umma_bf16_2cta_lo(tmem_d, a_lo + 2 * j, b_lo + 2 * j, idesc, (acc | j) != 0 ? 1u : 0u);
+          umma_commit_2cta_mc_u32(empty0 + stage * 8, 0b11);
+          acc = 1;
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2cta_mc_u32(tfull0 + as * 8, 0b11);
       }
-      umma_commit_2cta_mc(&tmem_full[as], 0b11);
-    }
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue (both CTAs, own 128 rows)

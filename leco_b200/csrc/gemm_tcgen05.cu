@@ -446,7 +446,13 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
   }
 
   const int nsm = sm_count();
-  const bool splitk_ok = a->splitk_ws && !a->cta_pair && !a->out_fp32 && a->epilogue == 0 && batch0 * batch1 == 1 &&
+  // cta_pair: 0 = 1-CTA kernel, 1 = 2-CTA kernel, 2 = choose.  Measured (profiles/r1_gemm_shape_modes_2cta.json): the
+  // CTA pair shares the B tile, so the TMA-bound long-K GEMMs gain 11-17 % (3x3 convs at the 64x64 / 32x32 levels, ff2);
+  // short-K GEMMs (K <= 640) lose to the extra cluster handshakes, and small-M GEMMs are better served by split-K.
+  const bool pair = a->cta_pair == 1 ||
+                    (a->cta_pair == 2 && p.chunks1 >= 16 && p.tiles_m >= 16 && a->epilogue == 0 && batch0 * batch1 == 1 &&
+                     !a->fl_ad && !a->out_fp32);
+  const bool splitk_ok = a->splitk_ws && !pair && !a->out_fp32 && a->epilogue == 0 && batch0 * batch1 == 1 &&
                          (size_t)a->M * a->N * 4 <= (size_t)a->splitk_ws_bytes && a->N % 4 == 0 && !a->fl_t_out;
   int k_split = 1;
   const int bn = pick_block_n(*a, p.tiles_m, batch0 * batch1, nsm, p.chunks1, splitk_ok ? 8 : 1, &k_split);
@@ -458,7 +464,7 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
     const uint64_t bs0 = batch0 > 1 ? (uint64_t)a->b_bs0 : (uint64_t)a->ldb * a->N;
     const uint64_t bs1 = batch1 > 1 ? (uint64_t)a->b_bs1 : bs0 * batch0;
     const uint64_t str[3] = {(uint64_t)a->ldb * 2, bs0 * 2, bs1 * 2};
-    const uint32_t box_b[4] = {BLOCK_K, (uint32_t)((a->epilogue == 1 || a->cta_pair) ? bn / 2 : bn), 1, 1};
+    const uint32_t box_b[4] = {BLOCK_K, (uint32_t)((a->epilogue == 1 || pair) ? bn / 2 : bn), 1, 1};
     if (make_tmap_bf16_4d(&p.tm_b, a->b, dims, str, box_b)) return -3;
   }
   if (a->a2) {
@@ -472,14 +478,14 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
     if (make_tmap_bf16_4d(&p.tm_a2, a->a2, dims_a, str_a, box2)) return -3;
     const uint64_t dims_b[4] = {(uint64_t)a->K2, (uint64_t)a->N, 1, 1};
     const uint64_t str_b[3] = {(uint64_t)a->ldb2 * 2, (uint64_t)a->ldb2 * a->N * 2, (uint64_t)a->ldb2 * a->N * 2};
-    const uint32_t box_b2[4] = {BLOCK_K, (uint32_t)((a->epilogue == 1 || a->cta_pair) ? bn / 2 : bn), 1, 1};
+    const uint32_t box_b2[4] = {BLOCK_K, (uint32_t)((a->epilogue == 1 || pair) ? bn / 2 : bn), 1, 1};
     if (make_tmap_bf16_4d(&p.tm_b2, a->b2, dims_b, str_b, box_b2)) return -3;
   }
   if (a->fl_ad) {
     LECO_REQUIRE(a->fl_bup && a->fl_kl >= 16 && a->fl_kl <= FL_MAX_KL && a->fl_kl % 16 == 0 && a->fl_rank >= 1 &&
                      a->fl_rank <= a->fl_kl,
                  "leco_gemm_bf16: fused LoRA needs kl in {16..64} and 1 <= rank <= kl (kl=%d rank=%d)", a->fl_kl, a->fl_rank);
-    LECO_REQUIRE(!a->a2 && !a->cta_pair && !a->out_fp32 && batch0 * batch1 == 1 && a->fl_ld_ad % 8 == 0 &&
+    LECO_REQUIRE(!a->a2 && !pair && !a->out_fp32 && batch0 * batch1 == 1 && a->fl_ld_ad % 8 == 0 &&
                      a->fl_ld_bup % 8 == 0,
                  "leco_gemm_bf16: fused LoRA excludes the T segment / 2-CTA / fp32 out / batching");
     const uint64_t dims[4] = {(uint64_t)a->K, (uint64_t)a->fl_kl, 1, 1};
@@ -513,7 +519,7 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
   p.out_fp32 = a->out_fp32;
 
   p.k_splits = 1;
-  if (a->cta_pair) return launch_gemm_2cta(p, bn, stream);
+  if (pair) return launch_gemm_2cta(p, bn, stream);
   long long total_tiles = 1LL * p.tiles_m * p.tiles_n * batch0 * batch1;
   // split-K: few output tiles but a long K (the 16x16 / 8x8 UNet levels at small batch): spread the K range
   // over idle SMs; partial sums meet in an fp32 workspace, splitk_finalize_kernel applies the epilogue

@@ -14,7 +14,7 @@ from . import capi
 from .capi import GemmArgs
 
 BF16 = torch.bfloat16
-GEMM_2CTA = int(__import__('os').environ.get('LECO_GEMM_2CTA', '0'))  # 1: cta_group::2 kernel for plain/conv GEMMs
+GEMM_2CTA = int(__import__('os').environ.get('LECO_GEMM_2CTA', '2'))  # 0: never, 1: always, 2: library chooses per shape
 
 
 _GEMM_DEBUG_MODE = int(__import__('os').environ.get('LECO_GEMM_DEBUG', '0'))
@@ -120,7 +120,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
             _req_bf16(fl_t_out, "fl_t_out")
             assert fl_t_out.shape == (M, kl) and fl_t_out.stride(1) == 1
             g.fl_t_out, g.fl_ld_t = _ptr(fl_t_out), fl_t_out.stride(0)
-    if SPLIT_K and not g.cta_pair:
+    if SPLIT_K and g.cta_pair != 1:
         ws = _splitk_workspace(a.device)
         g.splitk_ws, g.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4
     capi.check(lib.leco_gemm_bf16(ctypes.byref(g), _stream()), "leco_gemm_bf16")
