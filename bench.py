@@ -285,7 +285,7 @@ def run_ours(args):
             "e2e": {"value": val_e2e, "unit": "latents/s", "h2d_bytes_per_step": trainer.h2d_bytes,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<160> implicit-GEMM conv3x3 320->320 @64x64, "
+            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_2cta_kernel<160> (library-chosen) implicit-GEMM conv3x3 320->320 @64x64, "
                          f"{n_s} samples (M=16384,N=320,K=2880)", "achieved": kern_tf, "peak": burst,
                          "unit": "TFLOP/s", "frac": kern_tf / burst, "traffic": traffic, "peak_source": how,
                          "ms": kern_ms},

@@ -11,7 +11,7 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
     --log-file gpurun_out/final_launches.csv python tests/gpu_checks/profile_step.py --k 1 > gpurun_out/final_prof.log 2>&1
 echo "launches=$?"
 # full-section capture of the dominant kernel (implicit-GEMM conv 320->320 @64x64, 4 samples)
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05_kernel --launch-skip 4 \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 --launch-skip 4 \
     --launch-count 1 -f -o gpurun_out/final_conv python tests/gpu_checks/gemm_cases.py perf_conv_64_320 \
     > gpurun_out/final_ncu_conv.log 2>&1
 echo "ncu_conv=$?"
