@@ -145,6 +145,30 @@ class LoRANetwork(nn.Module):
         else:
             torch.save(sd, file)
 
+    def load_weights(self, file, strict: bool = True):
+        """Inverse of save_weights (the reference has none; SURVEY §8f rank 3: needed for resume and for the
+        notebook's inference cell).  Accepts the kohya / A1111 key set `<name>.alpha|lora_down.weight|lora_up.weight`
+        from a .safetensors or torch file; values are copied IN PLACE so the flat operand buffer (and any CUDA graph
+        that captured its address) stays valid."""
+        if os.path.splitext(file)[1] == ".safetensors":
+            from safetensors.torch import load_file
+            sd = load_file(file)
+        else:
+            sd = torch.load(file, map_location="cpu")
+        own = {k: v for k, v in self.state_dict().items() if k.startswith("lora")}
+        missing = [k for k in own if k not in sd]
+        unexpected = [k for k in sd if k not in own]
+        if strict and (missing or unexpected):
+            raise KeyError(f"load_weights: missing {missing[:3]}{'...' if len(missing) > 3 else ''}, "
+                           f"unexpected {unexpected[:3]}{'...' if len(unexpected) > 3 else ''}")
+        with torch.no_grad():
+            for k, dst in own.items():
+                if k in sd:
+                    if tuple(sd[k].shape) != tuple(dst.shape):
+                        raise ValueError(f"load_weights: {k} has shape {tuple(sd[k].shape)}, expected {tuple(dst.shape)}")
+                    dst.copy_(sd[k].to(device=dst.device, dtype=dst.dtype))
+        return missing, unexpected
+
     def __enter__(self):
         for lora in self.unet_loras:
             lora.multiplier = 1.0

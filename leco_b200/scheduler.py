@@ -67,12 +67,9 @@ class DDIMScheduler:
         if eta != 0.0:
             raise NotImplementedError("leco_b200 DDIM implements eta=0 (the reference never passes eta)")
         cx, ce = self.coefficients(int(timestep))
-        if sample.is_cuda:
-            from . import ops
-            prev = ops.axpby(sample, model_output, cx, ce)
-        else:  # host tensors: scheduler bookkeeping only (never the GPU hot path)
-            prev = (cx * sample.float() + ce * model_output.float()).to(sample.dtype)
-        return SimpleNamespace(prev_sample=prev)
+        from . import ops
+        # no host fallback: ops.axpby raises for CPU tensors / a missing CUDA library
+        return SimpleNamespace(prev_sample=ops.axpby(sample, model_output, cx, ce))
 
 
 def create_noise_scheduler(scheduler_name: str = "ddim", prediction_type: str = "epsilon"):

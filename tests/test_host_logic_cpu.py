@@ -29,9 +29,12 @@ def test_ddim_matches_oracle(ptype):
     g = torch.Generator().manual_seed(0)
     x, e = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
     for t in (980, 500, 20, 0):
-        pa = a.step(e, t, x).prev_sample
+        cx, ce = a.coefficients(t)              # the affine map the GPU kernels apply (guided_step / axpby)
+        pa = cx * x + ce * e
         pb = b.step(e, t, x).prev_sample
         assert (pa - pb).abs().max().item() < 2e-6
+    with pytest.raises(RuntimeError):           # product scheduler has no host arithmetic path
+        a.step(e, 980, x)
     assert a.init_noise_sigma == 1.0 and a.scale_model_input(x, 3) is x
     with pytest.raises(ValueError):
         create_noise_scheduler("nope")
@@ -78,6 +81,34 @@ def test_save_weights_format(tmp_path):
         assert sd[k].dtype == torch.bfloat16 and torch.equal(sd[k], want[k]), k
     assert "lora_unet_down_blocks_0_attentions_0_proj_in.alpha" in sd
     assert sd["lora_unet_mid_block_attentions_0_transformer_blocks_0_attn2_to_k.lora_down.weight"].shape == (4, 128)
+
+
+def test_load_weights_round_trip(tmp_path):
+    """save_weights -> load_weights restores every adapter tensor in place."""
+    a, _ = _nets()
+    g = torch.Generator().manual_seed(3)
+    for l in a.unet_loras:
+        l.lora_up.weight.data = 0.1 * torch.randn(l.lora_up.weight.shape, generator=g)
+    want = {k: v.clone() for k, v in a.state_dict().items() if k.startswith("lora")}
+    f = str(tmp_path / "ckpt.safetensors")
+    a.save_weights(f)
+    ptrs = [l.lora_up.weight.data_ptr() for l in a.unet_loras]
+    for l in a.unet_loras:
+        l.lora_up.weight.data.zero_()
+        l.lora_down.weight.data.zero_()
+    missing, unexpected = a.load_weights(f)
+    assert not missing and not unexpected
+    assert ptrs == [l.lora_up.weight.data_ptr() for l in a.unet_loras]      # in place: flat buffer / graphs stay valid
+    for k, v in a.state_dict().items():
+        if k.startswith("lora"):
+            assert torch.equal(v, want[k]), k
+    import pytest
+    sd = {k: v for k, v in want.items() if "mid_block" not in k}
+    torch.save(sd, str(tmp_path / "partial.pt"))
+    with pytest.raises(KeyError):
+        a.load_weights(str(tmp_path / "partial.pt"))
+    missing, _ = a.load_weights(str(tmp_path / "partial.pt"), strict=False)
+    assert missing and all("mid_block" in k for k in missing)
 
 
 def test_c3lier_aliasing_contract():
