@@ -1,7 +1,14 @@
 import os
 import sys
 
-import pytest
+# CPU suite hygiene (must run before torch / libgomp initialise): forward runs on the main thread's OpenMP pool and
+# backward on the autograd thread's own pool.  With the default of one pool thread per core both pools together
+# oversubscribe the machine and their spin-waiting idle threads slowed single tests from 18 s to 8 min.  Four
+# threads per pool and sleeping (not spinning) idle threads keep the whole suite at about a minute.
+os.environ.setdefault("OMP_NUM_THREADS", "4")
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+
+import pytest  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
