@@ -405,6 +405,8 @@ CASES = [
     ("perf_8k", case_perf, dict(M=8192, N=8192, K=8192, iters=5)),
     ("perf_8k_bn128", case_perf, dict(M=8192, N=8192, K=8192, block_n=128, iters=5)),
     ("perf_conv_64_320", case_perf, dict(M=0, N=320, K=0, conv=(4, 64, 64, 320))),
+    ("perfauto_conv_64_320", case_perf, dict(M=0, N=320, K=0, conv=(4, 64, 64, 320), cta_pair=2)),
+    ("perfauto_qkv_320", case_perf, dict(M=16384, N=320, K=320, cta_pair=2, graph=True)),
     ("perf_conv_16_1280", case_perf, dict(M=0, N=1280, K=0, conv=(4, 16, 16, 1280))),
 ]
 
