@@ -233,7 +233,7 @@ def leco_iteration(unet, scheduler, network, optimizer, lr_scheduler, prompt_pai
                      neutral_latents=neutral, unconditional_latents=uncond)   # :265-270
     loss.backward()                                                          # :279
     if record is not None:
-        record.update(k=k, timestep=int(t_cur), denoised=denoised.detach().float().cpu(),
+        record.update(k=k, timestep=int(t_cur), height=height, width=width, denoised=denoised.detach().float().cpu(),
                       positive=positive, neutral=neutral, unconditional=uncond,
                       target=target.detach(), loss=float(loss.item()))
     optimizer.step()                                                         # :280
@@ -290,7 +290,8 @@ def leco_iteration_xl(unet, scheduler, network, optimizer, lr_scheduler, prompt_
                      unconditional_latents=uncond)
     loss.backward()
     if record is not None:
-        record.update(k=k, timestep=int(t_cur), loss=float(loss.item()))
+        record.update(k=k, timestep=int(t_cur), loss=float(loss.item()), height=height, width=width,
+                      time_ids=[float(v) for v in ids.flatten().tolist()])
     optimizer.step()
     lr_scheduler.step()
     return float(loss.item())

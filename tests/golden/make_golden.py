@@ -68,6 +68,16 @@ PROMPTS_YAML = """
   guidance_scale: 1.5
   resolution: 128
   batch_size: 1
+- target: "oil painting"
+  positive: "oil painting"
+  unconditional: ""
+  neutral: ""
+  action: "erase"
+  guidance_scale: 1.0
+  resolution: 384
+  dynamic_resolution: true
+  dynamic_crops: true
+  batch_size: 1
 """
 
 CONFIG_YAML = """
@@ -187,12 +197,14 @@ def run_oracle_train(arch: str, iters: int, max_steps: int, v_pred: bool, prompt
             target=emb[s.target], positive=emb[s.positive], unconditional=emb[s.unconditional],
             neutral=emb[s.neutral], guidance_scale=s.guidance_scale, resolution=s.resolution,
             dynamic_resolution=s.dynamic_resolution, batch_size=s.batch_size, action=s.action))
-    losses, ks = [], []
+    losses, ks, extra = [], [], []
     for _ in range(iters):
         rec = {}
         losses.append(leco_ref.leco_iteration(unet, sched, net, opt, lrs, pairs,
                                               max_denoising_steps=max_steps, record=rec))
         ks.append(rec["k"])
+        extra.append([rec["height"], rec["width"]])
+    run_oracle_train.last_hw = extra
     return losses, ks, net.lora_state_dict(torch.float32)
 
 
@@ -242,7 +254,10 @@ def run_reference_train_xl(arch: str, iters: int, max_steps: int):
         return orig_diff(*a, **kw)
     with tempfile.TemporaryDirectory() as tmp:
         pfile = os.path.join(tmp, "prompts.yaml")
-        open(pfile, "w").write(PROMPTS_YAML)
+        # REFERENCE BUG 2: predict_noise_xl (train_util.py:248-251) calls rescale_noise_cfg(noise_pred[2B], noise_pred_text[B])
+        # and throws the result away; the shapes only broadcast for B == 1, so the XL loop crashes for batch_size > 1.
+        # The XL golden therefore uses batch_size 1 everywhere.
+        open(pfile, "w").write(PROMPTS_YAML.replace("batch_size: 2", "batch_size: 1"))
         cfile = os.path.join(tmp, "config.yaml")
         open(cfile, "w").write(CONFIG_YAML.format(prompts=pfile, arch=arch, iters=iters, max_steps=max_steps,
                                                  out=os.path.join(tmp, "out"), v_pred="false"))
@@ -292,19 +307,21 @@ def run_oracle_train_xl(arch: str, iters: int, max_steps: int, prompt_settings):
             neutral=emb[s.neutral], guidance_scale=s.guidance_scale, resolution=s.resolution,
             dynamic_resolution=s.dynamic_resolution, batch_size=s.batch_size, action=s.action,
             dynamic_crops=s.dynamic_crops))
-    losses, ks = [], []
+    losses, ks, extra = [], [], []
     for _ in range(iters):
         rec = {}
         losses.append(leco_ref.leco_iteration_xl(unet, sched, net, opt, lrs, pairs, max_denoising_steps=max_steps,
                                                  record=rec))
         ks.append(rec["k"])
+        extra.append({"hw": [rec["height"], rec["width"]], "time_ids": rec["time_ids"]})
+    run_oracle_train_xl.last_extra = extra
     return losses, ks, net.lora_state_dict(torch.float32)
 
 
 def main():
     torch.set_num_threads(4)
     out = {}
-    for arch, iters, max_steps, v_pred in (("tiny21", 4, 8, True), ("tiny15", 3, 6, False)):
+    for arch, iters, max_steps, v_pred in (("tiny21", 6, 8, True), ("tiny15", 5, 6, False)):
         ref_losses, ref_ks, ref_sd, prompts = run_reference_train(arch, iters, max_steps, v_pred)
         ora_losses, ora_ks, ora_sd = run_oracle_train(arch, iters, max_steps, v_pred, prompts)
         assert ref_ks == ora_ks, (ref_ks, ora_ks)
@@ -319,18 +336,24 @@ def main():
             "first_keys": keys[:6], "last_keys": keys[-3:],
             "digests": {k: tensor_digest(ref_sd[k]) for k in keys[:12] + keys[-12:]},
             "total_abs": float(sum(v.double().abs().sum() for v in ref_sd.values())),
+            "hw": run_oracle_train.last_hw,   # (height, width) per iteration: the dynamic_resolution prompt draws buckets
         }
+        print(arch, "hw", out[arch]["hw"], "k", ref_ks)
         print(arch, "reference == oracle bit-exact;", "losses", ref_losses, "k", ref_ks)
-    ref_losses, ref_ks, ref_sd, prompts = run_reference_train_xl("tinyxl", 3, 6)
-    ora_losses, ora_ks, ora_sd = run_oracle_train_xl("tinyxl", 3, 6, prompts)
+    assert any(hw != [128, 128] for a in ("tiny21", "tiny15") for hw in out[a]["hw"]), \
+        "the dynamic_resolution prompt was never drawn"
+    ref_losses, ref_ks, ref_sd, prompts = run_reference_train_xl("tinyxl", 5, 6)
+    ora_losses, ora_ks, ora_sd = run_oracle_train_xl("tinyxl", 5, 6, prompts)
     assert ref_ks == ora_ks and ref_losses == ora_losses, (ref_ks, ora_ks, ref_losses, ora_losses)
     assert sorted(ref_sd.keys()) == sorted(ora_sd.keys())
     for k in ref_sd:
         assert torch.equal(ref_sd[k], ora_sd[k]), k
     keys = sorted(ref_sd.keys())
-    out["tinyxl"] = {"seed": SEED, "iters": 3, "max_denoising_steps": 6, "lr": 1e-3, "losses": ref_losses,
+    out["tinyxl"] = {"seed": SEED, "iters": 5, "max_denoising_steps": 6, "lr": 1e-3, "losses": ref_losses,
                      "k": ref_ks, "n_keys": len(keys),
-                     "total_abs": float(sum(v.double().abs().sum() for v in ref_sd.values()))}
+                     "total_abs": float(sum(v.double().abs().sum() for v in ref_sd.values())),
+                     "extra": run_oracle_train_xl.last_extra}   # (h, w) and add_time_ids per iteration (dynamic crops)
+    assert any(e["time_ids"][2:4] != [0.0, 0.0] for e in out["tinyxl"]["extra"]), "dynamic crops never drawn"
     print("tinyxl (train_lora_xl.train) reference == oracle bit-exact;", "losses", ref_losses, "k", ref_ks)
     out["_meta"] = {"torch": torch.__version__,
                     "how": "reference train_lora.train() (unmodified) on oracle UNet/DDIM, CPU fp32"}

@@ -83,6 +83,41 @@ def test_save_weights_format(tmp_path):
     assert sd["lora_unet_mid_block_attentions_0_transformer_blocks_0_attn2_to_k.lora_down.weight"].shape == (4, 128)
 
 
+def test_rng_helpers_draw_like_the_oracle():
+    """Bucket resolution and SDXL add_time_ids (with dynamic crops) consume the global CPU generator exactly like
+    the pinned oracle (train_util.py:295-330, :404-416): same values, same generator state afterwards."""
+    from leco_b200 import train_util as tu
+    from leco_b200.trainer import get_random_resolution_in_bucket as bucket
+    from oracle import leco_ref
+    for seed in (0, 1, 7):
+        torch.manual_seed(seed)
+        a = [bucket(512), bucket(384), tu.get_add_time_ids(192, 320, dynamic_crops=True),
+             tu.get_add_time_ids(128, 128, dynamic_crops=False), torch.rand(1)]
+        torch.manual_seed(seed)
+        b = [leco_ref.get_random_resolution_in_bucket(512), leco_ref.get_random_resolution_in_bucket(384),
+             leco_ref.get_add_time_ids(192, 320, dynamic_crops=True),
+             leco_ref.get_add_time_ids(128, 128, dynamic_crops=False), torch.rand(1)]
+        assert a[0] == b[0] and a[1] == b[1]
+        assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+    assert tu.get_add_time_ids(1024, 1024).tolist() == [[1024, 1024, 0, 0, 1024, 1024]]   # SURVEY 8c known answer (10)
+
+
+def test_trainer_prompt_dedup_rules():
+    """LecoTrainer batches identical prompts of the LoRA-off passes; identity must include the pooled embedding."""
+    from leco_b200.trainer import EmbedsXL, LecoTrainer, PromptPair
+    g = torch.Generator().manual_seed(0)
+    t1, t2 = torch.randn(1, 77, 8, generator=g), torch.randn(1, 77, 8, generator=g)
+    p1, p2 = torch.randn(1, 4, generator=g), torch.randn(1, 4, generator=g)
+    same = LecoTrainer._same_prompt
+    assert same(t1, t1) and same(t1, t1.clone()) and not same(t1, t2)
+    assert same(EmbedsXL(t1, p1), EmbedsXL(t1.clone(), p1.clone()))
+    assert not same(EmbedsXL(t1, p1), EmbedsXL(t1, p2)) and not same(EmbedsXL(t1, p1), t1)
+    assert PromptPair(t1, t1, t2, t2, guidance_scale=1.5, action="erase").signed_guidance() == -1.5
+    assert PromptPair(t1, t1, t2, t2, guidance_scale=1.5, action="enhance").signed_guidance() == 1.5
+    with pytest.raises(ValueError):
+        PromptPair(t1, t1, t2, t2, action="nope").signed_guidance()
+
+
 def test_load_weights_round_trip(tmp_path):
     """save_weights -> load_weights restores every adapter tensor in place."""
     a, _ = _nets()
