@@ -102,3 +102,24 @@ def test_leco_iteration_xl_matches_oracle(graphs):
         num += torch.dot(wa, wb).item()
         den += (wa.norm() * wb.norm()).item()
     assert num / den > 0.9, num / den
+
+
+def test_leco_iteration_dynamic_resolution_matches_oracle():
+    """dynamic_resolution prompts (train_lora.py:162-165): the bucket draw picks a different, usually non-square latent
+    size every iteration (here 24..40 on each side), so the trainer captures one graph pair per shape.  Same k draws,
+    losses within 5 % + the bf16 floor of the oracle's."""
+    import torch
+    from __graft_entry__ import _SETTINGS_DYN, engine_trainer, oracle_iterations
+    from tests.oracle_cache import cached
+    ref = cached("iters_tiny21_dyn", lambda: oracle_iterations(4, settings=_SETTINGS_DYN))
+    trainer, net = engine_trainer(use_graphs=True, settings=_SETTINGS_DYN)
+    torch.manual_seed(7)
+    got, ks, shapes = [], [], []
+    for _ in range(4):
+        got.append(trainer.iteration().item())
+        ks.append(trainer.last["k"])
+        shapes.append(tuple(trainer.last["denoised"].shape[-2:]))
+    assert ks == ref["k"]
+    assert len(set(shapes)) > 1 and any(h != w for h, w in shapes), shapes
+    for a, b in zip(got, ref["losses"]):
+        assert abs(a - b) <= 0.05 * abs(b) + BF16_LOSS_FLOOR, (got, ref["losses"])
