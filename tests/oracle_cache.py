@@ -46,6 +46,8 @@ def main():
     from __graft_entry__ import _SETTINGS_DYN
     cached("iters_tiny21_dyn", lambda: oracle_iterations(4, settings=_SETTINGS_DYN), write=True)
     print("iters dyn", flush=True)
+    cached("iters_tiny21_multi", lambda: oracle_iterations(5, multi=True), write=True)
+    print("iters multi", flush=True)
     from __graft_entry__ import oracle_iterations_xl
     cached("iters_tinyxl", lambda: oracle_iterations_xl(3), write=True)
     print("iters xl", flush=True)

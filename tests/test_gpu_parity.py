@@ -123,3 +123,23 @@ def test_leco_iteration_dynamic_resolution_matches_oracle():
     assert len(set(shapes)) > 1 and any(h != w for h, w in shapes), shapes
     for a, b in zip(got, ref["losses"]):
         assert abs(a - b) <= 0.05 * abs(b) + BF16_LOSS_FLOOR, (got, ref["losses"])
+
+
+def test_leco_iteration_multiple_pairs_enhance_matches_oracle():
+    """Two prompt pairs drawn at random per iteration (train_lora.py:149-151): an erase pair and an ENHANCE pair with
+    guidance 1.5 and neutral != unconditional (three distinct LoRA-off prompts, prompt_util.py:119-135)."""
+    import torch
+    from __graft_entry__ import engine_trainer, oracle_iterations
+    from tests.oracle_cache import cached
+    ref = cached("iters_tiny21_multi", lambda: oracle_iterations(5, multi=True))
+    trainer, net = engine_trainer(use_graphs=True, multi=True)
+    torch.manual_seed(7)
+    got, ks, acts = [], [], []
+    for _ in range(5):
+        got.append(trainer.iteration().item())
+        ks.append(trainer.last["k"])
+        acts.append(trainer.last["pair"].action)
+    assert ks == ref["k"]
+    assert "enhance" in acts and "erase" in acts, acts
+    for a, b in zip(got, ref["losses"]):
+        assert abs(a - b) <= 0.05 * abs(b) + BF16_LOSS_FLOOR, (got, ref["losses"])
