@@ -80,10 +80,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
-// One lane of a CONVERGED warp.  Role loops run warp-uniformly (all 32 lanes execute the waits and the index
-// arithmetic, so the compiler keeps descriptors / barrier addresses in uniform registers); only the single
-// tcgen05.mma / TMA / commit instructions sit under this predicate.  A role written as `if (lane == 0) {loop}`
-// instead forces every operand through R2UR moves: measured ~230 cycles per MMA issue, independent of N.
+// One lane of a CONVERGED warp (elect.sync).  Use it ONCE per role: `if (elect_one()) { whole persistent loop }`.
+// Measured (tests/gpu_checks/mma_probe.cu): a 4-MMA chunk costs 320 cycles (= the tensor floor at N=160) that way,
+// 564-677 cycles with a `lane == 0` predicate, and 614-727 cycles when the warp is re-elected every chunk.
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -16,8 +16,9 @@
 // * epilogue: bias, per-row-group bias (the ResnetBlock2D time-embedding add), residual
 //   add, GEGLU, bf16 or fp32 store.
 //
-// Roles: warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4-7 = epilogue (TMEM lane quadrant = warp % 4).
+// Roles: one elected lane of warp 0 = TMA producer, one elected lane of warp 1 = MMA issuer (each runs its whole
+// persistent loop inside a single elect.sync region), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM lane
+// quadrant = warp % 4).
 #include <stdio.h>
 
 #include "gemm_common.cuh"
