@@ -9,7 +9,7 @@ from tests.gpu_checks import gemm_cases, kernel_cases
 pytestmark = pytest.mark.gpu
 from __graft_entry__ import BF16_LOSS_FLOOR  # noqa: E402
 
-GEMM = [(n, f, kw) for n, f, kw in gemm_cases.CASES if not n.startswith("perf_")]
+GEMM = [(n, f, kw) for n, f, kw in gemm_cases.CASES if not n.startswith(("perf_", "perfauto_"))]
 KERN = [(n, f, kw) for n, f, kw in kernel_cases.CASES if n != "engine_fwd_sd21_64"]
 
 
