@@ -40,3 +40,28 @@ def test_product_path_has_no_cpu_fallback():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_argument_errors_come_back_as_codes_not_crashes():
+    """Error convention of the boundary: no exception / abort crosses the C ABI; a bad call returns a
+    negative code and leaves the reason in leco_last_error().  These checks run before any CUDA call, so they work on
+    a GPU-less host."""
+    import ctypes
+    lib = capi.load()
+    lib.leco_last_error.restype = ctypes.c_char_p
+    g = capi.GemmArgs()
+    assert lib.leco_gemm_bf16(ctypes.byref(g), None) < 0
+    assert b"null operand" in lib.leco_last_error()
+    dummy = ctypes.c_void_p(0x1000)                      # never dereferenced: validation fails first
+    g.a, g.b, g.d = dummy, dummy, dummy
+    g.M, g.N, g.K, g.lda, g.ldb, g.ldd = 128, 100, 64, 64, 64, 104
+    assert lib.leco_gemm_bf16(ctypes.byref(g), None) < 0
+    assert b"N%8" in lib.leco_last_error()
+    g.N, g.ldd, g.mode, g.cc, g.cn, g.ch, g.cw = 64, 64, 1, 32, 1, 8, 16   # conv with C % 64 != 0
+    g.K = 9 * 32
+    g.ldb = g.K
+    assert lib.leco_gemm_bf16(ctypes.byref(g), None) < 0
+    assert b"conv needs" in lib.leco_last_error()
+    import pytest
+    with pytest.raises(capi.LecoError):
+        capi.check(-1, "leco_gemm_bf16")
