@@ -22,6 +22,9 @@ extern "C" {
 
 const char* leco_last_error(void);
 int leco_abi_version(void);
+/* 1: reductions that normally meet in fp32 atomics (LoRA weight-gradient row splits, split-K) run in a fixed order, so
+ * a training step is bit-repeatable (slower).  Also switched on by LECO_DETERMINISTIC=1 in the environment. */
+int leco_set_deterministic(int on);
 /* number of kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t leco_launch_count(void);
 /* fills sm count / cc major / cc minor of the current device */
@@ -154,6 +157,17 @@ int leco_tn_reduce(const void* a, int64_t lda, const void* b, int64_t ldb, float
                    int N2, float scale, int transpose_out, void* stream);
 int leco_adamw_flat(void* params_bf16, float* grads, void* exp_avg, void* exp_avg_sq, int state_is_fp32,
                     const void* mask_u8, const float* hyper_dev, int64_t n, int zero_grad, void* stream);
+/* leco_optim_flat: the optimizers of train_util.get_optimizer (train_util.py:333-370) that have a closed elementwise
+ *   form, fused over the flat buffer: hyper16_dev = fp32[16] {lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+ *   mode (0 adamw | 1 adam | 2 lion), lr/(1-beta1^step), sqrt(1-beta2^step), 1-lr*wd, 1-beta1, 1-beta2, -, -, -}
+ *   (entries 8..12 are host double-precision values rounded to fp32; 0 = derive on the device).  With bf16 state the
+ *   kernel rounds to bf16 after every elementwise op exactly where torch's foreach optimizer does on bf16 parameters
+ *   (the reference keeps parameters, gradients and state in the training dtype, train_lora.py:78-89).
+ * leco_transpose_tiles: one launch transposing a list of [rows,cols] blocks between two flat bf16 buffers; tiles =
+ *   device array of {int64 src_off, dst_off; int32 rows, cols, r0, c0} (32x32 tiles). */
+int leco_optim_flat(void* params_bf16, float* grads, void* exp_avg, void* exp_avg_sq, int state_is_fp32,
+                    const void* mask_u8, const float* hyper16_dev, int64_t n, int zero_grad, void* stream);
+int leco_transpose_tiles(const void* src, void* dst, const void* tiles, int n_tiles, void* stream);
 int leco_guided_step(const float* eps_pair, const float* x, float* x_out, float* guided_out, const float* coef_dev,
                      int64_t half_numel, void* stream);
 int leco_loss(const float* target, const float* positive, const float* neutral, const float* uncond,

@@ -23,6 +23,16 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<int> g_deterministic{-1};
+bool deterministic() {
+  int v = g_deterministic.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("LECO_DETERMINISTIC");
+    v = (e && e[0] == '1') ? 1 : 0;
+    g_deterministic.store(v);
+  }
+  return v == 1;
+}
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -101,7 +111,11 @@ int make_tmap_bf16_4d(CUtensorMap* out, const void* base, const uint64_t dims[4]
 }  // namespace leco
 
 extern "C" const char* leco_last_error(void) { return leco::last_error(); }
-extern "C" int leco_abi_version(void) { return 1; }
+extern "C" int leco_abi_version(void) { return 2; }
+extern "C" int leco_set_deterministic(int on) {
+  leco::g_deterministic.store(on ? 1 : 0);
+  return 0;
+}
 extern "C" int64_t leco_launch_count(void) { return leco::g_launches.load(); }
 extern "C" int leco_device_info(int32_t* sm, int32_t* major, int32_t* minor) {
   int dev = 0;

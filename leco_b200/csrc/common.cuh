@@ -41,6 +41,9 @@ int sm_count();
 // TMEM allocation, descriptor prefetch, block scheduling) overlaps the tail of kernel N — also inside captured
 // CUDA graphs.  LECO_PDL=0 in the environment turns the attribute off (the device instructions become no-ops).
 bool pdl_enabled();
+// leco_set_deterministic(1) / LECO_DETERMINISTIC=1: reductions that normally meet in fp32 atomics (LoRA weight-gradient
+// row splits, split-K partial sums) run in one fixed order instead, so a step is bit-repeatable (slower).
+bool deterministic();
 
 // 4-D bf16 tensor map, dims/strides innermost first; stride[0] is implied (2 bytes).
 // box[i] elements per dim; swizzle 128B; OOB reads fill with zeros.

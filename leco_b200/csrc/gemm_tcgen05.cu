@@ -453,7 +453,7 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
   const bool pair = a->cta_pair == 1 ||
                     (a->cta_pair == 2 && p.chunks1 >= 16 && p.tiles_m >= 16 && a->epilogue == 0 && batch0 * batch1 == 1 &&
                      !a->fl_ad && !a->out_fp32);
-  const bool splitk_ok = a->splitk_ws && !pair && !a->out_fp32 && a->epilogue == 0 && batch0 * batch1 == 1 &&
+  const bool splitk_ok = a->splitk_ws && !deterministic() && !pair && !a->out_fp32 && a->epilogue == 0 && batch0 * batch1 == 1 &&
                          (size_t)a->M * a->N * 4 <= (size_t)a->splitk_ws_bytes && a->N % 4 == 0 && !a->fl_t_out;
   int k_split = 1;
   const int bn = pick_block_n(*a, p.tiles_m, batch0 * batch1, nsm, p.chunks1, splitk_ok ? 8 : 1, &k_split);

@@ -9,10 +9,13 @@
 //   * leco_loss    : erase/enhance MSE objective (prompt_util.py:107-135) + its gradient
 //                    w.r.t. the target prediction, on device (the reference does this on the CPU).
 #include "../../include/leco_b200.h"
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace leco {
 void count_launch();
+bool deterministic();
 
 constexpr int TN_TILE_N1 = 128;
 constexpr int TN_ROWS = 32;
@@ -83,36 +86,103 @@ tn_reduce_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __nv_
   }
 }
 
-// hyper (device, fp32[8]): lr, beta1, beta2, eps, weight_decay, step, grad_scale, unused
+// Flat optimizer step (train_lora.py:89,280 / train_util.py:333-370: adamw, adam, lion) over ONE buffer.
+// hyper (device, fp32[8] or fp32[16]): lr, beta1, beta2, eps, weight_decay, step, grad_scale, mode
+//   (0 AdamW, 1 Adam with L2 decay, 2 Lion); fp32[16] adds host-computed double-precision scalars
+//   [8] lr/(1-beta1^step), [9] sqrt(1-beta2^step), [10] 1-lr*wd, [11] 1-beta1, [12] 1-beta2 (0 = derive here).
+// TState = bf16 reproduces the reference bit-for-bit where it can: parameters, gradients and optimizer state all
+// live in the training dtype (network.to(dtype) precedes the optimizer, train_lora.py:78-89) and torch's foreach
+// implementation rounds to that dtype after EVERY elementwise op (mul, lerp, addcmul, sqrt, div, add, addcdiv);
+// `rb()` marks those rounding points.  TState = float keeps fp32 moments and a single rounding of the parameter.
+__device__ __forceinline__ float rb(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
 template <typename TState>
-__global__ void adamw_flat_kernel(__nv_bfloat16* __restrict__ p, float* __restrict__ g, TState* __restrict__ m,
+__global__ void optim_flat_kernel(__nv_bfloat16* __restrict__ p, float* __restrict__ g, TState* __restrict__ m,
                                   TState* __restrict__ v, const uint8_t* __restrict__ mask,
-                                  const float* __restrict__ hyper, long long n, int zero_grad) {
+                                  const float* __restrict__ hyper, int hyper_len, long long n, int zero_grad) {
   pdl_entry();
+  constexpr bool kRef = !std::is_same<TState, float>::value;   // reference rounding semantics
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], step = hyper[5],
               gs = hyper[6];
-  const float bc1 = 1.0f - powf(b1, step), bc2 = 1.0f - powf(b2, step);
-  const float step_size = lr / bc1;
-  const float inv_bc2_sqrt = rsqrtf(bc2);
+  const int mode = (int)hyper[7];
+  float step_size = 0.f, bc2_sqrt = 0.f, decay = 0.f, omb1 = 0.f, omb2 = 0.f;
+  if (hyper_len >= 16) {
+    step_size = hyper[8];
+    bc2_sqrt = hyper[9];
+    decay = hyper[10];
+    omb1 = hyper[11];
+    omb2 = hyper[12];
+  }
+  if (step_size == 0.f) step_size = lr / (1.0f - powf(b1, step));
+  if (bc2_sqrt == 0.f) bc2_sqrt = sqrtf(1.0f - powf(b2, step));
+  if (decay == 0.f) decay = 1.0f - lr * wd;
+  if (omb1 == 0.f) omb1 = 1.0f - b1;
+  if (omb2 == 0.f) omb2 = 1.0f - b2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     if (mask && !mask[i]) {
       if (zero_grad) g[i] = 0.f;
       continue;
     }
-    // the reference holds parameters, grads and Adam state in the training dtype (bf16,
-    // train_lora.py:78): round the gradient the same way before it enters the moments
-    const float grad = __bfloat162float(__float2bfloat16(g[i] * gs));
+    float grad = rb(g[i] * gs);   // the reference's .grad is a bf16 tensor
     float w = __bfloat162float(p[i]);
-    w *= (1.0f - lr * wd);
-    const float mi = (float)m[i] * b1 + (1.0f - b1) * grad;  // lerp
-    const float vi = (float)v[i] * b2 + (1.0f - b2) * grad * grad;
-    m[i] = (TState)mi;
-    v[i] = (TState)vi;
-    const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
-    w -= step_size * (mi / denom);
-    p[i] = __float2bfloat16(w);
+    const float m0 = (float)m[i];
+    if (mode == 2) {
+      // lion_pytorch.update_fn: p *= 1-lr*wd; u = sign(m*b1 + (1-b1) g); p -= lr*u; m = m*b2 + (1-b2) g
+      if (wd != 0.f) w = kRef ? rb(w * decay) : w * decay;
+      float u = kRef ? rb(rb(m0 * b1) + omb1 * grad) : fmaf(omb1, grad, m0 * b1);
+      const float sg = (u > 0.f) ? 1.f : ((u < 0.f) ? -1.f : 0.f);
+      w = w - lr * sg;
+      const float mn = kRef ? rb(rb(m0 * b2) + omb2 * grad) : fmaf(omb2, grad, m0 * b2);
+      m[i] = (TState)mn;
+      p[i] = __float2bfloat16(w);
+    } else {
+      if (mode == 1) {            // torch.optim.Adam: L2 decay enters the gradient
+        if (wd != 0.f) grad = kRef ? rb(grad + wd * w) : fmaf(wd, w, grad);
+      } else if (wd != 0.f) {     // AdamW: decoupled decay, _foreach_mul_(params, 1 - lr*wd)
+        w = kRef ? rb(w * decay) : w * decay;
+      }
+      float mi, vi, denom;
+      if (kRef) {
+        mi = rb(m0 + omb1 * (grad - m0));                 // _foreach_lerp_(exp_avgs, grads, 1-beta1)
+        vi = rb(rb((float)v[i] * b2) + omb2 * grad * grad);  // _foreach_mul_(beta2); _foreach_addcmul_(g, g, 1-beta2)
+        denom = rb(rb(rb(sqrtf(vi)) / bc2_sqrt) + eps);    // _foreach_sqrt; _foreach_div_; _foreach_add_
+      } else {
+        mi = m0 * b1 + omb1 * grad;
+        vi = (float)v[i] * b2 + omb2 * grad * grad;
+        denom = sqrtf(vi) / bc2_sqrt + eps;
+      }
+      m[i] = (TState)mi;
+      v[i] = (TState)vi;
+      w = w - step_size * (mi / denom);                    // _foreach_addcdiv_(params, exp_avgs, denom, -step_size)
+      p[i] = __float2bfloat16(w);
+    }
     if (zero_grad) g[i] = 0.f;
+  }
+}
+
+// One launch that transposes every [rows, cols] block listed in `tiles` (32x32 tiles of the adapter operands
+// ad [Kl,K] / bup [N,Kl] of all fused sites) from the flat parameter buffer into the flat transposed buffer:
+// the backward GEMMs need ad^T / bup^T, which only change at the optimizer step.
+struct TransposeTile {
+  long long src_off, dst_off;   // element offsets of the matrix in the two flat buffers
+  int rows, cols, r0, c0;       // matrix shape, tile origin
+};
+__global__ void __launch_bounds__(256) transpose_tiles_kernel(const __nv_bfloat16* __restrict__ src,
+                                                              __nv_bfloat16* __restrict__ dst,
+                                                              const TransposeTile* __restrict__ tiles) {
+  pdl_entry();
+  __shared__ __nv_bfloat16 t[32][33];
+  const TransposeTile tt = tiles[blockIdx.x];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = tt.r0 + i, c = tt.c0 + tx;
+    if (r < tt.rows && c < tt.cols) t[i][tx] = src[tt.src_off + (long long)r * tt.cols + c];
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = tt.c0 + i, r = tt.r0 + tx;   // dst is [cols, rows]
+    if (r < tt.rows && c < tt.cols) dst[tt.dst_off + (long long)c * tt.rows + r] = t[tx][i];
   }
 }
 
@@ -199,6 +269,8 @@ extern "C" int leco_tn_reduce(const void* a, int64_t lda, const void* b, int64_t
   const int want = (148 * 4 + col_blocks - 1) / col_blocks;
   if (splits > want) splits = want;
   if (splits < 1) splits = 1;
+  // leco_set_deterministic(1): one row split, so every output element receives exactly one (ordered) add per call
+  if (deterministic()) splits = 1;
   int rows_per = (int)((M + splits - 1) / splits);
   rows_per = (rows_per + TN_ROWS - 1) / TN_ROWS * TN_ROWS;
   splits = (int)((M + rows_per - 1) / rows_per);
@@ -209,20 +281,42 @@ extern "C" int leco_tn_reduce(const void* a, int64_t lda, const void* b, int64_t
   return 0;
 }
 
-extern "C" int leco_adamw_flat(void* params_bf16, float* grads, void* exp_avg, void* exp_avg_sq, int state_is_fp32,
-                               const void* mask_u8, const float* hyper_dev, int64_t n, int zero_grad, void* stream) {
-  LECO_REQUIRE(params_bf16 && grads && exp_avg && exp_avg_sq && hyper_dev && n > 0, "leco_adamw_flat: null / empty");
+static int launch_optim(void* params_bf16, float* grads, void* exp_avg, void* exp_avg_sq, int state_is_fp32,
+                        const void* mask_u8, const float* hyper_dev, int hyper_len, int64_t n, int zero_grad,
+                        void* stream) {
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   count_launch();
   if (state_is_fp32)
-    LECO_LAUNCH(adamw_flat_kernel<float>, (int)blocks, 256, 0, STREAM(stream), 
-        BFW(params_bf16), grads, reinterpret_cast<float*>(exp_avg), reinterpret_cast<float*>(exp_avg_sq),
-        reinterpret_cast<const uint8_t*>(mask_u8), hyper_dev, n, zero_grad);
+    LECO_LAUNCH(optim_flat_kernel<float>, (int)blocks, 256, 0, STREAM(stream), BFW(params_bf16), grads,
+                reinterpret_cast<float*>(exp_avg), reinterpret_cast<float*>(exp_avg_sq),
+                reinterpret_cast<const uint8_t*>(mask_u8), hyper_dev, hyper_len, (long long)n, zero_grad);
   else
-    LECO_LAUNCH(adamw_flat_kernel<__nv_bfloat16>, (int)blocks, 256, 0, STREAM(stream), 
-        BFW(params_bf16), grads, BFW(exp_avg), BFW(exp_avg_sq), reinterpret_cast<const uint8_t*>(mask_u8),
-        hyper_dev, n, zero_grad);
+    LECO_LAUNCH(optim_flat_kernel<__nv_bfloat16>, (int)blocks, 256, 0, STREAM(stream), BFW(params_bf16), grads,
+                BFW(exp_avg), BFW(exp_avg_sq), reinterpret_cast<const uint8_t*>(mask_u8), hyper_dev, hyper_len,
+                (long long)n, zero_grad);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int leco_adamw_flat(void* params_bf16, float* grads, void* exp_avg, void* exp_avg_sq, int state_is_fp32,
+                               const void* mask_u8, const float* hyper_dev, int64_t n, int zero_grad, void* stream) {
+  LECO_REQUIRE(params_bf16 && grads && exp_avg && exp_avg_sq && hyper_dev && n > 0, "leco_adamw_flat: null / empty");
+  return launch_optim(params_bf16, grads, exp_avg, exp_avg_sq, state_is_fp32, mask_u8, hyper_dev, 8, n, zero_grad, stream);
+}
+
+extern "C" int leco_optim_flat(void* params_bf16, float* grads, void* exp_avg, void* exp_avg_sq, int state_is_fp32,
+                               const void* mask_u8, const float* hyper16_dev, int64_t n, int zero_grad, void* stream) {
+  LECO_REQUIRE(params_bf16 && grads && exp_avg && exp_avg_sq && hyper16_dev && n > 0, "leco_optim_flat: null / empty");
+  return launch_optim(params_bf16, grads, exp_avg, exp_avg_sq, state_is_fp32, mask_u8, hyper16_dev, 16, n, zero_grad, stream);
+}
+
+extern "C" int leco_transpose_tiles(const void* src, void* dst, const void* tiles, int n_tiles, void* stream) {
+  LECO_REQUIRE(src && dst && tiles && n_tiles > 0, "leco_transpose_tiles: null / empty");
+  static_assert(sizeof(TransposeTile) == 32, "tile descriptor is 32 bytes (int64 x2 + int32 x4)");
+  count_launch();
+  LECO_LAUNCH(transpose_tiles_kernel, n_tiles, 256, 0, STREAM(stream), BF(src), BFW(dst),
+              reinterpret_cast<const TransposeTile*>(tiles));
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -32,6 +32,8 @@ import torch.nn as nn
 from .unet import down_as_rows, rows_as_down
 
 PREFIX = "lora_unet"
+MAX_SITE_RANK = 64   # stacked (padded) adapter rank that rides as ONE tensor-core K-segment; larger ranks work too
+                     # (unet._linear / _conv3x3 run the LoRA branch as a second accumulate-GEMM then)
 # The reference keeps these as module-level lists and EXTENDS THE FIRST IN PLACE for c3lier
 # (train_lora.py:44-46): callers that do the same to `DEFAULT_TARGET_REPLACE` here get the
 # same behaviour, because the constructor reads the list at call time.
@@ -167,6 +169,8 @@ class LoRANetwork(nn.Module):
                     if tuple(sd[k].shape) != tuple(dst.shape):
                         raise ValueError(f"load_weights: {k} has shape {tuple(sd[k].shape)}, expected {tuple(dst.shape)}")
                     dst.copy_(sd[k].to(device=dst.device, dtype=dst.dtype))
+        if self.flat is not None:
+            self.flat.refresh_transposed()
         return missing, unexpected
 
     def __enter__(self):
@@ -206,7 +210,7 @@ class LoRANetwork(nn.Module):
             raise NotImplementedError(
                 f"leco_b200: {len(self.unet_loras) - covered} adapters sit on layers without a fused engine site")
         dev, dt = p0.device, p0.dtype
-        st = FlatState(torch.zeros(total, device=dev, dtype=dt), torch.zeros(total, device=dev, dtype=torch.float32),
+        st = FlatState(torch.zeros(total, device=dev, dtype=dt), torch.zeros(total + 8, device=dev, dtype=torch.float32),
                        torch.zeros(total, device=dev, dtype=torch.uint8))
         for s, (off, kl) in zip(sites, offsets):
             na, nb = kl * s.k_in, s.n_total * kl
@@ -227,44 +231,134 @@ class LoRANetwork(nn.Module):
                 k0 += r
             s.bind_native(ad, bup, g_ad, g_bup)
         st.n_real = int(st.mask.sum().item())
+        st.build_transposed(sites, offsets)
         self.flat = st
         return st
+
+    def adapter_grads(self):
+        """[d lora_down.weight, d lora_up.weight] per adapter in `prepare_optimizer_params` order, read out of the
+        flat fp32 gradient buffer (views shaped like the parameters; valid until the optimizer zeroes the buffer)."""
+        if self.flat is None:
+            raise RuntimeError("adapter_grads needs the flat layout (network on CUDA, bound to an EngineUNet)")
+        views = {}
+        for s in self._engine[0].lora_sites():
+            ads = s.adapters()
+            if ads is None:
+                continue
+            k0 = 0
+            for a, n0 in zip(ads, s.n_offsets):
+                wd, wu = a.lora_down.weight, a.lora_up.weight
+                r, n = wd.shape[0], wu.shape[0]
+                views[id(a)] = (rows_as_down(s.g_ad[k0:k0 + r], wd.shape), s.g_bup[n0:n0 + n, k0:k0 + r].reshape(wu.shape))
+                k0 += r
+        out = []
+        for lora in self.unet_loras:
+            out += list(views[id(lora)])
+        return out
 
 
 class FlatState:
     """Flat adapter storage: bf16 params, fp32 grads, uint8 mask (1 = a real LoRA element, 0 = operand
-    padding / off-block zero that must never be updated)."""
+    padding / off-block zero that must never be updated).  `grads` is a view of `grads_ext`, which carries one more
+    fp32 slot (`loss_slot`) so that data-parallel training reduces gradient and loss in ONE all-reduce."""
 
-    def __init__(self, params, grads, mask):
-        self.params, self.grads, self.mask = params, grads, mask
+    def __init__(self, params, grads_ext, mask):
+        n = params.numel()
+        self.params, self.grads_ext, self.mask = params, grads_ext, mask
+        self.grads = grads_ext[:n]
+        self.loss_slot = grads_ext[n:n + 1]
         self.n_real = 0
+        self.params_t = None      # flat buffer of the transposed operands (ad^T, bup^T per site)
+        self._tiles = None
+        self._n_tiles = 0
+
+    def build_transposed(self, sites, offsets):
+        """Static (ad^T [K,Kl], bup^T [Kl,N]) views per site + the 32x32 tile table of the one-launch refresh."""
+        import struct
+        self.params_t = torch.zeros_like(self.params)
+        recs = []
+        for s, (off, kl) in zip(sites, offsets):
+            na, nb = kl * s.k_in, s.n_total * kl
+            s.static_t = (self.params_t[off:off + na].view(s.k_in, kl), self.params_t[off + na:off + na + nb].view(kl, s.n_total))
+            s.flat_state = self
+            for o, rows, cols in ((off, kl, s.k_in), (off + na, s.n_total, kl)):
+                for r0 in range(0, rows, 32):
+                    for c0 in range(0, cols, 32):
+                        recs.append(struct.pack("<qqiiii", o, o, rows, cols, r0, c0))
+        self._n_tiles = len(recs)
+        self._tiles = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(self.params.device)
+        self.refresh_transposed()
+
+    def refresh_transposed(self):
+        """Bring every site's (ad^T, bup^T) up to date with the parameters: ONE kernel launch.  Called before every
+        pass that differentiates (LecoTrainer.iteration, EngineUNet.forward under autograd), so in-place parameter
+        edits by any optimizer / loader are picked up."""
+        if self.params_t is not None:
+            from . import ops
+            ops.transpose_tiles(self.params, self.params_t, self._tiles, self._n_tiles)
 
 
-class FlatAdamW:
-    """torch.optim.AdamW semantics (train_lora.py:89, train_util.py:357-360) as ONE fused kernel over
-    the flat LoRA buffer; optimizer state lives in the parameter dtype like the reference's
-    (`network.to(dtype)` before the optimizer is built, train_lora.py:78-89) unless state_fp32."""
+OPTIMIZER_MODES = {"adamw": 0, "adam": 1, "lion": 2}
 
-    def __init__(self, flat: FlatState, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
-                 state_fp32: bool = False):
+
+class FlatOptimizer:
+    """The reference's optimizers (train_util.get_optimizer, train_util.py:333-370) that have a closed elementwise
+    form — torch.optim.AdamW / torch.optim.Adam / lion_pytorch.Lion — as ONE fused kernel over the flat LoRA buffer.
+    Optimizer state lives in the parameter dtype like the reference's (`network.to(dtype)` precedes the optimizer,
+    train_lora.py:78-89) and the kernel then rounds where torch's foreach implementation rounds; `state_fp32=True`
+    keeps fp32 moments instead (no intermediate rounding).  `param_groups[0]["lr"]` is read at every step, so any
+    torch.optim.lr_scheduler-style driver works (train_lora.py:281)."""
+
+    def __init__(self, flat: FlatState, name: str = "adamw", lr=1e-3, betas=None, eps=1e-8, weight_decay=None,
+                 state_fp32: bool = False, **unknown):
+        name = name.lower()
+        if name not in OPTIMIZER_MODES:
+            raise ValueError("Optimizer must be adam, adamw, lion or Prodigy")
+        if unknown:
+            raise TypeError(f"{name}: unexpected optimizer arguments {sorted(unknown)}")
+        self.mode = OPTIMIZER_MODES[name]
+        if betas is None:
+            betas = (0.9, 0.99) if name == "lion" else (0.9, 0.999)
+        if weight_decay is None:
+            weight_decay = 1e-2 if name == "adamw" else 0.0
         self.flat = flat
         sd = torch.float32 if state_fp32 else flat.params.dtype
         self.exp_avg = torch.zeros_like(flat.params, dtype=sd)
-        self.exp_avg_sq = torch.zeros_like(flat.params, dtype=sd)
+        self.exp_avg_sq = torch.zeros_like(flat.params, dtype=sd) if self.mode != 2 else self.exp_avg
         self.step_count = 0
-        self.lr = lr
-        self.defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
-        self.hyper = torch.zeros(8, device=flat.params.device, dtype=torch.float32)
+        self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
+        self.param_groups = [dict(self.defaults, params=[flat.params])]
+        self.hyper = torch.zeros(16, device=flat.params.device, dtype=torch.float32)
+
+    @property
+    def lr(self):
+        return self.param_groups[0]["lr"]
+
+    @lr.setter
+    def lr(self, v):
+        self.param_groups[0]["lr"] = v
 
     def step(self, grad_scale: float = 1.0):
         from . import ops
         self.step_count += 1
-        d = self.defaults
+        g = self.param_groups[0]
+        lr, (b1, b2), eps, wd = float(g["lr"]), g["betas"], g["eps"], g["weight_decay"]
+        t = self.step_count
+        # double-precision host scalars exactly as torch forms them (adam.py: bias corrections, step size)
+        bc1, bc2 = 1 - b1 ** t, 1 - b2 ** t
         # pageable source: the copy is staged before this call returns, so the host values can change
-        self.hyper.copy_(torch.tensor([self.lr, d["betas"][0], d["betas"][1], d["eps"], d["weight_decay"],
-                                       float(self.step_count), grad_scale, 0.0], dtype=torch.float32))
-        ops.adamw_flat(self.flat.params, self.flat.grads, self.exp_avg, self.exp_avg_sq, self.flat.mask, self.hyper,
+        self.hyper.copy_(torch.tensor([lr, b1, b2, eps, wd, float(t), grad_scale, float(self.mode),
+                                       lr / bc1, bc2 ** 0.5, 1 - lr * wd, 1 - b1, 1 - b2, 0, 0, 0], dtype=torch.float32))
+        ops.optim_flat(self.flat.params, self.flat.grads, self.exp_avg, self.exp_avg_sq, self.flat.mask, self.hyper,
                        zero_grad=True)
 
     def zero_grad(self):
         self.flat.grads.zero_()
+
+
+class FlatAdamW(FlatOptimizer):
+    """torch.optim.AdamW (train_lora.py:89, train_util.py:357-360): the example configs' optimizer."""
+
+    def __init__(self, flat: FlatState, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+                 state_fp32: bool = False):
+        super().__init__(flat, "adamw", lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, state_fp32=state_fp32)

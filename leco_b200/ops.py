@@ -384,6 +384,24 @@ def adamw_flat(params, grads, exp_avg, exp_avg_sq, mask, hyper, zero_grad=True):
                                       params.numel(), int(zero_grad), _stream()), "leco_adamw_flat")
 
 
+def optim_flat(params, grads, exp_avg, exp_avg_sq, mask, hyper16, zero_grad=True):
+    """leco_optim_flat: AdamW / Adam / Lion over the flat buffer (hyper16 = fp32[16], see include/leco_b200.h)."""
+    assert hyper16.numel() >= 16 and hyper16.dtype == torch.float32
+    capi.check(_lib().leco_optim_flat(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq),
+                                      int(exp_avg.dtype == torch.float32), _ptr(mask), _ptr(hyper16),
+                                      params.numel(), int(zero_grad), _stream()), "leco_optim_flat")
+
+
+def transpose_tiles(src_flat, dst_flat, tiles, n_tiles):
+    capi.check(_lib().leco_transpose_tiles(_ptr(src_flat), _ptr(dst_flat), _ptr(tiles), int(n_tiles), _stream()),
+               "leco_transpose_tiles")
+
+
+def set_deterministic(on: bool):
+    """Fixed-order reductions (no fp32 atomics across CTAs, no split-K): bit-repeatable steps, slower."""
+    capi.check(_lib().leco_set_deterministic(int(bool(on))), "leco_set_deterministic")
+
+
 def guided_step(eps_pair, x, coef, want_x=True, want_guided=False):
     half = eps_pair.numel() // 2
     shape = (eps_pair.shape[0] // 2,) + tuple(eps_pair.shape[1:])

@@ -80,3 +80,66 @@ def get_add_time_ids(height: int, width: int, dynamic_crops: bool = False, dtype
     if 256 * len(ids) + 1280 != 2816:
         raise ValueError("Model expects an added time embedding vector of length 2816")
     return torch.tensor([ids], dtype=dtype)
+
+
+# --------------------------------------------------------------------------- optimizer / LR factories
+class _LrProxy:
+    """Drives torch.optim.lr_scheduler classes for an optimizer that is not a torch.optim.Optimizer (the fused flat
+    optimizer): a real one-parameter SGD carries the schedule, its lr is mirrored into the fused optimizer."""
+
+    def __init__(self, target, scheduler_ctor):
+        self.target = target
+        self._opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=float(target.lr))
+        self._sched = scheduler_ctor(self._opt)
+        self.target.lr = self._opt.param_groups[0]["lr"]
+
+    def step(self):
+        self._opt.step()
+        self._sched.step()
+        self.target.lr = self._opt.param_groups[0]["lr"]
+
+    def get_last_lr(self):
+        return self._sched.get_last_lr()
+
+
+def get_optimizer(name: str):
+    """train_util.py:333-370.  Returns a constructor `f(params_or_flat, lr=..., **kwargs)`.  adamw / adam / lion are
+    the fused flat-buffer kernels; the adaptive-step-size families (dadapt*, prodigy) and the bitsandbytes 8-bit
+    variants need third-party packages that neither the reference image nor this one ships."""
+    from .lora import OPTIMIZER_MODES, FlatOptimizer
+    name = name.lower()
+    if name.startswith("dadapt"):
+        if name not in ("dadaptadam", "dadaptlion"):
+            raise ValueError("DAdapt optimizer must be dadaptadam or dadaptlion")
+        raise NotImplementedError("dadaptation is not installed (optional in the reference too)")
+    if name.endswith("8bit"):
+        if name not in ("adam8bit", "lion8bit"):
+            raise ValueError("8bit optimizer must be adam8bit or lion8bit")
+        raise NotImplementedError("bitsandbytes is not installed (the reference marks this path unverified)")
+    if name in OPTIMIZER_MODES:
+        return lambda flat, **kw: FlatOptimizer(flat, name, **kw)
+    if name == "prodigy":
+        raise NotImplementedError("prodigyopt is not installed (optional in the reference too)")
+    raise ValueError("Optimizer must be adam, adamw, lion or Prodigy")
+
+
+def get_lr_scheduler(name, optimizer, max_iterations, lr_min, **kwargs):
+    """train_util.py:373-401: the same torch.optim.lr_scheduler classes with the same arguments.  NB the reference's
+    "linear" branch passes `factor=0.5` to LinearLR, whose parameter is `start_factor`: as shipped it raises
+    TypeError; the evident intent (start at half the rate) is implemented."""
+    S = torch.optim.lr_scheduler
+    if name == "cosine":
+        ctor = lambda o: S.CosineAnnealingLR(o, T_max=max_iterations, eta_min=lr_min, **kwargs)        # noqa: E731
+    elif name == "cosine_with_restarts":
+        ctor = lambda o: S.CosineAnnealingWarmRestarts(o, T_0=max_iterations // 10, T_mult=2, eta_min=lr_min, **kwargs)  # noqa: E731
+    elif name == "step":
+        ctor = lambda o: S.StepLR(o, step_size=max_iterations // 100, gamma=0.999, **kwargs)          # noqa: E731
+    elif name == "constant":
+        ctor = lambda o: S.ConstantLR(o, factor=1, **kwargs)                                           # noqa: E731
+    elif name == "linear":
+        ctor = lambda o: S.LinearLR(o, start_factor=0.5, total_iters=max_iterations // 100, **kwargs)  # noqa: E731
+    else:
+        raise ValueError("Scheduler must be cosine, cosine_with_restarts, step, linear or constant")
+    if isinstance(optimizer, torch.optim.Optimizer):
+        return ctor(optimizer)
+    return _LrProxy(optimizer, ctor)

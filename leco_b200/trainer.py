@@ -35,7 +35,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import capi, ops
-from .lora import FlatAdamW, LoRANetwork
+from .lora import FlatOptimizer, LoRANetwork
 from .scheduler import DDIMScheduler
 from .train_util import get_add_time_ids
 from .unet import EngineUNet, Tape
@@ -93,9 +93,12 @@ class _Graphed:
 
 class LecoTrainer:
     def __init__(self, unet: EngineUNet, network: LoRANetwork, scheduler: DDIMScheduler,
-                 prompt_pairs: Sequence[PromptPair], *, lr: float = 1e-4, optimizer_kwargs: Optional[dict] = None,
+                 prompt_pairs: Sequence[PromptPair], *, lr: float = 1e-4, optimizer: str = "adamw",
+                 optimizer_kwargs: Optional[dict] = None, lr_scheduler: str = "constant", iterations: int = 1000,
+                 lr_scheduler_kwargs: Optional[dict] = None,
                  max_denoising_steps: int = 50, denoise_guidance: float = 3.0, device="cuda",
-                 rank: int = 0, world_size: int = 1, use_cuda_graphs: bool = True, state_fp32: bool = False):
+                 rank: int = 0, world_size: int = 1, use_cuda_graphs: bool = True, state_fp32: bool = False,
+                 hoist_cross_kv: bool = True):
         if network.flat is None:
             raise RuntimeError("LecoTrainer needs the flat LoRA layout: move the network to CUDA first "
                                "(network.to('cuda', dtype=torch.bfloat16))")
@@ -106,7 +109,14 @@ class LecoTrainer:
         self.device = torch.device(device)
         self.rank, self.world = rank, world_size
         self.use_graphs = use_cuda_graphs
-        self.optimizer = FlatAdamW(network.flat, lr=lr, state_fp32=state_fp32, **(optimizer_kwargs or {}))
+        # optimizer + LR schedule exactly as train_lora.py:80-95 builds them (train_util.get_optimizer / get_lr_scheduler)
+        self.optimizer = FlatOptimizer(network.flat, optimizer, lr=lr, state_fp32=state_fp32, **(optimizer_kwargs or {}))
+        from .train_util import get_lr_scheduler
+        self.lr_scheduler = get_lr_scheduler(lr_scheduler, self.optimizer, max_iterations=iterations, lr_min=lr / 100,
+                                             **(lr_scheduler_kwargs or {}))
+        self.hoist_cross_kv = hoist_cross_kv
+        self._pool = None           # one CUDA-graph memory pool shared by every captured shape (dynamic_resolution)
+        self._ar_events = []        # (start, end) CUDA events around the data-parallel all-reduce
         self.act_dtype = unet._act_dtype
         self.xl = bool(unet.spec.text_time)
         for p in self.pairs:
@@ -174,10 +184,16 @@ class LecoTrainer:
                         torch.tensor(coef, dtype=torch.float32, device=self.device))
         return self._tables
 
+    def _graph_pool(self):
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
+        return self._pool
+
     # ------------------------------------------------------------------ one denoise step
     def _denoise_body(self, st):
         x2 = st["x"].repeat(2, 1, 1, 1)
-        eps = self.unet.run(x2, st["t"], st["ctx"], self._added(st, x2.shape[0], "pooled"), None)
+        eps = self.unet.run(x2, st["t"], st["ctx"], self._added(st, x2.shape[0], "pooled"), None,
+                            kv_cache=st.get("kv"))
         x_new, _ = ops.guided_step(eps, st["x"], st["coef"], True, False)
         st["x"].copy_(x_new)
 
@@ -195,6 +211,11 @@ class LecoTrainer:
         if self.xl:
             g.static["pooled"] = torch.zeros((2 * bl, self.unet.spec.add_text_dim), device=dev, dtype=self.act_dtype)
             g.static["ids"] = torch.zeros((2 * bl, 6), device=dev, dtype=torch.float32)
+        if self.hoist_cross_kv:
+            # K|V of the text embedding per cross-attention layer: constant over the k steps of one iteration
+            # (they depend on the prompt and the adapter state only), computed once by iteration() into these buffers
+            g.static["kv"] = [torch.zeros(shape, device=dev, dtype=self.act_dtype)
+                              for shape in self.unet.cross_kv_shapes(2 * bl * 77)]
         if self.use_graphs:
             self.network.__enter__()
             side = torch.cuda.Stream()
@@ -205,7 +226,7 @@ class LecoTrainer:
             torch.cuda.synchronize()
             g.graph = torch.cuda.CUDAGraph()
             c0 = capi.launch_count()
-            with torch.cuda.graph(g.graph):
+            with torch.cuda.graph(g.graph, pool=self._graph_pool()):
                 self._denoise_body(g.static)
             g.launches = capi.launch_count() - c0
             self.network.__exit__(None, None, None)
@@ -228,6 +249,7 @@ class LecoTrainer:
         tape.backward()
         net.__exit__(None, None, None)
         st["loss"].copy_(loss)
+        st["eps_t"].copy_(eps_t)
 
     def _tail_graph(self, bl, h, w, D, groups, slots, sgn_g):
         key = (bl, h, w, D, groups, slots, sgn_g)
@@ -240,23 +262,28 @@ class LecoTrainer:
                     "t": torch.zeros((groups * bl,), device=dev, dtype=torch.float32),
                     "ctx_ng": torch.zeros((groups * bl * 77, D), device=dev, dtype=self.act_dtype),
                     "ctx_t": torch.zeros((bl * 77, D), device=dev, dtype=self.act_dtype),
-                    "loss": torch.zeros((1,), device=dev, dtype=torch.float32)}
+                    "loss": torch.zeros((1,), device=dev, dtype=torch.float32),
+                    "eps_t": torch.zeros((bl, UNET_IN_CHANNELS, h, w), device=dev, dtype=torch.float32)}
         if self.xl:
             P = self.unet.spec.add_text_dim
             g.static["pooled_ng"] = torch.zeros((groups * bl, P), device=dev, dtype=self.act_dtype)
             g.static["pooled_t"] = torch.zeros((bl, P), device=dev, dtype=self.act_dtype)
             g.static["ids"] = torch.zeros((groups * bl, 6), device=dev, dtype=torch.float32)
         if self.use_graphs:
+            # a new shape can first appear while gradients are being accumulated (step_optimizer=False, or
+            # dynamic_resolution mid-run): the warm-up pass must not disturb them
+            keep = self.network.flat.grads.clone()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 self._tail_body(g.static, groups, slots, bl, sgn_g)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            self.network.flat.grads.zero_()                      # the warm-up accumulated a gradient
+            self.network.flat.grads.copy_(keep)                  # drop what the warm-up accumulated
+            del keep
             g.graph = torch.cuda.CUDAGraph()
             c0 = capi.launch_count()
-            with torch.cuda.graph(g.graph):
+            with torch.cuda.graph(g.graph, pool=self._graph_pool()):
                 self._tail_body(g.static, groups, slots, bl, sgn_g)
             g.launches = capi.launch_count() - c0
         self._tail[key] = g
@@ -270,6 +297,7 @@ class LecoTrainer:
         host draw + H2D copy of the latent noise (inputs already resident in HBM)."""
         sched = self.scheduler
         launches0 = capi.launch_count()
+        self.network.flat.refresh_transposed()       # ad^T / bup^T for the backward GEMMs (one launch)
         tbl_t, tbl_coef = self._tables or self._sched_tables()
         sched.set_timesteps(self.max_steps)
         # ---- RNG draws: same generator, same order as train_lora.py:149-177
@@ -297,6 +325,10 @@ class LecoTrainer:
             ids = get_add_time_ids(height, width, dynamic_crops=pair.dynamic_crops).to(self.device, dtype=torch.float32)
             st["ids"].copy_(ids.reshape(1, 6).expand(2 * bl, 6))
             st["pooled"].copy_(self._pooled([pair.unconditional, pair.target], bl))
+        if "kv" in st:                               # once per iteration instead of once per denoise step
+            self.network.__enter__()
+            self.unet.cross_kv(st["ctx"], out=st["kv"])
+            self.network.__exit__(None, None, None)
         if dg.graph is None:
             self.network.__enter__()
         for i in range(k):
@@ -339,17 +371,32 @@ class LecoTrainer:
             self._tail_body(ts, len(distinct), tuple(slots), bl, pair.signed_guidance())
         loss = ts["loss"]
 
-        # ---- data-parallel exchange: one all-reduce of the flat LoRA gradient (+ the scalar loss)
+        # ---- data-parallel exchange: ONE all-reduce of the flat fp32 LoRA gradient; the scalar loss rides in the
+        # buffer's last slot
         if self.world > 1:
             import torch.distributed as dist
-            dist.all_reduce(self.network.flat.grads)
-            dist.all_reduce(loss)
-            loss.mul_(1.0 / self.world)
+            flat = self.network.flat
+            flat.loss_slot.copy_(loss)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_reduce(flat.grads_ext)
+            e1.record()
+            self._ar_events = (self._ar_events + [(e0, e1)])[-32:]
+            loss = flat.loss_slot * (1.0 / self.world)
         if step_optimizer:
             self.optimizer.step(grad_scale=1.0 / self.world)
+            self.lr_scheduler.step()                          # train_lora.py:281
         self.launches += capi.launch_count() - launches0     # eager launches (graph replays were added above)
-        self.last = {"k": k, "timestep": t_star, "denoised": st["x"], "pair": pair}
+        self.last = {"k": k, "timestep": t_star, "denoised": st["x"], "pair": pair, "target": ts["eps_t"],
+                     "lr": self.optimizer.lr}
         return loss
+
+    def allreduce_ms(self) -> Optional[float]:
+        """Mean device time of the data-parallel all-reduce over the last iterations (None on one rank)."""
+        if not self._ar_events:
+            return None
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in self._ar_events) / len(self._ar_events)
 
     def _stage_noise(self, noise, bl, h, w, dst):
         """Host noise slice of this rank -> pinned staging -> device (the only per-step H2D traffic)."""

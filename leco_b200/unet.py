@@ -310,6 +310,8 @@ class LoraSite:
         self._versions = None
         self._native = False
         self.ranks = None
+        self.static_t = None   # (ad^T, bup^T) static views (leco_b200.lora.FlatState.build_transposed)
+        self.flat_state = None
 
     def bind_native(self, ad, bup, g_ad, g_bup):
         """The adapter Parameters are views of `ad`/`bup` (leco_b200.lora flat layout): no packing,
@@ -345,10 +347,9 @@ class LoraSite:
                 return self.ad, self.bup
             self._native = False  # parameters were re-homed (e.g. .to()): fall back to packing
             self.ad = self.bup = self.g_ad = self.g_bup = None
+            self.static_t = self.flat_state = None
         ranks = [a.lora_down.weight.shape[0] for a in ads]
         kl = (sum(ranks) + 15) // 16 * 16
-        if kl > 64:
-            raise RuntimeError(f"leco_b200: fused LoRA rank {sum(ranks)} > 64 is unsupported")
         vers = tuple((a.lora_down.weight._version, a.lora_up.weight._version, a.lora_down.weight.data_ptr())
                      for a in ads)
         if self.ad is None or self.ad.shape[0] != kl or self.ad.device != device:
@@ -367,6 +368,14 @@ class LoraSite:
             self._versions = vers
         self.ranks = ranks
         return self.ad, self.bup
+
+    def transposed(self, be):
+        """(ad^T [K, Kl], bup^T [Kl, N]) for the backward GEMMs.  A trainer that owns the parameters keeps them in
+        static buffers refreshed ONCE per optimizer step (`static_t`, one launch for all sites: they only change
+        there); otherwise they are formed on the fly."""
+        if self.static_t is not None:
+            return self.static_t
+        return be.transpose2d(self.ad), be.transpose2d(self.bup)
 
     # fp32 gradient accumulators in operand layout (zeroed per backward)
     def begin_grad(self, be):
@@ -542,7 +551,16 @@ class EngineUNet(nn.Module):
         wo = self.conv_out.weight.detach().to(device=device, dtype=dtype)
         P.conv_out_w = wo.permute(0, 2, 3, 1).reshape(wo.shape[0], 9, wo.shape[1]).contiguous()
         P.conv_out_b = self.conv_out.bias.detach().to(device=device, dtype=dtype).contiguous()
+        old = getattr(self, "_P", None)
         self._P = P
+        if old is not None:
+            # a re-pack (weights edited / moved) keeps the LoraSite objects: an adapter network bound to them
+            # (leco_b200.lora.bind_flat: flat operand views, static transposes) stays bound
+            self._P = old
+            old_owners = self._site_owners()
+            self._P = P
+            for o_new, o_old in zip(self._site_owners(), old_owners):
+                o_new.site = o_old.site
         self._packed = True
         self._pack_device = device
         return self
@@ -551,30 +569,61 @@ class EngineUNet(nn.Module):
         if not self._packed or self._pack_device != device:
             self.pack(device)
 
+    def _apply(self, fn, *a, **k):          # .to() / .cuda() / .half(): the kernel-layout copies are stale
+        self._packed = False
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):     # in-place weight edits after a pack
+        self._packed = False
+        return super().load_state_dict(*a, **k)
+
     # ---- ops with backward rules ---------------------------------------------------------
+    def _tn_chunks(self, be, a, b, out, transpose_out=False):
+        """out (+)= a^T b with b's columns (the stacked adapter rank) taken 64 at a time (tn_reduce's tile)."""
+        kl = b.shape[1]
+        for c0 in range(0, kl, 64):
+            c1 = min(kl, c0 + 64)
+            be.tn_reduce(a, b[:, c0:c1], out[c0:c1] if transpose_out else out[:, c0:c1], transpose_out=transpose_out)
+
     def _linear(self, be, tape, x: Act, pk: LinearPack, residual: Optional[Act] = None, geglu=False,
-                conv_nhw=None):
-        """y = x W^T + b (+ s*(x A^T) B^T) (+ residual)   — lora.py:102-106 fused."""
+                conv_nhw=None, out=None):
+        """y = x W^T + b (+ s*(x A^T) B^T) (+ residual)   — lora.py:102-106 fused.  The LoRA branch is an extra
+        K-segment of the tensor-core GEMM when the site's stacked rank fits one (<= 64); larger ranks (the reference
+        accepts any) run it as a second accumulate-GEMM on the result."""
         act = pk.site.active()
         kw = {}
         T = ad = bup = None
         sm = 1.0
+        big = False
         rg_out = x.rg or (residual is not None and residual.rg) or act is not None
         need_grad = tape is not None and rg_out
         if act is not None:
             ads, mult = act
             ad, bup = pk.site.refresh(ads, x.t.device, x.t.dtype)
             sm = float(ads[0].scale) * mult
-            if self.fused_lora:   # T = s*m x A^T is formed inside the GEMM kernel (extra accumulator columns)
+            big = ad.shape[0] > 64
+            if self.fused_lora and not big:   # T = s*m x A^T is formed inside the GEMM kernel (extra accumulator columns)
                 kw.update(fl_ad=ad, fl_bup=bup, fl_scale=sm, fl_rank=sum(pk.site.ranks))
                 if need_grad:
                     T = be.zeros((x.t.shape[0], ad.shape[0]), x.t)
                     kw["fl_t_out"] = T
             else:
                 T = be.gemm(x.t, ad, alpha=sm)                  # T = s*m * x A^T   [M, Kl]
-                kw.update(lora_t=T, lora_up=bup)
-        y = be.gemm(x.t, pk.w, bias=pk.bias, residual=None if residual is None else residual.t, geglu=geglu, **kw)
-        out = Act(y, need_grad)
+                if not big:
+                    kw.update(lora_t=T, lora_up=bup)
+        res_t = None if residual is None else residual.t
+        if big:
+            pre = be.gemm(x.t, pk.w, bias=pk.bias, residual=res_t)
+            if geglu:
+                y = be.geglu_fwd(be.gemm(T, bup, residual=pre))
+                if out is not None:
+                    out.copy_(y)
+                    y = out
+            else:
+                y = be.gemm(T, bup, out, residual=pre)
+        else:
+            y = be.gemm(x.t, pk.w, out, bias=pk.bias, residual=res_t, geglu=geglu, **kw)
+        res = Act(y, need_grad)
         if need_grad:
             assert not geglu, "GEGLU epilogue is used on the no-grad path only"
 
@@ -585,53 +634,59 @@ class EngineUNet(nn.Module):
                 if residual is not None and residual.rg:
                     tape.accum(residual.t, gy, owned=False)
                 kw2 = {}
-                dT = None
+                dT = adT = None
                 if act is not None:
-                    bupT = be.transpose2d(bup)                       # [Kl, N]
-                    if self.fused_lora and x.rg:
+                    adT, bupT = pk.site.transposed(be)               # [K, Kl], [Kl, N]
+                    if self.fused_lora and x.rg and not big:
                         # one kernel: dT = s*m dY B (saved) and dx = dY W + dT A
                         dT = be.zeros((gy.shape[0], bupT.shape[0]), gy)
-                        kw2.update(fl_ad=bupT, fl_bup=be.transpose2d(ad), fl_scale=sm, fl_rank=sum(pk.site.ranks),
-                                   fl_t_out=dT)
+                        kw2.update(fl_ad=bupT, fl_bup=adT, fl_scale=sm, fl_rank=sum(pk.site.ranks), fl_t_out=dT)
                     else:
                         dT = be.gemm(gy, bupT, alpha=sm)             # s*m * dY B      [M, Kl]
-                        if x.rg:
-                            kw2.update(lora_t=dT, lora_up=be.transpose2d(ad))   # + dT A
+                        if x.rg and not big:
+                            kw2.update(lora_t=dT, lora_up=adT)       # + dT A
                     # dB[n,k] += sum_m dY[m,n] T[m,k]   (T already carries s*m)
-                    be.tn_reduce(gy, T, pk.site.grad_bup(be))
+                    self._tn_chunks(be, gy, T, pk.site.grad_bup(be))
                 if x.rg:
                     dx = be.gemm(gy, pk.wt, **kw2)
+                    if big:
+                        dx = be.gemm(dT, adT, residual=dx)
                     tape.accum(x.t, dx, owned=True)
                 if act is not None:
                     # dA[k,j] += sum_m dT[m,k] x[m,j]   -> accumulated transposed-in-place
-                    be.tn_reduce(x.t, dT, pk.site.grad_ad(be), transpose_out=True)
+                    self._tn_chunks(be, x.t, dT, pk.site.grad_ad(be), transpose_out=True)
             tape.record(bwd)
-        return out
+        return res
 
     def _conv3x3(self, be, tape, x: Act, pk: ConvPack, n, h, w, rowbias: Optional[Act] = None, rb_col0: int = 0,
                  residual: Optional[Act] = None):
         """3x3 / stride 1 / pad 1 conv as implicit GEMM (+ per-sample bias slice `rowbias[:, rb_col0:...]`,
         + residual).  A conv adapter (lora.py:68-82: 3x3 lora_down to r channels, 1x1 lora_up) adds
-        T = s*m*conv3x3(x, A) as the extra K-segment."""
+        T = s*m*conv3x3(x, A) as the extra K-segment (or, above rank 64, as a second accumulate-GEMM)."""
         act = pk.site.active()
         kw = {}
         T = ad = bup = None
         sm = 1.0
+        big = False
         if act is not None:
             ads, mult = act
             ad, bup = pk.site.refresh(ads, x.t.device, x.t.dtype)
             sm = float(ads[0].scale) * mult
-            if self.fused_lora:
+            big = ad.shape[0] > 64
+            if self.fused_lora and not big:
                 kw.update(fl_ad=ad, fl_bup=bup, fl_scale=sm, fl_rank=sum(pk.site.ranks))
                 if tape is not None:
                     T = be.zeros((x.t.shape[0], ad.shape[0]), x.t)
                     kw["fl_t_out"] = T
             else:
                 T = be.gemm(x.t, ad, alpha=sm, conv_nhw=(n, h, w))       # [M, Kl]
-                kw.update(lora_t=T, lora_up=bup)
+                if not big:
+                    kw.update(lora_t=T, lora_up=bup)
         rb = None if rowbias is None else rowbias.t[:, rb_col0:rb_col0 + pk.cout]
         y = be.gemm(x.t, pk.w, bias=pk.bias, rowbias=rb, rows_per_group=h * w,
                     residual=None if residual is None else residual.t, conv_nhw=(n, h, w), **kw)
+        if big:
+            y = be.gemm(T, bup, residual=y)
         rg = x.rg or (residual is not None and residual.rg) or (rowbias is not None and rowbias.rg) or act is not None
         out = Act(y, rg and tape is not None)
         if out.rg:
@@ -645,9 +700,10 @@ class EngineUNet(nn.Module):
                     tape.accum_cols(rowbias.t, rb_col0, be.rowgroup_sum(gy, n, h * w))
                 dx_lora = None
                 if act is not None:
-                    dT = be.gemm(gy, be.transpose2d(bup), alpha=sm)              # s*m * dY B   [M, Kl]
-                    be.tn_reduce(gy, T, pk.site.grad_bup(be))
-                    be.tn_reduce(be.im2col_s1(x.t, n, h, w), dT, pk.site.grad_ad(be), transpose_out=True)
+                    _, bupT = pk.site.transposed(be)
+                    dT = be.gemm(gy, bupT, alpha=sm)                             # s*m * dY B   [M, Kl]
+                    self._tn_chunks(be, gy, T, pk.site.grad_bup(be))
+                    self._tn_chunks(be, be.im2col_s1(x.t, n, h, w), dT, pk.site.grad_ad(be), transpose_out=True)
                     if x.rg:
                         kl = ad.shape[0]
                         # dx[p,c] += sum_{tap',kl} dT[p+off(tap'), kl] * A[kl, flip(tap'), c]
@@ -742,7 +798,7 @@ class EngineUNet(nn.Module):
         sc = x if rp.shortcut is None else self._linear(be, tape, x, rp.shortcut)
         return self._conv3x3(be, tape, hdn, rp.conv2, n, h, w, residual=sc)
 
-    def _transformer(self, be, tape, x: Act, tp, ctx: Act, n, h, w):
+    def _transformer(self, be, tape, x: Act, tp, ctx: Act, n, h, w, kv_cache=None):
         hw = h * w
         hdn = self._group_norm(be, tape, x, tp.norm, n, hw, False)
         hdn = self._linear(be, tape, hdn, tp.proj_in)
@@ -754,7 +810,10 @@ class EngineUNet(nn.Module):
             hdn = self._linear(be, tape, a, bp.out1, residual=hdn)
             n2 = self._layer_norm(be, tape, hdn, bp.norm2)
             q2 = self._linear(be, tape, n2, bp.q2)
-            kv = self._linear(be, tape, ctx, bp.kv2)
+            if kv_cache is not None:   # hoisted: K/V of the (per-iteration constant) text embedding, see cross_kv()
+                kv = Act(kv_cache.pop(0), False)
+            else:
+                kv = self._linear(be, tape, ctx, bp.kv2)
             skv = ctx.t.shape[0] // n
             a = self._attention(be, tape, q2, 0, kv, 0, kv, C, n, hw, skv, bp.heads, bp.dim_head)
             hdn = self._linear(be, tape, a, bp.out2, residual=hdn)
@@ -808,12 +867,47 @@ class EngineUNet(nn.Module):
         return out
 
     # ---- the forward program -----------------------------------------------------------
+    def _transformers_in_order(self):
+        """Transformer2DModel holders in forward-execution order (down, mid, up)."""
+        out = []
+        for blk in self.down_blocks:
+            if hasattr(blk, "attentions"):
+                out += list(blk.attentions)
+        out += list(self.mid_block.attentions)
+        for blk in self.up_blocks:
+            if hasattr(blk, "attentions"):
+                out += list(blk.attentions)
+        return out
+
+    def cross_kv(self, ctx2d: torch.Tensor, out: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
+        """K|V projections (`attn2.to_k | to_v`, adapters included at their current multiplier) of the text embedding
+        for every cross-attention layer in execution order.  They depend only on the prompt and the adapter state —
+        not on the latents or the timestep — so a k-step denoise loop computes them once and
+        hands the list to `run(kv_cache=...)`.  `out` = preallocated [rows, 2C] buffers to fill (CUDA-graph statics)."""
+        self._ensure_packed(ctx2d.device)
+        be, P = self.backend, self._P
+        ctx = Act(ctx2d, False)
+        res, i = [], 0
+        for t in self._transformers_in_order():
+            for bp in P.tr[id(t)].blocks:
+                res.append(self._linear(be, None, ctx, bp.kv2, out=None if out is None else out[i]).t)
+                i += 1
+        return res
+
+    def cross_kv_shapes(self, rows: int):
+        return [(rows, 2 * bp.heads * bp.dim_head) for t in self._transformers_in_order() for bp in self._P.tr[id(t)].blocks]
+
     def run(self, sample: torch.Tensor, t: torch.Tensor, ctx2d: torch.Tensor, added: Optional[dict] = None,
-            tape: Optional[Tape] = None):
+            tape: Optional[Tape] = None, kv_cache: Optional[List[torch.Tensor]] = None):
         """sample NCHW [N,4,h,w] (fp32 or activation dtype), t fp32 [N], ctx2d [N*S, D] activation
-        dtype -> (eps NCHW fp32 [N,4,h,w], final Act).  With `tape`, records the backward."""
+        dtype -> (eps NCHW fp32 [N,4,h,w], final Act).  With `tape`, records the backward.  `kv_cache` = result of
+        `cross_kv(ctx2d)` (no-grad passes only: the cross-attention adapters get no gradient through a cache)."""
+        self._ensure_packed(sample.device)
         be, s, P = self.backend, self.spec, self._P
         N, _, H, W = sample.shape
+        if kv_cache is not None:
+            assert tape is None, "kv_cache is for no-grad passes"
+            kv_cache = list(kv_cache)
         # -- time embedding (no trainable inputs in scope: time_emb_proj is only adapted by c3lier)
         te = be.timestep_embedding(t, s.block_out_channels[0])
         emb = be.gemm(be.silu(be.gemm(te, P.time1.w, bias=P.time1.bias)), P.time2.w, bias=P.time2.bias)
@@ -834,7 +928,7 @@ class EngineUNet(nn.Module):
             for i, r in enumerate(blk.resnets):
                 x = self._resnet(be, tape, x, P.res[id(r)], temb_all, N, h, w)
                 if hasattr(blk, "attentions"):
-                    x = self._transformer(be, tape, x, P.tr[id(blk.attentions[i])], ctx, N, h, w)
+                    x = self._transformer(be, tape, x, P.tr[id(blk.attentions[i])], ctx, N, h, w, kv_cache)
                 skips.append((x, h, w))
             if hasattr(blk, "downsamplers"):
                 x = self._conv_s2(be, tape, x, P.samp[id(blk.downsamplers[0])], N, h, w)
@@ -842,7 +936,7 @@ class EngineUNet(nn.Module):
                 skips.append((x, h, w))
         mb = self.mid_block
         x = self._resnet(be, tape, x, P.res[id(mb.resnets[0])], temb_all, N, h, w)
-        x = self._transformer(be, tape, x, P.tr[id(mb.attentions[0])], ctx, N, h, w)
+        x = self._transformer(be, tape, x, P.tr[id(mb.attentions[0])], ctx, N, h, w, kv_cache)
         x = self._resnet(be, tape, x, P.res[id(mb.resnets[1])], temb_all, N, h, w)
         for blk in self.up_blocks:
             for i, r in enumerate(blk.resnets):
@@ -851,7 +945,7 @@ class EngineUNet(nn.Module):
                 x = self._concat(be, tape, x, sk)
                 x = self._resnet(be, tape, x, P.res[id(r)], temb_all, N, h, w)
                 if hasattr(blk, "attentions"):
-                    x = self._transformer(be, tape, x, P.tr[id(blk.attentions[i])], ctx, N, h, w)
+                    x = self._transformer(be, tape, x, P.tr[id(blk.attentions[i])], ctx, N, h, w, kv_cache)
             if hasattr(blk, "upsamplers"):
                 x = self._upsample(be, tape, x, N, h, w)
                 h, w = h * 2, w * 2
@@ -869,22 +963,26 @@ class EngineUNet(nn.Module):
         return eps
 
     # ---- reference call surface -----------------------------------------------------------
-    def lora_sites(self) -> List[LoraSite]:
-        """Every GEMM site an adapter can attach to (lierla: the transformer projections; c3lier adds the
-        resnet convs / time_emb_proj / shortcuts and the down/up-sampler convs, SURVEY Q3)."""
+    def _site_owners(self):
+        """The packs (LinearPack / ConvPack) that own a LoraSite, in a fixed order."""
         out = []
         P = self._P
         for tp in P.tr.values():
-            out += [tp.proj_in.site, tp.proj_out.site]
+            out += [tp.proj_in, tp.proj_out]
             for bp in tp.blocks:
-                out += [bp.qkv.site, bp.out1.site, bp.q2.site, bp.kv2.site, bp.out2.site, bp.ff1.site, bp.ff2.site]
-        out += [pk.site for pk in P.temb]
+                out += [bp.qkv, bp.out1, bp.q2, bp.kv2, bp.out2, bp.ff1, bp.ff2]
+        out += list(P.temb)
         for rp in P.res.values():
-            out += [rp.conv1.site, rp.conv2.site]
+            out += [rp.conv1, rp.conv2]
             if rp.shortcut is not None:
-                out.append(rp.shortcut.site)
-        out += [pk.site for pk in P.samp.values()]
+                out.append(rp.shortcut)
+        out += list(P.samp.values())
         return out
+
+    def lora_sites(self) -> List[LoraSite]:
+        """Every GEMM site an adapter can attach to (lierla: the transformer projections; c3lier adds the
+        resnet convs / time_emb_proj / shortcuts and the down/up-sampler convs, SURVEY Q3)."""
+        return [o.site for o in self._site_owners()]
 
     def forward(self, sample, timestep, encoder_hidden_states=None, added_cond_kwargs=None, **_):
         """train_util.py:156-160 / :239-244.  Under autograd (grad enabled and an adapter with
@@ -905,6 +1003,8 @@ class EngineUNet(nn.Module):
             x_in = x_in.float()
         sites = [s for s in self.lora_sites() if s.active() is not None]
         if torch.is_grad_enabled() and sites:
+            for fs in {id(st.flat_state): st.flat_state for st in sites if st.flat_state is not None}.values():
+                fs.refresh_transposed()
             params = []
             for st in sites:
                 for a in st.adapters():

@@ -198,7 +198,11 @@ def leco_iteration(unet, scheduler, network, optimizer, lr_scheduler, prompt_pai
                    fixed_k: Optional[int] = None, record: Optional[dict] = None):
     """One pass of the loop body train_lora.py:141-302 (saving and logging excluded).
     RNG draw order is part of the contract: pair index, timesteps_to,
-    [bucket h, w], latent noise — all from the global CPU generator."""
+    [bucket h, w], latent noise — all from the global CPU generator.
+    `record["clock"]` (a perf_counter-like callable, bench.py's reference arm) adds the wall time of the
+    denoise loop (`t_denoise`) and of the whole iteration (`t_total`) to the record."""
+    clk = record.get("clock") if record is not None else None
+    t_begin = clk() if clk else 0.0
     with torch.no_grad():
         scheduler.set_timesteps(max_denoising_steps, device=device)          # :143-145
         optimizer.zero_grad()                                                # :147
@@ -215,6 +219,8 @@ def leco_iteration(unet, scheduler, network, optimizer, lr_scheduler, prompt_pai
             denoised = diffusion(unet, scheduler, latents,
                                  concat_embeddings(pair.unconditional, pair.target, pair.batch_size),
                                  start_timesteps=0, total_timesteps=k, guidance_scale=3)
+        if clk:
+            record["t_denoise"] = clk() - t_begin
         scheduler.set_timesteps(1000)                                        # :195
         t_cur = scheduler.timesteps[int(k * 1000 / max_denoising_steps)]     # :197-199
 
@@ -236,8 +242,13 @@ def leco_iteration(unet, scheduler, network, optimizer, lr_scheduler, prompt_pai
         record.update(k=k, timestep=int(t_cur), height=height, width=width, denoised=denoised.detach().float().cpu(),
                       positive=positive, neutral=neutral, unconditional=uncond,
                       target=target.detach(), loss=float(loss.item()))
+        if record.get("want_grads"):  # [d lora_down, d lora_up] per adapter, before the optimizer consumes them
+            record["grads"] = [p.grad.detach().float().cpu().clone() for l in network.unet_loras
+                               for p in (l.lora_down.weight, l.lora_up.weight)]
     optimizer.step()                                                         # :280
     lr_scheduler.step()                                                      # :281
+    if clk:
+        record["t_total"] = clk() - t_begin
     return float(loss.item())
 
 

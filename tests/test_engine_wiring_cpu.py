@@ -132,3 +132,86 @@ def test_c3lier_conv_adapters_match_oracle_autograd():
             if rel > worst:
                 worst, worst_name = rel, b.lora_name
     assert worst < 5e-3, (worst, worst_name)
+
+
+def test_high_rank_adapters_match_oracle_autograd():
+    """ranks whose stacked width exceeds one 64-wide tensor-core K-segment (rank 32: q|k|v stack 96,
+    c3lier time_emb_proj groups stack 128) take the accumulate-GEMM path; forward and gradients vs autograd."""
+    arch = "tiny15"
+    oracle = build_unet(arch)
+    eng = _engine(arch, oracle)
+    x, ctx, _ = _inputs(arch, n=2, hw=8)
+    t = torch.tensor(261)
+    targets = leco_ref.ATTN_TARGETS + leco_ref.CONV_TARGETS
+
+    def make(unet):
+        torch.manual_seed(11)
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = leco_ref.LoRANetworkRef(unet, rank=32, multiplier=1.0, alpha=8.0, targets=targets)
+        g = torch.Generator().manual_seed(5)
+        for l in net.unet_loras:
+            l.lora_up.weight.data = 0.02 * torch.randn(l.lora_up.weight.shape, generator=g)
+        return net
+
+    net_o, net_e = make(oracle), make(eng)
+    goal = torch.randn((2, 4, 8, 8), generator=torch.Generator().manual_seed(9))
+    outs = []
+    for unet, net in ((oracle, net_o), (eng, net_e)):
+        with net:
+            y = unet(x, t, encoder_hidden_states=ctx).sample
+        torch.nn.functional.mse_loss(y.float(), goal).backward()
+        outs.append(y.detach())
+    assert (outs[0] - outs[1]).abs().max().item() < 2e-4 * outs[0].abs().max().item() + 1e-5
+    worst, worst_name = 0.0, None
+    for a, b in zip(net_o.unet_loras, net_e.unet_loras):
+        for pa, pb in ((a.lora_down.weight, b.lora_down.weight), (a.lora_up.weight, b.lora_up.weight)):
+            assert pb.grad is not None, b.lora_name
+            rel = (pa.grad - pb.grad).abs().max().item() / (pa.grad.abs().max().item() + 1e-8)
+            if rel > worst:
+                worst, worst_name = rel, b.lora_name
+    assert worst < 5e-3, (worst, worst_name)
+
+
+@pytest.mark.parametrize("arch", ["tiny21", "tinyxl"])
+def test_hoisted_cross_attention_kv_is_exact(arch):
+    """`cross_kv` + `run(kv_cache=...)` (the K/V projections of the text embedding computed once per iteration) must
+    reproduce the plain forward bit-for-bit, adapters on."""
+    oracle = build_unet(arch)
+    eng = _engine(arch, oracle)
+    x, ctx, added = _inputs(arch)
+    torch.manual_seed(11)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = leco_ref.LoRANetworkRef(eng, rank=4, multiplier=1.0, alpha=1.0)
+    g = torch.Generator().manual_seed(5)
+    for l in net.unet_loras:
+        l.lora_up.weight.data = 0.05 * torch.randn(l.lora_up.weight.shape, generator=g)
+    t = torch.full((x.shape[0],), 481.0)
+    ctx2d = ctx.reshape(-1, ctx.shape[-1])
+    with torch.no_grad(), net:
+        eng._ensure_packed(x.device)
+        plain = eng.run(x, t, ctx2d, added, None)
+        kv = eng.cross_kv(ctx2d)
+        assert [tuple(k.shape) for k in kv] == eng.cross_kv_shapes(ctx2d.shape[0])
+        hoisted = eng.run(x, t, ctx2d, added, None, kv_cache=kv)
+    assert torch.equal(plain, hoisted)
+
+
+def test_repack_keeps_adapter_sites_and_sees_new_weights():
+    """an in-place weight edit after a pack must invalidate the kernel-layout copies, and the re-pack must
+    keep the LoraSite objects an adapter network is bound to."""
+    arch = "tiny21"
+    oracle = build_unet(arch)
+    eng = _engine(arch, oracle)
+    x, ctx, _ = _inputs(arch)
+    t = torch.tensor(481)
+    with torch.no_grad():
+        y0 = eng(x, t, encoder_hidden_states=ctx).sample
+    sites0 = eng.lora_sites()
+    other = build_unet(arch, seed=1)
+    eng.load_state_dict(other.state_dict())
+    with torch.no_grad():
+        y1 = eng(x, t, encoder_hidden_states=ctx).sample
+        ref = other(x, t, ctx).sample
+    assert all(a is b for a, b in zip(sites0, eng.lora_sites()))
+    assert not torch.allclose(y0, y1)
+    assert (y1 - ref).abs().max().item() < 2e-4 * ref.abs().max().item() + 1e-5

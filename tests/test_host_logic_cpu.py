@@ -175,3 +175,46 @@ def test_reference_lora_network_patches_engine_tree():
         from leco_b200.unet import find_adapter
         sites = [s for s in (eng.pack("cpu", torch.float32) or eng).lora_sites() if s.adapters() is not None]
         assert sum(len(s.members) for s in sites) == n
+
+
+def test_lr_scheduler_factory_matches_torch():
+    """train_util.get_lr_scheduler (train_util.py:373-401) drives the fused optimizer's lr through the same torch
+    scheduler classes and arguments; the reference steps it once per iteration (train_lora.py:281)."""
+    from leco_b200 import train_util as tu
+
+    class Opt:   # stands for FlatOptimizer: only `.lr` is touched
+        lr = 1e-3
+
+    for name in ("constant", "cosine", "cosine_with_restarts", "step", "linear"):
+        o = Opt()
+        sched = tu.get_lr_scheduler(name, o, max_iterations=200, lr_min=1e-5)
+        ref_opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1e-3)
+        S = torch.optim.lr_scheduler
+        ref = {"constant": lambda: S.ConstantLR(ref_opt, factor=1),
+               "cosine": lambda: S.CosineAnnealingLR(ref_opt, T_max=200, eta_min=1e-5),
+               "cosine_with_restarts": lambda: S.CosineAnnealingWarmRestarts(ref_opt, T_0=20, T_mult=2, eta_min=1e-5),
+               "step": lambda: S.StepLR(ref_opt, step_size=2, gamma=0.999),
+               "linear": lambda: S.LinearLR(ref_opt, start_factor=0.5, total_iters=2)}[name]()
+        for _ in range(50):
+            assert o.lr == ref_opt.param_groups[0]["lr"], name
+            sched.step()
+            ref_opt.step()
+            ref.step()
+    with pytest.raises(ValueError):
+        tu.get_lr_scheduler("bogus", Opt(), 10, 1e-5)
+
+
+def test_optimizer_factory_error_behaviour():
+    """train_util.get_optimizer (train_util.py:333-370): same names, same ValueError texts for unknown names."""
+    from leco_b200 import train_util as tu
+    for name in ("adamw", "AdamW", "adam", "lion"):
+        assert callable(tu.get_optimizer(name))
+    with pytest.raises(ValueError, match="Optimizer must be adam, adamw, lion or Prodigy"):
+        tu.get_optimizer("sgd")
+    with pytest.raises(ValueError, match="DAdapt optimizer must be"):
+        tu.get_optimizer("dadaptsgd")
+    with pytest.raises(ValueError, match="8bit optimizer must be"):
+        tu.get_optimizer("sgd8bit")
+    for name in ("dadaptadam", "adam8bit", "prodigy"):   # optional third-party packages, absent here as in the reference image
+        with pytest.raises(NotImplementedError):
+            tu.get_optimizer(name)
