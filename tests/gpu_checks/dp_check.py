@@ -67,7 +67,9 @@ def main():
         losses1 = [tr1.iteration().item() for _ in range(iters)]
         flat1 = net1.flat.params.float()
         mask = net1.flat.mask.bool()
-        from __graft_entry__ import BF16_LOSS_FLOOR
+        # two bf16 executions with different per-launch batch sizes (tile shapes, rounding order): the same loss up to
+        # 5 % plus the rounding variance floor of the objective measured in round 1 (1e-4, profiles/r1_dp_check_w2.json)
+        BF16_LOSS_FLOOR = 1e-4
         up_dp, up_1 = (flat - flat0)[mask], (flat1 - flat0)[mask]
         cos = float(torch.dot(up_dp, up_1) / (up_dp.norm() * up_1.norm() + 1e-30))
         result = {"world": world, "losses_dp": losses, "losses_single": losses1,

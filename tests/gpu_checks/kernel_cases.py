@@ -173,6 +173,133 @@ def case_training_kernels():
     return _merge(res)
 
 
+def _bf16_ulp_stats(got, ref):
+    """bf16 tensors: fraction of elements that are not bit-equal and the worst distance in bf16 ulps."""
+    import torch
+    a = got.view(torch.int16).to(torch.int32)
+    b = ref.view(torch.int16).to(torch.int32)
+    # map the sign-magnitude bit pattern to a monotonic integer line
+    a = torch.where(a < 0, -(a & 0x7FFF), a)
+    b = torch.where(b < 0, -(b & 0x7FFF), b)
+    d = (a - b).abs()
+    return (d != 0).float().mean().item(), int(d.max().item())
+
+
+def case_optimizers():
+    """leco_optim_flat with bf16 state (the benchmarked variant) vs the reference's optimizer objects on bf16
+    parameters: torch.optim.AdamW / Adam (foreach) and the published lion_pytorch update rule restated with torch
+    bf16 ops.  The kernel rounds where torch rounds, so the parameters must agree to the bit (a handful of 1-ulp
+    differences from fused multiply-adds inside torch's kernels are tolerated)."""
+    import torch
+    from leco_b200 import lora as plora
+    res = {}
+    n = 200000
+    g32 = [_rand((n,), 0.01 * (1 + s), 40 + s, torch.float32) for s in range(6)]
+    mask = (torch.rand(n, generator=torch.Generator().manual_seed(3)) < 0.9).to(torch.uint8).cuda()
+
+    def ours(name, steps, gscale=1.0, **kw):
+        p = _rand((n,), 0.05, 3)
+        flat = plora.FlatState(p, torch.zeros(n + 8, device="cuda"), mask)
+        opt = plora.FlatOptimizer(flat, name, **kw)
+        for s in range(steps):
+            flat.grads.copy_(g32[s] / gscale)
+            opt.step(grad_scale=gscale)
+        assert float(flat.grads.abs().max()) == 0.0      # zero_grad
+        return p, opt
+
+    def theirs(make, steps):
+        p0 = _rand((n,), 0.05, 3)
+        pt = torch.nn.Parameter(p0.clone())
+        opt = make([pt])
+        for s in range(steps):
+            pt.grad = (g32[s] * mask).bfloat16()
+            opt.step()
+        # masked-out elements (operand padding) are never touched by the fused kernel
+        return torch.where(mask.bool(), pt.data, p0)
+
+    def lion_ref(steps, lr=1e-4, b1=0.9, b2=0.99, wd=0.0):
+        p = _rand((n,), 0.05, 3)
+        p0 = p.clone()
+        m = torch.zeros_like(p)
+        for s in range(steps):
+            g = g32[s].bfloat16()
+            p.mul_(1 - lr * wd)
+            upd = m.clone().mul_(b1).add(g, alpha=1 - b1).sign_()
+            p.add_(upd, alpha=-lr)
+            m.mul_(b2).add_(g, alpha=1 - b2)
+        return torch.where(mask.bool(), p, p0)
+
+    for tag, name, kw, ref in (
+            ("adamw", "adamw", dict(lr=1e-3), lambda: theirs(lambda ps: torch.optim.AdamW(ps, lr=1e-3, foreach=True), 6)),
+            ("adamw_lr1e-4", "adamw", dict(lr=1e-4, weight_decay=0.1),
+             lambda: theirs(lambda ps: torch.optim.AdamW(ps, lr=1e-4, weight_decay=0.1, foreach=True), 6)),
+            ("adam", "adam", dict(lr=1e-3), lambda: theirs(lambda ps: torch.optim.Adam(ps, lr=1e-3, foreach=True), 6)),
+            ("adam_wd", "adam", dict(lr=1e-3, weight_decay=0.01),
+             lambda: theirs(lambda ps: torch.optim.Adam(ps, lr=1e-3, weight_decay=0.01, foreach=True), 6)),
+            ("lion", "lion", dict(lr=1e-4), lambda: lion_ref(6)),
+            ("lion_wd", "lion", dict(lr=1e-4, weight_decay=0.1), lambda: lion_ref(6, wd=0.1))):
+        p, _ = ours(name, 6, **kw)
+        frac, ulps = _bf16_ulp_stats(p, ref())
+        res[f"{tag}_bf16_state"] = {"rel": frac, "max_ulps": ulps, "ok": frac < 2e-3 and ulps <= 2, "max_abs_err": ulps,
+                                    "ref_absmax": 1.0}
+    # grad_scale (data-parallel mean) is applied before the bf16 rounding of the gradient
+    p_a, _ = ours("adamw", 4, gscale=0.5, lr=1e-3)
+    p_b, _ = ours("adamw", 4, gscale=1.0, lr=1e-3)
+    frac, ulps = _bf16_ulp_stats(p_a, p_b)
+    res["grad_scale"] = {"rel": frac, "max_ulps": ulps, "ok": frac < 2e-3 and ulps <= 1, "max_abs_err": ulps, "ref_absmax": 1.0}
+    return _merge(res)
+
+
+def case_transpose_tiles():
+    """FlatState.refresh_transposed: every site's static (ad^T, bup^T) equals the transposed operand, exactly."""
+    import torch
+    from leco_b200.lora import LoRANetwork
+    _, eng = _engine_pair("tiny15")
+    torch.manual_seed(11)
+    import leco_b200.lora as plora
+    saved = list(plora.DEFAULT_TARGET_REPLACE)
+    try:
+        plora.DEFAULT_TARGET_REPLACE += plora.UNET_TARGET_REPLACE_MODULE_CONV   # c3lier: conv sites too
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = LoRANetwork(eng, rank=8, multiplier=1.0, alpha=4.0)
+    finally:
+        plora.DEFAULT_TARGET_REPLACE[:] = saved
+    net.to("cuda", dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for l in net.unet_loras:
+            l.lora_up.weight.copy_((0.05 * torch.randn(l.lora_up.weight.shape, generator=g)).to("cuda", torch.bfloat16))
+    net.flat.refresh_transposed()
+    torch.cuda.synchronize()
+    bad = 0
+    sites = [s for s in eng.lora_sites() if s.adapters() is not None]
+    for s in sites:
+        adT, bupT = s.static_t
+        bad += int(not torch.equal(adT, s.ad.t())) + int(not torch.equal(bupT, s.bup.t()))
+    return {"ok": bad == 0 and len(sites) > 100, "rel": float(bad), "sites": len(sites)}
+
+
+def case_determinism():
+    """leco_set_deterministic(1): two fresh trainers on the same seeds give bit-identical losses and parameters."""
+    import torch
+    from leco_b200 import ops
+    from __graft_entry__ import engine_trainer
+    ops.set_deterministic(True)
+    try:
+        outs = []
+        for _ in range(2):
+            trainer, net = engine_trainer(use_graphs=True)
+            torch.manual_seed(7)
+            losses = [trainer.iteration().item() for _ in range(3)]
+            outs.append((losses, net.flat.params.clone()))
+        same_loss = outs[0][0] == outs[1][0]
+        same_p = torch.equal(outs[0][1], outs[1][1])
+    finally:
+        ops.set_deterministic(False)
+    return {"ok": bool(same_loss and same_p), "rel": 0.0 if same_loss and same_p else 1.0, "losses": outs[0][0],
+            "losses_2": outs[1][0], "params_equal": bool(same_p)}
+
+
 def case_attention(nb, sq, skv, heads, d, cross=False):
     import torch
     from leco_b200 import ops
@@ -282,8 +409,12 @@ def _make_net(unet, dev, mode=None):
     import torch
     from oracle import leco_ref
     torch.manual_seed(11)
-    kw = dict(rank=4, alpha=1.0) if mode is None else dict(
-        rank=4, alpha=2.0, targets=leco_ref.ATTN_TARGETS + leco_ref.CONV_TARGETS)
+    if mode is None:
+        kw = dict(rank=4, alpha=1.0)
+    elif mode == "rank32":   # stacked q|k|v rank 96 > one 64-wide K-segment: the accumulate-GEMM path
+        kw = dict(rank=32, alpha=8.0)
+    else:
+        kw = dict(rank=4, alpha=2.0, targets=leco_ref.ATTN_TARGETS + leco_ref.CONV_TARGETS)
     with contextlib.redirect_stdout(io.StringIO()):
         net = leco_ref.LoRANetworkRef(unet, multiplier=1.0, **kw)
     g = torch.Generator().manual_seed(5)
@@ -339,10 +470,11 @@ def case_engine_forward(arch, n=2, hw=16, time_it=False):
     return res
 
 
-def case_engine_grads(arch, n=2, hw=8, mode=None):
+def case_engine_grads(arch, n=2, hw=8, mode=None, cache_name=None):
     import torch
     from tests.oracle_cache import cached
-    ora = cached(f"grads_{arch}" if mode is None else f"grads_{mode}_{arch}", lambda: oracle_grads(arch, n, hw, mode))
+    ora = cached(cache_name or (f"grads_{arch}" if mode is None else f"grads_{mode}_{arch}"),
+                 lambda: oracle_grads(arch, n, hw, mode))
     _, eng = _engine_pair(arch)
     x, ctx, _ = _inputs(arch, n, hw)
     net_e = _make_net(eng, "cuda", mode).to(torch.bfloat16)
@@ -353,13 +485,19 @@ def case_engine_grads(arch, n=2, hw=8, mode=None):
     res = {"fwd": _cmp(ye, ora["y"], 3e-2)}
     num = den = worst = 0.0
     got = [p.grad for l in net_e.unet_loras for p in (l.lora_down.weight, l.lora_up.weight)]
+    cos_min, cos_weighted, wsum = 1.0, 0.0, 0.0
     for ga, gb in zip(ora["grads"], got):
         ga, gb = ga.float(), gb.float().cpu()
         num += (ga - gb).pow(2).sum().item()
         den += ga.pow(2).sum().item()
         worst = max(worst, (ga - gb).abs().max().item() / (ga.abs().max().item() + 1e-12))
+        c = (torch.dot(ga.reshape(-1), gb.reshape(-1)) / (ga.norm() * gb.norm()).clamp_min(1e-30)).item()
+        cos_min = min(cos_min, c)
+        cos_weighted += c * ga.pow(2).sum().item()
+        wsum += ga.pow(2).sum().item()
     rel = (num / den) ** 0.5
-    res["grads"] = {"rel": rel, "worst_tensor_rel": worst, "ok": rel < 5e-2, "max_abs_err": 0, "ref_absmax": den ** 0.5}
+    res["grads"] = {"rel": rel, "worst_tensor_rel": worst, "cos_min": cos_min, "cos_weighted": cos_weighted / wsum,
+                    "ok": rel < 5e-2, "max_abs_err": 0, "ref_absmax": den ** 0.5}
     dl = abs(ora["loss"] - le.item()) / ora["loss"]
     res["loss"] = {"rel": dl, "ok": dl < 2e-2, "max_abs_err": 0, "ref_absmax": ora["loss"]}
     return _merge(res)
@@ -369,6 +507,10 @@ CASES = [
     ("norms", case_norms, {}),
     ("elementwise", case_elementwise, {}),
     ("training_kernels", case_training_kernels, {}),
+    ("optimizers", case_optimizers, {}),
+    ("transpose_tiles", case_transpose_tiles, {}),
+    ("determinism", case_determinism, {}),
+    ("attn_self_4096_d64", case_attention, dict(nb=1, sq=4096, skv=4096, heads=5, d=64)),
     ("attn_self_1024_d64", case_attention, dict(nb=2, sq=1024, skv=1024, heads=5, d=64)),
     ("attn_cross_77", case_attention, dict(nb=2, sq=256, skv=77, heads=2, d=64, cross=True)),
     ("attn_self_d40", case_attention, dict(nb=2, sq=256, skv=256, heads=8, d=40)),
@@ -391,6 +533,7 @@ CASES = [
     ("engine_grads_tiny21", case_engine_grads, dict(arch="tiny21")),
     ("engine_grads_tiny15", case_engine_grads, dict(arch="tiny15")),
     ("engine_grads_c3lier_tiny15", case_engine_grads, dict(arch="tiny15", mode="c3lier")),
+    ("engine_grads_rank32_tiny21", case_engine_grads, dict(arch="tiny21", mode="rank32")),
     ("engine_fwd_sd21_64", case_engine_forward, dict(arch="sd21", n=2, hw=64, time_it=True)),
 ]
 

@@ -40,6 +40,8 @@ def main():
         print("grads", arch, flush=True)
     cached("grads_c3lier_tiny15", lambda: kc.oracle_grads("tiny15", 2, 8, "c3lier"), write=True)
     print("grads c3lier", flush=True)
+    cached("grads_rank32_tiny21", lambda: kc.oracle_grads("tiny21", 2, 8, "rank32"), write=True)
+    print("grads rank32", flush=True)
     from __graft_entry__ import oracle_iterations
     cached("iters_tiny21", lambda: oracle_iterations(3), write=True)
     print("iters", flush=True)

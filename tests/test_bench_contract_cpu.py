@@ -12,15 +12,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_work_model_matches_survey_numbers():
     # C2 (B=2, k=25) W_ref ~ 97 TFLOP, W_min ~ 89 TFLOP (3B LoRA-off samples; 2 distinct prompts -> 87.2)
-    assert abs(bench.w_ref_tflop(2, 25) - 97.22) < 0.05
-    assert abs(bench.w_min_tflop(2, 25, distinct_nograd=3) - 88.81) < 0.05
-    assert abs(bench.w_min_tflop(2, 25) - 87.20) < 0.05
-    assert bench.w_min_tflop(2, 25) < bench.w_ref_tflop(2, 25)
-    # one iteration = (k+4) CFG forwards + backward of 2B samples at 1.23 F
-    sec_cfg_fwd = 4.0                                   # 2 samples
-    per_sample = sec_cfg_fwd / 2
-    t_iter = 2 * 2 * 29 * per_sample + 2 * 2 * 1.23 * per_sample
-    assert abs(bench.cpu_latents_per_s(sec_cfg_fwd, 2, 25) - 2 / t_iter) < 1e-12
+    c2 = bench.CONFIGS["sd21"]
+    assert abs(bench.w_ref_tflop(c2, 25) - 97.22) < 0.05
+    assert abs(bench.w_min_tflop(c2, 25, distinct_nograd=3) - 88.81) < 0.05
+    assert abs(bench.w_min_tflop(c2, 25) - 87.20) < 0.05
+    assert bench.w_min_tflop(c2, 25) < bench.w_ref_tflop(c2, 25)
+    # C3 / C5-per-rank (B=4) W_ref ~ 194 TFLOP, C4 (SDXL) ~ 816 TFLOP
+    assert abs(bench.w_ref_tflop(bench.CONFIGS["sd21_b4"], 25) - 194.4) < 0.5
+    assert abs(bench.w_ref_tflop(bench.CONFIGS["sd15_c3lier"], 25) - 194.4) < 0.5
+    assert abs(bench.w_ref_tflop(bench.CONFIGS["sdxl"], 25) - 816) < 2
+
+
+def test_cpu_arm_projection_scales_only_the_denoise_loop():
+    """the reference arm measures COMPLETE iterations at a small k; the workload's k is reached by scaling the measured
+    per-denoise-step time, everything else (4 predictions, backward, AdamW) is taken as measured"""
+    pr = bench.cpu_projection(bench.CONFIGS["sd21"], t_den=[12.0, 14.0], t_tot=[100.0, 104.0], k_meas=1, batch_meas=2, k=25)
+    assert pr["measured"]["s_per_iteration"] == 102.0 and pr["measured"]["s_denoise_step"] == 13.0
+    assert pr["measured"]["s_rest_of_iteration"] == 89.0
+    assert abs(pr["projected"]["latents_per_s"] - 2 / (25 * 13.0 + 89.0)) < 1e-12
+    assert abs(pr["measured"]["latents_per_s"] - 2 / 102.0) < 1e-12
 
 
 REQUIRED = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -51,3 +61,22 @@ def test_committed_reference_arm_line():
     assert line["impl"] == "reference" and line["metric"] == "leco_train_latents_per_sec"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+
+
+def test_reference_arm_runs_complete_iterations_and_keeps_the_contract():
+    """`bench.py --impl reference` (reduced-width twin so it takes seconds here): the line is built from COMPLETE oracle
+    iterations with measured phases; `steps` is the number actually timed, not the number requested."""
+    import subprocess
+    import sys
+    pr = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "tiny21",
+                         "--steps", "20", "--warmup", "5"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert pr.returncode == 0, pr.stderr[-2000:]
+    line = json.loads(pr.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "leco_train_latents_per_sec" and line["unit"] == "latents/s"
+    assert line["steps"] == 2 and line["steps_requested"] == 20
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["value"] == line["value"] and cb["cores"] >= 1
+    m, p = cb["measured"], cb["projected"]
+    assert m["k"] == 1 and m["iterations"] == 2 and m["s_per_iteration"] > m["s_denoise_step"] > 0
+    assert abs(p["latents_per_s"] - m["prompt_batch"] / (25 * m["s_denoise_step"] + m["s_rest_of_iteration"])) < 1e-9
+    assert line["e2e"] == {"value": line["value"], "unit": "latents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -7,7 +7,14 @@ import pytest
 from tests.gpu_checks import gemm_cases, kernel_cases
 
 pytestmark = pytest.mark.gpu
-from __graft_entry__ import BF16_LOSS_FLOOR  # noqa: E402
+from __graft_entry__ import assert_losses_close  # noqa: E402
+
+
+def _bf16_yardstick(name, fn):
+    """The same oracle iterations executed the way the reference executes them (bf16, stock torch kernels on this
+    GPU): the measured tolerance of the loss comparisons (see __graft_entry__.loss_tolerance)."""
+    import torch
+    return fn(device="cuda", dtype=torch.bfloat16)
 
 GEMM = [(n, f, kw) for n, f, kw in gemm_cases.CASES if not n.startswith(("perf_", "perfauto_"))]
 KERN = [(n, f, kw) for n, f, kw in kernel_cases.CASES if n != "engine_fwd_sd21_64"]
@@ -51,24 +58,26 @@ def test_engine_not_worse_than_reference_numerics():
     assert e_engine < 1.5 * e_bf16 + 1e-3, (e_engine, e_bf16)
 
 
-@pytest.mark.parametrize("graphs", [False, True], ids=["eager", "cuda_graphs"])
-def test_leco_iteration_matches_oracle(graphs):
+@pytest.mark.parametrize("graphs,state_fp32", [(False, True), (True, True), (True, False)],
+                         ids=["eager", "cuda_graphs", "cuda_graphs_bf16_optimizer_state"])
+def test_leco_iteration_matches_oracle(graphs, state_fp32):
     """Three full LECO iterations (denoise loop, 4 predictions, erase loss, backward, AdamW) on the GPU
     vs oracle/leco_ref.leco_iteration (fp32 CPU, pinned against the reference's train loop) on the same
-    seeds.  Tolerance: 5% of the loss (bf16 network vs fp32 oracle)."""
+    seeds.  Tolerance: measured (bf16 torch execution of the same oracle, __graft_entry__.loss_tolerance).
+    The third variant runs the default / benchmarked optimizer (bf16 moments, the reference's rounding points)."""
     import torch
     from __graft_entry__ import engine_trainer, oracle_iterations
     from tests.oracle_cache import cached
     ref = cached("iters_tiny21", lambda: oracle_iterations(3))
-    trainer, net = engine_trainer(use_graphs=graphs)
+    yard = _bf16_yardstick("iters_tiny21", lambda **kw: oracle_iterations(3, **kw))
+    trainer, net = engine_trainer(use_graphs=graphs, state_fp32=state_fp32)
     torch.manual_seed(7)
     got, ks = [], []
     for _ in range(3):
         got.append(trainer.iteration().item())
         ks.append(trainer.last["k"])
-    assert ks == ref["k"]
-    for a, b in zip(got, ref["losses"]):
-        assert abs(a - b) <= 0.05 * abs(b) + BF16_LOSS_FLOOR, (got, ref["losses"])
+    assert ks == ref["k"] == yard["k"]
+    assert_losses_close(got, ref["losses"], yard["losses"])
     # adapter weights after 3 steps: same direction, same size
     num = den = 0.0
     for a, wb in zip(net.unet_loras, ref["lora_up"]):
@@ -87,6 +96,7 @@ def test_leco_iteration_xl_matches_oracle(graphs):
     from __graft_entry__ import engine_trainer_xl, oracle_iterations_xl
     from tests.oracle_cache import cached
     ref = cached("iters_tinyxl", lambda: oracle_iterations_xl(3))
+    yard = _bf16_yardstick("iters_tinyxl", lambda **kw: oracle_iterations_xl(3, **kw))
     trainer, net = engine_trainer_xl(use_graphs=graphs)
     torch.manual_seed(7)
     got, ks = [], []
@@ -94,8 +104,7 @@ def test_leco_iteration_xl_matches_oracle(graphs):
         got.append(trainer.iteration().item())
         ks.append(trainer.last["k"])
     assert ks == ref["k"]
-    for a, b in zip(got, ref["losses"]):
-        assert abs(a - b) <= 0.05 * abs(b) + BF16_LOSS_FLOOR, (got, ref["losses"])
+    assert_losses_close(got, ref["losses"], yard["losses"])
     num = den = 0.0
     for a, wb in zip(net.unet_loras, ref["lora_up"]):
         wa, wb = a.lora_up.weight.detach().float().cpu().reshape(-1), wb.float().reshape(-1)
@@ -112,6 +121,7 @@ def test_leco_iteration_dynamic_resolution_matches_oracle():
     from __graft_entry__ import _SETTINGS_DYN, engine_trainer, oracle_iterations
     from tests.oracle_cache import cached
     ref = cached("iters_tiny21_dyn", lambda: oracle_iterations(4, settings=_SETTINGS_DYN))
+    yard = _bf16_yardstick("iters_tiny21_dyn", lambda **kw: oracle_iterations(4, settings=_SETTINGS_DYN, **kw))
     trainer, net = engine_trainer(use_graphs=True, settings=_SETTINGS_DYN)
     torch.manual_seed(7)
     got, ks, shapes = [], [], []
@@ -121,8 +131,7 @@ def test_leco_iteration_dynamic_resolution_matches_oracle():
         shapes.append(tuple(trainer.last["denoised"].shape[-2:]))
     assert ks == ref["k"]
     assert len(set(shapes)) > 1 and any(h != w for h, w in shapes), shapes
-    for a, b in zip(got, ref["losses"]):
-        assert abs(a - b) <= 0.05 * abs(b) + BF16_LOSS_FLOOR, (got, ref["losses"])
+    assert_losses_close(got, ref["losses"], yard["losses"])
 
 
 def test_leco_iteration_multiple_pairs_enhance_matches_oracle():
@@ -132,6 +141,7 @@ def test_leco_iteration_multiple_pairs_enhance_matches_oracle():
     from __graft_entry__ import engine_trainer, oracle_iterations
     from tests.oracle_cache import cached
     ref = cached("iters_tiny21_multi", lambda: oracle_iterations(5, multi=True))
+    yard = _bf16_yardstick("iters_tiny21_multi", lambda **kw: oracle_iterations(5, multi=True, **kw))
     trainer, net = engine_trainer(use_graphs=True, multi=True)
     torch.manual_seed(7)
     got, ks, acts = [], [], []
@@ -141,5 +151,113 @@ def test_leco_iteration_multiple_pairs_enhance_matches_oracle():
         acts.append(trainer.last["pair"].action)
     assert ks == ref["k"]
     assert "enhance" in acts and "erase" in acts, acts
-    for a, b in zip(got, ref["losses"]):
-        assert abs(a - b) <= 0.05 * abs(b) + BF16_LOSS_FLOOR, (got, ref["losses"])
+    assert_losses_close(got, ref["losses"], yard["losses"])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Parity at the BASELINE size (configs[1]: SD2.1 architecture, 64x64 latents, prompt batch 2) — VERDICT r1 "next" #1.
+# The fp32 oracle side is a committed fixture (tests/fullsize.py); the tolerance is MEASURED on this GPU by running the
+# same oracle code in bf16 through stock torch kernels (= the reference's own numerics).
+# ----------------------------------------------------------------------------------------------------------------------
+def test_fullsize_sd21_lora_gradients():
+    """LoRA gradients of one grad pass, SD2.1 full size, 2 samples at 64x64 (M = 8192 token rows at the top level):
+    through the 2-CTA / split-K GEMMs, tn_reduce at full M and attention backward at S = 4096, vs fp32 oracle autograd."""
+    res = kernel_cases.case_engine_grads("sd21", n=2, hw=64, cache_name="grads_sd21_full")
+    g = res["parts"]["grads"]
+    assert res["ok"] and g["rel"] < 5e-2 and g["cos_weighted"] > 0.99, res
+
+
+def test_fullsize_sd21_iteration():
+    """One complete LECO iteration at BASELINE configs[1] size with k = 3 denoise steps and non-zero adapters: denoised
+    latents (row a7), target prediction, loss, every LoRA gradient, and the AdamW update (default bf16 optimizer state)
+    against the fp32 oracle — each bounded by 1.5x the error of the plain-bf16 torch execution of the same oracle."""
+    import torch
+    from tests import fullsize as fs
+    from tests.oracle_cache import cached
+    ref = cached("iter_sd21_full", fs.oracle_iteration_full)
+    yard = fs.torch_bf16_iteration_full()
+    torch.cuda.empty_cache()
+    got = fs.engine_iteration_full()
+    assert got["k"] == ref["k"] == yard["k"] == fs.K_FIXED and got["timestep"] == ref["timestep"]
+    report = {}
+    for key in ("denoised", "target"):
+        e, b = fs.rel_rms(got[key], ref[key]), fs.rel_rms(yard[key], ref[key])
+        report[key] = (e, b)
+        assert e <= 1.5 * b + 1e-3, (key, report)
+    e, b = abs(got["loss"] - ref["loss"]) / ref["loss"], abs(yard["loss"] - ref["loss"]) / ref["loss"]
+    report["loss"] = (got["loss"], yard["loss"], ref["loss"])
+    assert e <= 1.5 * b + 0.02, report
+    e, b = fs.grads_rel_l2(got["grads"], ref["grads"]), fs.grads_rel_l2(yard["grads"], ref["grads"])
+    cos = fs.grads_cosines(got["grads"], ref["grads"])
+    cos_b = fs.grads_cosines(yard["grads"], ref["grads"])
+    report["grads"] = (e, b, min(cos), min(cos_b), sum(cos) / len(cos))
+    assert e <= max(5e-2, 1.5 * b), report
+    assert sum(cos) / len(cos) > 0.99 and min(cos) >= min(0.9, min(cos_b) - 0.05), report
+    # AdamW update direction (bf16 parameters: an lr-sized step is ~1 ulp, so compare in aggregate)
+    num = sum(torch.dot(a.reshape(-1).float(), b_.reshape(-1).float()).item() for a, b_ in zip(got["update"], yard["update"]))
+    den = (sum(a.float().pow(2).sum().item() for a in got["update"]) * sum(b_.float().pow(2).sum().item() for b_ in yard["update"])) ** 0.5
+    report["update_cos_vs_torch_bf16"] = num / den
+    assert num / den > 0.9, report
+    print("fullsize iteration report:", report)
+
+
+def test_load_weights_under_captured_graphs(tmp_path):
+    """save_weights -> load_weights round trip on the GPU while CUDA graphs that captured the flat
+    operand buffer are alive: values are copied in place, the next iteration uses them (resume)."""
+    import torch
+    from __graft_entry__ import engine_trainer
+    trainer, net = engine_trainer(use_graphs=True)
+    torch.manual_seed(7)
+    trainer.iteration()
+    f = str(tmp_path / "ckpt.safetensors")
+    net.save_weights(f, dtype=torch.bfloat16)
+    snap = net.flat.params.clone()
+    torch.manual_seed(99)
+    rng = torch.get_rng_state()
+    loss_a = trainer.iteration(step_optimizer=False).item()
+    net.flat.grads.zero_()
+    with torch.no_grad():
+        net.flat.params.mul_(0.5)                      # wreck the adapters ...
+    net.load_weights(f)                                 # ... and restore them from the file, in place
+    assert torch.equal(net.flat.params, snap)
+    torch.set_rng_state(rng)
+    loss_b = trainer.iteration(step_optimizer=False).item()
+    assert abs(loss_a - loss_b) <= 2e-3 * abs(loss_a), (loss_a, loss_b)   # same graphs, same weights (atomics: not bitwise)
+
+
+def test_lr_schedule_reaches_the_fused_optimizer():
+    """train_lora.py:281 steps the LR scheduler every iteration: cosine schedule through LecoTrainer."""
+    import math
+    import torch
+    from __graft_entry__ import engine_trainer
+    trainer, net = engine_trainer(use_graphs=True)
+    from leco_b200.train_util import get_lr_scheduler
+    trainer.lr_scheduler = get_lr_scheduler("cosine", trainer.optimizer, max_iterations=10, lr_min=1e-5)
+    lr0 = trainer.optimizer.lr
+    torch.manual_seed(7)
+    lrs = []
+    for _ in range(3):
+        trainer.iteration()
+        lrs.append(trainer.last["lr"])
+    expect = [1e-5 + (lr0 - 1e-5) * (1 + math.cos(math.pi * t / 10)) / 2 for t in (1, 2, 3)]
+    assert all(abs(a - b) < 1e-9 for a, b in zip(lrs, expect)), (lrs, expect)
+
+
+def test_data_parallel_two_gpus_nccl():
+    """SURVEY §8e on real hardware: 2 ranks x local batch 1 through LecoTrainer.iteration's NCCL branch (one all-reduce
+    of gradient + loss) vs one rank at batch 2.  Needs 2 GPUs (skipped on the 1-GPU test box; `gpurun --gpus 2`)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out", "dp_check_w2.json")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29531", os.path.join(root, "tests", "gpu_checks", "dp_check.py")]
+    pr = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert pr.returncode == 0, pr.stderr[-3000:]
+    res = json.load(open(out))
+    assert res["ok"], res
