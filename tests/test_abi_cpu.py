@@ -13,7 +13,7 @@ def test_library_builds_and_loads():
     path = build_library(verbose=False)
     assert os.path.exists(path)
     lib = capi.load()
-    assert lib.leco_abi_version() == 1
+    assert lib.leco_abi_version() == 2
     assert lib.leco_launch_count() >= 0
 
 
