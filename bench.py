@@ -428,6 +428,7 @@ def run_ours(args):
     sec, loss_a, _ = timed(trainer, args.steps, e2e=False)
     launches = trainer.launches
     sec_e2e, loss_b, _ = timed(trainer, args.steps, e2e=True)
+    h2d_bytes = trainer.h2d_bytes          # host noise of one step (pinned staging -> device), counted by the trainer
     clocks = sampler.stop() if sampler else None
     ar_ms = trainer.allreduce_ms()
     peak_mem = torch.cuda.max_memory_allocated(dev)
@@ -457,7 +458,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": config_dict(name, cfg, world, k, b_global),
             "iterations_per_sec": it_s, "loss": loss_b,
-            "e2e": {"value": val_e2e, "unit": "latents/s", "h2d_bytes_per_step": trainer.h2d_bytes,
+            "e2e": {"value": val_e2e, "unit": "latents/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "random_k": {"value": b_global * n_rk / sec_rk, "unit": "latents/s", "steps": n_rk, "ms_per_step": 1000.0 * sec_rk / n_rk,

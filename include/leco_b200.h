@@ -170,6 +170,14 @@ int leco_optim_flat(void* params_bf16, float* grads, void* exp_avg, void* exp_av
 int leco_transpose_tiles(const void* src, void* dst, const void* tiles, int n_tiles, void* stream);
 int leco_guided_step(const float* eps_pair, const float* x, float* x_out, float* guided_out, const float* coef_dev,
                      int64_t half_numel, void* stream);
+/* leco_sched_step: the general scheduler update (DDPM / LMS / Euler-ancestral of model_util.py:247-274) fused with the CFG
+ *   combine: guided = e_u + g(e_c - e_u); d = dx x + dg guided -> hist[slot] (LMS derivative ring, 4 x half_numel, may
+ *   be NULL); x_out = cx x + ce guided + cn noise + sum_j l_j hist[(slot-j)&3].  coef_dev = fp32[12]
+ *   {g, cx, ce, cn, in_scale, dx, dg, l0, l1, l2, l3, slot}.  noise may be NULL (cn ignored).
+ * leco_scale_by_dev: y = x * coef_dev[idx] — scheduler.scale_model_input (train_util.py:153) with the factor on the device. */
+int leco_sched_step(const float* eps_pair, const float* x, const float* noise, float* hist, float* x_out,
+                    const float* coef_dev, int64_t half_numel, void* stream);
+int leco_scale_by_dev(const float* x, float* y, const float* coef_dev, int idx, int64_t n, void* stream);
 int leco_loss(const float* target, const float* positive, const float* neutral, const float* uncond,
               float sign_times_guidance, float* loss_out, float* dtarget, int64_t numel, void* stream);
 /* out = a*x + b*y (the DDIM update for drop-in scheduler.step callers, train_util.py:190) */

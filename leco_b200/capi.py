@@ -99,6 +99,8 @@ _OPS: list[tuple[str, list]] = [
     ("leco_transpose_tiles", [P, P, P, I, P]),
     ("leco_set_deterministic", [I]),
     ("leco_guided_step", [P, P, P, P, P, L, P]),
+    ("leco_sched_step", [P, P, P, P, P, P, L, P]),
+    ("leco_scale_by_dev", [P, P, P, I, L, P]),
     ("leco_loss", [P, P, P, P, F, P, P, L, P]),
     ("leco_axpby", [P, P, P, F, F, L, I, P]),
     ("leco_cast_f32_to_bf16", [P, P, L, P]),

@@ -38,7 +38,7 @@ struct GemmParams {
   long long ldws;
   // in-kernel LoRA (lora.py:102-106 in ONE kernel): the stacked lora_down rows `Ad` ride along as fl_kl extra
   // B rows, so accumulator columns [BN, BN+fl_kl) hold T_raw = x.Ad^T; the epilogue adds fl_scale*T_raw.Bup^T
-  CUtensorMap tm_ad;
+  CUtensorMap tm_ad, tm_bup;      // stacked lora_down rows [fl_kl][K]; stacked lora_up [N][fl_kl] (box BN x 64, zero filled)
   int fl_kl;                      // 0 = off; else 16/32/48/64 padded stacked rank
   int fl_rank;                    // real stacked rank (columns >= fl_rank of T are zero)
   float fl_scale;                 // alpha/rank * multiplier
@@ -55,13 +55,19 @@ struct GemmCfg {
   static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   // as many stages as fit 227 KB: with the role loops at the tensor floor the main loop is bound by bytes in flight
-  static constexpr int STAGES = FL ? (BN >= 160 ? 4 : (BN >= 128 ? 5 : 6)) : ((BN >= 256) ? 4 : (BN >= 160 ? 6 : (BN >= 128 ? 7 : 9)));
-  static_assert(STAGES * STAGE_BYTES + 1024 + 256 <= 232448, "stage ring exceeds 227 KB");
+  // in-kernel LoRA: T = fl_scale * x.Ad^T is re-staged by the epilogue warps as a bf16 A-operand tile (128 rows x 128 B,
+  // K-major SW128) and the lora_up rows of the N tile arrive by TMA (BN rows x 128 B, double buffered): the up
+  // projection T.Bup^T is then ONE more UMMA K-step on the same accumulator
+  static constexpr int T_TILE_BYTES = FL ? BLOCK_M * BLOCK_K * 2 : 0;
+  static constexpr int BUP_TILE_BYTES = FL ? BN * BLOCK_K * 2 : 0;
+  static constexpr int FL_BYTES = T_TILE_BYTES + 2 * BUP_TILE_BYTES;
+  static constexpr int STAGES = FL ? (BN >= 160 ? 3 : (BN >= 128 ? 4 : 6)) : ((BN >= 256) ? 4 : (BN >= 160 ? 6 : (BN >= 128 ? 7 : 9)));
+  static_assert(STAGES * STAGE_BYTES + FL_BYTES + 1024 + 256 <= 232448, "stage ring exceeds 227 KB");
   // accumulator stage stride in TMEM columns (power of two so a stage never straddles an
   // alignment boundary): 64 / 128 / 256
   static constexpr int ACC_STRIDE = FL ? 256 : ((BN <= 64) ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FL_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ void epi_store_bf16(__nv_bfloat16* dst, const float (&v)[32], int ncols_valid) {
@@ -139,47 +145,8 @@ __device__ __forceinline__ void epi_add_q(float (&v)[32], const uint4 (&q)[4]) {
   }
 }
 
-// v[j] += fl_scale * sum_k T_raw[k] * Bup[n0 + j][k] for the 32 output columns of one chunk.  T_raw is re-read
-// from TMEM in groups of 8 columns (cheap) so no large register array is live.
-__device__ __forceinline__ void epi_lora_add(float (&v)[32], const GemmParams& p, uint32_t t_addr, long long ncol0,
-                                             int nvalid) {
-  const int groups = (p.fl_rank + 7) >> 3;
-  for (int g = 0; g < groups; ++g) {
-    uint32_t traw[8];
-    tmem_ld_32x32b_x8(t_addr + g * 8, traw);
-    tmem_ld_wait();
-    float t[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t[k] = __uint_as_float(traw[k]) * p.fl_scale;
-    const __nv_bfloat16* bp = p.fl_bup + ncol0 * p.fl_ld_bup + g * 8;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < nvalid) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(bp + j * p.fl_ld_bup));
-        float a = v[j];
-        a = fmaf(t[0], bf16_lo(q.x), a);
-        a = fmaf(t[1], bf16_hi(q.x), a);
-        a = fmaf(t[2], bf16_lo(q.y), a);
-        a = fmaf(t[3], bf16_hi(q.y), a);
-        a = fmaf(t[4], bf16_lo(q.z), a);
-        a = fmaf(t[5], bf16_hi(q.z), a);
-        a = fmaf(t[6], bf16_lo(q.w), a);
-        a = fmaf(t[7], bf16_hi(q.w), a);
-        v[j] = a;
-      }
-    }
-  }
-}
-
-// One output tile: TMEM accumulator (this thread's row r of lane quadrant q) -> epilogue -> global.
-// `trow` = TMEM address of the row's first accumulator column; (mt, nt, b0, b1) identify the tile.
-template <int BN>
-__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t trow, int r, int mt, int nt, int b0,
-                                                   int b1) {
-  const bool geglu = (p.epilogue == 1);
-  const int n0 = nt * BN;
-  long long m;
-  bool row_ok;
+// Output row of tile row r: (global row m, row inside the problem?)
+__device__ __forceinline__ void gemm_epi_row(const GemmParams& p, int r, int mt, long long& m, bool& row_ok) {
   if (p.mode == 0) {
     m = static_cast<long long>(mt) * BLOCK_M + r;
     row_ok = m < p.M;
@@ -195,22 +162,44 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
     }
     m = static_cast<long long>(img_n0 * p.ch + img_h0) * p.cw + r;
   }
-  const long long boff = b0 * p.d_bs0 + b1 * p.d_bs1;
-  if (p.fl_kl && p.fl_t_out && nt == 0) {  // save fl_scale*T for the backward (dB = dY^T T)
-    for (int g = 0; g < p.fl_kl / 8; ++g) {
-      uint32_t traw[8];
-      tmem_ld_32x32b_x8(trow + BN + g * 8, traw);
-      tmem_ld_wait();
-      if (row_ok) {
-        uint4 o;
-        o.x = pack_bf16(__uint_as_float(traw[0]) * p.fl_scale, __uint_as_float(traw[1]) * p.fl_scale);
-        o.y = pack_bf16(__uint_as_float(traw[2]) * p.fl_scale, __uint_as_float(traw[3]) * p.fl_scale);
-        o.z = pack_bf16(__uint_as_float(traw[4]) * p.fl_scale, __uint_as_float(traw[5]) * p.fl_scale);
-        o.w = pack_bf16(__uint_as_float(traw[6]) * p.fl_scale, __uint_as_float(traw[7]) * p.fl_scale);
-        *reinterpret_cast<uint4*>(p.fl_t_out + m * p.fl_ld_t + g * 8) = o;
-      }
-    }
+}
+
+// In-kernel LoRA, epilogue half: this thread's row of T_raw = x.Ad^T (accumulator columns [BN, BN+fl_kl), fp32) is
+// scaled, rounded to bf16 (the same rounding point as the separate T GEMM) and written into the K-major SW128 smem
+// tile the up-projection UMMA reads as its A operand: row r = 128 B, 16-byte chunk c at ((c ^ (r & 7)) << 4).
+// With fl_t_out the row is also saved to global memory (the backward needs T: dB = dY^T T).
+template <int BN>
+__device__ __forceinline__ void gemm_fl_stage_t(const GemmParams& p, uint32_t trow, int r, int mt, int nt,
+                                                uint8_t* s_t) {
+  long long m;
+  bool row_ok;
+  gemm_epi_row(p, r, mt, m, row_ok);
+  const bool save = p.fl_t_out && nt == 0 && row_ok;
+  for (int g = 0; g < p.fl_kl / 8; ++g) {
+    uint32_t traw[8];
+    tmem_ld_32x32b_x8(trow + BN + g * 8, traw);
+    tmem_ld_wait();
+    uint4 o;
+    o.x = pack_bf16(__uint_as_float(traw[0]) * p.fl_scale, __uint_as_float(traw[1]) * p.fl_scale);
+    o.y = pack_bf16(__uint_as_float(traw[2]) * p.fl_scale, __uint_as_float(traw[3]) * p.fl_scale);
+    o.z = pack_bf16(__uint_as_float(traw[4]) * p.fl_scale, __uint_as_float(traw[5]) * p.fl_scale);
+    o.w = pack_bf16(__uint_as_float(traw[6]) * p.fl_scale, __uint_as_float(traw[7]) * p.fl_scale);
+    *reinterpret_cast<uint4*>(s_t + r * 128 + ((g ^ (r & 7)) << 4)) = o;
+    if (save) *reinterpret_cast<uint4*>(p.fl_t_out + m * p.fl_ld_t + g * 8) = o;
   }
+}
+
+// One output tile: TMEM accumulator (this thread's row r of lane quadrant q) -> epilogue -> global.
+// `trow` = TMEM address of the row's first accumulator column; (mt, nt, b0, b1) identify the tile.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t trow, int r, int mt, int nt, int b0,
+                                                   int b1) {
+  const bool geglu = (p.epilogue == 1);
+  const int n0 = nt * BN;
+  long long m;
+  bool row_ok;
+  gemm_epi_row(p, r, mt, m, row_ok);
+  const long long boff = b0 * p.d_bs0 + b1 * p.d_bs1;
 
   if (p.k_splits > 1) {
     // partial accumulator of one K-slice -> fp32 workspace (bias / residual are applied by the finalize kernel)
@@ -225,9 +214,6 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
-      // tcgen05.ld is warp-aligned: every lane runs it, invalid rows just add nothing (nvalid 0).
-      // Linear in T: each K-slice adds its own part.
-      if (p.fl_kl) epi_lora_add(v, p, trow + BN, col0, ok ? nvalid : 0);
       if (ok) {
         float* dst = p.ws + m * p.ldws + col0;
 #pragma unroll
@@ -259,7 +245,6 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
-      if (p.fl_kl) epi_lora_add(v, p, trow + BN, col0, ok ? nvalid : 0);  // all lanes (aligned TMEM loads inside)
       if (ok) {
         if (p.bias) epi_add_q(v, cur.b);
         if (p.rowbias) epi_add_q(v, cur.rb);
@@ -288,10 +273,6 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       for (int j = 0; j < 32; ++j) {
         h[j] = __uint_as_float(rh[j]) * p.alpha;
         g[j] = __uint_as_float(rg[j]) * p.alpha;
-      }
-      if (p.fl_kl) {  // all lanes (aligned TMEM loads inside)
-        epi_lora_add(h, p, trow + BN, ocol0, ok ? 32 : 0);
-        epi_lora_add(g, p, trow + BN, p.N / 2 + ocol0, ok ? 32 : 0);
       }
       if (ok) {
         if (p.bias) {

@@ -37,12 +37,21 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smem_t = smem + STAGES * Cfg::STAGE_BYTES;                  // FL: T tile (A operand of the up projection)
+  uint8_t* smem_bup = smem_t + Cfg::T_TILE_BYTES;                      // FL: 2 x lora_up tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::FL_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]       MMA -> epilogue
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  // in-kernel LoRA (FL): T staged (epilogue -> MMA), T consumed (MMA -> epilogue), lora_up tile landed / consumed,
+  // accumulator complete INCLUDING the up projection (MMA -> epilogue)
+  uint64_t* t_full = bars + 2 * STAGES + 4;     // [1] count 4
+  uint64_t* t_empty = t_full + 1;               // [1]
+  uint64_t* bup_full = t_full + 2;              // [2]
+  uint64_t* bup_empty = t_full + 4;             // [2]
+  uint64_t* acc2_full = t_full + 6;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -50,7 +59,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_a);
     tma_prefetch_desc(&p.tm_b);
-    if (FL) tma_prefetch_desc(&p.tm_ad);
+    if (FL) {
+      tma_prefetch_desc(&p.tm_ad);
+      tma_prefetch_desc(&p.tm_bup);
+    }
     if (p.has_seg2) {
       tma_prefetch_desc(&p.tm_a2);
       tma_prefetch_desc(&p.tm_b2);
@@ -64,6 +76,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);
+    }
+    if (FL) {
+      mbar_init(t_full, 4);
+      mbar_init(t_empty, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bup_full[i], 1);
+        mbar_init(&bup_empty[i], 1);
+        mbar_init(&acc2_full[i], 1);
+      }
     }
     fence_barrier_init();
   }
@@ -97,7 +118,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     uint32_t phase = 0;
     const uint32_t tx1 = p.a_tx_bytes + BN * BLOCK_K * 2 + (FL ? p.fl_kl * BLOCK_K * 2 : 0);
     const int dbg = p.dbg;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int itp = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++itp) {
       // per-tile index math runs on ONE lane's latency chain: skip every division the common case does not need
       int ks = 0, t2 = tile, bidx = 0, b0 = 0, b1 = 0;
       if (splits > 1) {
@@ -122,6 +144,20 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         c_end1 = (int)((long long)(ks + 1) * p.chunks1 / splits);
       }
       const bool seg2 = p.has_seg2 && ks == splits - 1;
+      if (FL) {
+        // stacked lora_up rows of this N tile ([BN] x fl_kl, zero filled to 64 columns) for the up-projection UMMA
+        const int bb = itp & 1;
+        const uint32_t bf = smem_u32(&bup_full[bb]);
+        const uint32_t sbup = smem_u32(smem_bup) + bb * Cfg::BUP_TILE_BYTES;
+        mbar_wait(&bup_empty[bb], ((itp >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx_u32(bf, Cfg::BUP_TILE_BYTES);
+        if (p.epilogue == 1) {
+          tma_load_4d_u32(sbup, &p.tm_bup, bf, 0, nt * (BN / 2), 0, 0);
+          tma_load_4d_u32(sbup + (BN / 2) * BLOCK_K * 2, &p.tm_bup, bf, 0, p.N / 2 + nt * (BN / 2), 0, 0);
+        } else {
+          tma_load_4d_u32(sbup, &p.tm_bup, bf, 0, n0, 0, 0);
+        }
+      }
       // filter-tap counters of the implicit conv (mode 1): chunk c = (tap, cc), tap = kh*3 + kw
       int cc = 0, kw = 0, kh = 0;
       if (p.mode != 0) {
@@ -204,6 +240,24 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    // FL: the up projection of tile i (acc += T.Bup^T, one UMMA per 16 ranks) can only be issued once the epilogue
+    // warps have re-staged T; it is slipped in after the first chunks of tile i+1's main loop so the tensor pipe
+    // never waits for that round trip
+    int pend_it = -1;
+    const uint32_t idesc_up = umma_idesc_bf16_m128(BN);
+    auto issue_up = [&](int it_) {
+      const int as_ = it_ & 1, bb = it_ & 1;
+      mbar_wait(t_full, it_ & 1);
+      mbar_wait(&bup_full[bb], (it_ >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ta = umma_desc_lo(smem_u32(smem_t));
+      const uint32_t tb = umma_desc_lo(smem_u32(smem_bup) + bb * Cfg::BUP_TILE_BYTES);
+      const uint32_t d = tmem_base + as_ * Cfg::ACC_STRIDE;
+      for (int j = 0; j < p.fl_kl / 16; ++j) umma_bf16_lo(d, ta + 2 * j, tb + 2 * j, idesc_up, 1u);
+      umma_commit(&acc2_full[as_]);
+      umma_commit(t_empty);
+      umma_commit(&bup_empty[bb]);
+    };
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -239,6 +293,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           stage = 0;
           phase ^= 1;
         }
+        if (FL && pend_it >= 0 && c - c_begin == 2) {
+          issue_up(pend_it);
+          pend_it = -1;
+        }
       }
       for (int c = c_fast; c < c_end; ++c) {
         mbar_wait_u32(full0 + stage * 8, phase);
@@ -260,8 +318,14 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           phase ^= 1;
         }
       }
-      umma_commit_u32(tfull0 + as * 8);  // accumulator complete -> epilogue
+      if (FL && pend_it >= 0) {   // tile shorter than three chunks
+        issue_up(pend_it);
+        pend_it = -1;
+      }
+      umma_commit_u32(tfull0 + as * 8);  // accumulator complete (FL: up to the up projection) -> epilogue
+      if (FL) pend_it = it;
     }
+    if (FL && pend_it >= 0) issue_up(pend_it);
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
@@ -281,6 +345,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       mbar_wait_backoff(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
+      if (FL) {
+        mbar_wait(t_empty, (it & 1) ^ 1);            // the previous tile's up projection has consumed the T tile
+        gemm_fl_stage_t<BN>(p, trow, r, mt, nt, smem_t);
+        tc_fence_before();
+        fence_proxy_async_smem();                    // generic-proxy smem writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_full);
+        mbar_wait(&acc2_full[as], aphase);           // accumulator now holds x.W^T + T.Bup^T
+        tc_fence_after();
+      }
       if (p.dbg != 3) gemm_epilogue_tile<BN>(p, trow, r, mt, nt, b0, b1);  // dbg 3: perf triage without the epilogue
       tc_fence_before();
       __syncwarp();
@@ -493,6 +567,13 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
     const uint64_t str[3] = {(uint64_t)a->fl_ld_ad * 2, (uint64_t)a->fl_ld_ad * a->fl_kl * 2, (uint64_t)a->fl_ld_ad * a->fl_kl * 2};
     const uint32_t box[4] = {BLOCK_K, (uint32_t)a->fl_kl, 1, 1};
     if (make_tmap_bf16_4d(&p.tm_ad, a->fl_ad, dims, str, box)) return -3;
+    {
+      // stacked lora_up [N][fl_kl]: one box = the N tile's rows x 64 columns (columns >= fl_kl are TMA zero fill)
+      const uint64_t dims_u[4] = {(uint64_t)a->fl_kl, (uint64_t)a->N, 1, 1};
+      const uint64_t str_u[3] = {(uint64_t)a->fl_ld_bup * 2, (uint64_t)a->fl_ld_bup * a->N * 2, (uint64_t)a->fl_ld_bup * a->N * 2};
+      const uint32_t box_u[4] = {BLOCK_K, (uint32_t)(a->epilogue == 1 ? bn / 2 : bn), 1, 1};
+      if (make_tmap_bf16_4d(&p.tm_bup, a->fl_bup, dims_u, str_u, box_u)) return -3;
+    }
     p.fl_kl = a->fl_kl;
     p.fl_rank = a->fl_rank;
     p.fl_scale = a->fl_scale;

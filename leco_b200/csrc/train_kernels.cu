@@ -202,6 +202,46 @@ __global__ void guided_step_kernel(const float* __restrict__ eps, const float* _
   }
 }
 
+// General scheduler step (DDPM / LMS / Euler-ancestral, model_util.py:247-274; DDIM keeps the lean kernel above):
+//   guided = e_u + g (e_c - e_u)
+//   d      = dx x + dg guided                    -> hist[slot]      (LMS derivative history, 4 deep)
+//   x'     = cx x + ce guided + cn noise + sum_j l_j hist[(slot - j) & 3]
+// coef (device, fp32[12]) = {g, cx, ce, cn, in_scale, dx, dg, l0, l1, l2, l3, slot}; noise / hist may be NULL.
+__global__ void sched_step_kernel(const float* __restrict__ eps, const float* __restrict__ x,
+                                  const float* __restrict__ noise, float* __restrict__ hist, float* __restrict__ x_out,
+                                  const float* __restrict__ coef, long long half) {
+  pdl_entry();
+  const float g = coef[0], cx = coef[1], ce = coef[2], cn = coef[3], dx = coef[5], dg = coef[6];
+  const float l0 = coef[7], l1 = coef[8], l2 = coef[9], l3 = coef[10];
+  const int slot = (int)coef[11];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < half;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float eu = eps[i], ec = eps[half + i];
+    const float gd = eu + g * (ec - eu);
+    const float xv = x[i];
+    float r = cx * xv + ce * gd;
+    if (noise) r = fmaf(cn, noise[i], r);
+    if (hist) {
+      const float d = dx * xv + dg * gd;
+      hist[(long long)slot * half + i] = d;
+      r = fmaf(l0, d, r);
+      if (l1 != 0.f) r = fmaf(l1, hist[(long long)((slot - 1) & 3) * half + i], r);
+      if (l2 != 0.f) r = fmaf(l2, hist[(long long)((slot - 2) & 3) * half + i], r);
+      if (l3 != 0.f) r = fmaf(l3, hist[(long long)((slot - 3) & 3) * half + i], r);
+    }
+    x_out[i] = r;
+  }
+}
+
+// y = x * coef[idx]   (UNet input scaling 1/sqrt(sigma^2+1) of the sigma schedulers, coefficient on the device)
+__global__ void scale_by_dev_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ coef,
+                                    int idx, long long n) {
+  pdl_entry();
+  const float s = coef[idx];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = x[i] * s;
+}
+
 // loss = mean((t - (nn + sgn*gs*(pp - uu)))^2);  dt = 2 (t - goal) / numel.   single block, deterministic
 __global__ void leco_loss_kernel(const float* __restrict__ t, const float* __restrict__ pp,
                                  const float* __restrict__ nn, const float* __restrict__ uu, float sgn_gs,
@@ -328,6 +368,28 @@ extern "C" int leco_guided_step(const float* eps_pair, const float* x, float* x_
   if (blocks > 148 * 4) blocks = 148 * 4;
   count_launch();
   LECO_LAUNCH(guided_step_kernel, (int)blocks, 256, 0, STREAM(stream), eps_pair, x, x_out, guided_out, coef_dev, half_numel);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int leco_sched_step(const float* eps_pair, const float* x, const float* noise, float* hist, float* x_out,
+                               const float* coef_dev, int64_t half_numel, void* stream) {
+  LECO_REQUIRE(eps_pair && x && x_out && coef_dev && half_numel > 0, "leco_sched_step: null pointer");
+  long long blocks = (half_numel + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  count_launch();
+  LECO_LAUNCH(sched_step_kernel, (int)blocks, 256, 0, STREAM(stream), eps_pair, x, noise, hist, x_out, coef_dev,
+              (long long)half_numel);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int leco_scale_by_dev(const float* x, float* y, const float* coef_dev, int idx, int64_t n, void* stream) {
+  LECO_REQUIRE(x && y && coef_dev && n > 0 && idx >= 0, "leco_scale_by_dev: bad arguments");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  count_launch();
+  LECO_LAUNCH(scale_by_dev_kernel, (int)blocks, 256, 0, STREAM(stream), x, y, coef_dev, idx, (long long)n);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

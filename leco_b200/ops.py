@@ -412,6 +412,25 @@ def guided_step(eps_pair, x, coef, want_x=True, want_guided=False):
     return x_out, g_out
 
 
+def sched_step(eps_pair, x, coef, noise=None, hist=None, out=None):
+    """General scheduler update fused with the CFG combine (see include/leco_b200.h: leco_sched_step)."""
+    half = eps_pair.numel() // 2
+    assert x.dtype == torch.float32 and eps_pair.dtype == torch.float32 and x.numel() == half and coef.numel() >= 12
+    out = torch.empty_like(x) if out is None else out
+    if hist is not None:
+        assert hist.dtype == torch.float32 and hist.numel() == 4 * half and hist.is_contiguous()
+    capi.check(_lib().leco_sched_step(_ptr(eps_pair), _ptr(x), _ptr(noise), _ptr(hist), _ptr(out), _ptr(coef), half,
+                                      _stream()), "leco_sched_step")
+    return out
+
+
+def scale_by_dev(x, coef, idx: int):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty_like(x)
+    capi.check(_lib().leco_scale_by_dev(_ptr(x), _ptr(y), _ptr(coef), idx, x.numel(), _stream()), "leco_scale_by_dev")
+    return y
+
+
 def leco_loss(target, positive, neutral, uncond, sign_times_guidance: float, want_grad=True):
     loss = torch.empty((1,), device=target.device, dtype=torch.float32)
     dt = torch.empty_like(target) if want_grad else None

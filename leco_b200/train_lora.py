@@ -1,0 +1,116 @@
+"""`train(config, prompts)` — the reference's driver (train_lora.py:34-321) on the fused trainer.
+
+    python -m leco_b200.train_lora --config_file examples/config.yaml
+
+Same sequence: load models -> LoRANetwork(rank, alpha, training_method) with the c3lier target aliasing (:44-46) ->
+optimizer from `train.optimizer` / `optimizer_args` ("k=v k=v", ast.literal_eval, :80-89) -> LR schedule (:90-95) ->
+encode each distinct prompt once (:106-132) -> `iterations` passes of the loop body (LecoTrainer.iteration) -> periodic
+saves that skip i == 0 and i == iterations-1, final `<name>_last.safetensors` (:292-309; SURVEY Q13: the weights are
+saved in `train.precision`, `save.precision` is ignored, no metadata is written).  `config` / `prompts` may be the
+reference's own pydantic objects or the dataclasses of leco_b200.config_util."""
+from __future__ import annotations
+
+import argparse
+import ast
+from pathlib import Path
+from typing import Callable, List, Optional
+
+import torch
+
+from . import config_util, lora, model_util
+from .lora import LoRANetwork
+from .trainer import LecoTrainer, PromptPair
+
+
+def parse_optimizer_args(s: Optional[str]) -> dict:
+    """train_lora.py:81-87."""
+    out = {}
+    if s is not None and len(s) > 0:
+        for arg in s.split(" "):
+            key, value = arg.split("=")
+            out[key] = ast.literal_eval(value)
+    return out
+
+
+def train(config, prompts, *, device="cuda", rank: int = 0, world_size: int = 1,
+          on_iteration: Optional[Callable[[int, float], None]] = None, xl: bool = False) -> List[float]:
+    save_path = Path(config.save.path)
+    weight_dtype = config_util.parse_precision(config.train.precision)
+    save_weight_dtype = config_util.parse_precision(config.train.precision)      # sic
+    if weight_dtype != torch.bfloat16:
+        raise NotImplementedError("leco_b200 kernels run the UNet in bf16 (train.precision: bfloat16); the reference's "
+                                  "README calls fp16 unstable and fp32 is the CPU-oracle configuration")
+    if xl:
+        _, encoders, unet, scheduler = model_util.load_models_xl(config.pretrained_model.name_or_path,
+                                                                 scheduler_name=config.train.noise_scheduler, device=device)
+        text_encoder = encoders[0]
+    else:
+        _, text_encoder, unet, scheduler = model_util.load_models(
+            config.pretrained_model.name_or_path, scheduler_name=config.train.noise_scheduler,
+            v2=config.pretrained_model.v2, v_pred=config.pretrained_model.v_pred, device=device)
+    unet.enable_xformers_memory_efficient_attention()      # train_lora.py:68 (a no-op: attention is the fused kernel)
+    unet.requires_grad_(False)
+    unet.eval()
+
+    saved_targets = list(lora.DEFAULT_TARGET_REPLACE)
+    try:
+        if config.network.type == "c3lier":                 # train_lora.py:44-46 extends the module-level list in place
+            lora.DEFAULT_TARGET_REPLACE += lora.UNET_TARGET_REPLACE_MODULE_CONV
+        network = LoRANetwork(unet, rank=config.network.rank, multiplier=1.0, alpha=config.network.alpha,
+                              train_method=config.network.training_method).to(device, dtype=weight_dtype)
+    finally:
+        lora.DEFAULT_TARGET_REPLACE[:] = saved_targets
+
+    print("Prompts")
+    cache = {}
+    pairs = []
+    for s in prompts:
+        print(s)
+        for p in (s.target, s.positive, s.neutral, s.unconditional):
+            if p not in cache:
+                cache[p] = model_util.encode_prompts(None, text_encoder, [p])
+        pairs.append(PromptPair(target=cache[s.target], positive=cache[s.positive], unconditional=cache[s.unconditional],
+                                neutral=cache[s.neutral], guidance_scale=s.guidance_scale, resolution=s.resolution,
+                                dynamic_resolution=s.dynamic_resolution, batch_size=s.batch_size, action=s.action,
+                                dynamic_crops=getattr(s, "dynamic_crops", False)))
+    del text_encoder
+
+    trainer = LecoTrainer(unet, network, scheduler, pairs, lr=config.train.lr, optimizer=config.train.optimizer,
+                          optimizer_kwargs=parse_optimizer_args(config.train.optimizer_args),
+                          lr_scheduler=config.train.lr_scheduler, iterations=config.train.iterations,
+                          max_denoising_steps=config.train.max_denoising_steps, device=device, rank=rank,
+                          world_size=world_size)
+    losses = []
+    for i in range(config.train.iterations):
+        loss = trainer.iteration()
+        if on_iteration is not None or config.logging.verbose:
+            v = float(loss.item())           # reading the loss synchronises; the plain loop never does
+            losses.append(v)
+            if on_iteration is not None:
+                on_iteration(i, v)
+            if config.logging.verbose:
+                print(f"iteration {i}: loss*1k {v * 1000:.4f} lr {trainer.last['lr']:.3e} k {trainer.last['k']}")
+        if i % config.save.per_steps == 0 and i != 0 and i != config.train.iterations - 1 and rank == 0:
+            print("Saving...")
+            save_path.mkdir(parents=True, exist_ok=True)
+            network.save_weights(str(save_path / f"{config.save.name}_{i}steps.safetensors"), dtype=save_weight_dtype)
+    if rank == 0:
+        print("Saving...")
+        save_path.mkdir(parents=True, exist_ok=True)
+        network.save_weights(str(save_path / f"{config.save.name}_last.safetensors"), dtype=save_weight_dtype)
+    print("Done.")
+    return losses
+
+
+def main(args=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config_file", required=True, help="Config file for training.")
+    ap.add_argument("--xl", action="store_true", help="SDXL loop (train_lora_xl.py)")
+    a = ap.parse_args(args)
+    config = config_util.load_config_from_yaml(a.config_file)
+    prompts = config_util.load_prompts_from_yaml(config.prompts_file)
+    train(config, prompts, xl=a.xl)
+
+
+if __name__ == "__main__":
+    main()

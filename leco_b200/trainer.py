@@ -36,7 +36,7 @@ import torch
 
 from . import capi, ops
 from .lora import FlatOptimizer, LoRANetwork
-from .scheduler import DDIMScheduler
+from .scheduler import ROW, DDIMScheduler
 from .train_util import get_add_time_ids
 from .unet import EngineUNet, Tape
 
@@ -115,6 +115,9 @@ class LecoTrainer:
         self.lr_scheduler = get_lr_scheduler(lr_scheduler, self.optimizer, max_iterations=iterations, lr_min=lr / 100,
                                              **(lr_scheduler_kwargs or {}))
         self.hoist_cross_kv = hoist_cross_kv
+        # DDIM keeps the lean CFG+update kernel; DDPM / LMS / Euler-a (model_util.py:247-274) use the general one
+        self.general_sched = not isinstance(scheduler, DDIMScheduler)
+        self.scaled_input = float(scheduler.init_noise_sigma) != 1.0      # sigma schedulers scale the UNet input
         self._pool = None           # one CUDA-graph memory pool shared by every captured shape (dynamic_resolution)
         self._ar_events = []        # (start, end) CUDA events around the data-parallel all-reduce
         self.act_dtype = unet._act_dtype
@@ -178,8 +181,8 @@ class LecoTrainer:
         """Device tables for the 50-step grid: timestep and (guidance, cx, ce) per step."""
         s = self.scheduler
         s.set_timesteps(self.max_steps)
-        ts = [int(t) for t in s.timesteps]
-        coef = [[self.denoise_guidance, *s.coefficients(t)] for t in ts]
+        ts = [float(t) for t in s.timesteps]
+        coef = s.table(self.denoise_guidance)       # rows [guidance, cx, ce, cn, in_scale, dx, dg, l0..l3, slot]
         self._tables = (torch.tensor(ts, dtype=torch.float32, device=self.device),
                         torch.tensor(coef, dtype=torch.float32, device=self.device))
         return self._tables
@@ -191,11 +194,15 @@ class LecoTrainer:
 
     # ------------------------------------------------------------------ one denoise step
     def _denoise_body(self, st):
-        x2 = st["x"].repeat(2, 1, 1, 1)
+        x_in = ops.scale_by_dev(st["x"], st["coef"], 4) if self.scaled_input else st["x"]   # scale_model_input
+        x2 = x_in.repeat(2, 1, 1, 1)
         eps = self.unet.run(x2, st["t"], st["ctx"], self._added(st, x2.shape[0], "pooled"), None,
                             kv_cache=st.get("kv"))
-        x_new, _ = ops.guided_step(eps, st["x"], st["coef"], True, False)
-        st["x"].copy_(x_new)
+        if self.general_sched:
+            ops.sched_step(eps, st["x"], st["coef"], noise=st.get("noise"), hist=st.get("hist"), out=st["x"])
+        else:
+            x_new, _ = ops.guided_step(eps, st["x"], st["coef"], True, False)
+            st["x"].copy_(x_new)
 
     def _denoise_graph(self, bl, h, w, D):
         key = (bl, h, w, D)
@@ -206,8 +213,12 @@ class LecoTrainer:
         dev = self.device
         g.static = {"x": torch.zeros((bl, UNET_IN_CHANNELS, h, w), device=dev, dtype=torch.float32),
                     "t": torch.zeros((2 * bl,), device=dev, dtype=torch.float32),
-                    "coef": torch.zeros((3,), device=dev, dtype=torch.float32),
+                    "coef": torch.zeros((ROW,), device=dev, dtype=torch.float32),
                     "ctx": torch.zeros((2 * bl * 77, D), device=dev, dtype=self.act_dtype)}
+        if self.scheduler.needs_noise:
+            g.static["noise"] = torch.zeros((bl, UNET_IN_CHANNELS, h, w), device=dev, dtype=torch.float32)
+        if self.scheduler.history:
+            g.static["hist"] = torch.zeros((4, bl * UNET_IN_CHANNELS * h * w), device=dev, dtype=torch.float32)
         if self.xl:
             g.static["pooled"] = torch.zeros((2 * bl, self.unet.spec.add_text_dim), device=dev, dtype=self.act_dtype)
             g.static["ids"] = torch.zeros((2 * bl, 6), device=dev, dtype=torch.float32)
@@ -238,12 +249,13 @@ class LecoTrainer:
         """groups = number of distinct LoRA-off prompts, slots = (i_pos, i_neu, i_unc) into them."""
         net = self.network
         net.__exit__(None, None, None)                           # multiplier 0: LoRA-off passes
-        xr = st["x"].repeat(groups, 1, 1, 1)
+        x_in = ops.scale_by_dev(st["x"], st["in_scale"], 0) if self.scaled_input else st["x"]   # scale_model_input at t*
+        xr = x_in.repeat(groups, 1, 1, 1)
         eps_ng = self.unet.run(xr, st["t"][: groups * bl], st["ctx_ng"], self._added(st, groups * bl, "pooled_ng"), None)
         pos, neu, unc = (eps_ng[i * bl:(i + 1) * bl] for i in slots)
         net.__enter__()                                          # multiplier 1: target pass with tape
         tape = Tape(ops)
-        eps_t = self.unet.run(st["x"], st["t"][:bl], st["ctx_t"], self._added(st, bl, "pooled_t"), tape)
+        eps_t = self.unet.run(x_in, st["t"][:bl], st["ctx_t"], self._added(st, bl, "pooled_t"), tape)
         loss, dt = ops.leco_loss(eps_t, pos, neu, unc, sgn_g, True)
         tape.grads["eps"] = dt
         tape.backward()
@@ -263,7 +275,8 @@ class LecoTrainer:
                     "ctx_ng": torch.zeros((groups * bl * 77, D), device=dev, dtype=self.act_dtype),
                     "ctx_t": torch.zeros((bl * 77, D), device=dev, dtype=self.act_dtype),
                     "loss": torch.zeros((1,), device=dev, dtype=torch.float32),
-                    "eps_t": torch.zeros((bl, UNET_IN_CHANNELS, h, w), device=dev, dtype=torch.float32)}
+                    "eps_t": torch.zeros((bl, UNET_IN_CHANNELS, h, w), device=dev, dtype=torch.float32),
+                    "in_scale": torch.ones((1,), device=dev, dtype=torch.float32)}
         if self.xl:
             P = self.unet.spec.add_text_dim
             g.static["pooled_ng"] = torch.zeros((groups * bl, P), device=dev, dtype=self.act_dtype)
@@ -329,11 +342,19 @@ class LecoTrainer:
             self.network.__enter__()
             self.unet.cross_kv(st["ctx"], out=st["kv"])
             self.network.__exit__(None, None, None)
+        step_noise = None
+        if sched.needs_noise:
+            # diffusers draws randn on the model's device every step (global CUDA generator); one draw of the GLOBAL
+            # batch for all k steps, sliced per rank, keeps an R-GPU run identical to the 1-GPU run
+            step_noise = torch.randn((k, pair.batch_size, UNET_IN_CHANNELS, h, w), device=self.device)[
+                :, self.rank * bl:(self.rank + 1) * bl]
         if dg.graph is None:
             self.network.__enter__()
         for i in range(k):
             st["t"].copy_(tbl_t[i].expand(2 * bl))
             st["coef"].copy_(tbl_coef[i])
+            if step_noise is not None:
+                st["noise"].copy_(step_noise[i])
             if dg.graph is not None:
                 dg.graph.replay()
                 self.launches += dg.launches
@@ -358,6 +379,8 @@ class LecoTrainer:
         ts = tg.static
         ts["x"].copy_(st["x"])
         ts["t"].fill_(t_star)
+        if self.scaled_input:
+            ts["in_scale"].fill_(sched.in_scale_at_train_timestep(int(t_star)))
         ts["ctx_ng"].copy_(self._ctx(distinct, bl))
         ts["ctx_t"].copy_(self._ctx([pair.target], bl))
         if self.xl:

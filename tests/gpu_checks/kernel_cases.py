@@ -173,16 +173,61 @@ def case_training_kernels():
     return _merge(res)
 
 
-def _bf16_ulp_stats(got, ref):
-    """bf16 tensors: fraction of elements that are not bit-equal and the worst distance in bf16 ulps."""
+def case_sched_step():
+    """leco_sched_step / leco_scale_by_dev vs the coefficient-row formula (pinned against the oracle's DDPM / LMS /
+    Euler-a restatements on the CPU by tests/test_host_logic_cpu.py) over a 6-step chain incl. the LMS history ring, and
+    the drop-in `scheduler.step()` surface on device tensors."""
     import torch
-    a = got.view(torch.int16).to(torch.int32)
-    b = ref.view(torch.int16).to(torch.int32)
-    # map the sign-magnitude bit pattern to a monotonic integer line
-    a = torch.where(a < 0, -(a & 0x7FFF), a)
-    b = torch.where(b < 0, -(b & 0x7FFF), b)
-    d = (a - b).abs()
-    return (d != 0).float().mean().item(), int(d.max().item())
+    from leco_b200 import ops
+    from leco_b200.scheduler import create_noise_scheduler
+    res = {}
+    g = torch.Generator().manual_seed(3)
+    for name in ("ddpm", "lms", "euler_a"):
+        for ptype in ("epsilon", "v_prediction"):
+            s = create_noise_scheduler(name, ptype)
+            s.set_timesteps(50)
+            rows = torch.tensor(s.table(3.0), dtype=torch.float32, device="cuda")
+            x = (torch.randn((2, 4, 8, 8), generator=g) * float(s.init_noise_sigma)).cuda()
+            xr = x.double().cpu()
+            hist = torch.zeros((4, x.numel()), device="cuda") if s.history else None
+            hist_r = []
+            x_drop = x.clone()
+            worst = worst_drop = 0.0
+            for i in range(6):
+                eps = torch.randn((4, 4, 8, 8), generator=g).cuda()
+                noise = torch.randn((2, 4, 8, 8), generator=g).cuda() if s.needs_noise else None
+                row = [float(v) for v in rows[i].double().cpu()]
+                gd = (eps[:2] + 3.0 * (eps[2:] - eps[:2])).double().cpu()
+                xin = ops.scale_by_dev(x, rows[i], 4)
+                worst = max(worst, (xin.double().cpu() - xr * row[4]).abs().max().item())
+                ref = row[1] * xr + row[2] * gd + (row[3] * noise.double().cpu() if noise is not None else 0)
+                if s.history:
+                    hist_r.append(row[5] * xr + row[6] * gd)
+                    hist_r = hist_r[-4:]
+                    for c, h in zip(row[7:11], reversed(hist_r)):
+                        ref = ref + c * h
+                # drop-in surface: scheduler.step(model_output, t, sample) with the same guided prediction and noise
+                x_drop = s.step(gd.float().cuda(), s.timesteps[i], x_drop, noise=noise).prev_sample
+                ops.sched_step(eps, x, rows[i], noise=noise, hist=hist, out=x)
+                scale = ref.abs().max().item() + 1e-9
+                worst = max(worst, (x.double().cpu() - ref).abs().max().item() / scale)
+                worst_drop = max(worst_drop, (x_drop.double().cpu() - ref).abs().max().item() / scale)
+                xr = ref
+            res[f"{name}_{ptype}"] = {"rel": worst, "ok": worst < 1e-5, "max_abs_err": worst, "ref_absmax": 1.0}
+            res[f"{name}_{ptype}_dropin"] = {"rel": worst_drop, "ok": worst_drop < 1e-5, "max_abs_err": worst_drop, "ref_absmax": 1.0}
+    return _merge(res)
+
+
+def _bf16_ulp_stats(got, ref, floor=1e-3):
+    """bf16 tensors: fraction of elements that are not bit-equal and the worst distance in bf16 ulps, an ulp being that
+    of max(|ref|, floor) (parameters that pass through zero have arbitrarily small ulps of their own; `floor` = a tenth
+    of a typical update keeps the measure meaningful there)."""
+    import torch
+    g, r = got.float(), ref.float()
+    mism = (got.view(torch.int16) != ref.view(torch.int16)).float().mean().item()
+    mag = torch.maximum(r.abs(), torch.full_like(r, floor))
+    ulp = torch.exp2(torch.floor(torch.log2(mag)) - 7)      # bf16: 8 significant bits
+    return mism, float(((g - r).abs() / ulp).max().item())
 
 
 def case_optimizers():
@@ -508,6 +553,7 @@ CASES = [
     ("elementwise", case_elementwise, {}),
     ("training_kernels", case_training_kernels, {}),
     ("optimizers", case_optimizers, {}),
+    ("sched_step", case_sched_step, {}),
     ("transpose_tiles", case_transpose_tiles, {}),
     ("determinism", case_determinism, {}),
     ("attn_self_4096_d64", case_attention, dict(nb=1, sq=4096, skv=4096, heads=5, d=64)),

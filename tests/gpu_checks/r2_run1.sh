@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 T0=$(date +%s)
-timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/r2a_pytest.log 2>&1; echo "pytest=$? t=$(( $(date +%s) - T0 ))"
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/r2a_pytest.log 2>&1; echo "pytest=$? t=$(( $(date +%s) - T0 ))"
 tail -30 gpurun_out/r2a_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2a_smoke.log 2>&1; echo "smoke=$? t=$(( $(date +%s) - T0 ))"
 tail -3 gpurun_out/r2a_smoke.log

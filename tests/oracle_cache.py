@@ -50,6 +50,8 @@ def main():
     print("iters dyn", flush=True)
     cached("iters_tiny21_multi", lambda: oracle_iterations(5, multi=True), write=True)
     print("iters multi", flush=True)
+    cached("iters_tiny21_lms", lambda: oracle_iterations(3, scheduler="lms"), write=True)
+    print("iters lms", flush=True)
     from __graft_entry__ import oracle_iterations_xl
     cached("iters_tinyxl", lambda: oracle_iterations_xl(3), write=True)
     print("iters xl", flush=True)

@@ -218,3 +218,81 @@ def test_optimizer_factory_error_behaviour():
     for name in ("dadaptadam", "adam8bit", "prodigy"):   # optional third-party packages, absent here as in the reference image
         with pytest.raises(NotImplementedError):
             tu.get_optimizer(name)
+
+
+@pytest.mark.parametrize("name", ["ddim", "ddpm", "lms", "euler_a"])
+@pytest.mark.parametrize("ptype", ["epsilon", "v_prediction"])
+def test_scheduler_coefficient_rows_match_oracle(name, ptype):
+    """model_util.create_noise_scheduler's four schedulers (model_util.py:230-278): the product states every update as
+    x' = cx x + ce m + cn noise + sum_j l_j d_{-j} (d = dx x + dg m); applied in plain fp64 torch those rows must
+    reproduce the oracle's restatement of diffusers' step(), its timesteps, input scaling and init_noise_sigma."""
+    prod, ora = create_noise_scheduler(name, ptype), oracle_sched(name, ptype)
+    assert abs(float(prod.init_noise_sigma) - float(ora.init_noise_sigma)) < 1e-5
+    for n in (50, 1000):
+        prod.set_timesteps(n)
+        ora.set_timesteps(n)
+        assert torch.allclose(prod.timesteps.double(), ora.timesteps.double(), atol=1e-9)
+    # the 1000-step grid of the four predictions (train_lora.py:195-199)
+    for t in (999, 499, 19):
+        x = torch.randn(2, 4, 8, 8, dtype=torch.float64)
+        assert torch.allclose(ora.scale_model_input(x, ora.timesteps[999 - t]), x * prod.in_scale_at_train_timestep(t),
+                              rtol=1e-5, atol=1e-7)
+    prod.set_timesteps(50)
+    ora.set_timesteps(50)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 4, 8, 8, generator=g, dtype=torch.float64) * float(ora.init_noise_sigma)
+    hist = []
+    for i, t in enumerate(ora.timesteps[:9]):
+        m = torch.randn(x.shape, generator=g, dtype=torch.float64)
+        noise = torch.randn(x.shape, generator=g, dtype=torch.float64)
+        row = prod.plan(i)
+        _, cx, ce, cn, s_in, dx, dg, l0, l1, l2, l3, slot = row
+        assert torch.allclose(ora.scale_model_input(x, t), x * s_in, rtol=1e-5, atol=1e-7)
+        kw = {"noise": noise} if name in ("ddpm", "euler_a") else {}
+        ref = ora.step(m, t, x, **kw).prev_sample
+        got = cx * x + ce * m + cn * noise
+        if name == "lms":
+            hist.append(dx * x + dg * m)
+            hist = hist[-4:]
+            assert int(slot) == i % 4
+            for c, h in zip((l0, l1, l2, l3), reversed(hist)):
+                got = got + c * h
+        else:
+            assert (dx, dg, l0, l1, l2, l3) == (0.0,) * 6
+        assert torch.allclose(got, ref.double(), rtol=2e-4, atol=2e-4 * float(ref.abs().max())), (name, ptype, i)
+        x = ref.double()
+    with pytest.raises(ValueError):
+        create_noise_scheduler("heun")
+
+
+@pytest.mark.skipif(not reference_available(), reason="needs /root/reference")
+def test_config_mirror_parses_the_reference_examples_like_the_reference():
+    """leco_b200.config_util (used where the reference's files are absent) vs the reference's own config_util /
+    prompt_util on every example YAML: same values field by field (incl. the `lr: 1e-4` string coercion)."""
+    import glob
+    import sys
+    from leco_b200 import config_util as cu
+    from oracle.ref_loader import load_reference
+    ref = load_reference()
+    for path in sorted(glob.glob("/root/reference/examples/*config*.yaml")):
+        mine, theirs = cu.load_config_from_yaml(path), ref.config_util.load_config_from_yaml(path)
+        for section in ("pretrained_model", "network", "train", "save", "logging", "other"):
+            a, b = getattr(mine, section), getattr(theirs, section)
+            for k, v in b.dict().items():
+                assert getattr(a, k) == v, (path, section, k)
+        assert mine.prompts_file == theirs.prompts_file
+    for path in sorted(glob.glob("/root/reference/examples/*prompts*.yaml")):
+        mine, theirs = cu.load_prompts_from_yaml(path), ref.prompt_util.load_prompts_from_yaml(path)
+        assert len(mine) == len(theirs)
+        for a, b in zip(mine, theirs):
+            for k, v in b.dict().items():
+                assert getattr(a, k) == v, (path, k)
+
+
+def test_optimizer_args_parsing_and_save_cadence():
+    """train_lora.py:81-87 ("k=v k=v" through ast.literal_eval) and :292-309 (periodic saves skip i == 0 and the last)."""
+    from leco_b200.train_lora import parse_optimizer_args
+    assert parse_optimizer_args("") == {} and parse_optimizer_args(None) == {}
+    assert parse_optimizer_args("weight_decay=0.1 betas=(0.9,0.99)") == {"weight_decay": 0.1, "betas": (0.9, 0.99)}
+    saves = [i for i in range(500) if i % 200 == 0 and i != 0 and i != 499]
+    assert saves == [200, 400]
