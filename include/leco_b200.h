@@ -136,6 +136,11 @@ int leco_flash_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, 
 int64_t leco_group_norm_workspace_bytes(int n, int G);
 int leco_group_norm(const void* x, void* y, void* stats, const void* gamma, const void* beta, int n, int hw, int C,
                     int G, float eps, int silu, void* workspace, void* stream);
+/* single-launch forward (statistics + normalise behind a per-sample grid barrier).  `barriers` is a PERSISTENT caller-owned
+ * buffer of leco_group_norm_barrier_bytes(n) bytes that was zero when first used and is never written by anyone else. */
+int64_t leco_group_norm_barrier_bytes(int n);
+int leco_group_norm_fused(const void* x, void* y, void* stats, const void* gamma, const void* beta, int n, int hw, int C,
+                          int G, float eps, int silu, void* workspace, void* barriers, void* stream);
 int leco_group_norm_bwd(const void* x, const void* dz, void* dx, const void* stats, const void* gamma,
                         const void* beta, int n, int hw, int C, int G, int silu, void* workspace, void* stream);
 int leco_layer_norm(const void* x, void* y, void* stats, const void* gamma, const void* beta, int64_t M, int C,

@@ -63,6 +63,8 @@ def load():
     lib.leco_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
     lib.leco_group_norm_workspace_bytes.restype = c_int64
     lib.leco_group_norm_workspace_bytes.argtypes = [c_int32, c_int32]
+    lib.leco_group_norm_barrier_bytes.restype = c_int64
+    lib.leco_group_norm_barrier_bytes.argtypes = [c_int32]
     _declare_ops(lib)
     _lib = lib
     return lib
@@ -91,6 +93,7 @@ _OPS: list[tuple[str, list]] = [
     ("leco_flash_attn_fwd", [P, L, P, L, P, L, P, L, P, L, I, I, I, I, I, F, P]),
     ("leco_group_norm", [P, P, P, P, P, I, I, I, I, F, I, P, P]),
     ("leco_group_norm_bwd", [P, P, P, P, P, P, I, I, I, I, I, P, P]),
+    ("leco_group_norm_fused", [P, P, P, P, P, I, I, I, I, F, I, P, P, P]),
     ("leco_layer_norm", [P, P, P, P, P, L, I, F, P]),
     ("leco_layer_norm_bwd", [P, P, P, P, P, L, I, P]),
     ("leco_tn_reduce", [P, L, P, L, P, L, L, I, I, F, I, P]),
@@ -109,7 +112,7 @@ _OPS: list[tuple[str, list]] = [
 
 # every symbol include/leco_b200.h declares (tests check the .so exports all of them)
 EXPORTED = ["leco_last_error", "leco_abi_version", "leco_launch_count", "leco_device_info",
-            "leco_gemm_bf16", "leco_group_norm_workspace_bytes"] + [n for n, _ in _OPS]
+            "leco_gemm_bf16", "leco_group_norm_workspace_bytes", "leco_group_norm_barrier_bytes"] + [n for n, _ in _OPS]
 
 
 def _declare_ops(lib):

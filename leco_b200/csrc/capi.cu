@@ -71,8 +71,18 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+static int make_tmap_impl(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                          const uint32_t box[4], CUtensorMapSwizzle swz);
 int make_tmap_bf16_4d(CUtensorMap* out, const void* base, const uint64_t dims[4],
                       const uint64_t strides_bytes[3], const uint32_t box[4]) {
+  return make_tmap_impl(out, base, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+int make_tmap_bf16_4d_sw64(CUtensorMap* out, const void* base, const uint64_t dims[4],
+                           const uint64_t strides_bytes[3], const uint32_t box[4]) {
+  return make_tmap_impl(out, base, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+static int make_tmap_impl(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                          const uint32_t box[4], CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -96,7 +106,7 @@ int make_tmap_bf16_4d(CUtensorMap* out, const void* base, const uint64_t dims[4]
     }
   }
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): dims {%llu,%llu,%llu,%llu} strides {%llu,%llu,%llu} box {%u,%u,%u,%u}",

@@ -49,6 +49,10 @@ bool deterministic();
 // box[i] elements per dim; swizzle 128B; OOB reads fill with zeros.
 int make_tmap_bf16_4d(CUtensorMap* out, const void* base, const uint64_t dims[4],
                       const uint64_t strides_bytes[3], const uint32_t box[4]);
+// same with a 64-byte swizzle (box[0] = 32 bf16): the epilogue's TMA-store slabs.  `quiet` = no error text on failure
+// (the caller falls back to direct stores).
+int make_tmap_bf16_4d_sw64(CUtensorMap* out, const void* base, const uint64_t dims[4],
+                           const uint64_t strides_bytes[3], const uint32_t box[4]);
 
 // ---------------------------------------------------------------- device ----
 #ifdef __CUDACC__
@@ -207,6 +211,20 @@ __device__ __forceinline__ void tma_load_4d_u32(uint32_t smem_dst, const CUtenso
       :
       : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+// TMA store (shared -> global, bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the N most recent bulk groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
 // ---- tcgen05 / TMEM ----

@@ -108,10 +108,10 @@ template <int BN>
 struct Gemm2Cfg {
   static constexpr int B_STAGE_BYTES = (BN / 2) * BLOCK_K * 2;  // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 7 : (BN >= 160 ? 8 : (BN >= 128 ? 9 : 10));  // fill 227 KB
+  static constexpr int STAGES = (BN >= 256) ? 6 : (BN >= 160 ? 8 : (BN >= 128 ? 9 : 10));  // fill 227 KB
   static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 256;
   static_assert(SMEM_BYTES <= 232448, "stage ring exceeds 227 KB");
 };
 
@@ -125,7 +125,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;   // 4 x one 32x32 bf16 slab (TMA-store staging)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;                     // [STAGES]  used in the leader only
   uint64_t* empty_bar = bars + STAGES;           // [STAGES]  per CTA
   uint64_t* tmem_full = bars + 2 * STAGES;       // [2]       per CTA
@@ -299,12 +300,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
       if (mt < p.tiles_m) {
-        gemm_epilogue_tile<BN>(p, trow, r, mt, nt, b0, b1);
+        gemm_epilogue_tile<BN>(p, trow, r, mt, nt, b0, b1, smem_epi + q * EPI_SLAB_BYTES);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tmem_empty[as], 0);
     }
+    if (lane == 0) bulk_wait_group_read<0>();   // the last TMA stores must have read their slab before smem is released
   }
 
   tc_fence_before();

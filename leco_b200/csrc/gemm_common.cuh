@@ -38,6 +38,11 @@ struct GemmParams {
   long long ldws;
   // in-kernel LoRA (lora.py:102-106 in ONE kernel): the stacked lora_down rows `Ad` ride along as fl_kl extra
   // B rows, so accumulator columns [BN, BN+fl_kl) hold T_raw = x.Ad^T; the epilogue adds fl_scale*T_raw.Bup^T
+  // epilogue output through TMA (tm_d: D as {N, M, batch0, batch1}, box 32 x 32, 64-byte swizzle): each epilogue warp stages
+  // its 32 rows x 32 columns (bf16) in shared memory and issues ONE bulk tensor store per chunk -> full 64-byte row
+  // segments instead of one 16-byte store per lane and row.  0 = direct stores (fp32 out, split-K, ragged conv tiles).
+  CUtensorMap tm_d;
+  int tma_store;
   CUtensorMap tm_ad, tm_bup;      // stacked lora_down rows [fl_kl][K]; stacked lora_up [N][fl_kl] (box BN x 64, zero filled)
   int fl_kl;                      // 0 = off; else 16/32/48/64 padded stacked rank
   int fl_rank;                    // real stacked rank (columns >= fl_rank of T are zero)
@@ -48,6 +53,8 @@ struct GemmParams {
   long long fl_ld_t;
 };
 constexpr int FL_MAX_KL = 64;
+constexpr int EPI_SLAB_BYTES = 32 * 32 * 2;            // one warp's staging slab: 32 rows x 32 bf16 columns
+constexpr int EPI_STAGE_BYTES = 4 * EPI_SLAB_BYTES;    // four epilogue warps
 
 template <int BN, bool FL = false>
 struct GemmCfg {
@@ -61,13 +68,13 @@ struct GemmCfg {
   static constexpr int T_TILE_BYTES = FL ? BLOCK_M * BLOCK_K * 2 : 0;
   static constexpr int BUP_TILE_BYTES = FL ? BN * BLOCK_K * 2 : 0;
   static constexpr int FL_BYTES = T_TILE_BYTES + 2 * BUP_TILE_BYTES;
-  static constexpr int STAGES = FL ? (BN >= 160 ? 3 : (BN >= 128 ? 4 : 6)) : ((BN >= 256) ? 4 : (BN >= 160 ? 6 : (BN >= 128 ? 7 : 9)));
-  static_assert(STAGES * STAGE_BYTES + FL_BYTES + 1024 + 256 <= 232448, "stage ring exceeds 227 KB");
+  static constexpr int STAGES = FL ? (BN >= 160 ? 3 : (BN >= 128 ? 4 : 5)) : ((BN >= 256) ? 4 : (BN >= 160 ? 6 : (BN >= 128 ? 6 : 9)));
+  static_assert(STAGES * STAGE_BYTES + FL_BYTES + EPI_STAGE_BYTES + 1024 + 256 <= 232448, "stage ring exceeds 227 KB");
   // accumulator stage stride in TMEM columns (power of two so a stage never straddles an
   // alignment boundary): 64 / 128 / 256
   static constexpr int ACC_STRIDE = FL ? 256 : ((BN <= 64) ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FL_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FL_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ void epi_store_bf16(__nv_bfloat16* dst, const float (&v)[32], int ncols_valid) {
@@ -107,6 +114,33 @@ __device__ __forceinline__ void epi_add_bf16(float (&v)[32], const __nv_bfloat16
       v[g * 8 + 6] += bf16_lo(q.w);
       v[g * 8 + 7] += bf16_hi(q.w);
     }
+  }
+}
+
+// One warp's 32 rows x 32 columns of bf16 output -> its shared-memory slab (row = 64 B, 16-byte chunk c of row l at
+// ((c ^ ((l >> 1) & 3)) << 4): the 64-byte swizzle of tm_d, conflict-free for a warp-wide 16-byte store) -> ONE TMA
+// store.  The slab is single-buffered: the lane that issues the stores first waits until its previous bulk group has
+// finished reading shared memory.  Rows / columns outside the tensor are clipped by the TMA unit.
+__device__ __forceinline__ void epi_store_tma(const GemmParams& p, uint8_t* slab, int lane, const float (&v)[32], int col0,
+                                              long long row0, int b0, int b1) {
+  if (lane == 0) bulk_wait_group_read<0>();
+  __syncwarp();
+  uint8_t* rowp = slab + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 o;
+    o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+    o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+    o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+    o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+    *reinterpret_cast<uint4*>(rowp + ((g ^ sw) << 4)) = o;
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_4d(&p.tm_d, smem_u32(slab), col0, (int)row0, b0, b1);
+    bulk_commit_group();
   }
 }
 
@@ -193,13 +227,16 @@ __device__ __forceinline__ void gemm_fl_stage_t(const GemmParams& p, uint32_t tr
 // `trow` = TMEM address of the row's first accumulator column; (mt, nt, b0, b1) identify the tile.
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t trow, int r, int mt, int nt, int b0,
-                                                   int b1) {
+                                                   int b1, uint8_t* slab) {
   const bool geglu = (p.epilogue == 1);
   const int n0 = nt * BN;
   long long m;
   bool row_ok;
   gemm_epi_row(p, r, mt, m, row_ok);
   const long long boff = b0 * p.d_bs0 + b1 * p.d_bs1;
+  const int lane = r & 31;
+  const long long m_warp = m - lane;      // first output row of this warp's 32-row slab
+  const bool tma_out = p.tma_store != 0;  // kernel-uniform
 
   if (p.k_splits > 1) {
     // partial accumulator of one K-slice -> fp32 workspace (bias / residual are applied by the finalize kernel)
@@ -249,6 +286,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
         if (p.bias) epi_add_q(v, cur.b);
         if (p.rowbias) epi_add_q(v, cur.rb);
         if (p.residual) epi_add_q(v, cur.rs);
+      }
+      if (tma_out) {
+        if (nvalid > 0) epi_store_tma(p, slab, lane, v, col0, m_warp, b0, b1);   // warp-uniform condition
+      } else if (ok) {
         if (p.out_fp32)
           epi_store_f32(reinterpret_cast<float*>(p.d) + boff + m * p.ldd + col0, v, nvalid);
         else
@@ -281,8 +322,9 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) h[j] = h[j] * gelu_erf_fast(g[j]);
-        epi_store_bf16(reinterpret_cast<__nv_bfloat16*>(p.d) + boff + m * p.ldd + ocol0, h, nvalid);
+        if (!tma_out) epi_store_bf16(reinterpret_cast<__nv_bfloat16*>(p.d) + boff + m * p.ldd + ocol0, h, nvalid);
       }
+      if (tma_out && nvalid > 0) epi_store_tma(p, slab, lane, h, ocol0, m_warp, b0, b1);
     }
   }
 }

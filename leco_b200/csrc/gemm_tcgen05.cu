@@ -39,7 +39,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint8_t* smem_t = smem + STAGES * Cfg::STAGE_BYTES;                  // FL: T tile (A operand of the up projection)
   uint8_t* smem_bup = smem_t + Cfg::T_TILE_BYTES;                      // FL: 2 x lora_up tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::FL_BYTES);
+  uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES + Cfg::FL_BYTES;  // 4 x one 32x32 bf16 slab (TMA-store staging)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]       MMA -> epilogue
@@ -355,11 +356,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         mbar_wait(&acc2_full[as], aphase);           // accumulator now holds x.W^T + T.Bup^T
         tc_fence_after();
       }
-      if (p.dbg != 3) gemm_epilogue_tile<BN>(p, trow, r, mt, nt, b0, b1);  // dbg 3: perf triage without the epilogue
+      if (p.dbg != 3) gemm_epilogue_tile<BN>(p, trow, r, mt, nt, b0, b1, smem_epi + q * EPI_SLAB_BYTES);  // dbg 3: no epilogue
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
     }
+    if (lane == 0) bulk_wait_group_read<0>();   // the last TMA stores must have read their slab before smem is released
   }
   tc_fence_before();
   __syncthreads();
@@ -601,6 +603,20 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
   p.out_fp32 = a->out_fp32;
 
   p.k_splits = 1;
+  // TMA-store epilogue: bf16 output whose tile rows are 128 consecutive output rows (matrix mode; conv tiles made of
+  // whole image rows that tile the image exactly), no split-K
+  static const bool tma_store_enabled = [] { const char* e = getenv("LECO_TMA_STORE"); return !(e && e[0] == '0'); }();
+  const bool rows_contig = a->mode == 0 || (p.rows_per_tile == BLOCK_M && (p.nb > 1 || a->ch % p.hb == 0));
+  if (tma_store_enabled && !a->out_fp32 && rows_contig && k_split <= 1 && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0 &&
+      (batch0 == 1 || a->d_bs0 % 8 == 0) && (batch1 == 1 || a->d_bs1 % 8 == 0)) {
+    const int n_out = a->epilogue == 1 ? a->N / 2 : a->N;
+    const uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)a->M, (uint64_t)batch0, (uint64_t)batch1};
+    const uint64_t bs0 = batch0 > 1 ? (uint64_t)a->d_bs0 : (uint64_t)a->ldd * a->M;
+    const uint64_t bs1 = batch1 > 1 ? (uint64_t)a->d_bs1 : bs0 * batch0;
+    const uint64_t str[3] = {(uint64_t)a->ldd * 2, bs0 * 2, bs1 * 2};
+    const uint32_t box[4] = {32, 32, 1, 1};
+    p.tma_store = make_tmap_bf16_4d_sw64(&p.tm_d, a->d, dims, str, box) == 0 ? 1 : 0;
+  }
   if (pair) return launch_gemm_2cta(p, bn, stream);
   long long total_tiles = 1LL * p.tiles_m * p.tiles_n * batch0 * batch1;
   // split-K: few output tiles but a long K (the 16x16 / 8x8 UNet levels at small batch): spread the K range

@@ -30,13 +30,59 @@ constexpr int GN_MAX_SPLITS = 64;
 
 // ---- pass 1 (forward): partial[n][split][g] = (sum x, sum x^2)
 // blockDim.x = vpp * R (vpp = C/8 vector columns, R row lanes); each thread owns one vector column.
+// Ordered (deterministic) block reduction of per-thread 8-channel partial sums into per-group sums: every thread parks
+// its 2 x 8 values in shared memory ([2][R][C] floats, dynamic), then one thread per group adds them in a fixed order.
+__device__ __forceinline__ void gn_block_group_sums(float* red, const float (&s1)[8], const float (&s2)[8], int v, int rl,
+                                                    int R, int C, int G, float2* dst) {
+  if (rl < R) {
+    float* d1 = red + (size_t)rl * C + v * 8;
+    float* d2 = red + (size_t)(R + rl) * C + v * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      d1[j] = s1[j];
+      d2[j] = s2[j];
+    }
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int q = 0; q < R; ++q)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        a += red[(size_t)q * C + c];
+        b += red[(size_t)(R + q) * C + c];
+      }
+    dst[g] = make_float2(a, b);
+  }
+}
+// Ordered fold of the per-split partials of sample n: warp w handles groups w, w+nwarps, ...; lanes stride the splits,
+// then a fixed xor-shuffle tree.  Result (sum, sum2) per group in `out` (shared).
+__device__ __forceinline__ void gn_fold_partials(const float2* partial, int n, int splits, int G, float (*out)[2]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;   // FULL warps only
+  for (int g = (warp < nwarps ? warp : G); g < G; g += nwarps) {
+    float a = 0.f, b = 0.f;
+    for (int q = lane; q < splits; q += 32) {
+      const float2 pp = partial[((size_t)n * splits + q) * G + g];
+      a += pp.x;
+      b += pp.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      out[g][0] = a;
+      out[g][1] = b;
+    }
+  }
+}
+
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ partial, int hw, int C,
                                 int G, int vpp, int splits) {
   pdl_entry();
-  __shared__ float sm[GN_MAX_GROUPS][2];
+  extern __shared__ float gn_red[];
   const int n = blockIdx.x, sp = blockIdx.y;
-  for (int i = threadIdx.x; i < G * 2; i += blockDim.x) (&sm[0][0])[i] = 0.f;
-  __syncthreads();
   const int R = blockDim.x / vpp;
   const int v = threadIdx.x % vpp, rl = threadIdx.x / vpp;
   const int rows_per = (hw + splits - 1) / splits;
@@ -77,17 +123,8 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __r
         s2[j] = fmaf(f[j], f[j], s2[j]);
       }
     }
-    const int cpg = C / G;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (v * 8 + j) / cpg;
-      atomicAdd(&sm[g][0], s1[j]);
-      atomicAdd(&sm[g][1], s2[j]);
-    }
   }
-  __syncthreads();
-  for (int g = threadIdx.x; g < G; g += blockDim.x)
-    partial[((size_t)n * splits + sp) * G + g] = make_float2(sm[g][0], sm[g][1]);
+  gn_block_group_sums(gn_red, s1, s2, v, rl, R, C, G, partial + ((size_t)n * splits + sp) * G);
 }
 
 // ---- pass 2 (forward): y = (x-mean)*rstd*gamma+beta [silu]; also writes stats[n][g] = (mean, rstd)
@@ -103,14 +140,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
   __shared__ float acc[GN_MAX_GROUPS][2];
   const int n = blockIdx.x;
   const int cpg = C / G;
-  for (int i = threadIdx.x; i < G * 2; i += blockDim.x) (&acc[0][0])[i] = 0.f;
-  __syncthreads();
-  // all threads fold the per-split partial sums (splits*G entries) instead of G threads walking them serially
-  for (int i = threadIdx.x; i < splits * G; i += blockDim.x) {
-    const float2 p = partial[(size_t)n * splits * G + i];
-    atomicAdd(&acc[i % G][0], p.x);
-    atomicAdd(&acc[i % G][1], p.y);
-  }
+  gn_fold_partials(partial, n, splits, G, acc);   // ordered: deterministic
   __syncthreads();
   if (threadIdx.x < G) {
     const float cnt = (float)hw * (float)cpg;
@@ -171,16 +201,190 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
   }
 }
 
+// ---- fused forward: statistics + normalise(+SiLU) in ONE launch.
+// grid (n, bps): block (n, sp) owns rows [sp*rows_per, ...) of sample n.  Phase 1 = its partial group sums (ordered
+// shared-memory reduction: deterministic) -> partial[n][sp][g]; a per-sample arrive/wait barrier in global memory
+// (self-resetting generation counter, so it survives CUDA-graph replays); phase 2 = every block folds the sample's
+// partials in a fixed order and normalises its own rows, which are still L2/L1 resident.  All blocks of a launch must be
+// co-resident (n*bps <= a fraction of 148 x 8 blocks of 256 threads, enforced by the host); PDL is safe: dependents only
+// launch once every block here has started.
+struct GnBarrier {
+  unsigned int count, gen;
+};
+__global__ void __launch_bounds__(384)
+gn_fused_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, float2* __restrict__ partial,
+                float2* __restrict__ stats, GnBarrier* __restrict__ bars, const __nv_bfloat16* __restrict__ gamma,
+                const __nv_bfloat16* __restrict__ beta, int hw, int C, int G, float eps, int silu, int vpp) {
+  pdl_entry();
+  extern __shared__ float gn_red[];                 // [2][R][C]: per-thread partial sums, then reused
+  __shared__ float2 ms[GN_MAX_GROUPS];
+  const int n = blockIdx.x, sp = blockIdx.y, bps = gridDim.y;
+  const int R = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp, rl = threadIdx.x / vpp;
+  const int rows_per = (hw + bps - 1) / bps;
+  const int r0 = sp * rows_per, r1 = min(hw, r0 + rows_per);
+  const int cpg = C / G;
+  const __nv_bfloat16* xb = x + ((size_t)n * hw) * C + v * 8;
+  // ---------------- phase 1: partial sums of this block's rows
+  {
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    if (rl < R) {
+      int r = r0 + rl;
+      for (; r + 3 * R < r1; r += 4 * R) {  // four independent 16-byte loads in flight
+        const v8 qa = *reinterpret_cast<const v8*>(xb + (size_t)r * C);
+        const v8 qb = *reinterpret_cast<const v8*>(xb + (size_t)(r + R) * C);
+        const v8 qc = *reinterpret_cast<const v8*>(xb + (size_t)(r + 2 * R) * C);
+        const v8 qd = *reinterpret_cast<const v8*>(xb + (size_t)(r + 3 * R) * C);
+        float f[8], g[8];
+        up8(qa, f);
+        up8(qb, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += f[j] + g[j];
+          s2[j] = fmaf(f[j], f[j], fmaf(g[j], g[j], s2[j]));
+        }
+        up8(qc, f);
+        up8(qd, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += f[j] + g[j];
+          s2[j] = fmaf(f[j], f[j], fmaf(g[j], g[j], s2[j]));
+        }
+      }
+      for (; r < r1; r += R) {
+        float f[8];
+        up8(*reinterpret_cast<const v8*>(xb + (size_t)r * C), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += f[j];
+          s2[j] = fmaf(f[j], f[j], s2[j]);
+        }
+      }
+      float* d1 = gn_red + (size_t)rl * C + v * 8;
+      float* d2 = gn_red + (size_t)(R + rl) * C + v * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        d1[j] = s1[j];
+        d2[j] = s2[j];
+      }
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {   // fixed summation order: deterministic
+      float a = 0.f, b = 0.f;
+      for (int q = 0; q < R; ++q)
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+          a += gn_red[(size_t)q * C + c];
+          b += gn_red[(size_t)(R + q) * C + c];
+        }
+      partial[((size_t)n * bps + sp) * G + g] = make_float2(a, b);
+    }
+  }
+  // ---------------- per-sample barrier
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned int* genp = &bars[n].gen;
+    const unsigned int gen = *genp;
+    __threadfence();
+    if (atomicAdd(&bars[n].count, 1u) == (unsigned)bps - 1u) {
+      bars[n].count = 0;
+      __threadfence();
+      atomicAdd(&bars[n].gen, 1u);
+    } else {
+      const long long t0 = clock64();
+      while (*genp == gen) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000LL) {
+          printf("leco_b200: group-norm grid barrier watchdog (sample %d block %d of %d)\n", n, sp, bps);
+          __trap();
+        }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  // ---------------- phase 2: statistics (every block, fixed order) + normalise own rows
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;   // FULL warps only
+    for (int g = (warp < nwarps ? warp : G); g < G; g += nwarps) {
+      float a = 0.f, b = 0.f;
+      for (int q = lane; q < bps; q += 32) {
+        const float2 pp = __ldcg(&partial[((size_t)n * bps + q) * G + g]);
+        a += pp.x;
+        b += pp.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (lane == 0) {
+        const float cnt = (float)hw * (float)cpg;
+        const float mean = a / cnt;
+        const float var = fmaxf(b / cnt - mean * mean, 0.f);
+        const float2 rr = make_float2(mean, rsqrtf(var + eps));
+        ms[g] = rr;
+        if (sp == 0) stats[(size_t)n * G + g] = rr;
+      }
+    }
+  }
+  __syncthreads();
+  if (rl >= R) return;
+  float sc[8], sh[8];
+  {
+    float gm[8], bt[8];
+    up8(__ldg(reinterpret_cast<const v8*>(gamma + v * 8)), gm);
+    up8(__ldg(reinterpret_cast<const v8*>(beta + v * 8)), bt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 m = ms[(v * 8 + j) / cpg];
+      sc[j] = m.y * gm[j];
+      sh[j] = fmaf(-m.x, sc[j], bt[j]);
+    }
+  }
+  __nv_bfloat16* yb = y + ((size_t)n * hw) * C + v * 8;
+  int r = r0 + rl;
+  for (; r + R < r1; r += 2 * R) {  // two independent 16-byte loads in flight
+    float f[8], g[8];
+    const v8 qa = *reinterpret_cast<const v8*>(xb + (size_t)r * C);
+    const v8 qb = *reinterpret_cast<const v8*>(xb + (size_t)(r + R) * C);
+    up8(qa, f);
+    up8(qb, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sc[j], sh[j]);
+      g[j] = fmaf(g[j], sc[j], sh[j]);
+      if (silu) {
+        f[j] = silu_fast(f[j]);
+        g[j] = silu_fast(g[j]);
+      }
+    }
+    *reinterpret_cast<v8*>(yb + (size_t)r * C) = pk8(f);
+    *reinterpret_cast<v8*>(yb + (size_t)(r + R) * C) = pk8(g);
+  }
+  for (; r < r1; r += R) {
+    float f[8];
+    up8(*reinterpret_cast<const v8*>(xb + (size_t)r * C), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (silu) f[j] = silu_fast(f[j]);
+    }
+    *reinterpret_cast<v8*>(yb + (size_t)r * C) = pk8(f);
+  }
+}
+
 // ---- backward pass 1: partial[n][split][g] = (sum g, sum g*xhat) with g = dy*gamma (dy through SiLU')
 __global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
                                     const float2* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
                                     const __nv_bfloat16* __restrict__ beta, float2* __restrict__ partial, int hw,
                                     int C, int G, int vpp, int splits, int silu) {
   pdl_entry();
-  __shared__ float sm[GN_MAX_GROUPS][2];
+  extern __shared__ float gn_red[];
   __shared__ float2 ms[GN_MAX_GROUPS];
   const int n = blockIdx.x, sp = blockIdx.y;
-  for (int i = threadIdx.x; i < G * 2; i += blockDim.x) (&sm[0][0])[i] = 0.f;
   for (int i = threadIdx.x; i < G; i += blockDim.x) ms[i] = stats[(size_t)n * G + i];
   __syncthreads();
   const int R = blockDim.x / vpp;
@@ -211,16 +415,8 @@ __global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const _
         s2[j] = fmaf(g, xh, s2[j]);
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (v * 8 + j) / cpg;
-      atomicAdd(&sm[g][0], s1[j]);
-      atomicAdd(&sm[g][1], s2[j]);
-    }
   }
-  __syncthreads();
-  for (int g = threadIdx.x; g < G; g += blockDim.x)
-    partial[((size_t)n * splits + sp) * G + g] = make_float2(sm[g][0], sm[g][1]);
+  gn_block_group_sums(gn_red, s1, s2, v, rl, R, C, G, partial + ((size_t)n * splits + sp) * G);
 }
 
 // ---- backward pass 2: dx = rstd * (g - mean(g) - xhat * mean(g*xhat))
@@ -235,13 +431,7 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
   const int n = blockIdx.x;
   const int cpg = C / G;
   __shared__ float acc[GN_MAX_GROUPS][2];
-  for (int i = threadIdx.x; i < G * 2; i += blockDim.x) (&acc[0][0])[i] = 0.f;
-  __syncthreads();
-  for (int i = threadIdx.x; i < splits * G; i += blockDim.x) {
-    const float2 p = partial[(size_t)n * splits * G + i];
-    atomicAdd(&acc[i % G][0], p.x);
-    atomicAdd(&acc[i % G][1], p.y);
-  }
+  gn_fold_partials(partial, n, splits, G, acc);   // ordered: deterministic
   __syncthreads();
   if (threadIdx.x < G) {
     const float cnt = (float)hw * (float)cpg;
@@ -410,8 +600,8 @@ extern "C" int leco_group_norm(const void* x, void* y, void* stats /*float2[n*G]
   int vpp, threads, splits;
   LECO_REQUIRE(gn_launch_cfg(hw, C, &vpp, &threads, &splits) == 0, "leco_group_norm: C=%d too wide", C);
   count_launch();
-  LECO_LAUNCH(gn_stats_kernel, dim3(n, splits), threads, 0, STREAM(stream), BF(x), reinterpret_cast<float2*>(workspace), hw,
-                                                                  C, G, vpp, splits);
+  LECO_LAUNCH(gn_stats_kernel, dim3(n, splits), threads, (size_t)2 * (threads / vpp) * C * sizeof(float), STREAM(stream), BF(x),
+              reinterpret_cast<float2*>(workspace), hw, C, G, vpp, splits);
   LECO_CHECK_CUDA(cudaGetLastError());
   // pass 2: ~8 blocks per SM over the whole batch, but at least 4 pixel rows per thread so the prologue amortises
   const int R = threads / vpp;
@@ -426,6 +616,36 @@ extern "C" int leco_group_norm(const void* x, void* y, void* stats /*float2[n*G]
   return 0;
 }
 
+// Fused single-launch GroupNorm forward.  workspace: float2[n * GN_MAX_SPLITS * G] (any contents); barriers:
+// PERSISTENT device buffer of >= n * 8 bytes that was ZERO when first used (the per-sample barrier state lives there
+// across launches / graph replays: leco_group_norm_barrier_bytes).
+extern "C" int64_t leco_group_norm_barrier_bytes(int n) { return (int64_t)n * (int64_t)sizeof(GnBarrier); }
+
+extern "C" int leco_group_norm_fused(const void* x, void* y, void* stats, const void* gamma, const void* beta, int n,
+                                     int hw, int C, int G, float eps, int silu, void* workspace, void* barriers,
+                                     void* stream) {
+  LECO_REQUIRE(x && y && stats && gamma && beta && workspace && barriers, "leco_group_norm_fused: null pointer");
+  LECO_REQUIRE(C % 8 == 0 && G > 0 && G <= GN_MAX_GROUPS && C % G == 0, "leco_group_norm_fused: C=%d G=%d unsupported", C, G);
+  int vpp, threads, splits;
+  LECO_REQUIRE(gn_launch_cfg(hw, C, &vpp, &threads, &splits) == 0 && threads <= 384, "leco_group_norm_fused: C=%d too wide", C);
+  const int R = threads / vpp;
+  const size_t smem = (size_t)2 * R * C * sizeof(float);
+  LECO_REQUIRE(smem <= 48 * 1024, "leco_group_norm_fused: C=%d needs %zu B of shared memory", C, smem);
+  // every block of the launch must be resident at once (grid barrier): ask the runtime how many fit
+  int per_sm = 0;
+  LECO_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, threads, smem));
+  int bps = splits;
+  const int cap = (sm_count() * per_sm) / (n < 1 ? 1 : n);
+  if (bps > cap) bps = cap;
+  LECO_REQUIRE(bps >= 1, "leco_group_norm_fused: batch %d too large for the single-launch kernel", n);
+  count_launch();
+  LECO_LAUNCH(gn_fused_kernel, dim3(n, bps), threads, smem, STREAM(stream), BF(x), BFW(y),
+              reinterpret_cast<float2*>(workspace), reinterpret_cast<float2*>(stats),
+              reinterpret_cast<GnBarrier*>(barriers), BF(gamma), BF(beta), hw, C, G, eps, silu, vpp);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int leco_group_norm_bwd(const void* x, const void* dz, void* dx, const void* stats, const void* gamma,
                                    const void* beta, int n, int hw, int C, int G, int silu, void* workspace,
                                    void* stream) {
@@ -434,7 +654,7 @@ extern "C" int leco_group_norm_bwd(const void* x, const void* dz, void* dx, cons
   int vpp, threads, splits;
   LECO_REQUIRE(gn_launch_cfg(hw, C, &vpp, &threads, &splits) == 0, "leco_group_norm_bwd: C=%d too wide", C);
   count_launch();
-  LECO_LAUNCH(gn_bwd_stats_kernel, dim3(n, splits), threads, 0, STREAM(stream), 
+  LECO_LAUNCH(gn_bwd_stats_kernel, dim3(n, splits), threads, (size_t)2 * (threads / vpp) * C * sizeof(float), STREAM(stream), 
       BF(x), BF(dz), reinterpret_cast<const float2*>(stats), BF(gamma), BF(beta),
       reinterpret_cast<float2*>(workspace), hw, C, G, vpp, splits, silu);
   LECO_CHECK_CUDA(cudaGetLastError());

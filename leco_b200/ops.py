@@ -329,6 +329,19 @@ def _gn_workspace(dev, n, G):
     return _gn_ws[key]
 
 
+GN_FUSED = int(__import__('os').environ.get('LECO_GN_FUSED', '1'))   # 1: single-launch GroupNorm forward
+_GN_BARRIERS = {}
+
+
+def _gn_barriers(dev) -> torch.Tensor:
+    """Persistent zero-initialised per-sample barrier state of the single-launch GroupNorm (one per device; created on
+    first use, i.e. during the eager warm-up that precedes any graph capture)."""
+    b = _GN_BARRIERS.get(dev)
+    if b is None:
+        b = _GN_BARRIERS[dev] = torch.zeros(4096 * 8, device=dev, dtype=torch.uint8)
+    return b
+
+
 def group_norm(x: torch.Tensor, n: int, hw: int, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float,
                silu_act: bool):
     C = x.shape[1]
@@ -336,6 +349,11 @@ def group_norm(x: torch.Tensor, n: int, hw: int, gamma: torch.Tensor, beta: torc
     y = torch.empty_like(x)
     stats = torch.empty((n, groups, 2), device=x.device, dtype=torch.float32)
     ws = torch.empty(int(_lib().leco_group_norm_workspace_bytes(n, groups)), device=x.device, dtype=torch.uint8)
+    if GN_FUSED and n <= 148 and C <= 3072 and n <= 4096:
+        capi.check(_lib().leco_group_norm_fused(_ptr(x), _ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), n, hw, C, groups,
+                                                eps, int(silu_act), _ptr(ws), _ptr(_gn_barriers(x.device)), _stream()),
+                   "leco_group_norm_fused")
+        return y, stats
     capi.check(_lib().leco_group_norm(_ptr(x), _ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), n, hw, C, groups,
                                       eps, int(silu_act), _ptr(ws), _stream()), "leco_group_norm")
     return y, stats

@@ -480,8 +480,9 @@ class EngineUNet(nn.Module):
         self._act_dtype = torch.bfloat16
         self._last_tape: Optional[Tape] = None
         self.attention_impl = "auto"
-        # LoRA branch computed inside the GEMM kernel (True) or as a separate T GEMM + extra K-segment (False)
-        self.fused_lora = bool(int(__import__('os').environ.get('LECO_FUSED_LORA', '0')))
+        # LoRA branch computed inside the GEMM kernel (True: x.A^T rides along as extra accumulator columns, T.B^T is a second
+        # UMMA on the same accumulator; measured 250 vs 264 ms / iteration) or as a separate T GEMM + extra K-segment (False)
+        self.fused_lora = bool(int(__import__('os').environ.get('LECO_FUSED_LORA', '1')))
 
     # ---- reference-facing no-ops -------------------------------------------------------
     def enable_xformers_memory_efficient_attention(self, *a, **k):  # train_lora.py:68

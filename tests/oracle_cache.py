@@ -32,7 +32,8 @@ def cached(name: str, fn, write: bool = False):
 
 def main():
     from tests.gpu_checks import kernel_cases as kc
-    for arch, n, hw in (("tiny21", 2, 16), ("tiny15", 2, 16), ("tinyxl", 2, 16), ("tiny21", 2, 32), ("sd21", 2, 64)):
+    for arch, n, hw in (("tiny21", 2, 16), ("tiny15", 2, 16), ("tinyxl", 2, 16), ("tiny21", 2, 32), ("sd21", 2, 64),
+                        ("sd15", 2, 64), ("sdxl", 2, 128)):
         cached(f"fwd_{arch}_{n}_{hw}", lambda: kc.oracle_forward(arch, n, hw), write=True)
         print("fwd", arch, n, hw, flush=True)
     for arch in ("tiny21", "tiny15"):
