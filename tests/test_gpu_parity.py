@@ -214,6 +214,11 @@ def test_fullsize_sd21_lora_gradients():
     through the 2-CTA / split-K GEMMs, tn_reduce at full M and attention backward at S = 4096, vs fp32 oracle autograd."""
     res = kernel_cases.case_engine_grads("sd21", n=2, hw=64, cache_name="grads_sd21_full")
     g = res["parts"]["grads"]
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        json.dump(res, open(os.path.join(out, "fullsize_grads_report.json"), "w"), indent=1)
     assert res["ok"] and g["rel"] < 5e-2 and g["cos_weighted"] > 0.99, res
 
 
@@ -249,6 +254,12 @@ def test_fullsize_sd21_iteration():
     report["update_cos_vs_torch_bf16"] = num / den
     assert num / den > 0.9, report
     print("fullsize iteration report:", report)
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):   # measured numbers for DESIGN.md / profiles (engine vs plain-bf16 torch, both against the fp32 oracle)
+        json.dump({k: list(v) if isinstance(v, tuple) else v for k, v in report.items()},
+                  open(os.path.join(out, "fullsize_iteration_report.json"), "w"), indent=1)
 
 
 def test_load_weights_under_captured_graphs(tmp_path):
