@@ -129,6 +129,20 @@ int leco_flash_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, 
                         const void* v_t, int64_t skv_pad, void* out, int64_t ldo, int batch, int heads, int sq,
                         int skv, int d, float scale, void* stream);
 
+/* leco_flash_attn_fwd_lse: the same forward, additionally writing lse[batch][heads][sq] (fp32, log2 domain) for the backward.
+ * leco_flash_attn_bwd: fused backward (dQ, dK, dV; S / P / dP / dS never reach HBM) of the reference's one grad pass
+ *   through attention (train_lora.py:279).  dvec = rowsum(dO o O) from leco_attn_bwd_prep; dq_acc = ZEROED fp32
+ *   [batch][heads][sq][64] workspace (per-key-tile partial dQ meet there in fp32 reductions), cast by leco_attn_dq_cast. */
+int leco_flash_attn_fwd_lse(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                            int64_t ldo, float* lse, int batch, int heads, int sq, int skv, int d, float scale,
+                            void* stream);
+int leco_attn_bwd_prep(const void* o, int64_t ldo, const void* dout, int64_t lddo, float* dvec, int batch, int heads, int sq,
+                       int d, void* stream);
+int leco_flash_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout,
+                        int64_t lddo, const float* lse, const float* dvec, float* dq_acc, void* dk, int64_t lddk, void* dv,
+                        int64_t lddv, int batch, int heads, int sq, int skv, int d, float scale, void* stream);
+int leco_attn_dq_cast(const float* dq_acc, void* dq, int64_t lddq, int batch, int heads, int sq, int d, void* stream);
+
 /* ---------------------------------------------------------------------------------
  * GroupNorm(+SiLU) / LayerNorm (diffusers ResnetBlock2D.norm1/2, Transformer2DModel.norm,
  * BasicTransformerBlock.norm1-3), forward and backward-data.  stats = float2 (mean, rstd).

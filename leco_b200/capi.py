@@ -91,6 +91,10 @@ _OPS: list[tuple[str, list]] = [
     ("leco_softmax_rows", [P, P, L, I, I, L, L, P]),
     ("leco_softmax_bwd_rows", [P, P, P, L, I, I, L, L, F, P]),
     ("leco_flash_attn_fwd", [P, L, P, L, P, L, P, L, P, L, I, I, I, I, I, F, P]),
+    ("leco_flash_attn_fwd_lse", [P, L, P, L, P, L, P, L, P, I, I, I, I, I, F, P]),
+    ("leco_attn_bwd_prep", [P, L, P, L, P, I, I, I, I, P]),
+    ("leco_flash_attn_bwd", [P, L, P, L, P, L, P, L, P, P, P, P, L, P, L, I, I, I, I, I, F, P]),
+    ("leco_attn_dq_cast", [P, P, L, I, I, I, I, P]),
     ("leco_group_norm", [P, P, P, P, P, I, I, I, I, F, I, P, P]),
     ("leco_group_norm_bwd", [P, P, P, P, P, P, I, I, I, I, I, P, P]),
     ("leco_group_norm_fused", [P, P, P, P, P, I, I, I, I, F, I, P, P, P]),

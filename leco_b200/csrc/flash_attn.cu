@@ -10,9 +10,9 @@
 //                            never waits for a TMEM rescale.
 // Nothing of S or P ever touches HBM: algorithmic traffic is Q, K, V, O once (K/V re-reads hit L2).
 // Roles: warp 0 lane 0 TMA, warp 1 lane 0 MMA issue, warp 2 TMEM alloc, warps 4-7 and 8-11 = two softmax
-// warpgroups: thread (wg, row) owns keys [64*wg, 64*wg+64) of S row `row` and output columns [32*wg, 32*wg+32);
-// only the running row max crosses warpgroups (one smem exchange + named barrier per tile), the two partial
-// row sums are added once at the end.  exp2 is the MUFU-bound part: splitting the keys halves it per thread.
+// warpgroups: warpgroup w owns the KV tiles j = w (mod 2) with its own online-softmax state per row; the two partial
+// results (max, sum, 64 output columns) are merged once per CTA at the end.  exp2 is the MUFU-bound part (16 / clk / SM
+// measured, tests/gpu_checks/micro_probe.cu): two decoupled warpgroups keep it fed.
 //
 // V operand: v_mode 0 = V tile [keys, d] used directly as an MN-major B operand;
 //            v_mode 1 = a pre-transposed V^T [d, keys] (K-major B operand, like the GEMM kernel).
@@ -39,6 +39,7 @@ struct FlashParams {
   long long ld_out;
   int sq, skv, heads, d, n_kv_tiles, v_mode;
   float scale_log2;  // softmax scale * log2(e)
+  float* lse;        // optional [batch][heads][sq]: log2-domain log-sum-exp (max*scale_log2 + log2(sum)) for the backward
 };
 
 // MN-major B operand (V tile as stored: keys x d), 128B swizzle: 8 key-rows of 128 B per atom.
@@ -105,11 +106,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 8);
-      mbar_init(&p_full[i], 8);
+      mbar_init(&s_empty[i], 4);   // buffer i belongs to softmax warpgroup i (4 warps)
+      mbar_init(&p_full[i], 4);
       mbar_init(&p_empty[i], 1);
       mbar_init(&pv_full[i], 1);
-      mbar_init(&pv_empty[i], 8);
+      mbar_init(&pv_empty[i], 4);
     }
     fence_barrier_init();
   }
@@ -193,117 +194,164 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax + output
-    const int wg = (warp - 4) >> 2;          // 0: keys 0-63 / out cols 0-31, 1: keys 64-127 / out cols 32-63
+    // Warpgroup w owns the KV tiles j = w, w+2, w+4, ... (all 128 keys of them): thread (w, row) keeps its OWN online-
+    // softmax state (running max, row sum, 64 output columns) over those tiles, so the two warpgroups never talk to
+    // each other inside the loop (the per-tile max exchange through a named barrier was the top stall of the previous
+    // version: ncu `stalled_barrier` 1.56 per issue) and each has two tile periods to turn a tile around.  The two
+    // partial results are merged once at the end (split-KV combine).
+    const int wg = (warp - 4) >> 2;
     const int q = warp & 3;                  // TMEM lane quadrant
     const int r = q * 32 + lane;             // row of the query tile
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    float m_run = -INFINITY, l_part = 0.f, alpha_prev = 1.f;
-    float o[FA_D / 2];
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+    float o[FA_D];
 #pragma unroll
-    for (int i = 0; i < FA_D / 2; ++i) o[i] = 0.f;
+    for (int i = 0; i < FA_D; ++i) o[i] = 0.f;
 
-    auto fold_pv = [&](int j, float alpha) {  // o = o*alpha + PV_j[:, 32*wg : 32*wg+32]
+    auto fold_pv = [&](int j, float alpha) {  // o = o*alpha + PV_j   (buffer j & 1 == wg)
       const int pb = j & 1;
       mbar_wait(&pv_full[pb], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t raw[32];
-      tmem_ld_32x32b_x32(tmem_pv + lane_off + pb * FA_D + wg * 32, raw);
-      tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(raw[i]));
+      for (int h = 0; h < 2; ++h) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(tmem_pv + lane_off + pb * FA_D + h * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], alpha, __uint_as_float(raw[i]));
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pv_empty[pb]);
     };
 
-    // One KV tile of the online softmax.  RG (= this half tile runs past skv) is a compile-time flag: written as a
-    // run-time `if (ragged)` the per-score masks became ~400 predicated instructions per tile that take issue slots
-    // even when off (ncu: the kernel is issue-bound, ALU the busiest pipe), so the ragged tile gets its own copy.
+    // One KV tile of the online softmax.  RG (= the tile runs past skv) is a compile-time flag: as a run-time test the
+    // per-score masks become predicated instructions that take issue slots even when off.
     auto softmax_tile = [&](int j, auto rg_tag) {
       constexpr bool ragged = decltype(rg_tag)::value;
       const int sb = j & 1;
-      const int kv0 = j * FA_BN + wg * 64;     // first key of this thread's half
+      const int kv0 = j * FA_BN;
+      // this warpgroup's previous tile first (o = o*alpha_{j-2} + PV_{j-2}): frees the PV accumulator before P_j is
+      // even staged, so PV_j can start the moment P_j is ready
+      if (j >= 2) fold_pv(j - 2, alpha_prev);
       mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t s_addr = tmem_s + lane_off + sb * FA_BN + wg * 64;
-      // this thread's 64 scores: both TMEM loads in flight, one wait; S is then free for the next QK^T
-      uint32_t s0[32], s1[32];
-      tmem_ld_32x32b_x32(s_addr, s0);
-      tmem_ld_32x32b_x32(s_addr + 32, s1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[sb]);
+      const uint32_t s_addr = tmem_s + lane_off + sb * FA_BN;
+      // pass 1: row max over the 128 scores (32 at a time: the scores are re-read in pass 2 instead of living in
+      // 128 registers; TMEM reads are cheap, 4 KB per warp-load at ~43 cycles)
       float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32];
+        tmem_ld_32x32b_x32(s_addr + c * 32, sv);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float a = __uint_as_float(s0[i]), b2 = __uint_as_float(s1[i]);
-        if constexpr (ragged) {
-          if (kv0 + i >= p.skv) a = -INFINITY;
-          if (kv0 + 32 + i >= p.skv) b2 = -INFINITY;
+        for (int i = 0; i < 32; ++i) {
+          float a = __uint_as_float(sv[i]);
+          if constexpr (ragged) {
+            if (kv0 + c * 32 + i >= p.skv) a = -INFINITY;
+          }
+          mx = fmaxf(mx, a);
         }
-        mx = fmaxf(mx, fmaxf(a, b2));
       }
-      mx_buf[(sb * 2 + wg) * 128 + r] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // the two softmax warpgroups only
-      const float m_new = fmaxf(m_run, fmaxf(mx, mx_buf[(sb * 2 + (wg ^ 1)) * 128 + r]));
+      const float m_new = fmaxf(m_run, mx);
       const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);  // first tile: ex2(-inf) = 0
       const float mb = m_new * p.scale_log2;
-      // p = 2^(s*c - m*c) -> bf16 -> swizzled A-operand tile (this half = 64 keys = one 128-byte row)
+      // pass 2: p = 2^(s*c - m*c) -> bf16 -> swizzled A-operand tile (two 64-key chunks of [128 rows x 128 B])
       mbar_wait(&p_empty[sb], ((j >> 1) & 1) ^ 1);
-      uint8_t* prow = sP + sb * FA_P_BYTES + wg * (FA_P_BYTES / 2) + r * 128;
-      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;  // four partial sums: no 64-long dependent FADD chain
-#define FA_EXP_HALF(SRC, KOFF, CHUNK0)                                                        \
-  _Pragma("unroll") for (int t = 0; t < 4; ++t) {                                             \
-    uint32_t pk[4];                                                                           \
-    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                           \
-      const int i = t * 8 + u * 2;                                                            \
-      float p0 = ex2_approx(fmaf(__uint_as_float(SRC[i]), p.scale_log2, -mb));                \
-      float p1 = ex2_approx(fmaf(__uint_as_float(SRC[i + 1]), p.scale_log2, -mb));            \
-      if constexpr (ragged) {                                                                 \
-        if (kv0 + KOFF + i >= p.skv) p0 = 0.f;                                                \
-        if (kv0 + KOFF + i + 1 >= p.skv) p1 = 0.f;                                            \
-      }                                                                                       \
-      if (u == 0) rs0 += p0 + p1; else if (u == 1) rs1 += p0 + p1; else if (u == 2) rs2 += p0 + p1; else rs3 += p0 + p1; \
-      pk[u] = pack_bf16(p0, p1);                                                              \
-    }                                                                                         \
-    *reinterpret_cast<uint4*>(prow + (((CHUNK0 + t) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]); \
-  }
-      FA_EXP_HALF(s0, 0, 0)
-      FA_EXP_HALF(s1, 32, 4)
-#undef FA_EXP_HALF
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;  // four partial sums: no long dependent FADD chain
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32];
+        tmem_ld_32x32b_x32(s_addr + c * 32, sv);
+        tmem_ld_wait();
+        if (c == 3) {               // S fully consumed: the next QK^T of this buffer may start
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[sb]);
+        }
+        uint8_t* prow = sP + sb * FA_P_BYTES + (c >> 1) * (FA_P_BYTES / 2) + r * 128;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = t * 8 + u * 2;
+            float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), p.scale_log2, -mb));
+            float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, -mb));
+            if constexpr (ragged) {
+              if (kv0 + c * 32 + i >= p.skv) p0 = 0.f;
+              if (kv0 + c * 32 + i + 1 >= p.skv) p1 = 0.f;
+            }
+            if (u == 0) rs0 += p0 + p1; else if (u == 1) rs1 += p0 + p1; else if (u == 2) rs2 += p0 + p1; else rs3 += p0 + p1;
+            pk[u] = pack_bf16(p0, p1);
+          }
+          *reinterpret_cast<uint4*>(prow + ((((c & 1) * 4 + t) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[sb]);
-      l_part = l_part * alpha + ((rs0 + rs1) + (rs2 + rs3));
+      l_run = l_run * alpha + ((rs0 + rs1) + (rs2 + rs3));
       m_run = m_new;
-      if (j > 0) fold_pv(j - 1, alpha_prev);
       alpha_prev = alpha;
     };
-    for (int j = 0; j < n_tiles; ++j) {
-      if (j * FA_BN + wg * 64 + 64 > p.skv)
+    int last = -1;
+    for (int j = wg; j < n_tiles; j += 2) {
+      if (j * FA_BN + FA_BN > p.skv)
         softmax_tile(j, std::true_type{});
       else
         softmax_tile(j, std::false_type{});
+      last = j;
     }
-    fold_pv(n_tiles - 1, alpha_prev);
-    // total row sum = sum of the two warpgroups' partial sums (same running max in both)
-    mx_buf[512 + wg * 128 + r] = l_part;  // separate slots: the max slots may still be read by the partner
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float l_tot = l_part + mx_buf[512 + (wg ^ 1) * 128 + r];
-    const int row = qt * FA_BM + r;
-    if (row < p.sq) {
-      const float inv = 1.0f / l_tot;
-      __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.sq + row) * p.ld_out + head * p.d + wg * 32;
+    if (last >= 0) fold_pv(last, alpha_prev);
+    // ---- merge the two partial softmax results: each warpgroup finishes 32 of the 64 output columns.  The partner's
+    // half travels through this warpgroup's own P buffer (free: its last PV has been folded), column-major so that
+    // consecutive lanes hit consecutive words.  (Static register indices only: `o` must stay in registers.)
+    {
+      float* xo = reinterpret_cast<float*>(sP + wg * FA_P_BYTES);         // [32 cols][128 rows]
+      if (wg == 0) {
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        if (wg * 32 + c8 * 8 < p.d) {
-          uint4 v;
-          v.x = pack_bf16(o[c8 * 8 + 0] * inv, o[c8 * 8 + 1] * inv);
-          v.y = pack_bf16(o[c8 * 8 + 2] * inv, o[c8 * 8 + 3] * inv);
-          v.z = pack_bf16(o[c8 * 8 + 4] * inv, o[c8 * 8 + 5] * inv);
-          v.w = pack_bf16(o[c8 * 8 + 6] * inv, o[c8 * 8 + 7] * inv);
-          *reinterpret_cast<uint4*>(dst + c8 * 8) = v;
+        for (int i = 0; i < 32; ++i) xo[i * 128 + r] = o[32 + i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xo[i * 128 + r] = o[i];
+      }
+      mx_buf[wg * 128 + r] = m_run;
+      mx_buf[256 + wg * 128 + r] = l_run;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the two softmax warpgroups only, once per CTA
+    {
+      const float m_o = mx_buf[(wg ^ 1) * 128 + r], l_o = mx_buf[256 + (wg ^ 1) * 128 + r];
+      const float m_tot = fmaxf(m_run, m_o);          // finite: tile 0 has at least one valid key
+      const float a_me = ex2_approx((m_run - m_tot) * p.scale_log2);
+      const float a_ot = ex2_approx((m_o - m_tot) * p.scale_log2);
+      const float l_tot = l_run * a_me + l_o * a_ot;
+      const float* xi = reinterpret_cast<const float*>(sP + (wg ^ 1) * FA_P_BYTES);
+      const int row = qt * FA_BM + r;
+      const float inv = 1.0f / l_tot;
+      float f[32];
+      if (wg == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = (o[i] * a_me + xi[i * 128 + r] * a_ot) * inv;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = (o[32 + i] * a_me + xi[i * 128 + r] * a_ot) * inv;
+      }
+      if (row < p.sq) {
+        if (p.lse && wg == 0)
+          p.lse[(static_cast<long long>(b) * p.heads + head) * p.sq + row] = m_tot * p.scale_log2 + log2f(l_tot);
+        __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.sq + row) * p.ld_out + head * p.d + wg * 32;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          if (wg * 32 + c8 * 8 < p.d) {
+            uint4 v;
+            v.x = pack_bf16(f[c8 * 8 + 0], f[c8 * 8 + 1]);
+            v.y = pack_bf16(f[c8 * 8 + 2], f[c8 * 8 + 3]);
+            v.z = pack_bf16(f[c8 * 8 + 4], f[c8 * 8 + 5]);
+            v.w = pack_bf16(f[c8 * 8 + 6], f[c8 * 8 + 7]);
+            *reinterpret_cast<uint4*>(dst + c8 * 8) = v;
+          }
         }
       }
     }
@@ -319,9 +367,24 @@ using namespace leco;
 
 // q/k/v: [rows, ld] bf16 buffers whose columns [head*d, head*d+d) hold that head (strides in elements).
 // v_t != NULL selects v_mode 1: v_t is V^T laid out [batch][heads][d][skv_pad] (skv_pad multiple of 8).
+static int flash_fwd_impl(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                          const void* v_t, int64_t skv_pad, void* out, int64_t ldo, float* lse, int batch, int heads,
+                          int sq, int skv, int d, float scale, void* stream);
 extern "C" int leco_flash_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                    const void* v_t, int64_t skv_pad, void* out, int64_t ldo, int batch, int heads,
                                    int sq, int skv, int d, float scale, void* stream) {
+  return flash_fwd_impl(q, ldq, k, ldk, v, ldv, v_t, skv_pad, out, ldo, nullptr, batch, heads, sq, skv, d, scale, stream);
+}
+// same, additionally writing lse[batch][heads][sq] (fp32, log2 domain) for leco_flash_attn_bwd
+extern "C" int leco_flash_attn_fwd_lse(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                       void* out, int64_t ldo, float* lse, int batch, int heads, int sq, int skv, int d,
+                                       float scale, void* stream) {
+  LECO_REQUIRE(lse, "leco_flash_attn_fwd_lse: null lse");
+  return flash_fwd_impl(q, ldq, k, ldk, v, ldv, nullptr, 0, out, ldo, lse, batch, heads, sq, skv, d, scale, stream);
+}
+static int flash_fwd_impl(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                          const void* v_t, int64_t skv_pad, void* out, int64_t ldo, float* lse, int batch, int heads,
+                          int sq, int skv, int d, float scale, void* stream) {
   LECO_REQUIRE(q && k && out && (v || v_t), "leco_flash_attn_fwd: null pointer");
   LECO_REQUIRE(d % 8 == 0 && d <= FA_D, "leco_flash_attn_fwd: head dim %d unsupported (<=64, multiple of 8)", d);
   LECO_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldo % 8 == 0, "leco_flash_attn_fwd: strides must be multiples of 8");
@@ -360,6 +423,7 @@ extern "C" int leco_flash_attn_fwd(const void* q, int64_t ldq, const void* k, in
   p.d = d;
   p.n_kv_tiles = (skv + FA_BN - 1) / FA_BN;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse = lse;
   static bool attr_set = false;
   if (!attr_set) {
     LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));

@@ -416,8 +416,10 @@ def transpose_tiles(src_flat, dst_flat, tiles, n_tiles):
 
 
 def set_deterministic(on: bool):
-    """Fixed-order reductions (no fp32 atomics across CTAs, no split-K): bit-repeatable steps, slower."""
+    """Fixed-order reductions (no fp32 atomics across CTAs, no split-K, materialised attention backward): bit-repeatable
+    steps, slower."""
     capi.check(_lib().leco_set_deterministic(int(bool(on))), "leco_set_deterministic")
+    _DETERMINISTIC[0] = bool(on)
 
 
 def guided_step(eps_pair, x, coef, want_x=True, want_guided=False):
@@ -536,9 +538,47 @@ def flash_attention(qt, kt, vt, nb, sq, skv, heads, d, scale, v_mode=None):
     return o
 
 
+# grad pass: "flash" = fused forward (+lse) and fused backward kernel; "v0" = materialised P (always used for head dims
+# > 64 and under leco_set_deterministic: the fused backward reduces dQ over key tiles with fp32 atomics)
+ATTENTION_BWD_IMPL = _os.environ.get("LECO_ATTENTION_BWD", "flash")
+_DETERMINISTIC = [_os.environ.get("LECO_DETERMINISTIC", "0") == "1"]
+
+
+def flash_attention_lse(qt, kt, vt, nb, sq, skv, heads, d, scale):
+    """Fused forward that also returns lse [nb, heads, sq] (fp32, log2 domain) for flash_attention_bwd."""
+    o = torch.empty((nb * sq, heads * d), device=qt.device, dtype=BF16)
+    lse = torch.empty((nb, heads, sq), device=qt.device, dtype=torch.float32)
+    capi.check(_lib().leco_flash_attn_fwd_lse(_ptr(qt), qt.stride(0), _ptr(kt), kt.stride(0), _ptr(vt), vt.stride(0),
+                                              _ptr(o), o.stride(0), _ptr(lse), nb, heads, sq, skv, d, scale, _stream()),
+               "leco_flash_attn_fwd_lse")
+    return o, lse
+
+
+def flash_attention_bwd(go, qt, kt, vt, o, lse, nb, sq, skv, heads, d, scale, dq_out, dk_out, dv_out):
+    """Fused attention backward: writes d(q), d(k), d(v) into the given [rows, heads*d] views (any may be None)."""
+    _req_bf16(go, "go")
+    assert go.stride(1) == 1 and o.stride(1) == 1
+    dvec = torch.empty((nb, heads, sq), device=go.device, dtype=torch.float32)
+    capi.check(_lib().leco_attn_bwd_prep(_ptr(o), o.stride(0), _ptr(go), go.stride(0), _ptr(dvec), nb, heads, sq, d,
+                                         _stream()), "leco_attn_bwd_prep")
+    dq_acc = torch.zeros((nb, heads, sq, 64), device=go.device, dtype=torch.float32)
+    capi.check(_lib().leco_flash_attn_bwd(_ptr(qt), qt.stride(0), _ptr(kt), kt.stride(0), _ptr(vt), vt.stride(0),
+                                          _ptr(go), go.stride(0), _ptr(lse), _ptr(dvec), _ptr(dq_acc),
+                                          _ptr(dk_out), 0 if dk_out is None else dk_out.stride(0),
+                                          _ptr(dv_out), 0 if dv_out is None else dv_out.stride(0),
+                                          nb, heads, sq, skv, d, scale, _stream()), "leco_flash_attn_bwd")
+    if dq_out is not None:
+        capi.check(_lib().leco_attn_dq_cast(_ptr(dq_acc), _ptr(dq_out), dq_out.stride(0), nb, heads, sq, d, _stream()),
+                   "leco_attn_dq_cast")
+
+
 def attention(qt, kt, vt, nb, sq, skv, heads, d, scale, save_for_bwd=False):
-    if not save_for_bwd and ATTENTION_IMPL == "flash" and d <= 64 and d % 8 == 0:
+    flash_ok = ATTENTION_IMPL == "flash" and d <= 64 and d % 8 == 0
+    if not save_for_bwd and flash_ok:
         return flash_attention(qt, kt, vt, nb, sq, skv, heads, d, scale), None
+    if save_for_bwd and flash_ok and ATTENTION_BWD_IMPL == "flash" and not _DETERMINISTIC[0]:
+        o, lse = flash_attention_lse(qt, kt, vt, nb, sq, skv, heads, d, scale)
+        return o, ("flash", o, lse)
     return attention_v0(qt, kt, vt, nb, sq, skv, heads, d, scale, save_for_bwd)
 
 
@@ -557,6 +597,9 @@ def attention_v0(qt, kt, vt, nb, sq, skv, heads, d, scale, save_for_bwd=False):
 
 def attention_bwd(go, qt, kt, vt, saved, nb, sq, skv, heads, d, scale, dq_out, dk_out, dv_out):
     """Writes d(q), d(k), d(v) into the given [rows, heads*d] views (any may be None)."""
+    if saved[0] == "flash":
+        _, o, lse = saved
+        return flash_attention_bwd(go, qt, kt, vt, o, lse, nb, sq, skv, heads, d, scale, dq_out, dk_out, dv_out)
     (P,) = saved
     skv_pad = P.shape[-1]
     pad = skv_pad if skv_pad != skv else 0

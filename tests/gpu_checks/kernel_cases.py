@@ -345,10 +345,14 @@ def case_determinism():
             "losses_2": outs[1][0], "params_equal": bool(same_p)}
 
 
-def case_attention(nb, sq, skv, heads, d, cross=False):
+def case_attention(nb, sq, skv, heads, d, cross=False, bwd_impl="flash"):
+    """grad-pass attention (forward that saves for the backward + backward) vs plain fp32 torch.  bwd_impl "flash" =
+    fused tcgen05 forward (+lse) and fused backward kernel (head dims <= 64); "v0" = the materialised path (used for
+    larger head dims and under leco_set_deterministic)."""
     import torch
     from leco_b200 import ops
     from tests import torch_backend as tb
+    ops.ATTENTION_BWD_IMPL = bwd_impl
     C = heads * d
     if cross:
         qbuf, kvbuf = _rand((nb * sq, C), seed=1), _rand((nb * skv, 2 * C), seed=2)
@@ -358,6 +362,9 @@ def case_attention(nb, sq, skv, heads, d, cross=False):
         qt, kt, vt = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
     scale = d ** -0.5
     o, saved = ops.attention(qt, kt, vt, nb, sq, skv, heads, d, scale, True)
+    used = "flash" if saved[0] == "flash" else "v0"
+    if bwd_impl == "flash" and d <= 64:
+        assert used == "flash", "the fused backward path was not taken"
     oref, _ = tb.attention(qt.cpu(), kt.cpu(), vt.cpu(), nb, sq, skv, heads, d, scale, False)
     res = {"fwd": _cmp(o, oref)}
     go = _rand((nb * sq, C), seed=3)
@@ -557,7 +564,13 @@ CASES = [
     ("transpose_tiles", case_transpose_tiles, {}),
     ("determinism", case_determinism, {}),
     ("attn_self_4096_d64", case_attention, dict(nb=1, sq=4096, skv=4096, heads=5, d=64)),
+    ("attn_self_4096_d64_v0", case_attention, dict(nb=1, sq=4096, skv=4096, heads=5, d=64, bwd_impl="v0")),
     ("attn_self_1024_d64", case_attention, dict(nb=2, sq=1024, skv=1024, heads=5, d=64)),
+    ("attn_self_1024_d64_v0", case_attention, dict(nb=2, sq=1024, skv=1024, heads=5, d=64, bwd_impl="v0")),
+    ("attn_cross_77_v0", case_attention, dict(nb=2, sq=256, skv=77, heads=2, d=64, cross=True, bwd_impl="v0")),
+    ("attn_cross_77_sq4096", case_attention, dict(nb=1, sq=4096, skv=77, heads=5, d=64, cross=True)),
+    ("attn_self_300_ragged", case_attention, dict(nb=2, sq=300, skv=300, heads=3, d=64)),
+    ("attn_self_d160_v0", case_attention, dict(nb=1, sq=256, skv=256, heads=2, d=160)),
     ("attn_cross_77", case_attention, dict(nb=2, sq=256, skv=77, heads=2, d=64, cross=True)),
     ("attn_self_d40", case_attention, dict(nb=2, sq=256, skv=256, heads=8, d=40)),
     ("attn_self_64_d8", case_attention, dict(nb=2, sq=64, skv=64, heads=8, d=8)),
