@@ -425,7 +425,10 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     trainer.launches = 0
+    trainer.profile_phases = True
     sec, loss_a, _ = timed(trainer, args.steps, e2e=False)
+    phases = trainer.phase_ms()
+    trainer.profile_phases = False
     launches = trainer.launches
     sec_e2e, loss_b, _ = timed(trainer, args.steps, e2e=True)
     h2d_bytes = trainer.h2d_bytes          # host noise of one step (pinned staging -> device), counted by the trainer
@@ -468,6 +471,10 @@ def run_ours(args):
                               w_ref_tflop(cfg, k) * world, "achieved": wmin / (sec / args.steps),
                               "peak": sustained * world, "unit": "TFLOP/s",
                               "frac": wmin / (sec / args.steps) / (sustained * world), "peak_source": how},
+            "phases": None if phases is None else {
+                **phases, "denoise_step_ms": phases["denoise_loop_ms"] / max(1.0, phases["mean_k"]),
+                "what": "CUDA events inside the timed region: k-step CFG denoise loop (LoRA on) | 3 LoRA-off + 1 LoRA-on "
+                        "predictions, loss, backward, optimizer"},
             "peak_memory_bytes": int(peak_mem),
             "clocks": clocks,
         }

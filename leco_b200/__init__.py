@@ -6,8 +6,9 @@ train_lora.py loop body).  There is no CPU or PyTorch fallback: without the buil
 (`python -m leco_b200.build`) and a CUDA device the compute entry points raise.
 """
 from .unet import SPECS, EngineUNet, UNetSpec  # noqa: F401
-from .lora import LoRANetwork, LoRAModule, FlatAdamW  # noqa: F401
-from .scheduler import DDIMScheduler, create_noise_scheduler  # noqa: F401
+from .lora import LoRANetwork, LoRAModule, FlatAdamW, FlatOptimizer  # noqa: F401
+from .scheduler import (DDIMScheduler, DDPMScheduler, EulerAncestralDiscreteScheduler, LMSDiscreteScheduler,  # noqa: F401
+                        create_noise_scheduler)
 
-__all__ = ["SPECS", "EngineUNet", "UNetSpec", "LoRANetwork", "LoRAModule", "FlatAdamW", "DDIMScheduler",
-           "create_noise_scheduler"]
+__all__ = ["SPECS", "EngineUNet", "UNetSpec", "LoRANetwork", "LoRAModule", "FlatAdamW", "FlatOptimizer", "DDIMScheduler",
+           "DDPMScheduler", "LMSDiscreteScheduler", "EulerAncestralDiscreteScheduler", "create_noise_scheduler"]

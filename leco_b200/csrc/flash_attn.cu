@@ -239,22 +239,31 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
       const uint32_t s_addr = tmem_s + lane_off + sb * FA_BN;
       // pass 1: row max over the 128 scores (32 at a time: the scores are re-read in pass 2 instead of living in
       // 128 registers; TMEM reads are cheap, 4 KB per warp-load at ~43 cycles)
-      float mx = -INFINITY;
+      // (four independent running maxima: a single one is a 128-long dependent FMNMX chain = ~500 cycles of pure
+      // latency per tile for a warp that shares its scheduler with just one other softmax warp)
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t sv[32];
         tmem_ld_32x32b_x32(s_addr + c * 32, sv);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float a = __uint_as_float(sv[i]);
+        for (int i = 0; i < 32; i += 4) {
+          float a0 = __uint_as_float(sv[i]), a1 = __uint_as_float(sv[i + 1]), a2 = __uint_as_float(sv[i + 2]),
+                a3 = __uint_as_float(sv[i + 3]);
           if constexpr (ragged) {
-            if (kv0 + c * 32 + i >= p.skv) a = -INFINITY;
+            if (kv0 + c * 32 + i >= p.skv) a0 = -INFINITY;
+            if (kv0 + c * 32 + i + 1 >= p.skv) a1 = -INFINITY;
+            if (kv0 + c * 32 + i + 2 >= p.skv) a2 = -INFINITY;
+            if (kv0 + c * 32 + i + 3 >= p.skv) a3 = -INFINITY;
           }
-          mx = fmaxf(mx, a);
+          mx0 = fmaxf(mx0, a0);
+          mx1 = fmaxf(mx1, a1);
+          mx2 = fmaxf(mx2, a2);
+          mx3 = fmaxf(mx3, a3);
         }
       }
-      const float m_new = fmaxf(m_run, mx);
+      const float m_new = fmaxf(fmaxf(m_run, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
       const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);  // first tile: ex2(-inf) = 0
       const float mb = m_new * p.scale_log2;
       // pass 2: p = 2^(s*c - m*c) -> bf16 -> swizzled A-operand tile (two 64-key chunks of [128 rows x 128 B])

@@ -4,6 +4,8 @@
 //   LayerNorm: one warp per row, row held in registers, exact two-pass variance.
 // Statistics are fp32; gamma/beta are frozen (no parameter gradients are ever needed:
 // LECO trains only the LoRA matrices, train_lora.py:69).
+#include <stdlib.h>
+
 #include "../../include/leco_b200.h"
 #include "common.cuh"
 
@@ -26,7 +28,7 @@ __device__ __forceinline__ float dsilu_f(float y) {
 }
 
 constexpr int GN_MAX_GROUPS = 64;
-constexpr int GN_MAX_SPLITS = 64;
+constexpr int GN_MAX_SPLITS = 128;
 
 // ---- pass 1 (forward): partial[n][split][g] = (sum x, sum x^2)
 // blockDim.x = vpp * R (vpp = C/8 vector columns, R row lanes); each thread owns one vector column.
@@ -575,8 +577,13 @@ static int gn_launch_cfg(int hw, int C, int* vpp, int* threads, int* splits) {
   int R = 256 / *vpp;
   if (R < 1) R = 1;
   *threads = *vpp * R;
-  int s = hw / 16;   // >= 16 pixel rows per block; many small blocks keep enough loads in flight
+  // >= `rows` pixel rows per block; many small blocks keep enough loads in flight.  LECO_GN_ROWS / LECO_GN_SPLITS
+  // override the defaults (tuning hooks of tests/gpu_checks/kernel_cases.py::case_norm_perf)
+  static const int env_rows = [] { const char* e = getenv("LECO_GN_ROWS"); return e ? atoi(e) : 16; }();
+  static const int env_max = [] { const char* e = getenv("LECO_GN_SPLITS"); return e ? atoi(e) : 64; }();
+  int s = hw / (env_rows > 0 ? env_rows : 16);
   if (s < 1) s = 1;
+  if (s > env_max) s = env_max;
   if (s > GN_MAX_SPLITS) s = GN_MAX_SPLITS;
   *splits = s;
   return 0;
@@ -605,8 +612,10 @@ extern "C" int leco_group_norm(const void* x, void* y, void* stats /*float2[n*G]
   LECO_CHECK_CUDA(cudaGetLastError());
   // pass 2: ~8 blocks per SM over the whole batch, but at least 4 pixel rows per thread so the prologue amortises
   const int R = threads / vpp;
-  int gy = (8 * 148) / (n < 1 ? 1 : n);
-  if (gy > hw / (4 * R)) gy = hw / (4 * R);
+  static const int env_bpsm = [] { const char* e = getenv("LECO_GN_APPLY_BPSM"); return e ? atoi(e) : 8; }();
+  static const int env_rpt = [] { const char* e = getenv("LECO_GN_APPLY_RPT"); return e ? atoi(e) : 4; }();
+  int gy = (env_bpsm * 148) / (n < 1 ? 1 : n);
+  if (gy > hw / (env_rpt * R)) gy = hw / (env_rpt * R);
   if (gy < 1) gy = 1;
   count_launch();
   LECO_LAUNCH(gn_apply_kernel, dim3(n, gy), threads, 0, STREAM(stream), BF(x), BFW(y), reinterpret_cast<const float2*>(workspace),

@@ -120,6 +120,8 @@ class LecoTrainer:
         self.scaled_input = float(scheduler.init_noise_sigma) != 1.0      # sigma schedulers scale the UNet input
         self._pool = None           # one CUDA-graph memory pool shared by every captured shape (dynamic_resolution)
         self._ar_events = []        # (start, end) CUDA events around the data-parallel all-reduce
+        self.profile_phases = False  # record CUDA events at the phase boundaries of iteration() (bench.py)
+        self._phase_events = []
         self.act_dtype = unet._act_dtype
         self.xl = bool(unet.spec.text_time)
         for p in self.pairs:
@@ -310,6 +312,9 @@ class LecoTrainer:
         host draw + H2D copy of the latent noise (inputs already resident in HBM)."""
         sched = self.scheduler
         launches0 = capi.launch_count()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if self.profile_phases else None
+        if ev:
+            ev[0].record()
         self.network.flat.refresh_transposed()       # ad^T / bup^T for the backward GEMMs (one launch)
         tbl_t, tbl_coef = self._tables or self._sched_tables()
         sched.set_timesteps(self.max_steps)
@@ -363,6 +368,8 @@ class LecoTrainer:
         if dg.graph is None:
             self.network.__exit__(None, None, None)
 
+        if ev:
+            ev[1].record()
         # ---- tail at t* = timesteps_1000[int(k*1000/max)] = 999 - int(k*1000/max)
         t_star = float(999 - int(k * 1000 / self.max_steps))
         distinct: List[torch.Tensor] = []
@@ -409,10 +416,24 @@ class LecoTrainer:
         if step_optimizer:
             self.optimizer.step(grad_scale=1.0 / self.world)
             self.lr_scheduler.step()                          # train_lora.py:281
+        if ev:
+            ev[2].record()
+            self._phase_events = (self._phase_events + [(k, ev)])[-64:]
         self.launches += capi.launch_count() - launches0     # eager launches (graph replays were added above)
         self.last = {"k": k, "timestep": t_star, "denoised": st["x"], "pair": pair, "target": ts["eps_t"],
                      "lr": self.optimizer.lr}
         return loss
+
+    def phase_ms(self):
+        """Mean device ms of (the k-step denoise loop, everything after it: 4 predictions, loss, backward, optimizer)
+        and the mean k over the recorded iterations (profile_phases=True)."""
+        if not self._phase_events:
+            return None
+        torch.cuda.synchronize()
+        n = len(self._phase_events)
+        den = sum(e[0].elapsed_time(e[1]) for _, e in self._phase_events) / n
+        tail = sum(e[1].elapsed_time(e[2]) for _, e in self._phase_events) / n
+        return {"denoise_loop_ms": den, "tail_ms": tail, "mean_k": sum(k for k, _ in self._phase_events) / n}
 
     def allreduce_ms(self) -> Optional[float]:
         """Mean device time of the data-parallel all-reduce over the last iterations (None on one rank)."""

@@ -68,6 +68,59 @@ def case_norms():
     return _merge(res)
 
 
+def case_norm_perf():
+    """Perf triage (not a parity case): GroupNorm / LayerNorm at the SD2.1 denoise-forward shapes (4 samples), timed in a
+    CUDA graph of 20 back-to-back launches (warm L2, like the real forward), vs the HBM roofline of 3 passes x 2 B."""
+    import torch
+    from leco_b200 import ops
+    res = {"ok": True}
+    for (n, hw, c, silu) in ((4, 4096, 320, True), (4, 4096, 640, True), (4, 4096, 960, True), (4, 1024, 640, True),
+                             (4, 1024, 1280, True), (4, 1024, 1920, True), (4, 256, 1280, True), (4, 256, 2560, True),
+                             (4, 64, 1280, True)):
+        x = _rand((n * hw, c), seed=1)
+        gm, bt = _rand((c,), 0.2, 2) + 1.0, _rand((c,), 0.2, 3)
+        for _ in range(3):
+            ops.group_norm(x, n, hw, gm, bt, 32, 1e-5, silu)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(20):
+                ops.group_norm(x, n, hw, gm, bt, 32, 1e-5, silu)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 100 * 1e3
+        res[f"gn_{hw}_{c}_us"] = round(us, 2)
+        res[f"gn_{hw}_{c}_gbs"] = round(3 * 2 * n * hw * c / us / 1e3, 1)
+    for (m, c) in ((16384, 320), (4096, 640), (1024, 1280)):
+        x = _rand((m, c), seed=5)
+        gm, bt = _rand((c,), 0.2, 6) + 1.0, _rand((c,), 0.2, 7)
+        for _ in range(3):
+            ops.layer_norm(x, gm, bt, 1e-5, False)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(20):
+                ops.layer_norm(x, gm, bt, 1e-5, False)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 100 * 1e3
+        res[f"ln_{m}_{c}_us"] = round(us, 2)
+        res[f"ln_{m}_{c}_gbs"] = round(2 * 2 * m * c / us / 1e3, 1)
+    return res
+
+
 def case_elementwise():
     import torch
     from leco_b200 import ops
@@ -594,6 +647,7 @@ CASES = [
     ("engine_grads_c3lier_tiny15", case_engine_grads, dict(arch="tiny15", mode="c3lier")),
     ("engine_grads_rank32_tiny21", case_engine_grads, dict(arch="tiny21", mode="rank32")),
     ("engine_fwd_sd21_64", case_engine_forward, dict(arch="sd21", n=2, hw=64, time_it=True)),
+    ("perf_norms", case_norm_perf, {}),
 ]
 
 

@@ -17,7 +17,7 @@ def _bf16_yardstick(name, fn):
     return fn(device="cuda", dtype=torch.bfloat16)
 
 GEMM = [(n, f, kw) for n, f, kw in gemm_cases.CASES if not n.startswith(("perf_", "perfauto_"))]
-KERN = [(n, f, kw) for n, f, kw in kernel_cases.CASES if n != "engine_fwd_sd21_64"]
+KERN = [(n, f, kw) for n, f, kw in kernel_cases.CASES if n != "engine_fwd_sd21_64" and not n.startswith("perf_")]
 
 
 @pytest.mark.parametrize("name,fn,kw", GEMM, ids=[c[0] for c in GEMM])
@@ -154,13 +154,18 @@ def test_leco_iteration_stochastic_schedulers_run(name):
     and two identically seeded runs agree (device RNG included)."""
     import torch
     from __graft_entry__ import engine_trainer
+    from leco_b200 import ops
     vals = []
-    for _ in range(2):
-        trainer, net = engine_trainer(use_graphs=True, scheduler=name)
-        torch.manual_seed(7)
-        vals.append([trainer.iteration().item() for _ in range(2)])
+    ops.set_deterministic(True)      # ordered reductions: with the device RNG seeded alike the two runs must be bit-equal
+    try:
+        for _ in range(2):
+            trainer, net = engine_trainer(use_graphs=True, scheduler=name)
+            torch.manual_seed(7)
+            vals.append([trainer.iteration().item() for _ in range(2)])
+    finally:
+        ops.set_deterministic(False)
     assert all(v == v and v < 1e3 for v in vals[0]), vals
-    assert all(abs(a - b) <= 2e-2 * abs(a) for a, b in zip(*vals)), vals
+    assert vals[0] == vals[1], vals
 
 
 def test_leco_iteration_dynamic_resolution_matches_oracle():
