@@ -153,6 +153,10 @@ int leco_group_norm(const void* x, void* y, void* stats, const void* gamma, cons
 /* single-launch forward (statistics + normalise behind a per-sample grid barrier).  `barriers` is a PERSISTENT caller-owned
  * buffer of leco_group_norm_barrier_bytes(n) bytes that was zero when first used and is never written by anyone else. */
 int64_t leco_group_norm_barrier_bytes(int n);
+/* leco_group_norm_v2: two launches; the statistics kernel's last block per sample folds the partial sums (fixed order) and
+ * writes mean / rstd, the normalise kernel only reads them.  `counters`: persistent buffer as above (4 bytes per sample). */
+int leco_group_norm_v2(const void* x, void* y, void* stats, const void* gamma, const void* beta, int n, int hw, int C, int G,
+                       float eps, int silu, void* workspace, void* counters, void* stream);
 int leco_group_norm_fused(const void* x, void* y, void* stats, const void* gamma, const void* beta, int n, int hw, int C,
                           int G, float eps, int silu, void* workspace, void* barriers, void* stream);
 int leco_group_norm_bwd(const void* x, const void* dz, void* dx, const void* stats, const void* gamma,

@@ -378,6 +378,157 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
   }
 }
 
+// ---- forward v2: statistics kernel that FINISHES the statistics (the last block of a sample to arrive folds the
+// per-split partials in a fixed order and writes mean / rstd), so the normalise kernel starts with 2 x G floats instead
+// of re-folding splits x G partials in every one of its ~700 blocks (ncu: that prologue was most of its 18 us).
+// counters: persistent zero-initialised unsigned int per sample (self-resetting).
+__global__ void gn_stats_v2_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ partial,
+                                   float2* __restrict__ stats, unsigned int* __restrict__ counters, int hw, int C,
+                                   int G, int vpp, int splits, float eps) {
+  pdl_entry();
+  extern __shared__ float gn_red[];
+  __shared__ float facc[GN_MAX_GROUPS][2];
+  __shared__ unsigned int s_ticket;
+  const int n = blockIdx.x, sp = blockIdx.y;
+  const int R = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp, rl = threadIdx.x / vpp;
+  const int rows_per = (hw + splits - 1) / splits;
+  const int r0 = sp * rows_per, r1 = min(hw, r0 + rows_per);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (rl < R) {
+    const __nv_bfloat16* base = x + ((size_t)n * hw) * C + v * 8;
+    int r = r0 + rl;
+    for (; r + 7 * R < r1; r += 8 * R) {  // eight independent 16-byte loads in flight per thread
+      v8 q[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) q[u] = *reinterpret_cast<const v8*>(base + (size_t)(r + u * R) * C);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float f[8];
+        up8(q[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += f[j];
+          s2[j] = fmaf(f[j], f[j], s2[j]);
+        }
+      }
+    }
+    for (; r + R < r1; r += 2 * R) {
+      const v8 qa = *reinterpret_cast<const v8*>(base + (size_t)r * C);
+      const v8 qb = *reinterpret_cast<const v8*>(base + (size_t)(r + R) * C);
+      float f[8], g[8];
+      up8(qa, f);
+      up8(qb, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += f[j] + g[j];
+        s2[j] = fmaf(f[j], f[j], fmaf(g[j], g[j], s2[j]));
+      }
+    }
+    for (; r < r1; r += R) {
+      float f[8];
+      up8(*reinterpret_cast<const v8*>(base + (size_t)r * C), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += f[j];
+        s2[j] = fmaf(f[j], f[j], s2[j]);
+      }
+    }
+  }
+  gn_block_group_sums(gn_red, s1, s2, v, rl, R, C, G, partial + ((size_t)n * splits + sp) * G);
+  // ---- the last block of this sample finishes the statistics
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&counters[n], 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)splits - 1u) return;
+  __threadfence();
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;   // FULL warps only
+    for (int g = (warp < nwarps ? warp : G); g < G; g += nwarps) {
+      float a = 0.f, b = 0.f;
+      for (int q = lane; q < splits; q += 32) {
+        const float2 pp = __ldcg(&partial[((size_t)n * splits + q) * G + g]);
+        a += pp.x;
+        b += pp.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (lane == 0) {
+        facc[g][0] = a;
+        facc[g][1] = b;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const float cnt = (float)hw * (float)(C / G);
+    const float mean = facc[threadIdx.x][0] / cnt;
+    const float var = fmaxf(facc[threadIdx.x][1] / cnt - mean * mean, 0.f);
+    stats[(size_t)n * G + threadIdx.x] = make_float2(mean, rsqrtf(var + eps));
+  }
+  if (threadIdx.x == 0) counters[n] = 0;   // ready for the next launch (stream-ordered)
+}
+
+__global__ void gn_apply_v2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                   const float2* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
+                                   const __nv_bfloat16* __restrict__ beta, int hw, int C, int G, int silu, int vpp) {
+  pdl_entry();
+  const int n = blockIdx.x;
+  const int cpg = C / G;
+  const int R = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp, rl = threadIdx.x / vpp;
+  if (rl >= R) return;
+  float sc[8], sh[8];
+  {
+    float gm[8], bt[8];
+    up8(__ldg(reinterpret_cast<const v8*>(gamma + v * 8)), gm);
+    up8(__ldg(reinterpret_cast<const v8*>(beta + v * 8)), bt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 m = __ldg(&stats[(size_t)n * G + (v * 8 + j) / cpg]);
+      sc[j] = m.y * gm[j];
+      sh[j] = fmaf(-m.x, sc[j], bt[j]);
+    }
+  }
+  const int rows_per = (hw + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(hw, r0 + rows_per);
+  const __nv_bfloat16* xb = x + ((size_t)n * hw) * C + v * 8;
+  __nv_bfloat16* yb = y + ((size_t)n * hw) * C + v * 8;
+  int r = r0 + rl;
+  for (; r + 3 * R < r1; r += 4 * R) {  // four independent 16-byte loads in flight
+    v8 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const v8*>(xb + (size_t)(r + u * R) * C);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      up8(q[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[j] = fmaf(f[j], sc[j], sh[j]);
+        if (silu) f[j] = silu_fast(f[j]);
+      }
+      *reinterpret_cast<v8*>(yb + (size_t)(r + u * R) * C) = pk8(f);
+    }
+  }
+  for (; r < r1; r += R) {
+    float f[8];
+    up8(*reinterpret_cast<const v8*>(xb + (size_t)r * C), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (silu) f[j] = silu_fast(f[j]);
+    }
+    *reinterpret_cast<v8*>(yb + (size_t)r * C) = pk8(f);
+  }
+}
+
 // ---- backward pass 1: partial[n][split][g] = (sum g, sum g*xhat) with g = dy*gamma (dy through SiLU')
 __global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
                                     const float2* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
@@ -469,49 +620,59 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
 // ---------------------------------------------------------------- LayerNorm
 constexpr int LN_MAX_VEC = 8;  // per lane -> C <= 2048
 
-__global__ void ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                              float2* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
-                              const __nv_bfloat16* __restrict__ beta, long long M, int C, float eps) {
+// LayerNorm forward.  A row is handled by a GROUP of G lanes (G = 8 / 16 / 32, chosen so that a lane holds at most VPL
+// 8-channel vectors), i.e. 32/G rows per warp: all of a lane's loads are issued before the first use (VPL x 16 B in
+// flight per lane), the register footprint is VPL*8 floats (high occupancy), and no lane idles on narrow rows (C = 320
+// is 40 vectors: a full-warp-per-row mapping leaves 24 lanes empty in its second round).  Exact two-pass variance.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, float2* __restrict__ stats,
+              const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta, long long M, int C,
+              float eps, int G) {
   pdl_entry();
   const int lane = threadIdx.x & 31;
+  const int sub = lane % G, grp = lane / G, rpw = 32 / G;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int vpr = C / 8;
-  for (long long r = warp; r < M; r += nwarps) {
-    float f[LN_MAX_VEC][8];
+  const float inv_c = 1.0f / (float)C;
+  for (long long r0 = warp * rpw; r0 < M; r0 += nwarps * rpw) {
+    const long long r = r0 + grp;
+    const bool row_ok = r < M;
+    v8 q[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = sub + G * i;
+      q[i] = (row_ok && v < vpr) ? *reinterpret_cast<const v8*>(x + r * C + v * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    float f[VPL][8];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
-      const int v = lane + 32 * i;
-      if (v < vpr) {
-        up8(*reinterpret_cast<const v8*>(x + r * C + v * 8), f[i]);
+    for (int i = 0; i < VPL; ++i) {
+      up8(q[i], f[i]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += f[i][j];
-      }
+      for (int j = 0; j < 8; ++j) s += f[i][j];
     }
+    for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_c;
+    float qq = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / (float)C;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
-      const int v = lane + 32 * i;
-      if (v < vpr) {
+    for (int i = 0; i < VPL; ++i) {
+      if (sub + G * i < vpr) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float d = f[i][j] - mean;
-          q = fmaf(d, d, q);
+          qq = fmaf(d, d, qq);
         }
       }
     }
+    for (int o = G >> 1; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    const float rstd = rsqrtf(qq * inv_c + eps);
+    if (sub == 0 && stats && row_ok) stats[r] = make_float2(mean, rstd);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q / (float)C + eps);
-    if (lane == 0 && stats) stats[r] = make_float2(mean, rstd);
-#pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
-      const int v = lane + 32 * i;
-      if (v < vpr) {
+    for (int i = 0; i < VPL; ++i) {
+      const int v = sub + G * i;
+      if (row_ok && v < vpr) {
         float gm[8], bt[8], o[8];
         up8(__ldg(reinterpret_cast<const v8*>(gamma + v * 8)), gm);
         up8(__ldg(reinterpret_cast<const v8*>(beta + v * 8)), bt);
@@ -655,6 +816,32 @@ extern "C" int leco_group_norm_fused(const void* x, void* y, void* stats, const 
   return 0;
 }
 
+// Two-launch forward with the statistics finished by the statistics kernel (see gn_stats_v2_kernel).
+// counters: PERSISTENT caller-owned buffer of >= n * 4 bytes, zero when first used.
+extern "C" int leco_group_norm_v2(const void* x, void* y, void* stats, const void* gamma, const void* beta, int n, int hw,
+                                  int C, int G, float eps, int silu, void* workspace, void* counters, void* stream) {
+  LECO_REQUIRE(x && y && stats && gamma && beta && workspace && counters, "leco_group_norm_v2: null pointer");
+  LECO_REQUIRE(C % 8 == 0 && G > 0 && G <= GN_MAX_GROUPS && C % G == 0, "leco_group_norm_v2: C=%d G=%d unsupported", C, G);
+  int vpp, threads, splits;
+  LECO_REQUIRE(gn_launch_cfg(hw, C, &vpp, &threads, &splits) == 0, "leco_group_norm_v2: C=%d too wide", C);
+  const int R = threads / vpp;
+  count_launch();
+  LECO_LAUNCH(gn_stats_v2_kernel, dim3(n, splits), threads, (size_t)2 * R * C * sizeof(float), STREAM(stream), BF(x),
+              reinterpret_cast<float2*>(workspace), reinterpret_cast<float2*>(stats),
+              reinterpret_cast<unsigned int*>(counters), hw, C, G, vpp, splits, eps);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  static const int env_bpsm = [] { const char* e = getenv("LECO_GN_APPLY_BPSM"); return e ? atoi(e) : 8; }();
+  static const int env_rpt = [] { const char* e = getenv("LECO_GN_APPLY_RPT"); return e ? atoi(e) : 4; }();
+  int gy = (env_bpsm * 148) / (n < 1 ? 1 : n);
+  if (gy > hw / (env_rpt * R)) gy = hw / (env_rpt * R);
+  if (gy < 1) gy = 1;
+  count_launch();
+  LECO_LAUNCH(gn_apply_v2_kernel, dim3(n, gy), threads, 0, STREAM(stream), BF(x), BFW(y),
+              reinterpret_cast<const float2*>(stats), BF(gamma), BF(beta), hw, C, G, silu, vpp);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int leco_group_norm_bwd(const void* x, const void* dz, void* dx, const void* stats, const void* gamma,
                                    const void* beta, int n, int hw, int C, int G, int silu, void* workspace,
                                    void* stream) {
@@ -683,11 +870,22 @@ extern "C" int leco_layer_norm(const void* x, void* y, void* stats /*float2[M] o
                                const void* beta, int64_t M, int C, float eps, void* stream) {
   LECO_REQUIRE(x && y && gamma && beta, "leco_layer_norm: null pointer");
   LECO_REQUIRE(C % 8 == 0 && C <= 8 * 32 * LN_MAX_VEC, "leco_layer_norm: C=%d unsupported", C);
-  long long blocks = (M + 7) / 8;
+  const int vpr = C / 8;
+  // lanes per row: the smallest of 8 / 16 / 32 that keeps a lane at <= 5 vectors (else 32 lanes with up to 8)
+  int G = 8;
+  while (G < 32 && (vpr + G - 1) / G > 5) G *= 2;
+  const int vpl = (vpr + G - 1) / G;
+  const int rpw = 32 / G;
+  long long warps = (M + rpw - 1) / rpw;
+  long long blocks = (warps + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
   count_launch();
-  LECO_LAUNCH(ln_fwd_kernel, (int)blocks, 256, 0, STREAM(stream), BF(x), BFW(y), reinterpret_cast<float2*>(stats), BF(gamma),
-                                                       BF(beta), M, C, eps);
+  if (vpl <= 5)
+    LECO_LAUNCH((ln_fwd_kernel<5>), (int)blocks, 256, 0, STREAM(stream), BF(x), BFW(y), reinterpret_cast<float2*>(stats),
+                BF(gamma), BF(beta), (long long)M, C, eps, G);
+  else
+    LECO_LAUNCH((ln_fwd_kernel<LN_MAX_VEC>), (int)blocks, 256, 0, STREAM(stream), BF(x), BFW(y),
+                reinterpret_cast<float2*>(stats), BF(gamma), BF(beta), (long long)M, C, eps, G);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -606,7 +606,7 @@ class EngineUNet(nn.Module):
             if self.fused_lora and not big:   # T = s*m x A^T is formed inside the GEMM kernel (extra accumulator columns)
                 kw.update(fl_ad=ad, fl_bup=bup, fl_scale=sm, fl_rank=sum(pk.site.ranks))
                 if need_grad:
-                    T = be.zeros((x.t.shape[0], ad.shape[0]), x.t)
+                    T = be.empty((x.t.shape[0], ad.shape[0]), x.t)      # every row is written by the kernel (fl_t_out)
                     kw["fl_t_out"] = T
             else:
                 T = be.gemm(x.t, ad, alpha=sm)                  # T = s*m * x A^T   [M, Kl]
@@ -640,7 +640,7 @@ class EngineUNet(nn.Module):
                     adT, bupT = pk.site.transposed(be)               # [K, Kl], [Kl, N]
                     if self.fused_lora and x.rg and not big:
                         # one kernel: dT = s*m dY B (saved) and dx = dY W + dT A
-                        dT = be.zeros((gy.shape[0], bupT.shape[0]), gy)
+                        dT = be.empty((gy.shape[0], bupT.shape[0]), gy)
                         kw2.update(fl_ad=bupT, fl_bup=adT, fl_scale=sm, fl_rank=sum(pk.site.ranks), fl_t_out=dT)
                     else:
                         dT = be.gemm(gy, bupT, alpha=sm)             # s*m * dY B      [M, Kl]
@@ -677,7 +677,7 @@ class EngineUNet(nn.Module):
             if self.fused_lora and not big:
                 kw.update(fl_ad=ad, fl_bup=bup, fl_scale=sm, fl_rank=sum(pk.site.ranks))
                 if tape is not None:
-                    T = be.zeros((x.t.shape[0], ad.shape[0]), x.t)
+                    T = be.empty((x.t.shape[0], ad.shape[0]), x.t)      # every row is written by the kernel (fl_t_out)
                     kw["fl_t_out"] = T
             else:
                 T = be.gemm(x.t, ad, alpha=sm, conv_nhw=(n, h, w))       # [M, Kl]

@@ -260,6 +260,10 @@ def empty_like(x):
     return torch.zeros_like(x)
 
 
+def empty(shape, like, dtype=None):
+    return torch.zeros(shape, device=like.device, dtype=dtype or like.dtype)
+
+
 def zeros(shape, like, dtype=None):
     return torch.zeros(shape, device=like.device, dtype=dtype or like.dtype)
 
