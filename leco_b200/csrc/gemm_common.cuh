@@ -36,6 +36,9 @@ struct GemmParams {
   int k_splits;
   float* ws;
   long long ldws;
+  // split-K without a finalize launch: per-output-tile arrival counters (persistent, zero, self-resetting); the LAST
+  // K-slice CTA to arrive reads the summed tile back, applies the epilogue and re-zeroes the workspace tile
+  unsigned int* sk_counters;
   // in-kernel LoRA (lora.py:102-106 in ONE kernel): the stacked lora_down rows `Ad` ride along as fl_kl extra
   // B rows, so accumulator columns [BN, BN+fl_kl) hold T_raw = x.Ad^T; the epilogue adds fl_scale*T_raw.Bup^T
   // epilogue output through TMA (tm_d: D as {N, M, batch0, batch1}, box 32 x 32, 64-byte swizzle): each epilogue warp stages
@@ -227,7 +230,7 @@ __device__ __forceinline__ void gemm_fl_stage_t(const GemmParams& p, uint32_t tr
 // `trow` = TMEM address of the row's first accumulator column; (mt, nt, b0, b1) identify the tile.
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t trow, int r, int mt, int nt, int b0,
-                                                   int b1, uint8_t* slab) {
+                                                   int b1, uint8_t* slab, uint32_t* sk_ticket = nullptr) {
   const bool geglu = (p.epilogue == 1);
   const int n0 = nt * BN;
   long long m;
@@ -259,6 +262,52 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4), "f"(v[g * 4 + 0]),
                          "f"(v[g * 4 + 1]), "f"(v[g * 4 + 2]), "f"(v[g * 4 + 3])
                          : "memory");
+        }
+      }
+    }
+    if (p.sk_counters) {
+      // ---- in-kernel finalize: the four epilogue warps of this CTA meet, one thread takes a ticket for the output
+      // tile; the CTA holding the last ticket sees every K-slice's contribution (fence / atomic / fence) and finishes
+      __threadfence();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (r == 0) *sk_ticket = atomicAdd(&p.sk_counters[nt * p.tiles_m + mt], 1u);
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      const bool last = *sk_ticket == (unsigned)p.k_splits - 1u;
+      asm volatile("bar.sync 2, 128;" ::: "memory");   // everyone has read the ticket before it can be rewritten
+      if (last) {
+        __threadfence();
+        if (r == 0) p.sk_counters[nt * p.tiles_m + mt] = 0;
+        const __nv_bfloat16* rb_row = p.rowbias ? p.rowbias + (m / p.rows_per_group) * p.ld_rowbias : nullptr;
+        const __nv_bfloat16* res_row = p.residual ? p.residual + m * p.ldr : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          const int nvalid = p.N - col0;
+          const bool ok = row_ok && nvalid > 0;
+          float v[32];
+          if (ok) {
+            float* src = p.ws + m * p.ldws + col0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (g * 4 < nvalid) {
+                q4 = __ldcg(reinterpret_cast<const float4*>(src + g * 4));
+                __stcg(reinterpret_cast<float4*>(src + g * 4), make_float4(0.f, 0.f, 0.f, 0.f));   // leave it zeroed
+              }
+              v[g * 4 + 0] = q4.x;
+              v[g * 4 + 1] = q4.y;
+              v[g * 4 + 2] = q4.z;
+              v[g * 4 + 3] = q4.w;
+            }
+            if (p.bias) epi_add_bf16(v, p.bias + col0, nvalid);
+            if (rb_row) epi_add_bf16(v, rb_row + col0, nvalid);
+            if (res_row) epi_add_bf16(v, res_row + col0, nvalid);
+          }
+          if (tma_out) {
+            if (nvalid > 0) epi_store_tma(p, slab, lane, v, col0, m_warp, b0, b1);
+          } else if (ok) {
+            epi_store_bf16(reinterpret_cast<__nv_bfloat16*>(p.d) + m * p.ldd + col0, v, nvalid);
+          }
         }
       }
     }

@@ -356,7 +356,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         mbar_wait(&acc2_full[as], aphase);           // accumulator now holds x.W^T + T.Bup^T
         tc_fence_after();
       }
-      if (p.dbg != 3) gemm_epilogue_tile<BN>(p, trow, r, mt, nt, b0, b1, smem_epi + q * EPI_SLAB_BYTES);  // dbg 3: no epilogue
+      if (p.dbg != 3) gemm_epilogue_tile<BN>(p, trow, r, mt, nt, b0, b1, smem_epi + q * EPI_SLAB_BYTES, tmem_slot + 1);  // dbg 3: no epilogue
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -607,7 +607,13 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
   // whole image rows that tile the image exactly), no split-K
   static const bool tma_store_enabled = [] { const char* e = getenv("LECO_TMA_STORE"); return !(e && e[0] == '0'); }();
   const bool rows_contig = a->mode == 0 || (p.rows_per_tile == BLOCK_M && (p.nb > 1 || a->ch % p.hb == 0));
-  if (tma_store_enabled && !a->out_fp32 && rows_contig && k_split <= 1 && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0 &&
+  // split-K finalize inside the GEMM (last-arriving K-slice CTA): needs the arrival counters that live in the last
+  // 64 KiB of the caller's workspace
+  static const bool sk_fused = [] { const char* e = getenv("LECO_SPLITK_FUSED"); return !(e && e[0] == '0'); }();
+  constexpr long long SK_COUNTER_BYTES = 65536;
+  const bool sk_inkernel = sk_fused && k_split > 1 && (long long)p.tiles_m * ((a->N + bn - 1) / bn) <= SK_COUNTER_BYTES / 4 &&
+                           (long long)a->M * a->N * 4 <= a->splitk_ws_bytes - SK_COUNTER_BYTES;
+  if (tma_store_enabled && !a->out_fp32 && rows_contig && (k_split <= 1 || sk_inkernel) && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0 &&
       (batch0 == 1 || a->d_bs0 % 8 == 0) && (batch1 == 1 || a->d_bs1 % 8 == 0)) {
     const int n_out = a->epilogue == 1 ? a->N / 2 : a->N;
     const uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)a->M, (uint64_t)batch0, (uint64_t)batch1};
@@ -626,6 +632,8 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
     p.ws = reinterpret_cast<float*>(a->splitk_ws);
     p.ldws = a->N;
     total_tiles *= k_split;
+    if (sk_inkernel)
+      p.sk_counters = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(a->splitk_ws) + a->splitk_ws_bytes - SK_COUNTER_BYTES);
   }
   const int grid = (int)(total_tiles < nsm ? total_tiles : nsm);
   count_launch();
@@ -644,6 +652,6 @@ extern "C" int leco_gemm_bf16(const leco_gemm_args* a, void* stream_) {
       default: rc = launch_gemm<256, false>(p, grid, stream); break;
     }
   }
-  if (rc == 0 && p.k_splits > 1) rc = launch_splitk_finalize(p, stream);
+  if (rc == 0 && p.k_splits > 1 && !p.sk_counters) rc = launch_splitk_finalize(p, stream);
   return rc;
 }

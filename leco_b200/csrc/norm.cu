@@ -740,9 +740,9 @@ static int gn_launch_cfg(int hw, int C, int* vpp, int* threads, int* splits) {
   *threads = *vpp * R;
   // >= `rows` pixel rows per block; many small blocks keep enough loads in flight.  LECO_GN_ROWS / LECO_GN_SPLITS
   // override the defaults (tuning hooks of tests/gpu_checks/kernel_cases.py::case_norm_perf)
-  static const int env_rows = [] { const char* e = getenv("LECO_GN_ROWS"); return e ? atoi(e) : 16; }();
+  static const int env_rows = [] { const char* e = getenv("LECO_GN_ROWS"); return e ? atoi(e) : 32; }();
   static const int env_max = [] { const char* e = getenv("LECO_GN_SPLITS"); return e ? atoi(e) : 64; }();
-  int s = hw / (env_rows > 0 ? env_rows : 16);
+  int s = hw / (env_rows > 0 ? env_rows : 32);
   if (s < 1) s = 1;
   if (s > env_max) s = env_max;
   if (s > GN_MAX_SPLITS) s = GN_MAX_SPLITS;

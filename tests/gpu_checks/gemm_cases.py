@@ -358,6 +358,11 @@ CASES = [
     ("conv_24x40_rect", case_conv, dict(n=1, h=24, w=40, cin=64, cout=64)),
     ("conv_lora16", case_conv, dict(n=2, h=32, w=32, cin=128, cout=128, lora=16)),
     ("conv_plain", case_conv, dict(n=2, h=32, w=32, cin=64, cout=64, bias=False, rowbias=False, residual=False)),
+    # few-tile long-K problems: split-K with the finalize done by the last-arriving K-slice CTA (no finalize launch)
+    ("splitk_m256_bias_rb_res", case_matrix, dict(M=256, N=1280, K=5120, bias=True, rowbias=64, residual=True)),
+    ("splitk_m308_ragged", case_matrix, dict(M=308, N=1288, K=4096, bias=True, residual=True)),
+    ("splitk_conv_16_1280", case_conv, dict(n=4, h=16, w=16, cin=1280, cout=1280)),
+    ("splitk_conv_8_1280", case_conv, dict(n=4, h=8, w=8, cin=1280, cout=1280)),
     ("triage_mma_rate", case_mma_rate, dict()),
     ("triage_fl_perf", case_fl_perf, dict()),
     ("triage_shape_modes", case_shape_modes, dict()),
