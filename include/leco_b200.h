@@ -94,6 +94,9 @@ int leco_conv_in(const void* x, int x_is_fp32, const void* w, const void* bias, 
                  int cout, void* stream);
 int leco_conv_out(const void* x, const void* w, const void* bias, float* y, int n, int h, int w_, int c, int cout,
                   void* stream);
+/* conv_out as a tensor-core conv: leco_gemm_bf16 (mode 1, weights padded to N = 8, fp32 out) followed by this
+ * [n*hw][ld] fp32 (+ bias) -> NCHW fp32 repack */
+int leco_cols_to_nchw(const float* y8, int ld, const void* bias, float* out, int n, int hw, int cout, void* stream);
 int leco_conv_out_bwd(const float* dy, const void* w, void* dx, int n, int h, int w_, int c, int cout, void* stream);
 
 /* diffusers Timesteps(flip_sin_to_cos=True, freq_shift=0): out[n][dim] = [cos | sin] (bf16) */

@@ -75,6 +75,7 @@ _OPS: list[tuple[str, list]] = [
     ("leco_conv_in", [P, I, P, P, P, I, I, I, I, P]),
     ("leco_conv_out", [P, P, P, P, I, I, I, I, I, P]),
     ("leco_conv_out_bwd", [P, P, P, I, I, I, I, I, P]),
+    ("leco_cols_to_nchw", [P, I, P, P, I, I, I, P]),
     ("leco_timestep_embedding", [P, P, I, I, P]),
     ("leco_silu", [P, P, L, P]),
     ("leco_add_inplace", [P, P, L, P]),

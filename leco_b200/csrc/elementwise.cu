@@ -126,6 +126,25 @@ __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, const __nv_
   }
 }
 
+// [M = n*hw][ld] fp32 GEMM result (first cout columns) + bias -> NCHW fp32 [n][cout][hw]: the tail of conv_out when it
+// runs as a tcgen05 implicit-GEMM conv with N padded to 8
+__global__ void cols_to_nchw_kernel(const float* __restrict__ y8, int ld, const __nv_bfloat16* __restrict__ bias,
+                                    float* __restrict__ out, int n, int hw, int cout) {
+  pdl_entry();
+  const long long total = 1LL * n * hw;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(pix / hw);
+    const int p = (int)(pix - (long long)img * hw);
+    const float4 a = *reinterpret_cast<const float4*>(y8 + pix * ld);
+    const float4 b = *reinterpret_cast<const float4*>(y8 + pix * ld + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+      if (o < cout) out[((long long)img * cout + o) * hw + p] = v[o] + (bias ? __bfloat162float(bias[o]) : 0.f);
+  }
+}
+
 // conv_out backward-data: dy NCHW fp32 [n,cout,h,w] -> dx NHWC bf16 [n*h*w, c]
 // dx[p, ci] = sum_{o,tap} dy[o, p - off(tap)] * w[o][tap][ci]
 __global__ void conv_out_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ w,
@@ -488,6 +507,14 @@ extern "C" int leco_conv_out(const void* x, const void* w, const void* bias, flo
   count_launch();
   LECO_LAUNCH(conv_out_kernel, grid_for(1LL * n * h * wd * 32, 256), 256, 0, STREAM(stream), BF(x), BF(w), BF(bias), y, n,
                                                                                    h, wd, c, cout);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_cols_to_nchw(const float* y8, int ld, const void* bias, float* out, int n, int hw, int cout,
+                                 void* stream) {
+  LECO_REQUIRE(y8 && out && ld >= 8 && ld % 4 == 0 && cout >= 1 && cout <= 8, "leco_cols_to_nchw: bad args");
+  count_launch();
+  LECO_LAUNCH(cols_to_nchw_kernel, grid_for(1LL * n * hw, 256), 256, 0, STREAM(stream), y8, ld, BF(bias), out, n, hw, cout);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -103,6 +103,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   const int splits = p.k_splits;
   const int n_batches = p.batch0 * p.batch1;
   const int total_tiles = tiles_mn * n_batches * splits;
+  // Tile walk.  Plain kernels: tile = blockIdx.x + i*gridDim.x, M fastest (neighbouring CTAs share the B tile in L2).
+  // FL (in-kernel LoRA): each CTA owns a CONTIGUOUS run of tiles with N fastest, so consecutive tiles share their M
+  // rows and with them T = s*x.A^T: only the first tile of such a run ("fresh") computes the extra accumulator columns
+  // and re-stages T; the others just add T.Bup^T from the T tile already in shared memory (no extra MMA columns, no
+  // lora_down rows in their TMA traffic, no epilogue -> MMA round trip).  K-slices of a split-K problem each own a
+  // partial T, so there every tile is fresh.
+  const int tile_begin = FL ? (int)((long long)blockIdx.x * total_tiles / gridDim.x) : (int)blockIdx.x;
+  const int tile_end = FL ? (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x) : total_tiles;
+  const int tile_step = FL ? 1 : (int)gridDim.x;
 
   // Both role loops below are latency chains of ONE warp: every instruction per K chunk counts (the tensor
   // pipe needs a 4-MMA chunk every ~220-550 cycles).  So: 32-bit shared addresses computed with one IMAD per
@@ -117,10 +126,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     if (elect_one()) {
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx1 = p.a_tx_bytes + BN * BLOCK_K * 2 + (FL ? p.fl_kl * BLOCK_K * 2 : 0);
+    const uint32_t tx_plain = p.a_tx_bytes + BN * BLOCK_K * 2;
     const int dbg = p.dbg;
-    int itp = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++itp) {
+    int itp = 0, prev_mt = -1;
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++itp) {
       // per-tile index math runs on ONE lane's latency chain: skip every division the common case does not need
       int ks = 0, t2 = tile, bidx = 0, b0 = 0, b1 = 0;
       if (splits > 1) {
@@ -133,8 +142,17 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         b0 = bidx - b1 * p.batch0;
       }
       const int rem = t2 - bidx * tiles_mn;
-      const int nt = rem / p.tiles_m;
-      const int mt = rem - nt * p.tiles_m;
+      int nt, mt;
+      if (FL) {
+        mt = rem / p.tiles_n;
+        nt = rem - mt * p.tiles_n;
+      } else {
+        nt = rem / p.tiles_m;
+        mt = rem - nt * p.tiles_m;
+      }
+      const bool fresh = FL && (splits > 1 || mt != prev_mt);
+      prev_mt = mt;
+      const uint32_t tx1 = tx_plain + (fresh ? p.fl_kl * BLOCK_K * 2 : 0);
       const int n0 = nt * BN;
       int m0, img_n0, img_h0;
       gemm_tile_origin(p, mt, m0, img_n0, img_h0);
@@ -189,7 +207,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             } else {
               tma_load_4d_u32(sb, &p.tm_b, fb, c * BLOCK_K, n0, b0, b1);
             }
-            if (FL)  // stacked lora_down rows for this K chunk land right behind the W rows of the B tile
+            if (FL && fresh)  // stacked lora_down rows for this K chunk land right behind the W rows of the B tile
               tma_load_4d_u32(sb + BN * BLOCK_K * 2, &p.tm_ad, fb, c * BLOCK_K, 0, 0, 0);
           }
         }
@@ -234,7 +252,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer (one elected lane)
     if (elect_one()) {
-    const uint32_t idesc = umma_idesc_bf16_m128(BN + (FL ? p.fl_kl : 0));  // FL: extra columns = x.Ad^T
+    const uint32_t idesc_fresh = umma_idesc_bf16_m128(BN + (FL ? p.fl_kl : 0));  // FL: extra columns = x.Ad^T
+    const uint32_t idesc_plain = umma_idesc_bf16_m128(BN);
     const uint32_t a_lo0 = umma_desc_lo(sa0), b_lo0 = umma_desc_lo(sb0);
     const uint32_t tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
     const int dbg = p.dbg;
@@ -244,11 +263,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     // FL: the up projection of tile i (acc += T.Bup^T, one UMMA per 16 ranks) can only be issued once the epilogue
     // warps have re-staged T; it is slipped in after the first chunks of tile i+1's main loop so the tensor pipe
     // never waits for that round trip
-    int pend_it = -1;
+    int pend_it = -1, pend_fresh_idx = -1;   // pend_fresh_idx >= 0: the pending tile staged a new T (wait for it)
+    int n_fresh = 0, prev_mt = -1;
     const uint32_t idesc_up = umma_idesc_bf16_m128(BN);
-    auto issue_up = [&](int it_) {
+    auto issue_up = [&](int it_, int fresh_idx) {
       const int as_ = it_ & 1, bb = it_ & 1;
-      mbar_wait(t_full, it_ & 1);
+      if (fresh_idx >= 0) mbar_wait(t_full, fresh_idx & 1);
       mbar_wait(&bup_full[bb], (it_ >> 1) & 1);
       tc_fence_after();
       const uint32_t ta = umma_desc_lo(smem_u32(smem_t));
@@ -259,7 +279,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       umma_commit(t_empty);
       umma_commit(&bup_empty[bb]);
     };
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       int ks = 0, c_begin = 0, c_end1 = p.chunks1;
@@ -268,6 +288,14 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         c_begin = (int)((long long)ks * p.chunks1 / splits);
         c_end1 = (int)((long long)(ks + 1) * p.chunks1 / splits);
       }
+      bool fresh = false;
+      if (FL) {
+        const int t2 = tile / splits;
+        const int mt = (t2 % tiles_mn) / p.tiles_n;
+        fresh = splits > 1 || mt != prev_mt;
+        prev_mt = mt;
+      }
+      const uint32_t idesc = fresh ? idesc_fresh : idesc_plain;
       const bool seg2 = p.has_seg2 && ks == splits - 1;
       // chunks [c_begin, c_fast) are full 4-k-step chunks; the K tail and the LoRA segment take the generic path
       const int c_fast = (dbg == 1) ? c_begin : ((c_end1 == p.chunks1 && p.ksteps_last1 != 4) ? c_end1 - 1 : c_end1);
@@ -295,7 +323,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           phase ^= 1;
         }
         if (FL && pend_it >= 0 && c - c_begin == 2) {
-          issue_up(pend_it);
+          issue_up(pend_it, pend_fresh_idx);
           pend_it = -1;
         }
       }
@@ -320,39 +348,52 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         }
       }
       if (FL && pend_it >= 0) {   // tile shorter than three chunks
-        issue_up(pend_it);
+        issue_up(pend_it, pend_fresh_idx);
         pend_it = -1;
       }
       umma_commit_u32(tfull0 + as * 8);  // accumulator complete (FL: up to the up projection) -> epilogue
-      if (FL) pend_it = it;
+      if (FL) {
+        pend_it = it;
+        pend_fresh_idx = fresh ? n_fresh++ : -1;
+      }
     }
-    if (FL && pend_it >= 0) issue_up(pend_it);
+    if (FL && pend_it >= 0) issue_up(pend_it, pend_fresh_idx);
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;                  // TMEM lane quadrant of this warp
     const int r = q * 32 + lane;             // row inside the tile
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    int it = 0, prev_mt = -1;
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int t2 = tile / splits;
       const int bidx = t2 / tiles_mn;
       const int rem = t2 - bidx * tiles_mn;
-      const int nt = rem / p.tiles_m;
-      const int mt = rem - nt * p.tiles_m;
+      int nt, mt;
+      if (FL) {
+        mt = rem / p.tiles_n;
+        nt = rem - mt * p.tiles_n;
+      } else {
+        nt = rem / p.tiles_m;
+        mt = rem - nt * p.tiles_m;
+      }
+      const bool fresh = FL && (splits > 1 || mt != prev_mt);
+      prev_mt = mt;
       const int b1 = bidx / p.batch0;
       const int b0 = bidx - b1 * p.batch0;
       mbar_wait_backoff(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
       if (FL) {
-        mbar_wait(t_empty, (it & 1) ^ 1);            // the previous tile's up projection has consumed the T tile
-        gemm_fl_stage_t<BN>(p, trow, r, mt, nt, smem_t);
-        tc_fence_before();
-        fence_proxy_async_smem();                    // generic-proxy smem writes -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive(t_full);
+        if (fresh) {
+          mbar_wait(t_empty, (it & 1) ^ 1);          // the previous tile's up projection has consumed the T tile
+          gemm_fl_stage_t<BN>(p, trow, r, mt, nt, smem_t);
+          tc_fence_before();
+          fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_full);
+        }
         mbar_wait(&acc2_full[as], aphase);           // accumulator now holds x.W^T + T.Bup^T
         tc_fence_after();
       }

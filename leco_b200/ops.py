@@ -173,9 +173,28 @@ def conv_in(x_nchw: torch.Tensor, w_oihw: torch.Tensor, bias: torch.Tensor) -> t
     return y
 
 
+_CONV_OUT_W8 = {}
+CONV_OUT_GEMM = int(__import__('os').environ.get('LECO_CONV_OUT_GEMM', '1'))
+
+
 def conv_out(x: torch.Tensor, w_ohwi: torch.Tensor, bias: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
     cout, c = w_ohwi.shape[0], x.shape[1]
     y = torch.empty((n, cout, h, w), device=x.device, dtype=torch.float32)
+    if CONV_OUT_GEMM and c % 64 == 0 and w <= 128 and cout <= 8:
+        # tensor-core path: implicit-GEMM 3x3 conv with the 4 output channels padded to N = 8 (fp32 accumulate and
+        # output, like the CUDA-core kernel), then a repack to NCHW (+ bias).  The padded weight is cached per tensor.
+        key = (w_ohwi.data_ptr(), w_ohwi._version)
+        w8 = _CONV_OUT_W8.get(key)
+        if w8 is None:
+            w8 = torch.zeros((8, 9 * c), device=x.device, dtype=BF16)
+            w8[:cout] = w_ohwi.reshape(cout, 9 * c)
+            if len(_CONV_OUT_W8) > 16:
+                _CONV_OUT_W8.clear()
+            _CONV_OUT_W8[key] = w8
+        y8 = gemm(x, w8, conv_nhw=(n, h, w), out_fp32=True)
+        capi.check(_lib().leco_cols_to_nchw(_ptr(y8), 8, _ptr(bias), _ptr(y), n, h * w, cout, _stream()),
+                   "leco_cols_to_nchw")
+        return y
     capi.check(_lib().leco_conv_out(_ptr(x), _ptr(w_ohwi), _ptr(bias), _ptr(y), n, h, w, c, cout, _stream()),
                "leco_conv_out")
     return y

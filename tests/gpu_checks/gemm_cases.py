@@ -370,6 +370,10 @@ CASES = [
     ("fl_linear_qkv_r12_tout", case_fl, dict(M=4096, N=960, K=320, rank=12, t_out=True)),
     ("fl_linear_kl32_bn128", case_fl, dict(M=512, N=640, K=640, kl=32, rank=24, block_n=128, t_out=True)),
     ("fl_linear_bn64_ragged", case_fl, dict(M=300, N=72, K=128, block_n=64)),
+    # many tiles per CTA: runs of N tiles that share one staged T (the fresh / reuse logic of the N-inner tile walk)
+    ("fl_runs_qkv_16384", case_fl, dict(M=16384, N=960, K=320, rank=12, t_out=True)),
+    ("fl_runs_geglu_4096", case_fl, dict(M=4096, N=2560, K=320, geglu=True)),
+    ("fl_runs_ragged_m", case_fl, dict(M=5000, N=640, K=640, kl=32, rank=20, t_out=True)),
     ("fl_geglu", case_fl, dict(M=512, N=2560, K=320, geglu=True)),
     ("fl_splitk_m256", case_fl, dict(M=256, N=1280, K=5120)),
     ("fl_ctx_m308", case_fl, dict(M=308, N=640, K=1024, rank=8)),
