@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
 #pragma unroll
     for (int i = 0; i < FA_D; ++i) o[i] = 0.f;
 
-    auto fold_pv = [&](int j, float alpha) {  // o = o*alpha + PV_j   (buffer j & 1 == wg)
+    auto fold_pv = [&](int j, float alpha) {  // o = (o + PV_j) * alpha   (buffer j & 1 == wg; alpha == 1 almost always)
       const int pb = j & 1;
       mbar_wait(&pv_full[pb], (j >> 1) & 1);
       tc_fence_after();
@@ -218,55 +218,62 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
         tmem_ld_32x32b_x32(tmem_pv + lane_off + pb * FA_D + h * 32, raw);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], alpha, __uint_as_float(raw[i]));
+        for (int i = 0; i < 32; ++i) o[h * 32 + i] += __uint_as_float(raw[i]);
+      }
+      if (alpha != 1.0f) {
+#pragma unroll
+        for (int i = 0; i < FA_D; ++i) o[i] *= alpha;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pv_empty[pb]);
     };
 
-    // One KV tile of the online softmax.  RG (= the tile runs past skv) is a compile-time flag: as a run-time test the
-    // per-score masks become predicated instructions that take issue slots even when off.
-    auto softmax_tile = [&](int j, auto rg_tag) {
+    // One KV tile of the online softmax.  RG (= the tile runs past skv) and FIRST (= this warpgroup's first tile) are
+    // compile-time flags: as run-time tests the per-score masks become predicated instructions that take issue slots.
+    // LAZY MAX: only the first tile runs a separate max pass.  Every later tile exponentiates against the running max
+    // of the tiles BEFORE it (p may exceed 1 when the tile raises the max: harmless in bf16 / fp32) while tracking its
+    // own max in the same loop; the state is then rescaled once by alpha = 2^((m_old - m_new) c), which is exactly 1
+    // whenever the max did not move.  No second pass over TMEM, no max -> exp dependency inside a tile.
+    auto softmax_tile = [&](int j, auto rg_tag, auto first_tag) {
       constexpr bool ragged = decltype(rg_tag)::value;
+      constexpr bool first = decltype(first_tag)::value;
       const int sb = j & 1;
       const int kv0 = j * FA_BN;
-      // this warpgroup's previous tile first (o = o*alpha_{j-2} + PV_{j-2}): frees the PV accumulator before P_j is
-      // even staged, so PV_j can start the moment P_j is ready
+      // this warpgroup's previous tile first: frees the PV accumulator before P_j is even staged
       if (j >= 2) fold_pv(j - 2, alpha_prev);
       mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t s_addr = tmem_s + lane_off + sb * FA_BN;
-      // pass 1: row max over the 128 scores (32 at a time: the scores are re-read in pass 2 instead of living in
-      // 128 registers; TMEM reads are cheap, 4 KB per warp-load at ~43 cycles)
-      // (four independent running maxima: a single one is a 128-long dependent FMNMX chain = ~500 cycles of pure
-      // latency per tile for a warp that shares its scheduler with just one other softmax warp)
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      float m_ref = m_run;
+      if constexpr (first) {
+        // row max over the 128 scores, 32 at a time (four independent running maxima)
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32];
-        tmem_ld_32x32b_x32(s_addr + c * 32, sv);
-        tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) {
+          uint32_t sv[32];
+          tmem_ld_32x32b_x32(s_addr + c * 32, sv);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float a0 = __uint_as_float(sv[i]), a1 = __uint_as_float(sv[i + 1]), a2 = __uint_as_float(sv[i + 2]),
-                a3 = __uint_as_float(sv[i + 3]);
-          if constexpr (ragged) {
-            if (kv0 + c * 32 + i >= p.skv) a0 = -INFINITY;
-            if (kv0 + c * 32 + i + 1 >= p.skv) a1 = -INFINITY;
-            if (kv0 + c * 32 + i + 2 >= p.skv) a2 = -INFINITY;
-            if (kv0 + c * 32 + i + 3 >= p.skv) a3 = -INFINITY;
+          for (int i = 0; i < 32; i += 4) {
+            float a0 = __uint_as_float(sv[i]), a1 = __uint_as_float(sv[i + 1]), a2 = __uint_as_float(sv[i + 2]),
+                  a3 = __uint_as_float(sv[i + 3]);
+            if constexpr (ragged) {
+              if (kv0 + c * 32 + i >= p.skv) a0 = -INFINITY;
+              if (kv0 + c * 32 + i + 1 >= p.skv) a1 = -INFINITY;
+              if (kv0 + c * 32 + i + 2 >= p.skv) a2 = -INFINITY;
+              if (kv0 + c * 32 + i + 3 >= p.skv) a3 = -INFINITY;
+            }
+            mx0 = fmaxf(mx0, a0);
+            mx1 = fmaxf(mx1, a1);
+            mx2 = fmaxf(mx2, a2);
+            mx3 = fmaxf(mx3, a3);
           }
-          mx0 = fmaxf(mx0, a0);
-          mx1 = fmaxf(mx1, a1);
-          mx2 = fmaxf(mx2, a2);
-          mx3 = fmaxf(mx3, a3);
         }
+        m_ref = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       }
-      const float m_new = fmaxf(fmaxf(m_run, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
-      const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);  // first tile: ex2(-inf) = 0
-      const float mb = m_new * p.scale_log2;
-      // pass 2: p = 2^(s*c - m*c) -> bf16 -> swizzled A-operand tile (two 64-key chunks of [128 rows x 128 B])
+      const float mb = m_ref * p.scale_log2;
+      // p = 2^(s*c - m_ref*c) -> bf16 -> swizzled A-operand tile (two 64-key chunks of [128 rows x 128 B])
       mbar_wait(&p_empty[sb], ((j >> 1) & 1) ^ 1);
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;  // four partial sums: no long dependent FADD chain
 #pragma unroll 1
@@ -286,11 +293,16 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int i = t * 8 + u * 2;
-            float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), p.scale_log2, -mb));
-            float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, -mb));
+            float a0 = __uint_as_float(sv[i]), a1 = __uint_as_float(sv[i + 1]);
+            float p0 = ex2_approx(fmaf(a0, p.scale_log2, -mb));
+            float p1 = ex2_approx(fmaf(a1, p.scale_log2, -mb));
             if constexpr (ragged) {
-              if (kv0 + c * 32 + i >= p.skv) p0 = 0.f;
-              if (kv0 + c * 32 + i + 1 >= p.skv) p1 = 0.f;
+              if (kv0 + c * 32 + i >= p.skv) { p0 = 0.f; a0 = -INFINITY; }
+              if (kv0 + c * 32 + i + 1 >= p.skv) { p1 = 0.f; a1 = -INFINITY; }
+            }
+            if constexpr (!first) {
+              if (u == 0) mx0 = fmaxf(mx0, fmaxf(a0, a1)); else if (u == 1) mx1 = fmaxf(mx1, fmaxf(a0, a1));
+              else if (u == 2) mx2 = fmaxf(mx2, fmaxf(a0, a1)); else mx3 = fmaxf(mx3, fmaxf(a0, a1));
             }
             if (u == 0) rs0 += p0 + p1; else if (u == 1) rs1 += p0 + p1; else if (u == 2) rs2 += p0 + p1; else rs3 += p0 + p1;
             pk[u] = pack_bf16(p0, p1);
@@ -301,16 +313,25 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[sb]);
-      l_run = l_run * alpha + ((rs0 + rs1) + (rs2 + rs3));
+      float alpha = 1.0f, m_new = m_ref;
+      if constexpr (!first) {
+        m_new = fmaxf(fmaxf(m_run, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
+        alpha = ex2_approx((m_run - m_new) * p.scale_log2);   // exactly 1 when the max did not move
+      }
+      l_run = (l_run + ((rs0 + rs1) + (rs2 + rs3))) * alpha;
       m_run = m_new;
-      alpha_prev = alpha;
+      alpha_prev = alpha;       // applied to o when this tile's PV is folded: o = (o + PV_j) * alpha
     };
     int last = -1;
     for (int j = wg; j < n_tiles; j += 2) {
-      if (j * FA_BN + FA_BN > p.skv)
-        softmax_tile(j, std::true_type{});
-      else
-        softmax_tile(j, std::false_type{});
+      const bool rg = j * FA_BN + FA_BN > p.skv;
+      if (j == wg) {
+        if (rg) softmax_tile(j, std::true_type{}, std::true_type{});
+        else softmax_tile(j, std::false_type{}, std::true_type{});
+      } else {
+        if (rg) softmax_tile(j, std::true_type{}, std::false_type{});
+        else softmax_tile(j, std::false_type{}, std::false_type{});
+      }
       last = j;
     }
     if (last >= 0) fold_pv(last, alpha_prev);
