@@ -30,7 +30,8 @@ constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;              // 16 KiB
 constexpr int FA_KV_BYTES = FA_BN * FA_D * 2;             // 16 KiB
 constexpr int FA_P_BYTES = FA_BM * FA_BN * 2;             // 32 KiB (two 64-key chunks)
 constexpr int FA_SMEM = FA_Q_BYTES + (FA_KS + FA_VS) * FA_KV_BYTES + 2 * FA_P_BYTES + 1024 + 512 + (2 * 2 + 2) * 128 * 4;
-constexpr int FA_TMEM_COLS = 512;                         // S: 2 x 128, PV: 2 x 64
+constexpr int FA_TMEM_COLS = 512;                         // S: 3 x 128 (ring), PV: 2 x 64
+constexpr int FA_SB = 3;                                  // S ring depth
 constexpr int FA_THREADS = 384;                          // 4 control warps + 2 softmax warpgroups
 
 struct FlashParams {
@@ -76,9 +77,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
   uint64_t* k_empty = k_full + FA_KS;      // [KS]
   uint64_t* v_full = k_empty + FA_KS;      // [VS]
   uint64_t* v_empty = v_full + FA_VS;      // [VS]
-  uint64_t* s_full = v_empty + FA_VS;      // [2]
-  uint64_t* s_empty = s_full + 2;          // [2]
-  uint64_t* p_full = s_empty + 2;          // [2]
+  uint64_t* s_full = v_empty + FA_VS;      // [FA_SB]
+  uint64_t* s_empty = s_full + FA_SB;      // [FA_SB]
+  uint64_t* p_full = s_empty + FA_SB;      // [2]
   uint64_t* p_empty = p_full + 2;          // [2]
   uint64_t* pv_full = p_empty + 2;         // [2]
   uint64_t* pv_empty = pv_full + 2;        // [2]
@@ -104,9 +105,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < FA_SB; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);   // buffer i belongs to softmax warpgroup i (4 warps)
+      mbar_init(&s_empty[i], 4);   // one softmax warpgroup (4 warps) consumes a score tile
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&p_full[i], 4);
       mbar_init(&p_empty[i], 1);
       mbar_init(&pv_full[i], 1);
@@ -123,8 +126,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
-  const uint32_t tmem_s = tmem_base;        // + buf * 128
-  const uint32_t tmem_pv = tmem_base + 256; // + buf * 64
+  const uint32_t tmem_s = tmem_base;                    // + (j % 3) * 128: three score tiles in flight, so QK^T of tile
+                                                        // j+2 never waits for the warpgroup still reading tile j
+  const uint32_t tmem_pv = tmem_base + FA_SB * FA_BN;   // + (j & 1) * 64
 
   // Each role below is ONE elected lane running its whole loop (tests/gpu_checks/mma_probe.cu: re-electing the warp
   // every iteration costs ~700 cycles per round against ~60 for the single-lane loop).
@@ -155,9 +159,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
       const uint32_t idesc_pv = umma_idesc_bf16(FA_D, p.v_mode == 0);
       const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ));
       auto issue_s = [&](int j) {
-        const int ks = j % FA_KS, sb = j & 1;
+        const int ks = j % FA_KS, sb = j % FA_SB;
         mbar_wait(&k_full[ks], (j / FA_KS) & 1);
-        mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
+        mbar_wait(&s_empty[sb], ((j / FA_SB) & 1) ^ 1);
         tc_fence_after();
         const uint64_t dk = umma_desc_k_sw128(smem_u32(sK + ks * FA_KV_BYTES));
 #pragma unroll
@@ -167,8 +171,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
       };
       mbar_wait(q_full, 0);
       issue_s(0);
+      if (n_tiles > 1) issue_s(1);
       for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) issue_s(j + 1);
+        if (j + 2 < n_tiles) issue_s(j + 2);
         const int vs = j % FA_VS, pb = j & 1;
         mbar_wait(&p_full[pb], (j >> 1) & 1);
         mbar_wait(&v_full[vs], (j / FA_VS) & 1);
@@ -238,13 +243,14 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
     auto softmax_tile = [&](int j, auto rg_tag, auto first_tag) {
       constexpr bool ragged = decltype(rg_tag)::value;
       constexpr bool first = decltype(first_tag)::value;
-      const int sb = j & 1;
+      const int sb = j & 1;          // P / PV buffer of this tile
+      const int s3 = j % FA_SB;      // score buffer of this tile
       const int kv0 = j * FA_BN;
       // this warpgroup's previous tile first: frees the PV accumulator before P_j is even staged
       if (j >= 2) fold_pv(j - 2, alpha_prev);
-      mbar_wait(&s_full[sb], (j >> 1) & 1);
+      mbar_wait(&s_full[s3], (j / FA_SB) & 1);
       tc_fence_after();
-      const uint32_t s_addr = tmem_s + lane_off + sb * FA_BN;
+      const uint32_t s_addr = tmem_s + lane_off + s3 * FA_BN;
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
       float m_ref = m_run;
       if constexpr (first) {
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
         if (c == 3) {               // S fully consumed: the next QK^T of this buffer may start
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[sb]);
+          if (lane == 0) mbar_arrive(&s_empty[s3]);
         }
         uint8_t* prow = sP + sb * FA_P_BYTES + (c >> 1) * (FA_P_BYTES / 2) + r * 128;
 #pragma unroll
