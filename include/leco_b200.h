@@ -123,6 +123,18 @@ int leco_softmax_rows(const float* s, void* p, int64_t rows, int n_valid, int n_
 int leco_softmax_bwd_rows(const void* p, const float* dp, void* ds, int64_t rows, int n_valid, int n_pad,
                           int64_t ld_p, int64_t ld_dp, float scale, void* stream);
 
+/* ---- text-encoder prologue (replaces transformers' CLIPTextModel inside
+ * /root/reference/train_util.py:76-77 text_encode and :92-108 text_encode_xl).  The projections and LayerNorms of the
+ * encoder run on leco_gemm_bf16 / leco_layer_norm; these three are the pieces the UNet path has no use for:
+ *   leco_embed_tokens        out[r] = token_embedding[ids[r]] + position_embedding[r % seq]      (CLIPTextEmbeddings)
+ *   leco_softmax_rows_causal leco_softmax_rows with row r limited to columns <= r % sq           (causal mask)
+ *   leco_activation          kind 0 SiLU, 1 quick_gelu x*sigmoid(1.702x), 2 erf GELU             (CLIPMLP) */
+int leco_embed_tokens(const int* ids, const void* tok, const void* pos, void* out, int64_t rows, int seq, int dim,
+                      int vocab, void* stream);
+int leco_softmax_rows_causal(const float* s, void* p, int64_t rows, int n_valid, int n_pad, int64_t ld_s,
+                             int64_t ld_p, int sq, void* stream);
+int leco_activation(const void* x, void* y, int64_t numel, int kind, void* stream);
+
 /* ---------------------------------------------------------------------------------
  * leco_flash_attn_fwd — fused softmax(scale Q K^T) V, head dim <= 64, S/P never leave the SM.
  * Replaces xformers.memory_efficient_attention (enabled at train_lora.py:68).  q/k/v are [rows, ld]

@@ -90,6 +90,9 @@ _OPS: list[tuple[str, list]] = [
     ("leco_rowgroup_sum", [P, P, I, I, I, P]),
     ("leco_transpose", [P, P, I, I, I, L, L, L, L, L, L, I, I, P]),
     ("leco_softmax_rows", [P, P, L, I, I, L, L, P]),
+    ("leco_softmax_rows_causal", [P, P, L, I, I, L, L, I, P]),
+    ("leco_embed_tokens", [P, P, P, P, L, I, I, I, P]),
+    ("leco_activation", [P, P, L, I, P]),
     ("leco_softmax_bwd_rows", [P, P, P, L, I, I, L, L, F, P]),
     ("leco_flash_attn_fwd", [P, L, P, L, P, L, P, L, P, L, I, I, I, I, I, F, P]),
     ("leco_flash_attn_fwd_lse", [P, L, P, L, P, L, P, L, P, I, I, I, I, I, F, P]),

@@ -205,6 +205,41 @@ __global__ void silu_kernel(const bf16x8* __restrict__ x, bf16x8* __restrict__ y
     y[i] = pack8(f);
   }
 }
+// text-encoder MLP activations (transformers CLIPMLP, modeling_clip.py: ACT2FN[config.hidden_act]):
+// kind 1 = quick_gelu x*sigmoid(1.702x) (CLIP ViT-L), kind 2 = erf GELU (OpenCLIP ViT-H / bigG), kind 0 = SiLU
+__global__ void activation_kernel(const bf16x8* __restrict__ x, bf16x8* __restrict__ y, long long nvec, int kind) {
+  pdl_entry();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8(x[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      f[j] = kind == 1 ? f[j] / (1.0f + __expf(-1.702f * f[j])) : (kind == 2 ? gelu_erf_f(f[j]) : silu_f(f[j]));
+    y[i] = pack8(f);
+  }
+}
+// CLIPTextEmbeddings (modeling_clip.py): out[r] = token_embedding[ids[r]] + position_embedding[r % seq], fp32 add,
+// one bf16 rounding.  8 columns per thread.
+__global__ void embed_tokens_kernel(const int* __restrict__ ids, const bf16x8* __restrict__ tok,
+                                    const bf16x8* __restrict__ pos, bf16x8* __restrict__ out, long long rows, int seq,
+                                    int dvec, int vocab) {
+  pdl_entry();
+  const long long total = rows * dvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / dvec;
+    const int c = static_cast<int>(i - r * dvec);
+    int id = ids[r];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    float a[8], b[8];
+    unpack8(tok[(long long)id * dvec + c], a);
+    unpack8(pos[(r % seq) * dvec + c], b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    out[i] = pack8(a);
+  }
+}
 // y += x   (gradient accumulation)
 __global__ void add_inplace_kernel(bf16x8* __restrict__ y, const bf16x8* __restrict__ x, long long nvec) {
   pdl_entry();
@@ -433,14 +468,17 @@ __global__ void transpose_kernel(const __nv_bfloat16* __restrict__ in, __nv_bflo
 
 // row softmax: s fp32 [rows, ld_s] (first n_valid columns valid) -> p bf16 [rows, ld_p], columns
 // [n_valid, n_pad) written as 0.  One warp per row.
+// causal_sq > 0: row r only sees columns <= r % causal_sq (the text encoder's causal mask, CLIPTextTransformer).
 __global__ void softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, long long rows,
-                                    int n_valid, int n_pad, long long ld_s, long long ld_p) {
+                                    int n_valid_all, int n_pad, long long ld_s, long long ld_p, int causal_sq) {
   pdl_entry();
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long r = warp; r < rows; r += nwarps) {
     const float* sr = s + r * ld_s;
+    int n_valid = n_valid_all;
+    if (causal_sq > 0) n_valid = min(n_valid_all, static_cast<int>(r % causal_sq) + 1);
     float mx = -INFINITY;
     for (int j = lane; j < n_valid; j += 32) mx = fmaxf(mx, sr[j]);
 #pragma unroll
@@ -542,6 +580,25 @@ extern "C" int leco_silu(const void* x, void* y, int64_t numel, void* stream) {
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+extern "C" int leco_activation(const void* x, void* y, int64_t numel, int kind, void* stream) {
+  LECO_REQUIRE(x && y && numel % 8 == 0 && kind >= 0 && kind <= 2, "leco_activation: numel % 8 != 0 or unknown kind");
+  count_launch();
+  LECO_LAUNCH(activation_kernel, grid_for(numel / 8, 256), 256, 0, STREAM(stream), reinterpret_cast<const bf16x8*>(x),
+                                                                         reinterpret_cast<bf16x8*>(y), numel / 8, kind);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_embed_tokens(const int* ids, const void* tok, const void* pos, void* out, int64_t rows, int seq,
+                                 int dim, int vocab, void* stream) {
+  LECO_REQUIRE(ids && tok && pos && out && rows > 0 && seq > 0 && dim % 8 == 0 && vocab > 0, "leco_embed_tokens: bad args");
+  count_launch();
+  LECO_LAUNCH(embed_tokens_kernel, grid_for(rows * (dim / 8), 256), 256, 0, STREAM(stream), ids,
+                                                                           reinterpret_cast<const bf16x8*>(tok),
+                                                                           reinterpret_cast<const bf16x8*>(pos),
+                                                                           reinterpret_cast<bf16x8*>(out), rows, seq, dim / 8, vocab);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 extern "C" int leco_add_inplace(void* y, const void* x, int64_t numel, void* stream) {
   LECO_REQUIRE(x && y && numel % 8 == 0, "leco_add_inplace: numel must be a multiple of 8");
   count_launch();
@@ -639,7 +696,16 @@ extern "C" int leco_softmax_rows(const float* s, void* p, int64_t rows, int n_va
   LECO_REQUIRE(s && p && n_valid > 0 && n_pad >= n_valid, "leco_softmax_rows: bad args");
   count_launch();
   LECO_LAUNCH(softmax_rows_kernel, grid_for(rows * 32, 256), 256, 0, STREAM(stream), s, BFW(p), rows, n_valid, n_pad, ld_s,
-                                                                           ld_p);
+                                                                           ld_p, 0);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int leco_softmax_rows_causal(const float* s, void* p, int64_t rows, int n_valid, int n_pad, int64_t ld_s,
+                                        int64_t ld_p, int sq, void* stream) {
+  LECO_REQUIRE(s && p && n_valid > 0 && n_pad >= n_valid && sq > 0, "leco_softmax_rows_causal: bad args");
+  count_launch();
+  LECO_LAUNCH(softmax_rows_kernel, grid_for(rows * 32, 256), 256, 0, STREAM(stream), s, BFW(p), rows, n_valid, n_pad, ld_s,
+                                                                           ld_p, sq);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

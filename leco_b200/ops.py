@@ -223,6 +223,26 @@ def silu(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def activation(x: torch.Tensor, kind: int) -> torch.Tensor:
+    """kind 0 SiLU, 1 quick_gelu, 2 erf GELU (the text encoder's MLP, text_encoder.py)."""
+    _req_bf16(x, "x")
+    assert x.is_contiguous()
+    y = torch.empty_like(x)
+    capi.check(_lib().leco_activation(_ptr(x), _ptr(y), x.numel(), kind, _stream()), "leco_activation")
+    return y
+
+
+def embed_tokens(ids: torch.Tensor, tok: torch.Tensor, pos: torch.Tensor, seq: int) -> torch.Tensor:
+    """ids int32 [rows] -> bf16 [rows, D] = tok[ids] + pos[row % seq]."""
+    _req_bf16(tok, "tok"), _req_bf16(pos, "pos")
+    assert ids.dtype == torch.int32 and ids.is_contiguous() and tok.is_contiguous() and pos.is_contiguous()
+    assert pos.shape[0] >= seq and pos.shape[1] == tok.shape[1]
+    out = torch.empty((ids.numel(), tok.shape[1]), device=tok.device, dtype=BF16)
+    capi.check(_lib().leco_embed_tokens(_ptr(ids), _ptr(tok), _ptr(pos), _ptr(out), ids.numel(), seq, tok.shape[1],
+                                        tok.shape[0], _stream()), "leco_embed_tokens")
+    return out
+
+
 def add_(y: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     assert y.shape == x.shape and y.is_contiguous() and x.is_contiguous()
     capi.check(_lib().leco_add_inplace(_ptr(y), _ptr(x), y.numel(), _stream()), "leco_add_inplace")
@@ -318,13 +338,17 @@ def transpose_batched(src: torch.Tensor, cols_pad: int = 0) -> torch.Tensor:
     return out
 
 
-def softmax_rows(s: torch.Tensor, n_valid: int, n_pad: int) -> torch.Tensor:
-    """s: fp32 [..., ld] contiguous -> p bf16 [..., n_pad]."""
+def softmax_rows(s: torch.Tensor, n_valid: int, n_pad: int, causal_sq: int = 0) -> torch.Tensor:
+    """s: fp32 [..., ld] contiguous -> p bf16 [..., n_pad].  causal_sq > 0: row r sees columns <= r % causal_sq."""
     assert s.dtype == torch.float32 and s.is_contiguous()
     rows = s.numel() // s.shape[-1]
     p = torch.empty(s.shape[:-1] + (n_pad,), device=s.device, dtype=BF16)
-    capi.check(_lib().leco_softmax_rows(_ptr(s), _ptr(p), rows, n_valid, n_pad, s.shape[-1], n_pad, _stream()),
-               "leco_softmax_rows")
+    if causal_sq:
+        capi.check(_lib().leco_softmax_rows_causal(_ptr(s), _ptr(p), rows, n_valid, n_pad, s.shape[-1], n_pad,
+                                                   causal_sq, _stream()), "leco_softmax_rows_causal")
+    else:
+        capi.check(_lib().leco_softmax_rows(_ptr(s), _ptr(p), rows, n_valid, n_pad, s.shape[-1], n_pad, _stream()),
+                   "leco_softmax_rows")
     return p
 
 
@@ -622,12 +646,12 @@ def attention(qt, kt, vt, nb, sq, skv, heads, d, scale, save_for_bwd=False):
     return attention_v0(qt, kt, vt, nb, sq, skv, heads, d, scale, save_for_bwd)
 
 
-def attention_v0(qt, kt, vt, nb, sq, skv, heads, d, scale, save_for_bwd=False):
+def attention_v0(qt, kt, vt, nb, sq, skv, heads, d, scale, save_for_bwd=False, causal=False):
     skv_pad = (skv + 15) // 16 * 16
     q4, k4, v4 = _heads_view(qt, nb, sq, heads, d), _heads_view(kt, nb, skv, heads, d), _heads_view(vt, nb, skv, heads, d)
     S = torch.empty((nb, heads, sq, skv_pad), device=qt.device, dtype=torch.float32)
     gemm_batched(q4, k4, S, alpha=scale, n_pad=skv_pad if skv_pad != skv else 0)
-    P = softmax_rows(S, skv, skv_pad)
+    P = softmax_rows(S, skv, skv_pad, causal_sq=sq if causal else 0)
     del S
     Vt = transpose_batched(v4, cols_pad=skv_pad)               # [nb, heads, d, skv_pad]
     o = torch.empty((nb * sq, heads * d), device=qt.device, dtype=BF16)

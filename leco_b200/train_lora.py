@@ -41,13 +41,14 @@ def train(config, prompts, *, device="cuda", rank: int = 0, world_size: int = 1,
         raise NotImplementedError("leco_b200 kernels run the UNet in bf16 (train.precision: bfloat16); the reference's "
                                   "README calls fp16 unstable and fp32 is the CPU-oracle configuration")
     if xl:
-        _, encoders, unet, scheduler = model_util.load_models_xl(config.pretrained_model.name_or_path,
-                                                                 scheduler_name=config.train.noise_scheduler, device=device)
-        text_encoder = encoders[0]
+        tokenizer, text_encoder, unet, scheduler = model_util.load_models_xl(
+            config.pretrained_model.name_or_path, scheduler_name=config.train.noise_scheduler, device=device)
+        encode = model_util.encode_prompts_xl
     else:
-        _, text_encoder, unet, scheduler = model_util.load_models(
+        tokenizer, text_encoder, unet, scheduler = model_util.load_models(
             config.pretrained_model.name_or_path, scheduler_name=config.train.noise_scheduler,
             v2=config.pretrained_model.v2, v_pred=config.pretrained_model.v_pred, device=device)
+        encode = model_util.encode_prompts
     unet.enable_xformers_memory_efficient_attention()      # train_lora.py:68 (a no-op: attention is the fused kernel)
     unet.requires_grad_(False)
     unet.eval()
@@ -68,12 +69,12 @@ def train(config, prompts, *, device="cuda", rank: int = 0, world_size: int = 1,
         print(s)
         for p in (s.target, s.positive, s.neutral, s.unconditional):
             if p not in cache:
-                cache[p] = model_util.encode_prompts(None, text_encoder, [p])
+                cache[p] = encode(tokenizer, text_encoder, [p])      # train_lora.py:118-124: once per distinct prompt
         pairs.append(PromptPair(target=cache[s.target], positive=cache[s.positive], unconditional=cache[s.unconditional],
                                 neutral=cache[s.neutral], guidance_scale=s.guidance_scale, resolution=s.resolution,
                                 dynamic_resolution=s.dynamic_resolution, batch_size=s.batch_size, action=s.action,
                                 dynamic_crops=getattr(s, "dynamic_crops", False)))
-    del text_encoder
+    del tokenizer, text_encoder                # train_lora.py:134-137: the text side is freed before the loop
 
     trainer = LecoTrainer(unet, network, scheduler, pairs, lr=config.train.lr, optimizer=config.train.optimizer,
                           optimizer_kwargs=parse_optimizer_args(config.train.optimizer_args),

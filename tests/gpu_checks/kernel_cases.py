@@ -608,7 +608,93 @@ def case_engine_grads(arch, n=2, hw=8, mode=None, cache_name=None):
     return _merge(res)
 
 
+def case_text_kernels():
+    """leco_embed_tokens / leco_activation / leco_softmax_rows_causal vs plain torch (tests/torch_backend.py)."""
+    import torch
+    from leco_b200 import ops
+    from tests import torch_backend as tb
+    res = {}
+    tok, pos = _rand((600, 128), 0.1, 1), _rand((77, 128), 0.1, 2)
+    ids = torch.randint(0, 600, (3 * 77,), generator=torch.Generator().manual_seed(3)).int().cuda()
+    out = ops.embed_tokens(ids, tok, pos, 77)
+    ref = tb.embed_tokens(ids.cpu(), tok.cpu(), pos.cpu(), 77)
+    res["embed_tokens"] = _cmp(out, ref, tol=1e-6)                       # one rounding of an exact fp32 sum
+    res["embed_tokens"]["ok"] = bool(torch.equal(out.cpu(), ref))
+    x = _rand((231, 3072), 2.0, 4)
+    for kind, name in ((0, "silu"), (1, "quick_gelu"), (2, "gelu")):
+        res[f"act_{name}"] = _cmp(ops.activation(x, kind), tb.activation(x.cpu().float(), kind), tol=8e-3)
+    for (b, h, sq, pad) in ((2, 12, 77, 80), (1, 4, 64, 64), (3, 2, 5, 16)):
+        sc = (_rand((b, h, sq, pad), 3.0, 5, dtype=torch.float32)).contiguous()
+        p = ops.softmax_rows(sc, sq, pad, causal_sq=sq)
+        pr = tb.softmax_rows(sc.cpu(), sq, pad, causal_sq=sq)
+        res[f"softmax_causal_{sq}"] = _cmp(p, pr, tol=8e-3)
+        upper = torch.ones(sq, pad, dtype=torch.bool).triu(1)
+        res[f"softmax_causal_{sq}"]["ok"] &= bool((p.cpu().float()[..., upper] == 0).all())   # the mask is exact
+        o, _ = ops.attention_v0(*( _rand((b * sq, h * 64), 1.0, 6 + i) for i in range(3)), b, sq, sq, h, 64, 0.125, causal=True)
+        orf, _ = tb.attention_v0(*( _rand((b * sq, h * 64), 1.0, 6 + i).cpu() for i in range(3)), b, sq, sq, h, 64, 0.125, causal=True)
+        res[f"attn_causal_{sq}"] = _cmp(o, orf)
+    return _merge(res)
+
+
+def case_text_encoder(name, batch=3, golden=False):
+    """Engine CLIP text encoder vs the fp32 CPU oracle (oracle/clip_ref.py; golden=True: vs transformers' own outputs in
+    tests/golden/clip_tiny.pt).  Bound: no farther from fp32 than 1.5x a stock-torch bf16 run of the oracle + 0.5 %."""
+    import torch
+    from leco_b200.text_encoder import TEXT_SPECS, ClipTextEncoder, build_text_encoder
+    from oracle import clip_ref
+    from tests.clip_fixtures import token_ids_for
+    spec = TEXT_SPECS[name]
+    if golden:
+        blob = torch.load(os.path.join(ROOT, "tests", "golden", "clip_tiny.pt"), weights_only=False)[name]
+        enc = ClipTextEncoder(spec)
+        enc.load_state_dict({k: v.float() for k, v in blob["state_dict"].items()})
+        enc = enc.cuda()
+        ids = blob["ids"]
+    else:
+        enc = build_text_encoder(name, device="cpu", seed=1)
+        with torch.no_grad():
+            for p_ in enc.parameters():
+                p_.copy_(p_.to(torch.bfloat16).float())           # both sides see bf16-exact weights
+        enc = enc.cuda()
+        ids = token_ids_for(spec, batch, seed=2)
+    sd = {k: v.detach().float().cpu() for k, v in enc.state_dict().items()}
+    kw = dict(heads=spec.num_attention_heads, act=spec.hidden_act, eps=spec.layer_norm_eps, eos_token_id=spec.eos_token_id)
+    last, pooled, emb, hidden = clip_ref.clip_text_forward(sd, ids, **kw)
+    if golden:
+        assert (last - blob["last_hidden_state"]).abs().max() < 2e-5
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    y_last, _, y_emb, y_hidden = clip_ref.clip_text_forward(sd_gpu, ids.cuda(), dtype=torch.bfloat16, **kw)   # yardstick
+    t0 = time.time()
+    out = enc(ids, output_hidden_states=True)
+    torch.cuda.synchronize()
+    res = {}
+
+    def bound(got, want, yard, key):
+        want = want.float()
+        den = want.pow(2).mean().sqrt().item() + 1e-12
+        e = (got.float().cpu() - want).pow(2).mean().sqrt().item() / den
+        ey = (yard.float().cpu() - want).pow(2).mean().sqrt().item() / den
+        res[key] = {"rel": e, "bf16_torch_rel": ey, "ok": bool(torch.isfinite(got.float()).all()) and e <= 1.5 * ey + 5e-3,
+                    "max_abs_err": (got.float().cpu() - want).abs().max().item(), "ref_absmax": want.abs().max().item()}
+    bound(out.last_hidden_state, last, y_last, "last_hidden_state")
+    bound(out.hidden_states[-2], hidden[-2], y_hidden[-2], "penultimate")
+    if spec.projection_dim:
+        bound(out[0], emb, y_emb, "text_embeds")
+        res["first_is_text_embeds"] = {"rel": 0.0, "ok": out[0].shape == (ids.shape[0], spec.projection_dim)}
+    else:
+        res["first_is_last"] = {"rel": 0.0, "ok": out[0] is out.last_hidden_state and out[0].shape == last.shape}
+    r = _merge(res)
+    r["encode_s"] = round(time.time() - t0, 3)
+    return r
+
+
 CASES = [
+    ("text_kernels", case_text_kernels, {}),
+    ("text_encoder_tiny_golden", case_text_encoder, dict(name="tiny_clip", golden=True)),
+    ("text_encoder_tiny_proj_golden", case_text_encoder, dict(name="tiny_clip_proj", golden=True)),
+    ("text_encoder_clip_l", case_text_encoder, dict(name="clip_l", batch=4)),
+    ("text_encoder_openclip_h", case_text_encoder, dict(name="openclip_h", batch=2)),
+    ("text_encoder_openclip_bigg", case_text_encoder, dict(name="openclip_bigg", batch=2)),
     ("norms", case_norms, {}),
     ("elementwise", case_elementwise, {}),
     ("training_kernels", case_training_kernels, {}),

@@ -371,3 +371,62 @@ def test_train_driver_runs_an_examples_style_config(tmp_path):
     assert len(sd) == 192 * 3 and all(v.dtype == torch.bfloat16 for k, v in sd.items() if "lora_" in k.split(".")[-2])
     up = [v for k, v in sd.items() if k.endswith("lora_up.weight")]
     assert any(float(u.abs().max()) > 0 for u in up)           # lion moved the zero-initialised lora_up
+
+
+@pytest.mark.parametrize("arch", ["tiny21", "tinyxl"])
+def test_train_driver_from_a_checkpoint_directory(tmp_path, arch):
+    """SURVEY §8f rank 1 end to end: a diffusers-layout checkpoint directory (synthetic weights: nothing real exists
+    offline) -> `load_models[_xl]` reads topology, UNet weights, tokenizer(s) and CLIP text encoder(s) -> prompts are
+    tokenized and encoded ON THE GPU by the engine's text encoder (train_util.py:60-130) -> the loop trains.  The
+    embeddings the trainer sees are checked against the fp32 oracle on the same tokens."""
+    import torch
+    import yaml
+    from leco_b200 import config_util, model_util, train_lora
+    from leco_b200.unet import SPECS
+    from oracle import clip_ref
+    from tests.clip_fixtures import write_checkpoint_dir
+    d = write_checkpoint_dir(str(tmp_path / "ckpt"), arch, seed=5)
+    xl = SPECS[arch].text_time
+    prompts = ["van gogh style painting!", ""]
+    if xl:
+        toks, encs, unet, _ = model_util.load_models_xl(d)
+        out = model_util.encode_prompts_xl(toks, encs, prompts)
+        text, pooled = out.text_embeds, out.pooled_embeds
+    else:
+        tok, enc, unet, _ = model_util.load_models(d, v2=True, v_pred=True)
+        toks, encs = [tok], [enc]
+        text, pooled = model_util.encode_prompts(tok, enc, prompts), None
+    assert text.is_cuda and text.dtype == torch.bfloat16 and text.shape == (2, 77, SPECS[arch].cross_attention_dim)
+    parts = []
+    for t, e in zip(toks, encs):
+        ids = model_util.text_tokenize(t, prompts)
+        sd = {k: v.float().cpu() for k, v in e.state_dict().items()}
+        last, _, emb, hidden = clip_ref.clip_text_forward(sd, ids, heads=e.spec.num_attention_heads, act=e.spec.hidden_act,
+                                                          eos_token_id=e.spec.eos_token_id)
+        parts.append(hidden[-2] if xl else last)
+    want = torch.cat(parts, -1)
+    rel = ((text.float().cpu() - want).pow(2).mean().sqrt() / want.pow(2).mean().sqrt()).item()
+    assert rel < 1.5e-2, rel                                     # bf16 activations through 2-3 layers
+    if xl:
+        relp = ((pooled.float().cpu() - emb).pow(2).mean().sqrt() / emb.pow(2).mean().sqrt()).item()
+        assert pooled.shape == (2, SPECS[arch].add_text_dim) and relp < 1.5e-2, relp
+    del unet, encs
+
+    cfg = {"prompts_file": str(tmp_path / "prompts.yaml"),
+           "pretrained_model": {"name_or_path": d, "v2": not xl, "v_pred": not xl},
+           "network": {"type": "lierla", "rank": 4, "alpha": 1.0, "training_method": "full"},
+           "train": {"precision": "bfloat16", "noise_scheduler": "ddim", "iterations": 3, "lr": "1e-4", "optimizer": "adamw",
+                     "lr_scheduler": "constant", "max_denoising_steps": 8},
+           "save": {"name": "out", "path": str(tmp_path / "output"), "per_steps": 200, "precision": "bfloat16"},
+           "logging": {"use_wandb": False, "verbose": False}, "other": {"use_xformers": True}}
+    pr = [{"target": "van gogh", "positive": "van gogh", "unconditional": "", "neutral": "", "action": "erase",
+           "guidance_scale": 1.0, "resolution": 128, "dynamic_resolution": False, "batch_size": 1}]
+    (tmp_path / "config.yaml").write_text(yaml.safe_dump(cfg))
+    (tmp_path / "prompts.yaml").write_text(yaml.safe_dump(pr))
+    config = config_util.load_config_from_yaml(str(tmp_path / "config.yaml"))
+    settings = config_util.load_prompts_from_yaml(config.prompts_file)
+    torch.manual_seed(3)
+    seen = []
+    losses = train_lora.train(config, settings, xl=xl, on_iteration=lambda i, v: seen.append(v))
+    assert len(losses) == 3 and all(v == v and 0 < v < 50 for v in losses), losses
+    assert (tmp_path / "output" / "out_last.safetensors").is_file()

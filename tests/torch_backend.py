@@ -295,3 +295,35 @@ def attention_bwd(go, qt, kt, vt, saved, nb, sq, skv, heads, d, scale, dq_out, d
     for g, dst, s in ((q.grad, dq_out, sq), (k.grad, dk_out, skv), (v.grad, dv_out, skv)):
         if dst is not None:
             dst.copy_(g.permute(0, 2, 1, 3).reshape(nb * s, heads * d).to(dst.dtype))
+
+
+# ------------------------------------------------------------------ text-encoder prologue (leco_b200/text_encoder.py)
+def attention_v0(qt, kt, vt, nb, sq, skv, heads, d, scale, save_for_bwd=False, causal=False):
+    q, k, v = _heads(qt, nb, sq, heads, d), _heads(kt, nb, skv, heads, d), _heads(vt, nb, skv, heads, d)
+    s = q @ k.transpose(-1, -2) * scale
+    if causal:
+        s = s.masked_fill(torch.ones(sq, skv, dtype=torch.bool, device=s.device).triu(1), float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(nb * sq, heads * d).to(qt.dtype)
+    return o, ((p,) if save_for_bwd else None)
+
+
+def activation(x, kind):
+    xf = _f(x)
+    y = xf * torch.sigmoid(1.702 * xf) if kind == 1 else (F.gelu(xf) if kind == 2 else F.silu(xf))
+    return y.to(x.dtype)
+
+
+def embed_tokens(ids, tok, pos, seq):
+    rows = torch.arange(ids.numel(), device=ids.device) % seq
+    return (_f(tok)[ids.long()] + _f(pos)[rows]).to(tok.dtype)
+
+
+def softmax_rows(s, n_valid, n_pad, causal_sq=0):
+    rows = s.reshape(-1, s.shape[-1])[:, :n_valid].float().clone()
+    if causal_sq:
+        r = torch.arange(rows.shape[0], device=s.device) % causal_sq
+        rows = rows.masked_fill(torch.arange(n_valid, device=s.device)[None] > r[:, None], float("-inf"))
+    p = torch.zeros(rows.shape[0], n_pad, device=s.device)
+    p[:, :n_valid] = torch.softmax(rows, dim=-1)
+    return p.reshape(s.shape[:-1] + (n_pad,))
