@@ -425,6 +425,7 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     trainer.launches = 0
+    trainer._ar_events = []                # the warm-up all-reduces include NCCL's lazy communicator set-up
     trainer.profile_phases = True
     sec, loss_a, _ = timed(trainer, args.steps, e2e=False)
     phases = trainer.phase_ms()
@@ -480,6 +481,7 @@ def run_ours(args):
         }
         line.update(extra)
         if world > 1:
+            # event-to-event on rank 0: the collective itself plus the wait for the slowest rank to arrive
             line["allreduce"] = {"device_us_per_step": None if ar_ms is None else 1000.0 * ar_ms,
                                  "bytes": int(net.flat.grads_ext.numel() * 4),
                                  "what": "ONE ncclAllReduce of the flat fp32 LoRA gradient with the loss in its last slot"}

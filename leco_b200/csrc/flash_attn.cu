@@ -17,6 +17,7 @@
 // V operand: v_mode 0 = V tile [keys, d] used directly as an MN-major B operand;
 //            v_mode 1 = a pre-transposed V^T [d, keys] (K-major B operand, like the GEMM kernel).
 #include "../../include/leco_b200.h"
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -397,6 +398,332 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
   if (warp == 2) tmem_dealloc(tmem_base, FA_TMEM_COLS);
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Variant with P and O kept in tensor memory (default; LECO_FLASH_TS=0 selects the kernel above).
+//   * P_j (bf16) is written back INTO the score slot it was computed from (tcgen05.st, two keys per 32-bit column) and
+//     the PV product reads it from there as a TMEM A operand: no shared-memory P tile, no st.shared / proxy fence, and
+//     no p_empty wait (the slot's next user is a later QK^T, ordered behind this PV by the in-order tensor pipe);
+//   * each warpgroup's PV products ACCUMULATE in its own 64 TMEM columns over all of its tiles.  The softmax warps
+//     therefore never read a PV result inside the loop (the per-tile fold and its pv_full wait were 17 % of their
+//     stall samples, profiles/r2k_ncu_full_flash_fwd.txt).  The running max is lazy with a threshold: exponentials use
+//     a reference max that is only advanced when the true max has moved by more than 2^8 (P <= 256, harmless in
+//     bf16 / fp32); only then is the accumulator rescaled in TMEM, at the start of the warpgroup's next tile.
+// TMEM: 3 score/probability slots x 128 columns, then 2 x 64 output columns.
+constexpr int FT_SMEM = FA_Q_BYTES + (FA_KS + FA_VS) * FA_KV_BYTES + 2 * (32 * 128 * 4) + 1024 + 512 + (2 * 2 + 2) * 128 * 4;
+constexpr float FT_RESCALE_LOG2 = 8.0f;
+
+__global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_ts_kernel(const __grid_constant__ FlashParams p) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + FA_Q_BYTES;
+  uint8_t* sV = sK + FA_KS * FA_KV_BYTES;
+  float* sX = reinterpret_cast<float*>(sV + FA_VS * FA_KV_BYTES);   // [2 warpgroups][32 cols][128 rows] merge exchange
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 2 * 32 * 128);
+  uint64_t* q_full = bars;                 // [1]
+  uint64_t* k_full = bars + 1;             // [KS]
+  uint64_t* k_empty = k_full + FA_KS;      // [KS]
+  uint64_t* v_full = k_empty + FA_KS;      // [VS]
+  uint64_t* v_empty = v_full + FA_VS;      // [VS]
+  uint64_t* s_full = v_empty + FA_VS;      // [FA_SB]  QK^T of the slot finished
+  uint64_t* p_full = s_full + FA_SB;       // [FA_SB]  P written into the slot (and the accumulator rescaled if needed)
+  uint64_t* pv_done = p_full + FA_SB;      // [2]      per warpgroup: its latest PV finished
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  float* mx_buf = reinterpret_cast<float*>(tmem_slot + 2);  // [2 warpgroups][128 rows] maxima + [2][128] sums
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = p.n_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_q);
+    tma_prefetch_desc(&p.tm_k);
+    tma_prefetch_desc(&p.tm_v);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < FA_KS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < FA_VS; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < FA_SB; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);    // the four warps of the warpgroup that owns the tile
+    }
+    mbar_init(&pv_done[0], 1);
+    mbar_init(&pv_done[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, FA_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const uint32_t tmem_s = tmem_base;                    // + (j % 3) * 128
+  const uint32_t tmem_o = tmem_base + FA_SB * FA_BN;    // + warpgroup * 64
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one elected lane)
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, FA_Q_BYTES);
+      tma_load_4d(sQ, &p.tm_q, q_full, 0, qt * FA_BM, head, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int ks = j % FA_KS, vs = j % FA_VS;
+        mbar_wait(&k_empty[ks], ((j / FA_KS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[ks], FA_KV_BYTES);
+        tma_load_4d(sK + ks * FA_KV_BYTES, &p.tm_k, &k_full[ks], 0, j * FA_BN, head, b);
+        mbar_wait(&v_empty[vs], ((j / FA_VS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[vs], FA_KV_BYTES);
+        if (p.v_mode == 0) {
+          tma_load_4d(sV + vs * FA_KV_BYTES, &p.tm_v, &v_full[vs], 0, j * FA_BN, head, b);
+        } else {  // V^T [d, keys]: two 64-key chunks, each [64 d-rows x 128 B]
+          tma_load_4d(sV + vs * FA_KV_BYTES, &p.tm_v, &v_full[vs], j * FA_BN, 0, head, b);
+          tma_load_4d(sV + vs * FA_KV_BYTES + FA_KV_BYTES / 2, &p.tm_v, &v_full[vs], j * FA_BN + 64, 0, head, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one elected lane)
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc_bf16(FA_BN, false);
+      const uint32_t idesc_pv = umma_idesc_bf16(FA_D, p.v_mode == 0);
+      const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ));
+      // QK^T of tile j into slot j % 3.  The slot last held P_{j-3}; PV_{j-3} was issued before this call (program
+      // order of this lane) and the tensor pipe executes in issue order, so no barrier guards the reuse.  The softmax
+      // warps are done with the slot as well: p_full of tile j-3 was waited for before PV_{j-3} was issued.
+      auto issue_s = [&](int j) {
+        const int ks = j % FA_KS, sb = j % FA_SB;
+        mbar_wait(&k_full[ks], (j / FA_KS) & 1);
+        tc_fence_after();
+        const uint64_t dk = umma_desc_k_sw128(smem_u32(sK + ks * FA_KV_BYTES));
+#pragma unroll
+        for (int s = 0; s < FA_D / 16; ++s) umma_bf16(tmem_s + sb * FA_BN, dq + 2 * s, dk + 2 * s, idesc_s, s > 0 ? 1u : 0u);
+        umma_commit(&s_full[sb]);
+        umma_commit(&k_empty[ks]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      if (n_tiles > 1) issue_s(1);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 2 < n_tiles) issue_s(j + 2);
+        const int vs = j % FA_VS, sb = j % FA_SB, wg = j & 1;
+        mbar_wait(&p_full[sb], (j / FA_SB) & 1);
+        mbar_wait(&v_full[vs], (j / FA_VS) & 1);
+        tc_fence_after();
+        const uint32_t vbase = smem_u32(sV + vs * FA_KV_BYTES);
+        const uint32_t a_tmem = tmem_s + sb * FA_BN;       // P_j: 64 columns of packed bf16 pairs, 8 per K=16 step
+#pragma unroll
+        for (int s = 0; s < FA_BN / 16; ++s) {
+          uint64_t db;
+          if (p.v_mode == 0)
+            db = umma_desc_mn_sw128(vbase + s * 16 * 128);                       // 16 key rows per k-step
+          else
+            db = umma_desc_k_sw128(vbase + (s >> 2) * (FA_KV_BYTES / 2)) + 2 * (s & 3);
+          umma_bf16_ts(tmem_o + wg * FA_D, a_tmem + 8 * s, db, idesc_pv, (j >= 2 || s > 0) ? 1u : 0u);
+        }
+        umma_commit(&pv_done[wg]);
+        umma_commit(&v_empty[vs]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax + output
+    const int wg = (warp - 4) >> 2;
+    const int q = warp & 3;                  // TMEM lane quadrant
+    const int r = q * 32 + lane;             // row of the query tile
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t o_addr = tmem_o + lane_off + wg * FA_D;
+    float m_ref = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+
+    auto softmax_tile = [&](int j, auto rg_tag, auto first_tag) {
+      constexpr bool ragged = decltype(rg_tag)::value;
+      constexpr bool first = decltype(first_tag)::value;
+      const int s3 = j % FA_SB;
+      const int kv0 = j * FA_BN;
+      if constexpr (!first) {
+        // rare: the previous tile of this warpgroup moved the reference max -> rescale the accumulator in TMEM
+        if (__any_sync(0xffffffffu, alpha_prev != 1.0f)) {
+          mbar_wait(&pv_done[wg], ((j - 2) >> 1) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            uint32_t raw[32];
+            tmem_ld_32x32b_x32(o_addr + h * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha_prev);
+            tmem_st_32x32b_x32(o_addr + h * 32, raw);
+          }
+          tmem_st_wait();
+        }
+      }
+      mbar_wait(&s_full[s3], (j / FA_SB) & 1);
+      tc_fence_after();
+      const uint32_t s_addr = tmem_s + lane_off + s3 * FA_BN;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      if constexpr (first) {
+        // row max over the 128 scores, 32 at a time (four independent running maxima)
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t sv[32];
+          tmem_ld_32x32b_x32(s_addr + c * 32, sv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float a0 = __uint_as_float(sv[i]), a1 = __uint_as_float(sv[i + 1]), a2 = __uint_as_float(sv[i + 2]),
+                  a3 = __uint_as_float(sv[i + 3]);
+            if constexpr (ragged) {
+              if (kv0 + c * 32 + i >= p.skv) a0 = -INFINITY;
+              if (kv0 + c * 32 + i + 1 >= p.skv) a1 = -INFINITY;
+              if (kv0 + c * 32 + i + 2 >= p.skv) a2 = -INFINITY;
+              if (kv0 + c * 32 + i + 3 >= p.skv) a3 = -INFINITY;
+            }
+            mx0 = fmaxf(mx0, a0);
+            mx1 = fmaxf(mx1, a1);
+            mx2 = fmaxf(mx2, a2);
+            mx3 = fmaxf(mx3, a3);
+          }
+        }
+        m_ref = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      }
+      const float mb = m_ref * p.scale_log2;
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;  // four partial sums: no long dependent FADD chain
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32];
+        tmem_ld_32x32b_x32(s_addr + c * 32, sv);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = t * 8 + u * 2;
+            float a0 = __uint_as_float(sv[i]), a1 = __uint_as_float(sv[i + 1]);
+            float p0 = ex2_approx(fmaf(a0, p.scale_log2, -mb));
+            float p1 = ex2_approx(fmaf(a1, p.scale_log2, -mb));
+            if constexpr (ragged) {
+              if (kv0 + c * 32 + i >= p.skv) { p0 = 0.f; a0 = -INFINITY; }
+              if (kv0 + c * 32 + i + 1 >= p.skv) { p1 = 0.f; a1 = -INFINITY; }
+            }
+            if constexpr (!first) {
+              if (u == 0) mx0 = fmaxf(mx0, fmaxf(a0, a1)); else if (u == 1) mx1 = fmaxf(mx1, fmaxf(a0, a1));
+              else if (u == 2) mx2 = fmaxf(mx2, fmaxf(a0, a1)); else mx3 = fmaxf(mx3, fmaxf(a0, a1));
+            }
+            if (u == 0) rs0 += p0 + p1; else if (u == 1) rs1 += p0 + p1; else if (u == 2) rs2 += p0 + p1; else rs3 += p0 + p1;
+            pk[t * 4 + u] = pack_bf16(p0, p1);
+          }
+        }
+        // keys [32c, 32c+32) -> columns [16c, 16c+16) of the same slot: only score columns already read are overwritten
+        tmem_st_32x32b_x16(s_addr + c * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[s3]);
+      float alpha = 1.0f;
+      if constexpr (!first) {
+        const float m_true = fmaxf(fmaxf(m_ref, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
+        if ((m_true - m_ref) * p.scale_log2 > FT_RESCALE_LOG2) {
+          alpha = ex2_approx((m_ref - m_true) * p.scale_log2);
+          m_ref = m_true;
+        }
+      }
+      l_run = (l_run + ((rs0 + rs1) + (rs2 + rs3))) * alpha;
+      alpha_prev = alpha;       // applied to the accumulator once this tile's PV has been added to it
+    };
+    int last = -1;
+    for (int j = wg; j < n_tiles; j += 2) {
+      const bool rg = j * FA_BN + FA_BN > p.skv;
+      if (j == wg) {
+        if (rg) softmax_tile(j, std::true_type{}, std::true_type{});
+        else softmax_tile(j, std::false_type{}, std::true_type{});
+      } else {
+        if (rg) softmax_tile(j, std::true_type{}, std::false_type{});
+        else softmax_tile(j, std::false_type{}, std::false_type{});
+      }
+      last = j;
+    }
+    // ---- this warpgroup's accumulator, once: TMEM -> registers (scaled by the pending alpha of its last tile)
+    float o[FA_D];
+    if (last >= 0) {
+      mbar_wait(&pv_done[wg], (last >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(o_addr + h * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[h * 32 + i] = __uint_as_float(raw[i]) * alpha_prev;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < FA_D; ++i) o[i] = 0.f;
+    }
+    // ---- merge the two partial softmax results: each warpgroup finishes 32 of the 64 output columns
+    {
+      float* xo = sX + wg * 32 * 128;         // [32 cols][128 rows]
+      if (wg == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xo[i * 128 + r] = o[32 + i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xo[i * 128 + r] = o[i];
+      }
+      mx_buf[wg * 128 + r] = m_ref;
+      mx_buf[256 + wg * 128 + r] = l_run;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the two softmax warpgroups only, once per CTA
+    {
+      const float m_o = mx_buf[(wg ^ 1) * 128 + r], l_o = mx_buf[256 + (wg ^ 1) * 128 + r];
+      const float m_tot = fmaxf(m_ref, m_o);          // finite: tile 0 has at least one valid key
+      const float a_me = ex2_approx((m_ref - m_tot) * p.scale_log2);
+      const float a_ot = ex2_approx((m_o - m_tot) * p.scale_log2);
+      const float l_tot = l_run * a_me + l_o * a_ot;
+      const float* xi = sX + (wg ^ 1) * 32 * 128;
+      const int row = qt * FA_BM + r;
+      const float inv = 1.0f / l_tot;
+      float f[32];
+      if (wg == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = (o[i] * a_me + xi[i * 128 + r] * a_ot) * inv;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = (o[32 + i] * a_me + xi[i * 128 + r] * a_ot) * inv;
+      }
+      if (row < p.sq) {
+        if (p.lse && wg == 0)
+          p.lse[(static_cast<long long>(b) * p.heads + head) * p.sq + row] = m_tot * p.scale_log2 + log2f(l_tot);
+        __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.sq + row) * p.ld_out + head * p.d + wg * 32;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          if (wg * 32 + c8 * 8 < p.d) {
+            uint4 v;
+            v.x = pack_bf16(f[c8 * 8 + 0], f[c8 * 8 + 1]);
+            v.y = pack_bf16(f[c8 * 8 + 2], f[c8 * 8 + 3]);
+            v.z = pack_bf16(f[c8 * 8 + 4], f[c8 * 8 + 5]);
+            v.w = pack_bf16(f[c8 * 8 + 6], f[c8 * 8 + 7]);
+            *reinterpret_cast<uint4*>(dst + c8 * 8) = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, FA_TMEM_COLS);
+}
+
 }  // namespace leco
 
 using namespace leco;
@@ -463,11 +790,17 @@ static int flash_fwd_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
   static bool attr_set = false;
   if (!attr_set) {
     LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
     attr_set = true;
   }
+  // LECO_FLASH_TS=0: the variant that stages P through shared memory and folds PV in registers
+  static const bool use_ts = [] { const char* e = getenv("LECO_FLASH_TS"); return !(e && e[0] == '0'); }();
   dim3 grid((sq + FA_BM - 1) / FA_BM, heads, batch);
   count_launch();
-  LECO_LAUNCH(flash_attn_fwd_kernel, grid, FA_THREADS, FA_SMEM, reinterpret_cast<cudaStream_t>(stream), p);
+  if (use_ts)
+    LECO_LAUNCH(flash_attn_fwd_ts_kernel, grid, FA_THREADS, FT_SMEM, reinterpret_cast<cudaStream_t>(stream), p);
+  else
+    LECO_LAUNCH(flash_attn_fwd_kernel, grid, FA_THREADS, FA_SMEM, reinterpret_cast<cudaStream_t>(stream), p);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

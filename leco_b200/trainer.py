@@ -436,11 +436,14 @@ class LecoTrainer:
         return {"denoise_loop_ms": den, "tail_ms": tail, "mean_k": sum(k for k, _ in self._phase_events) / n}
 
     def allreduce_ms(self) -> Optional[float]:
-        """Mean device time of the data-parallel all-reduce over the last iterations (None on one rank)."""
+        """Median device time of the data-parallel all-reduce over the last iterations (None on one rank).  Event to
+        event on this rank, so it includes waiting for the slowest rank; the median keeps NCCL's lazy communicator
+        set-up inside the very first call out of the figure."""
         if not self._ar_events:
             return None
         torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in self._ar_events) / len(self._ar_events)
+        ts = sorted(a.elapsed_time(b) for a, b in self._ar_events)
+        return ts[len(ts) // 2]
 
     def _stage_noise(self, noise, bl, h, w, dst):
         """Host noise slice of this rank -> pinned staging -> device (the only per-step H2D traffic)."""
