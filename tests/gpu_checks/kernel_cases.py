@@ -429,8 +429,13 @@ def case_attention(nb, sq, skv, heads, d, cross=False, bwd_impl="flash"):
     return _merge(res)
 
 
-def case_flash(nb, sq, skv, heads, d, cross=False, v_mode=0, perf=False):
+def case_flash(nb, sq, skv, heads, d, cross=False, v_mode=0, perf=False, ts=None, qscale=1.0, kramp=0.0):
+    """ts: LECO_FLASH_TS for this process (None = library default, 0 = the shared-memory-P variant).  qscale / kramp
+    stretch the scores (and make later keys larger) so that the running max keeps moving by more than the lazy-rescale
+    threshold: the in-TMEM accumulator rescale of the default variant is then taken on most tiles."""
     import torch
+    if ts is not None:
+        os.environ["LECO_FLASH_TS"] = str(ts)
     from leco_b200 import ops
     from tests import torch_backend as tb
     C = heads * d
@@ -439,6 +444,13 @@ def case_flash(nb, sq, skv, heads, d, cross=False, v_mode=0, perf=False):
         qt, kt, vt = qbuf, kvbuf[:, :C], kvbuf[:, C:]
     else:
         qkv = _rand((nb * sq, 3 * C), seed=1)
+        if qscale != 1.0 or kramp:
+            q32 = qkv.float()
+            q32[:, :C] *= qscale
+            if kramp:
+                ramp = 0.5 + kramp * (torch.arange(nb * sq, device=q32.device) % skv).float() / skv
+                q32[:, C:2 * C] *= ramp[:, None]
+            qkv = q32.to(torch.bfloat16)
         qt, kt, vt = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
     scale = d ** -0.5
     o = ops.flash_attention(qt, kt, vt, nb, sq, skv, heads, d, scale, v_mode=v_mode)
@@ -723,6 +735,12 @@ CASES = [
     ("flash_sq64_m0", case_flash, dict(nb=3, sq=64, skv=64, heads=4, d=64, v_mode=0)),
     ("flash_sq200_skv300_m1", case_flash, dict(nb=1, sq=200, skv=300, heads=2, d=64, cross=True, v_mode=1)),
     ("flash_sq200_skv300_m0", case_flash, dict(nb=1, sq=200, skv=300, heads=2, d=64, cross=True, v_mode=0)),
+    ("flash_rescale_2048", case_flash, dict(nb=2, sq=2048, skv=2048, heads=4, d=64, qscale=8.0)),
+    ("flash_rescale_ramp_1000", case_flash, dict(nb=2, sq=1000, skv=1000, heads=4, d=64, qscale=3.0, kramp=6.0, v_mode=1)),
+    ("flash_rescale_2048_smemP", case_flash, dict(nb=2, sq=2048, skv=2048, heads=4, d=64, qscale=8.0, ts=0)),
+    ("flash_self_1024_m0_smemP", case_flash, dict(nb=2, sq=1024, skv=1024, heads=5, d=64, v_mode=0, ts=0)),
+    ("flash_cross_77_m1_smemP", case_flash, dict(nb=2, sq=256, skv=77, heads=2, d=64, cross=True, v_mode=1, ts=0)),
+    ("flash_perf_4096_m0_smemP", case_flash, dict(nb=4, sq=4096, skv=4096, heads=5, d=64, v_mode=0, perf=True, ts=0)),
     ("flash_perf_4096_m0", case_flash, dict(nb=4, sq=4096, skv=4096, heads=5, d=64, v_mode=0, perf=True)),
     ("flash_perf_4096_m1", case_flash, dict(nb=4, sq=4096, skv=4096, heads=5, d=64, v_mode=1, perf=True)),
     ("engine_fwd_tiny21", case_engine_forward, dict(arch="tiny21")),
