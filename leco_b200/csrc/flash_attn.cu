@@ -412,6 +412,59 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_kernel(const __g
 // TMEM: 3 score/probability slots x 128 columns, then 2 x 64 output columns.
 constexpr int FT_SMEM = FA_Q_BYTES + (FA_KS + FA_VS) * FA_KV_BYTES + 2 * (32 * 128 * 4) + 1024 + 512 + (2 * 2 + 2) * 128 * 4;
 constexpr float FT_RESCALE_LOG2 = 8.0f;
+// Which of the four score pairs of every 8 go through the FMA-pipe polynomial instead of the MUFU (bit u = pair u):
+// 0b1000 = a quarter of the exponentials.  ex2 runs at 16 / clk / SM (profiles/r2_micro_probe.txt) and is the floor of
+// this kernel; a degree-3 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below bf16's 2^-9) in packed f32x2
+// arithmetic moves part of that load to the FMA pipe, which has issue slots to spare once the rest of the row update
+// is packed too (FFMA2 scale/shift, FADD2 row sums, 3-input max).
+constexpr int FT_POLY_PAIRS = 0b1000;
+
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_pack_bits(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// 2^x for a packed pair on the FMA pipe: n = round(x) via the 1.5 * 2^23 trick, 2^(x - n) by a cubic, exponent add.
+__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& r0, float& r1) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  x2 = f2_pack(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const uint64_t magic = f2_pack(12582912.0f, 12582912.0f), nmagic = f2_pack(-12582912.0f, -12582912.0f);
+  const uint64_t t2 = f2_add(x2, magic);                                    // low mantissa bits = round(x)
+  const uint64_t n2 = f2_add(t2, nmagic);
+  const uint64_t f2 = f2_fma(n2, f2_pack(-1.0f, -1.0f), x2);                // x - round(x) in [-0.5, 0.5]
+  uint64_t q2 = f2_fma(f2, f2_pack(0.05517164617776871f, 0.05517164617776871f), f2_pack(0.2426111251115799f, 0.2426111251115799f));
+  q2 = f2_fma(q2, f2, f2_pack(0.6932609677314758f, 0.6932609677314758f));
+  q2 = f2_fma(q2, f2, f2_pack(0.9999280571937561f, 0.9999280571937561f));
+  float q0, q1, t0, t1;
+  f2_unpack(q2, q0, q1);
+  f2_unpack(t2, t0, t1);
+  r0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  r1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
 
 __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_ts_kernel(const __grid_constant__ FlashParams p) {
   pdl_launch_dependents();
@@ -597,6 +650,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_ts_kernel(const 
       }
       const float mb = m_ref * p.scale_log2;
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;  // four partial sums: no long dependent FADD chain
+      uint64_t rsp0 = 0, rsp1 = 0, rsp2 = 0, rsp3 = 0;   // the same, as packed f32x2 accumulators (full tiles)
+      const uint64_t c2 = f2_pack(p.scale_log2, p.scale_log2), nmb2 = f2_pack(-mb, -mb);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t sv[32];
@@ -608,23 +663,49 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_ts_kernel(const 
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int i = t * 8 + u * 2;
-            float a0 = __uint_as_float(sv[i]), a1 = __uint_as_float(sv[i + 1]);
-            float p0 = ex2_approx(fmaf(a0, p.scale_log2, -mb));
-            float p1 = ex2_approx(fmaf(a1, p.scale_log2, -mb));
             if constexpr (ragged) {
+              float a0 = __uint_as_float(sv[i]), a1 = __uint_as_float(sv[i + 1]);
+              float p0 = ex2_approx(fmaf(a0, p.scale_log2, -mb));
+              float p1 = ex2_approx(fmaf(a1, p.scale_log2, -mb));
               if (kv0 + c * 32 + i >= p.skv) { p0 = 0.f; a0 = -INFINITY; }
               if (kv0 + c * 32 + i + 1 >= p.skv) { p1 = 0.f; a1 = -INFINITY; }
+              if constexpr (!first) {
+                if (u == 0) mx0 = fmaxf(mx0, fmaxf(a0, a1)); else if (u == 1) mx1 = fmaxf(mx1, fmaxf(a0, a1));
+                else if (u == 2) mx2 = fmaxf(mx2, fmaxf(a0, a1)); else mx3 = fmaxf(mx3, fmaxf(a0, a1));
+              }
+              if (u == 0) rs0 += p0 + p1; else if (u == 1) rs1 += p0 + p1; else if (u == 2) rs2 += p0 + p1; else rs3 += p0 + p1;
+              pk[t * 4 + u] = pack_bf16(p0, p1);
+            } else {
+              // packed path: FFMA2 scale/shift, 2 x MUFU (or the FMA-pipe cubic), FADD2 row sum, 3-input max, F2FP
+              const uint64_t x2 = f2_fma(f2_pack_bits(sv[i], sv[i + 1]), c2, nmb2);
+              float p0, p1;
+              if ((FT_POLY_PAIRS >> u) & 1) {
+                ex2_poly2(x2, p0, p1);
+              } else {
+                float x0, x1;
+                f2_unpack(x2, x0, x1);
+                p0 = ex2_approx(x0);
+                p1 = ex2_approx(x1);
+              }
+              if constexpr (!first) {
+                const float a0 = __uint_as_float(sv[i]), a1 = __uint_as_float(sv[i + 1]);
+                if (u == 0) mx0 = max3f(mx0, a0, a1); else if (u == 1) mx1 = max3f(mx1, a0, a1);
+                else if (u == 2) mx2 = max3f(mx2, a0, a1); else mx3 = max3f(mx3, a0, a1);
+              }
+              const uint64_t pp = f2_pack(p0, p1);
+              if (u == 0) rsp0 = f2_add(rsp0, pp); else if (u == 1) rsp1 = f2_add(rsp1, pp);
+              else if (u == 2) rsp2 = f2_add(rsp2, pp); else rsp3 = f2_add(rsp3, pp);
+              pk[t * 4 + u] = pack_bf16(p0, p1);
             }
-            if constexpr (!first) {
-              if (u == 0) mx0 = fmaxf(mx0, fmaxf(a0, a1)); else if (u == 1) mx1 = fmaxf(mx1, fmaxf(a0, a1));
-              else if (u == 2) mx2 = fmaxf(mx2, fmaxf(a0, a1)); else mx3 = fmaxf(mx3, fmaxf(a0, a1));
-            }
-            if (u == 0) rs0 += p0 + p1; else if (u == 1) rs1 += p0 + p1; else if (u == 2) rs2 += p0 + p1; else rs3 += p0 + p1;
-            pk[t * 4 + u] = pack_bf16(p0, p1);
           }
         }
         // keys [32c, 32c+32) -> columns [16c, 16c+16) of the same slot: only score columns already read are overwritten
         tmem_st_32x32b_x16(s_addr + c * 16, pk);
+      }
+      if constexpr (!ragged) {
+        float lo, hi;
+        f2_unpack(f2_add(f2_add(rsp0, rsp1), f2_add(rsp2, rsp3)), lo, hi);
+        rs0 = lo + hi;
       }
       tmem_st_wait();
       tc_fence_before();
