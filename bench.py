@@ -308,7 +308,7 @@ def kernel_rooflines(cfg, dev, burst, how):
                          6, flush)
         fl = 4.0 * n_s * H * S * S * d
         tf = fl / (ms * 1e-3) / 1e12
-        out["roofline"] = {"bound": "tensor", "kernel": f"flash_attn_fwd_kernel softmax(QK^T/sqrt d)V, S={S}, d={d}, {n_s * H} (sample, head) "
+        out["roofline"] = {"bound": "tensor", "kernel": f"flash_attn_fwd_ts_kernel softmax(QK^T/sqrt d)V, S={S}, d={d}, {n_s * H} (sample, head) "
                            f"pairs — the time-dominant kernel of a denoise forward (profiles/ launch list)",
                            "achieved": tf, "peak": burst, "unit": "TFLOP/s", "frac": tf / burst,
                            "traffic": traffic("flash_kernel_traffic.json"), "peak_source": how, "ms": ms,
