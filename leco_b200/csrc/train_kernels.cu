@@ -9,6 +9,7 @@
 //   * leco_loss    : erase/enhance MSE objective (prompt_util.py:107-135) + its gradient
 //                    w.r.t. the target prediction, on device (the reference does this on the CPU).
 #include "../../include/leco_b200.h"
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -82,6 +83,116 @@ tn_reduce_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __nv_
       const int j = ty * JB + jj;
       if (jj < JB && j < N2)
         atomicAdd(transpose_out ? out + (long long)j * ldo + n : out + (long long)n * ldo + j, acc[i][jj] * scale);
+    }
+  }
+}
+
+// The same reduction on the tensor cores (default; LECO_TN_MMA=0 selects the FMA kernel above).  The contraction runs
+// over the ROWS of both operands, so both tiles sit in shared memory "the wrong way round" for mma.sync and are read
+// with ldmatrix.trans; rows are padded (272 B / 144 B) so the eight 16-byte row segments of one 8x8 matrix fall in
+// different banks.  One block = 128 columns of A x all N2 <= 64 columns of B x one row split; a warp owns 16 columns
+// of A.  Tiles of 32 rows stream through a 3-stage cp.async ring.  (mma.sync, not tcgen05: the output is at most
+// 128 x 64 per block and the op is bound by reading A once, not by math.)
+constexpr int TM_ROWS = 32, TM_STAGES = 3, TM_LDA = TN_TILE_N1 + 8, TM_LDB = 64 + 8;
+
+__device__ __forceinline__ void cp_async_16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256)
+tn_reduce_mma_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __nv_bfloat16* __restrict__ B,
+                     long long ldb, float* __restrict__ out, long long ldo, long long M, int N1, int N2, float scale,
+                     int rows_per_split, int transpose_out) {
+  pdl_entry();
+  __shared__ __align__(16) __nv_bfloat16 sA[TM_STAGES][TM_ROWS][TM_LDA];
+  __shared__ __align__(16) __nv_bfloat16 sB[TM_STAGES][TM_ROWS][TM_LDB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * TN_TILE_N1;
+  const long long m_begin = (long long)blockIdx.y * rows_per_split;
+  const long long m_end = min(M, m_begin + rows_per_split);
+  const int n_stages = (int)((m_end - m_begin + TM_ROWS - 1) / TM_ROWS);
+  const int pairs = (N2 + 15) >> 4;          // pairs of 8-wide B column tiles (1..4)
+
+  auto load_stage = [&](int st) {
+    const int buf = st % TM_STAGES;
+    const long long m0 = m_begin + (long long)st * TM_ROWS;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {            // A: 32 rows x 16 vectors
+      const int vi = threadIdx.x + t * 256;
+      const int r = vi >> 4, cv = vi & 15;
+      const bool ok = m0 + r < m_end && n0 + cv * 8 < N1;
+      cp_async_16_zfill(&sA[buf][r][cv * 8], ok ? A + (m0 + r) * lda + n0 + cv * 8 : A, ok);
+    }
+    {                                         // B: 32 rows x 8 vectors
+      const int r = threadIdx.x >> 3, cv = threadIdx.x & 7;
+      const bool ok = m0 + r < m_end && cv * 8 < N2;
+      cp_async_16_zfill(&sB[buf][r][cv * 8], ok ? B + (m0 + r) * ldb + cv * 8 : B, ok);
+    }
+  };
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int st = 0; st < TM_STAGES - 1; ++st) {
+    if (st < n_stages) load_stage(st);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // ldmatrix row addresses: lane l supplies row (l & 7) of matrix (l >> 3); matrices = (k 0-7 | k 8-15) x (col 0-7 | 8-15)
+  const int lm_row = (lane & 7) + ((lane >> 4) << 3);      // k offset inside the 16-row step
+  const int lm_col = ((lane >> 3) & 1) << 3;               // column offset 0 / 8
+  for (int st = 0; st < n_stages; ++st) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(TM_STAGES - 2) : "memory");
+    __syncthreads();
+    if (st + TM_STAGES - 1 < n_stages) load_stage(st + TM_STAGES - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int buf = st % TM_STAGES;
+#pragma unroll
+    for (int ks = 0; ks < TM_ROWS / 16; ++ks) {
+      uint32_t a0, a1, a2, a3;
+      // A'[m][k] = tile[k][m]: matrices in fragment order (m 0-7,k 0-7) (m 8-15,k 0-7) (m 0-7,k 8-15) (m 8-15,k 8-15)
+      ldmatrix_x4_trans(smem_u32(&sA[buf][ks * 16 + (lane & 7) + ((lane >> 4) << 3)][warp * 16 + (((lane >> 3) & 1) << 3)]),
+                        a0, a1, a2, a3);
+#pragma unroll
+      for (int pr = 0; pr < 4; ++pr) {
+        if (pr < pairs) {
+          uint32_t b0, b1, b2, b3;
+          // B'[k][n] = tile[k][n]: (k 0-7,n 0-7) (k 8-15,n 0-7) (k 0-7,n 8-15) (k 8-15,n 8-15)
+          ldmatrix_x4_trans(smem_u32(&sB[buf][ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3)][pr * 16 + ((lane >> 4) << 3)]),
+                            b0, b1, b2, b3);
+          mma_bf16_16816(acc[pr * 2], a0, a1, a2, a3, b0, b1);
+          mma_bf16_16816(acc[pr * 2 + 1], a0, a1, a2, a3, b2, b3);
+        }
+      }
+    }
+  }
+  (void)lm_row;
+  (void)lm_col;
+  // C fragment: rows (lane >> 2) and +8 of the warp's 16 A-columns, B-columns (lane & 3) * 2 + {0, 1}
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (nt < pairs * 2) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = n0 + warp * 16 + (lane >> 2) + ((e >> 1) << 3);
+        const int j = nt * 8 + (lane & 3) * 2 + (e & 1);
+        if (n < N1 && j < N2)
+          atomicAdd(transpose_out ? out + (long long)j * ldo + n : out + (long long)n * ldo + j, acc[nt][e] * scale);
+      }
     }
   }
 }
@@ -316,7 +427,11 @@ extern "C" int leco_tn_reduce(const void* a, int64_t lda, const void* b, int64_t
   splits = (int)((M + rows_per - 1) / rows_per);
   dim3 grid((N1 + TN_TILE_N1 - 1) / TN_TILE_N1, splits);
   count_launch();
-  LECO_LAUNCH(tn_reduce_kernel, grid, 256, 0, STREAM(stream), BF(a), lda, BF(b), ldb, out, ldo, M, N1, N2, scale, rows_per, transpose_out);
+  static const bool use_mma = [] { const char* e = getenv("LECO_TN_MMA"); return !(e && e[0] == '0'); }();
+  if (use_mma)
+    LECO_LAUNCH(tn_reduce_mma_kernel, grid, 256, 0, STREAM(stream), BF(a), lda, BF(b), ldb, out, ldo, M, N1, N2, scale, rows_per, transpose_out);
+  else
+    LECO_LAUNCH(tn_reduce_kernel, grid, 256, 0, STREAM(stream), BF(a), lda, BF(b), ldb, out, ldo, M, N1, N2, scale, rows_per, transpose_out);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -180,12 +180,29 @@ def case_training_kernels():
     import torch
     from leco_b200 import ops
     res = {}
-    for (M, N1, N2, tr) in ((16384, 960, 16, False), (1000, 320, 16, True), (4096, 2560, 32, False), (308, 1024, 16, True)):
+    for (M, N1, N2, tr) in ((16384, 960, 16, False), (1000, 320, 16, True), (4096, 2560, 32, False), (308, 1024, 16, True),
+                            (16384, 320, 64, False), (77, 1280, 48, True), (33, 200, 8, False), (2048, 328, 24, True)):
         a, b = _rand((M, N1), seed=1), _rand((M, N2), seed=2)
-        out = torch.zeros((N2, N1) if tr else (N1, N2), device="cuda")
+        out = torch.full((N2, N1) if tr else (N1, N2), 0.25, device="cuda")      # the kernel accumulates into `out`
         ops.tn_reduce(a, b, out, 0.5, transpose_out=tr)
-        ref = 0.5 * a.float().t() @ b.float()
+        ref = 0.25 + 0.5 * a.float().t() @ b.float()
         res[f"tn_{M}_{N1}_{N2}_{int(tr)}"] = _cmp(out, ref.t() if tr else ref, 2e-3)
+    # strided operands (column slices of wider buffers, as the backward passes them)
+    wide_a, wide_b = _rand((4096, 3 * 320), seed=5), _rand((4096, 96), seed=6)
+    out = torch.zeros((320, 32), device="cuda")
+    ops.tn_reduce(wide_a[:, 320:640], wide_b[:, 32:64], out, 1.0)
+    res["tn_strided"] = _cmp(out, wide_a[:, 320:640].float().t() @ wide_b[:, 32:64].float(), 2e-3)
+    t0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a, b = _rand((16384, 320), seed=1), _rand((16384, 16), seed=2)
+    out = torch.zeros((320, 16), device="cuda")
+    for _ in range(3):
+        ops.tn_reduce(a, b, out, 1.0)
+    t0[0].record()
+    for _ in range(20):
+        ops.tn_reduce(a, b, out, 1.0)
+    t0[1].record()
+    torch.cuda.synchronize()
+    res["tn_strided"]["tn_16384x320x16_us"] = t0[0].elapsed_time(t0[1]) * 50.0
     # fused AdamW vs torch.optim.AdamW on fp32 (bf16 rounding of params bounds the difference)
     n = 100000
     p0 = _rand((n,), 0.1, 3)
