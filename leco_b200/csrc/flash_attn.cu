@@ -1,4 +1,5 @@
-// Fused attention forward for sm_100a: O = softmax(scale * Q K^T) V per (sample, head), head dim <= 64.
+// Fused attention forward for sm_100a: O = softmax(scale * Q K^T) V per (sample, head), head dim <= 64 (two pipelined
+// kernels below) or <= 192 (flash_attn_fwd_wide_kernel at the end of the file).
 // Replaces xformers.memory_efficient_attention on the reference's path (train_lora.py:68).
 //
 // One CTA per (128-query tile, head, sample).  K/V tiles of 128 keys stream through TMA rings;
@@ -805,6 +806,303 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_ts_kernel(const 
   if (warp == 2) tmem_dealloc(tmem_base, FA_TMEM_COLS);
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Head dims 64 < d <= 192: SD1.5 keeps 8 heads at every level (BASELINE configs[2]), so its attention runs at d = 80
+// (32x32 latents) and d = 160 (16x16 and 8x8) besides d = 40.  Same TMEM-resident pipeline as the kernel above, cut
+// down to what fits: the head dim is handled as DC chunks of 64 columns (TMA zero-fills the columns past d, so every
+// operand tile is a proven [128 rows x 128 B] SW128 tile), QK^T accumulates over the chunks' K-steps (only the steps
+// that hold real columns are issued), PV is one N = 64 product per chunk into its own 64 accumulator columns, and ONE
+// softmax warpgroup walks all KV tiles (2 score/probability slots x 128 columns + DC x 64 output columns of TMEM; the
+// O tile of a 160-wide head no longer fits twice).  These levels hold <= 1024 tokens, the kernel is not a hot spot;
+// it exists so that no S x S tensor is materialised on the denoising path of any supported UNet.
+template <int DC>
+struct FwCfg {
+  static constexpr int KS = DC == 2 ? 3 : 2;               // K / V ring depths that fit 227 KB
+  static constexpr int VS = DC == 2 ? 2 : 1;
+  static constexpr int TILE = DC * FA_KV_BYTES;            // one K or V tile: DC chunks of [128 keys x 128 B]
+  static constexpr int SMEM = DC * FA_Q_BYTES + (KS + VS) * TILE + 1024 + 512;
+};
+constexpr int FW_THREADS = 256;                            // 4 control warps + 1 softmax warpgroup
+constexpr int FW_SB = 2;                                   // score / probability slots
+
+template <int DC>
+__global__ void __launch_bounds__(FW_THREADS, 1) flash_attn_fwd_wide_kernel(const __grid_constant__ FlashParams p) {
+  using C = FwCfg<DC>;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + DC * FA_Q_BYTES;
+  uint8_t* sV = sK + C::KS * C::TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + C::VS * C::TILE);
+  uint64_t* q_full = bars;                 // [1]
+  uint64_t* k_full = bars + 1;             // [KS]
+  uint64_t* k_empty = k_full + C::KS;      // [KS]
+  uint64_t* v_full = k_empty + C::KS;      // [VS]
+  uint64_t* v_empty = v_full + C::VS;      // [VS]
+  uint64_t* s_full = v_empty + C::VS;      // [FW_SB]  QK^T of the slot finished
+  uint64_t* p_full = s_full + FW_SB;       // [FW_SB]  P written into the slot (and the accumulator rescaled if needed)
+  uint64_t* pv_done = p_full + FW_SB;      // [1]      the latest PV finished
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = p.n_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_q);
+    tma_prefetch_desc(&p.tm_k);
+    tma_prefetch_desc(&p.tm_v);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < C::KS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < C::VS; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < FW_SB; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+    }
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, FA_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const uint32_t tmem_s = tmem_base;                    // + (j & 1) * 128
+  const uint32_t tmem_o = tmem_base + FW_SB * FA_BN;    // + chunk * 64
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one elected lane)
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, DC * FA_Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < DC; ++c) tma_load_4d(sQ + c * FA_Q_BYTES, &p.tm_q, q_full, c * 64, qt * FA_BM, head, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int ks = j % C::KS, vs = j % C::VS;
+        mbar_wait(&k_empty[ks], ((j / C::KS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[ks], C::TILE);
+#pragma unroll
+        for (int c = 0; c < DC; ++c)
+          tma_load_4d(sK + ks * C::TILE + c * FA_KV_BYTES, &p.tm_k, &k_full[ks], c * 64, j * FA_BN, head, b);
+        mbar_wait(&v_empty[vs], ((j / C::VS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[vs], C::TILE);
+#pragma unroll
+        for (int c = 0; c < DC; ++c)
+          tma_load_4d(sV + vs * C::TILE + c * FA_KV_BYTES, &p.tm_v, &v_full[vs], c * 64, j * FA_BN, head, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one elected lane)
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc_bf16(FA_BN, false);
+      const uint32_t idesc_pv = umma_idesc_bf16(64, true);
+      // QK^T of tile j into slot j & 1, accumulated over the head-dim chunks.  The slot last held P_{j-2}: PV_{j-2}
+      // was issued before this call and the tensor pipe executes in issue order; the softmax warps left the slot
+      // before that PV was issued (p_full).
+      auto issue_s = [&](int j) {
+        const int ks = j % C::KS, sb = j & 1;
+        mbar_wait(&k_full[ks], (j / C::KS) & 1);
+        tc_fence_after();
+        uint32_t acc = 0;
+#pragma unroll
+        for (int c = 0; c < DC; ++c) {
+          const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ + c * FA_Q_BYTES));
+          const uint64_t dk = umma_desc_k_sw128(smem_u32(sK + ks * C::TILE + c * FA_KV_BYTES));
+          const int nks = min(4, (p.d - c * 64 + 15) >> 4);      // K-steps of this chunk that hold real columns
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            if (s < nks) {
+              umma_bf16(tmem_s + sb * FA_BN, dq + 2 * s, dk + 2 * s, idesc_s, acc);
+              acc = 1;
+            }
+          }
+        }
+        umma_commit(&s_full[sb]);
+        umma_commit(&k_empty[ks]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      if (n_tiles > 1) issue_s(1);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int vs = j % C::VS, sb = j & 1;
+        mbar_wait(&p_full[sb], (j >> 1) & 1);
+        mbar_wait(&v_full[vs], (j / C::VS) & 1);
+        tc_fence_after();
+        const uint32_t vbase = smem_u32(sV + vs * C::TILE);
+        const uint32_t a_tmem = tmem_s + sb * FA_BN;       // P_j: 64 columns of packed bf16 pairs, 8 per K=16 step
+#pragma unroll
+        for (int s = 0; s < FA_BN / 16; ++s) {
+#pragma unroll
+          for (int c = 0; c < DC; ++c)
+            umma_bf16_ts(tmem_o + c * 64, a_tmem + 8 * s, umma_desc_mn_sw128(vbase + c * FA_KV_BYTES + s * 16 * 128),
+                         idesc_pv, (j > 0 || s > 0) ? 1u : 0u);
+        }
+        umma_commit(pv_done);
+        umma_commit(&v_empty[vs]);
+        if (j + 2 < n_tiles) issue_s(j + 2);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax + output (one warpgroup, all tiles)
+    const int q = warp & 3;                  // TMEM lane quadrant
+    const int r = q * 32 + lane;             // row of the query tile
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t o_addr = tmem_o + lane_off;
+    float m_ref = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+
+    auto softmax_tile = [&](int j, auto rg_tag, auto first_tag) {
+      constexpr bool ragged = decltype(rg_tag)::value;
+      constexpr bool first = decltype(first_tag)::value;
+      const int s2 = j & 1;
+      const int kv0 = j * FA_BN;
+      if constexpr (!first) {
+        // rare: the previous tile moved the reference max -> rescale the accumulator in TMEM once its PV has landed
+        if (__any_sync(0xffffffffu, alpha_prev != 1.0f)) {
+          mbar_wait(pv_done, (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int h = 0; h < 2 * DC; ++h) {
+            uint32_t raw[32];
+            tmem_ld_32x32b_x32(o_addr + h * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha_prev);
+            tmem_st_32x32b_x32(o_addr + h * 32, raw);
+          }
+          tmem_st_wait();
+        }
+      }
+      mbar_wait(&s_full[s2], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_addr = tmem_s + lane_off + s2 * FA_BN;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      if constexpr (first) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t sv[32];
+          tmem_ld_32x32b_x32(s_addr + c * 32, sv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float a0 = __uint_as_float(sv[i]), a1 = __uint_as_float(sv[i + 1]), a2 = __uint_as_float(sv[i + 2]),
+                  a3 = __uint_as_float(sv[i + 3]);
+            if constexpr (ragged) {
+              if (kv0 + c * 32 + i >= p.skv) a0 = -INFINITY;
+              if (kv0 + c * 32 + i + 1 >= p.skv) a1 = -INFINITY;
+              if (kv0 + c * 32 + i + 2 >= p.skv) a2 = -INFINITY;
+              if (kv0 + c * 32 + i + 3 >= p.skv) a3 = -INFINITY;
+            }
+            mx0 = fmaxf(mx0, a0);
+            mx1 = fmaxf(mx1, a1);
+            mx2 = fmaxf(mx2, a2);
+            mx3 = fmaxf(mx3, a3);
+          }
+        }
+        m_ref = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      }
+      const float mb = m_ref * p.scale_log2;
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32];
+        tmem_ld_32x32b_x32(s_addr + c * 32, sv);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = t * 8 + u * 2;
+            float a0 = __uint_as_float(sv[i]), a1 = __uint_as_float(sv[i + 1]);
+            float p0 = ex2_approx(fmaf(a0, p.scale_log2, -mb));
+            float p1 = ex2_approx(fmaf(a1, p.scale_log2, -mb));
+            if constexpr (ragged) {
+              if (kv0 + c * 32 + i >= p.skv) { p0 = 0.f; a0 = -INFINITY; }
+              if (kv0 + c * 32 + i + 1 >= p.skv) { p1 = 0.f; a1 = -INFINITY; }
+            }
+            if constexpr (!first) {
+              if (u == 0) mx0 = max3f(mx0, a0, a1); else if (u == 1) mx1 = max3f(mx1, a0, a1);
+              else if (u == 2) mx2 = max3f(mx2, a0, a1); else mx3 = max3f(mx3, a0, a1);
+            }
+            if (u == 0) rs0 += p0 + p1; else if (u == 1) rs1 += p0 + p1; else if (u == 2) rs2 += p0 + p1; else rs3 += p0 + p1;
+            pk[t * 4 + u] = pack_bf16(p0, p1);
+          }
+        }
+        // keys [32c, 32c+32) -> columns [16c, 16c+16) of the same slot: only score columns already read are overwritten
+        tmem_st_32x32b_x16(s_addr + c * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[s2]);
+      float alpha = 1.0f;
+      if constexpr (!first) {
+        const float m_true = fmaxf(fmaxf(m_ref, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
+        if ((m_true - m_ref) * p.scale_log2 > FT_RESCALE_LOG2) {
+          alpha = ex2_approx((m_ref - m_true) * p.scale_log2);
+          m_ref = m_true;
+        }
+      }
+      l_run = (l_run + ((rs0 + rs1) + (rs2 + rs3))) * alpha;
+      alpha_prev = alpha;       // applied to the accumulator once this tile's PV has been added to it
+    };
+    for (int j = 0; j < n_tiles; ++j) {
+      const bool rg = j * FA_BN + FA_BN > p.skv;
+      if (j == 0) {
+        if (rg) softmax_tile(j, std::true_type{}, std::true_type{});
+        else softmax_tile(j, std::false_type{}, std::true_type{});
+      } else {
+        if (rg) softmax_tile(j, std::true_type{}, std::false_type{});
+        else softmax_tile(j, std::false_type{}, std::false_type{});
+      }
+    }
+    // ---- the accumulator, once: TMEM -> registers -> bf16 rows (scaled by the pending alpha and 1 / row sum)
+    mbar_wait(pv_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const int row = qt * FA_BM + r;
+    const float fin = alpha_prev / l_run;          // l_run already carries alpha_prev
+    if (row < p.sq && p.lse)
+      p.lse[(static_cast<long long>(b) * p.heads + head) * p.sq + row] = m_ref * p.scale_log2 + log2f(l_run);
+    __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.sq + row) * p.ld_out + head * p.d;
+#pragma unroll 1
+    for (int h = 0; h < 2 * DC; ++h) {
+      if (h * 32 >= p.d) break;
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(o_addr + h * 32, raw);
+      tmem_ld_wait();
+      if (row < p.sq) {
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          if (h * 32 + c8 * 8 < p.d) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(raw[c8 * 8 + 0]) * fin, __uint_as_float(raw[c8 * 8 + 1]) * fin);
+            v.y = pack_bf16(__uint_as_float(raw[c8 * 8 + 2]) * fin, __uint_as_float(raw[c8 * 8 + 3]) * fin);
+            v.z = pack_bf16(__uint_as_float(raw[c8 * 8 + 4]) * fin, __uint_as_float(raw[c8 * 8 + 5]) * fin);
+            v.w = pack_bf16(__uint_as_float(raw[c8 * 8 + 6]) * fin, __uint_as_float(raw[c8 * 8 + 7]) * fin);
+            *reinterpret_cast<uint4*>(dst + h * 32 + c8 * 8) = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, FA_TMEM_COLS);
+}
+
 }  // namespace leco
 
 using namespace leco;
@@ -830,7 +1128,8 @@ static int flash_fwd_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
                           const void* v_t, int64_t skv_pad, void* out, int64_t ldo, float* lse, int batch, int heads,
                           int sq, int skv, int d, float scale, void* stream) {
   LECO_REQUIRE(q && k && out && (v || v_t), "leco_flash_attn_fwd: null pointer");
-  LECO_REQUIRE(d % 8 == 0 && d <= FA_D, "leco_flash_attn_fwd: head dim %d unsupported (<=64, multiple of 8)", d);
+  LECO_REQUIRE(d % 8 == 0 && d > 0 && d <= 192, "leco_flash_attn_fwd: head dim %d unsupported (<=192, multiple of 8)", d);
+  LECO_REQUIRE(d <= FA_D || !v_t, "leco_flash_attn_fwd: head dims above 64 take V in place (v_t must be NULL)");
   LECO_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldo % 8 == 0, "leco_flash_attn_fwd: strides must be multiples of 8");
   FlashParams p;
   memset(&p, 0, sizeof(p));
@@ -872,13 +1171,19 @@ static int flash_fwd_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
   if (!attr_set) {
     LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+    LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwCfg<2>::SMEM));
+    LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_wide_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwCfg<3>::SMEM));
     attr_set = true;
   }
   // LECO_FLASH_TS=0: the variant that stages P through shared memory and folds PV in registers
   static const bool use_ts = [] { const char* e = getenv("LECO_FLASH_TS"); return !(e && e[0] == '0'); }();
   dim3 grid((sq + FA_BM - 1) / FA_BM, heads, batch);
   count_launch();
-  if (use_ts)
+  if (d > 128)
+    LECO_LAUNCH(flash_attn_fwd_wide_kernel<3>, grid, FW_THREADS, FwCfg<3>::SMEM, reinterpret_cast<cudaStream_t>(stream), p);
+  else if (d > FA_D)
+    LECO_LAUNCH(flash_attn_fwd_wide_kernel<2>, grid, FW_THREADS, FwCfg<2>::SMEM, reinterpret_cast<cudaStream_t>(stream), p);
+  else if (use_ts)
     LECO_LAUNCH(flash_attn_fwd_ts_kernel, grid, FA_THREADS, FT_SMEM, reinterpret_cast<cudaStream_t>(stream), p);
   else
     LECO_LAUNCH(flash_attn_fwd_kernel, grid, FA_THREADS, FA_SMEM, reinterpret_cast<cudaStream_t>(stream), p);

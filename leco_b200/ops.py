@@ -586,10 +586,12 @@ import os as _os
 FLASH_V_MODE = int(_os.environ.get("LECO_FLASH_V_MODE", "0"))
 # "flash" (fused, no-grad path) or "v0" (materialised P; always used on the grad path)
 ATTENTION_IMPL = _os.environ.get("LECO_ATTENTION", "flash")
+# widest head the fused forward takes (LECO_FLASH_WIDE=0: heads above 64 use the materialised path, for A/B runs)
+FLASH_WIDE_MAX_D = 192 if _os.environ.get("LECO_FLASH_WIDE", "1") != "0" else 64
 
 
 def flash_attention(qt, kt, vt, nb, sq, skv, heads, d, scale, v_mode=None):
-    """Fused tcgen05 attention forward (head dim <= 64).  Views [rows, heads*d] with free row stride."""
+    """Fused tcgen05 attention forward (head dim <= 192).  Views [rows, heads*d] with free row stride."""
     v_mode = FLASH_V_MODE if v_mode is None else v_mode
     o = torch.empty((nb * sq, heads * d), device=qt.device, dtype=BF16)
     v_t, skv_pad = None, 0
@@ -637,8 +639,11 @@ def flash_attention_bwd(go, qt, kt, vt, o, lse, nb, sq, skv, heads, d, scale, dq
 
 
 def attention(qt, kt, vt, nb, sq, skv, heads, d, scale, save_for_bwd=False):
-    flash_ok = ATTENTION_IMPL == "flash" and d <= 64 and d % 8 == 0
-    if not save_for_bwd and flash_ok:
+    # forward: d <= 64 pipelined kernels, 64 < d <= 192 flash_attn_fwd_wide_kernel (SD1.5's d = 80 / 160 levels);
+    # the fused backward covers d <= 64, so wider heads keep the materialised path on the grad pass only
+    fwd_ok = ATTENTION_IMPL == "flash" and d % 8 == 0 and (d <= 64 or (d <= FLASH_WIDE_MAX_D and FLASH_V_MODE == 0))
+    flash_ok = fwd_ok and d <= 64
+    if not save_for_bwd and fwd_ok:
         return flash_attention(qt, kt, vt, nb, sq, skv, heads, d, scale), None
     if save_for_bwd and flash_ok and ATTENTION_BWD_IMPL == "flash" and not _DETERMINISTIC[0]:
         o, lse = flash_attention_lse(qt, kt, vt, nb, sq, skv, heads, d, scale)

@@ -760,6 +760,18 @@ CASES = [
     ("flash_perf_4096_m0_smemP", case_flash, dict(nb=4, sq=4096, skv=4096, heads=5, d=64, v_mode=0, perf=True, ts=0)),
     ("flash_perf_4096_m0", case_flash, dict(nb=4, sq=4096, skv=4096, heads=5, d=64, v_mode=0, perf=True)),
     ("flash_perf_4096_m1", case_flash, dict(nb=4, sq=4096, skv=4096, heads=5, d=64, v_mode=1, perf=True)),
+    # head dims above 64 (SD1.5: 8 heads at every level -> 80 at 32x32, 160 at 16x16 / 8x8; cross-attention Skv = 77)
+    ("flash_wide_d80_1024", case_flash, dict(nb=2, sq=1024, skv=1024, heads=8, d=80)),
+    ("flash_wide_d80_cross77", case_flash, dict(nb=2, sq=1024, skv=77, heads=8, d=80, cross=True)),
+    ("flash_wide_d160_256", case_flash, dict(nb=2, sq=256, skv=256, heads=8, d=160)),
+    ("flash_wide_d160_64", case_flash, dict(nb=2, sq=64, skv=64, heads=8, d=160)),
+    ("flash_wide_d160_cross77", case_flash, dict(nb=2, sq=256, skv=77, heads=8, d=160, cross=True)),
+    ("flash_wide_d128_sq200_skv300", case_flash, dict(nb=1, sq=200, skv=300, heads=2, d=128, cross=True)),
+    ("flash_wide_d96_rescale_1024", case_flash, dict(nb=2, sq=1024, skv=1024, heads=4, d=96, qscale=8.0)),
+    ("flash_wide_d192_576", case_flash, dict(nb=1, sq=576, skv=576, heads=3, d=192)),
+    ("flash_wide_d72_ramp_1000", case_flash, dict(nb=1, sq=1000, skv=1000, heads=2, d=72, qscale=3.0, kramp=6.0)),
+    ("flash_perf_wide_d80_1024", case_flash, dict(nb=8, sq=1024, skv=1024, heads=8, d=80, perf=True)),
+    ("flash_perf_wide_d160_256", case_flash, dict(nb=8, sq=256, skv=256, heads=8, d=160, perf=True)),
     ("engine_fwd_tiny21", case_engine_forward, dict(arch="tiny21")),
     ("engine_fwd_tiny15", case_engine_forward, dict(arch="tiny15")),
     ("engine_fwd_tinyxl", case_engine_forward, dict(arch="tinyxl")),
