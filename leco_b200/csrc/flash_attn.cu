@@ -1044,6 +1044,12 @@ __global__ void __launch_bounds__(FW_THREADS, 1) flash_attn_fwd_wide_kernel(cons
         // keys [32c, 32c+32) -> columns [16c, 16c+16) of the same slot: only score columns already read are overwritten
         tmem_st_32x32b_x16(s_addr + c * 16, pk);
       }
+      // Keep in step with pv_done: a parity wait is only meaningful while the barrier is in the awaited phase or the
+      // one after it, so every phase is observed exactly once and in order.  Phase j-1 is awaited HERE: PV_j cannot
+      // be issued before the arrival below (the barrier cannot run ahead), and PV_{j-1} was issued a whole softmax
+      // period ago (no stall in steady state).  Skipping phases let the final wait alias onto an older phase and read
+      // the accumulator before the last two PV products had landed (first GPU run of this kernel, 8-tile cases).
+      if constexpr (!first) mbar_wait(pv_done, (j - 1) & 1);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

@@ -1,8 +1,8 @@
 """In-graph kernel timeline of one LECO iteration (CUPTI through torch.profiler, no ncu): the launch lists under
 profiles/ are ncu passes (serialised, cold cache), this one shows what each kernel costs INSIDE the replayed CUDA graphs
 (warm L2, programmatic dependent launch overlapping prologues).  Per kernel name: launches, summed duration, and
-"wall" = time from the kernel's start to the next kernel's start (gaps and launch latency are charged to the kernel
-before them), for (a) the first CFG denoise step (up to guided_step_kernel) and (b) the whole iteration.
+"cost" = by how much the kernel extends the timeline past everything launched before it (end-to-end deltas: correct
+under PDL overlap), for (a) the first CFG denoise step (up to guided_step_kernel) and (b) the whole iteration.
 
   python tests/gpu_checks/timeline_step.py --k 2 --out gpurun_out/timeline_sd21.md
 """
@@ -25,21 +25,30 @@ def short(name: str) -> str:
 
 
 def table(events, title):
+    """Attribution by END times: under programmatic dependent launch a kernel starts (and its CUPTI duration begins)
+    while its predecessor is still running, so start-to-start or raw durations charge the predecessor's run time to
+    the wrong kernel.  cost_i = end_i - max(end of everything before it, start_i) = by how much kernel i extends the
+    timeline; time with no kernel resident is reported as idle (host gaps between graph replays)."""
     if not events:
         return f"### {title}\n(no kernels)\n"
     agg = {}
-    for i, e in enumerate(events):
-        nxt = events[i + 1]["ts"] if i + 1 < len(events) else e["ts"] + e["dur"]
+    prev_end, idle = events[0]["ts"], 0.0
+    for e in events:
+        st, en = e["ts"], e["ts"] + e["dur"]
+        if st > prev_end:
+            idle += st - prev_end
+        cost = max(en - max(prev_end, st), 0.0)
+        prev_end = max(prev_end, en)
         a = agg.setdefault(short(e["name"]), [0, 0.0, 0.0])
         a[0] += 1
         a[1] += e["dur"]
-        a[2] += max(nxt - e["ts"], 0.0)
-    span = events[-1]["ts"] + events[-1]["dur"] - events[0]["ts"]
-    busy = sum(e["dur"] for e in events)
-    rows = [f"### {title}\n", f"launches: {len(events)}   span: {span / 1e3:.3f} ms   summed kernel time: {busy / 1e3:.3f} ms\n",
-            "| kernel | launches | wall ms | wall share | avg wall us | avg kernel us |", "|---|---|---|---|---|---|"]
-    for name, (n, dur, wall) in sorted(agg.items(), key=lambda kv: -kv[1][2]):
-        rows.append(f"| `{name}` | {n} | {wall / 1e3:.3f} | {100 * wall / span:.1f}% | {wall / n:.1f} | {dur / n:.1f} |")
+        a[2] += cost
+    span = prev_end - events[0]["ts"]
+    rows = [f"### {title}\n", f"launches: {len(events)}   span: {span / 1e3:.3f} ms   idle (no kernel resident): {idle / 1e3:.3f} ms"
+            f"   busy: {(span - idle) / 1e3:.3f} ms\n",
+            "| kernel | launches | cost ms | share of busy | avg cost us | avg CUPTI duration us |", "|---|---|---|---|---|---|"]
+    for name, (n, dur, cost) in sorted(agg.items(), key=lambda kv: -kv[1][2]):
+        rows.append(f"| `{name}` | {n} | {cost / 1e3:.3f} | {100 * cost / max(span - idle, 1e-9):.1f}% | {cost / n:.1f} | {dur / n:.1f} |")
     return "\n".join(rows) + "\n"
 
 
@@ -90,15 +99,22 @@ def main():
         prof.export_chrome_trace(path)
         trace = json.load(open(path))
     ev = sorted((e for e in trace["traceEvents"] if e.get("cat") == "kernel"), key=lambda e: e["ts"])
+    names = sorted({e["name"] for e in ev})
+    with open(os.path.splitext(args.out)[0] + "_events.json", "w") as f:   # raw list for offline analysis
+        json.dump({"names": names, "events": [[names.index(e["name"]), round(e["ts"], 3), round(e["dur"], 3),
+                                               e.get("args", {}).get("grid", None)] for e in ev]}, f)
     first = next((i for i, e in enumerate(ev) if "guided_step" in e["name"] or "sched_step" in e["name"]), len(ev) - 1)
+    second = next((i for i in range(first + 1, len(ev)) if "guided_step" in ev[i]["name"] or "sched_step" in ev[i]["name"]),
+                  first) if args.k > 1 else first
     md = [f"# In-graph kernel timeline: {args.arch}, batch {args.batch}, {args.res} px, k = {args.k} "
           f"(torch.profiler / CUPTI, one iteration after 3 warm-up iterations)\n",
           table(ev[:first + 1], "first CFG denoise step (graph replay)"),
+          table(ev[first + 1:second + 1], "second CFG denoise step (graph replay; no iteration prologue)"),
           table(ev, f"whole iteration (k = {args.k} denoise steps + tail + optimizer)")]
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         f.write("\n".join(md))
-    print("\n".join(md)[:6000])
+    print("\n".join(md)[:9000])
 
 
 if __name__ == "__main__":
