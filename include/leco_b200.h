@@ -172,6 +172,11 @@ int64_t leco_group_norm_barrier_bytes(int n);
  * writes mean / rstd, the normalise kernel only reads them.  `counters`: persistent buffer as above (4 bytes per sample). */
 int leco_group_norm_v2(const void* x, void* y, void* stats, const void* gamma, const void* beta, int n, int hw, int C, int G,
                        float eps, int silu, void* workspace, void* counters, void* stream);
+/* leco_group_norm_v3: ONE launch with a thread-block cluster per sample (rows held in shared memory, partial sums
+ * exchanged through distributed shared memory) when a sample fits one cluster, leco_group_norm_v2 otherwise; same
+ * arguments and results (GroupNorm + SiLU of ResnetBlock2D / Transformer2DModel.norm, diffusers 0.20.0). */
+int leco_group_norm_v3(const void* x, void* y, void* stats, const void* gamma, const void* beta, int n, int hw, int C, int G,
+                       float eps, int silu, void* workspace, void* counters, void* stream);
 int leco_group_norm_fused(const void* x, void* y, void* stats, const void* gamma, const void* beta, int n, int hw, int C,
                           int G, float eps, int silu, void* workspace, void* barriers, void* stream);
 int leco_group_norm_bwd(const void* x, const void* dz, void* dx, const void* stats, const void* gamma,

@@ -103,6 +103,7 @@ _OPS: list[tuple[str, list]] = [
     ("leco_group_norm_bwd", [P, P, P, P, P, P, I, I, I, I, I, P, P]),
     ("leco_group_norm_fused", [P, P, P, P, P, I, I, I, I, F, I, P, P, P]),
     ("leco_group_norm_v2", [P, P, P, P, P, I, I, I, I, F, I, P, P, P]),
+    ("leco_group_norm_v3", [P, P, P, P, P, I, I, I, I, F, I, P, P, P]),
     ("leco_layer_norm", [P, P, P, P, P, L, I, F, P]),
     ("leco_layer_norm_bwd", [P, P, P, P, P, L, I, P]),
     ("leco_tn_reduce", [P, L, P, L, P, L, L, I, I, F, I, P]),

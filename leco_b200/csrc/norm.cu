@@ -529,6 +529,184 @@ __global__ void gn_apply_v2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
   }
 }
 
+// ---- forward v3: ONE launch, one thread-block CLUSTER per sample (in-graph timeline, profiles/r2x_timeline_sd21.md:
+// the statistics kernel costs 9-12 us at every size, 8 CTAs or 256, because its tail is a chain of global round trips
+// -- partial store, __threadfence, ticket atomic, __ldcg of the partials, statistics store -- and the normalise kernel
+// then waits for it and re-reads the tensor from L2: 16 us per GroupNorm, 61 GroupNorms per UNet forward).
+// Here CTA `rank` of the cluster keeps its rows [rank*rows_per, ...) of the sample in SHARED memory while summing them,
+// the per-CTA (sum, sum^2) per group are exchanged through distributed shared memory behind the hardware cluster barrier
+// (no global atomics, no fences), every CTA folds the CL partials in rank order (deterministic) and normalises its rows
+// straight out of shared memory: x is read once, y written once, one launch.
+constexpr int GNC_MAX_CL = 16;
+constexpr int GNC_THREADS = 512;
+__device__ __forceinline__ uint32_t gnc_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t gnc_cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void gnc_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void gnc_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// float2 at the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ float2 gnc_ld_peer_f2(const float2* local, uint32_t rank) {
+  uint32_t ra;
+  float2 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(ra) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(GNC_THREADS)
+gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, float2* __restrict__ stats,
+                  const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta, int hw, int C, int G,
+                  float eps, int silu, int vpp, int rows_per) {
+  pdl_entry();
+  extern __shared__ __align__(16) uint8_t gnc_smem[];     // [2][R][C] floats (reduction scratch) | [rows_per][C] bf16
+  __shared__ float2 part[GN_MAX_GROUPS];                  // this CTA's (sum, sum^2) per group; read by the whole cluster
+  __shared__ float2 gath[GNC_MAX_CL][GN_MAX_GROUPS];
+  __shared__ float2 ms[GN_MAX_GROUPS];
+  const int n = blockIdx.y;
+  const uint32_t rank = gnc_cluster_rank(), CL = gnc_cluster_size();
+  const int R = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp, rl = threadIdx.x / vpp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;    // FULL warps only
+  const int r0 = (int)rank * rows_per, r1 = min(hw, r0 + rows_per);
+  const int cpg = C / G;
+  float* red = reinterpret_cast<float*>(gnc_smem);
+  v8* slab = reinterpret_cast<v8*>(gnc_smem + (size_t)2 * R * C * sizeof(float));
+  // ---------------- phase 1: this CTA's rows -> shared memory, per-thread channel sums on the way
+  {
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    if (rl < R) {
+      const __nv_bfloat16* base = x + ((size_t)n * hw) * C + v * 8;
+      int r = r0 + rl;
+      for (; r + 7 * R < r1; r += 8 * R) {  // eight independent 16-byte loads in flight per thread
+        v8 q[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) q[u] = *reinterpret_cast<const v8*>(base + (size_t)(r + u * R) * C);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          slab[(size_t)(r + u * R - r0) * vpp + v] = q[u];
+          float f[8];
+          up8(q[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s1[j] += f[j];
+            s2[j] = fmaf(f[j], f[j], s2[j]);
+          }
+        }
+      }
+      for (; r < r1; r += R) {
+        const v8 q = *reinterpret_cast<const v8*>(base + (size_t)r * C);
+        slab[(size_t)(r - r0) * vpp + v] = q;
+        float f[8];
+        up8(q, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += f[j];
+          s2[j] = fmaf(f[j], f[j], s2[j]);
+        }
+      }
+      float* d1 = red + (size_t)rl * C + v * 8;
+      float* d2 = red + (size_t)(R + rl) * C + v * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        d1[j] = s1[j];
+        d2[j] = s2[j];
+      }
+    }
+  }
+  __syncthreads();
+  // ---------------- phase 2: ordered fold of the R x cpg parked values of each group (lanes stride, fixed xor tree)
+  if (warp < nwarps) {
+    const int items = R * cpg;
+    for (int g = warp; g < G; g += nwarps) {
+      float a = 0.f, b = 0.f;
+      for (int i = lane; i < items; i += 32) {
+        const int q = i / cpg, c = g * cpg + (i - q * cpg);
+        a += red[(size_t)q * C + c];
+        b += red[(size_t)(R + q) * C + c];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (lane == 0) part[g] = make_float2(a, b);
+    }
+  }
+  __syncthreads();
+  gnc_cluster_arrive();          // release: part[] of every CTA is visible cluster-wide after the wait
+  gnc_cluster_wait();
+  if (warp < nwarps) {
+    for (uint32_t w = warp; w < CL; w += nwarps)
+      for (int g = lane; g < G; g += 32) gath[w][g] = gnc_ld_peer_f2(&part[g], w);
+  }
+  __syncthreads();
+  gnc_cluster_arrive();          // "done reading my peers": nobody leaves before every reader has (wait at the end)
+  if (threadIdx.x < G) {
+    float a = 0.f, b = 0.f;
+    for (uint32_t w = 0; w < CL; ++w) {
+      a += gath[w][threadIdx.x].x;
+      b += gath[w][threadIdx.x].y;
+    }
+    const float cnt = (float)hw * (float)cpg;
+    const float mean = a / cnt;
+    const float var = fmaxf(b / cnt - mean * mean, 0.f);
+    const float2 m = make_float2(mean, rsqrtf(var + eps));
+    ms[threadIdx.x] = m;
+    if (rank == 0) stats[(size_t)n * G + threadIdx.x] = m;
+  }
+  __syncthreads();
+  // ---------------- phase 3: normalise (+SiLU) out of shared memory
+  if (rl < R) {
+    float sc[8], sh[8];
+    {
+      float gm[8], bt[8];
+      up8(__ldg(reinterpret_cast<const v8*>(gamma + v * 8)), gm);
+      up8(__ldg(reinterpret_cast<const v8*>(beta + v * 8)), bt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 m = ms[(v * 8 + j) / cpg];
+        sc[j] = m.y * gm[j];
+        sh[j] = fmaf(-m.x, sc[j], bt[j]);
+      }
+    }
+    __nv_bfloat16* yb = y + ((size_t)n * hw) * C + v * 8;
+    int r = r0 + rl;
+    for (; r + 3 * R < r1; r += 4 * R) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        up8(slab[(size_t)(r + u * R - r0) * vpp + v], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[j] = fmaf(f[j], sc[j], sh[j]);
+          if (silu) f[j] = silu_fast(f[j]);
+        }
+        *reinterpret_cast<v8*>(yb + (size_t)(r + u * R) * C) = pk8(f);
+      }
+    }
+    for (; r < r1; r += R) {
+      float f[8];
+      up8(slab[(size_t)(r - r0) * vpp + v], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[j] = fmaf(f[j], sc[j], sh[j]);
+        if (silu) f[j] = silu_fast(f[j]);
+      }
+      *reinterpret_cast<v8*>(yb + (size_t)r * C) = pk8(f);
+    }
+  }
+  gnc_cluster_wait();            // pairs with the second arrive: my part[] may be freed now
+}
+
 // ---- backward pass 1: partial[n][split][g] = (sum g, sum g*xhat) with g = dy*gamma (dy through SiLU')
 __global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
                                     const float2* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
@@ -840,6 +1018,85 @@ extern "C" int leco_group_norm_v2(const void* x, void* y, void* stats, const voi
               reinterpret_cast<const float2*>(stats), BF(gamma), BF(beta), hw, C, G, silu, vpp);
   LECO_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// One-launch cluster forward where a sample's rows fit the shared memory of one cluster (every GroupNorm of the SD1.x /
+// SD2.x / SDXL UNets at <= 64 samples' worth of 32x32 latents, and the 320-channel ones at 64x64), the two-launch v2 pair
+// otherwise.  LECO_GN_CLUSTER=0 disables the cluster path, =8 uses clusters of 8 (portable size).
+namespace leco {
+static int gnc_cluster_size_cfg() {
+  static const int v = [] {
+    const char* e = getenv("LECO_GN_CLUSTER");
+    const int c = e ? atoi(e) : GNC_MAX_CL;
+    return (c == 0 || c == 2 || c == 4 || c == 8 || c == 16) ? c : GNC_MAX_CL;
+  }();
+  return v;
+}
+constexpr size_t GNC_MAX_DYN_SMEM = 216 * 1024;      // + ~9.5 KB static: under the 227 KB per-CTA limit
+// 0 = launched; 1 = shape not eligible (caller falls back); <0 = error
+static int launch_gn_cluster(const void* x, void* y, void* stats, const void* gamma, const void* beta, int n, int hw,
+                             int C, int G, float eps, int silu, cudaStream_t stream) {
+  const int CL = gnc_cluster_size_cfg();
+  if (CL == 0 || n > 65535) return 1;
+  const int vpp = C / 8;
+  if (vpp > GNC_THREADS) return 1;
+  int R = GNC_THREADS / vpp;
+  if (R < 1) R = 1;
+  const int threads = vpp * R;
+  if (threads < 32) return 1;
+  const int rows_per = (hw + CL - 1) / CL;
+  const size_t smem = (size_t)2 * R * C * sizeof(float) + (size_t)rows_per * C * 2;
+  if (smem > GNC_MAX_DYN_SMEM) return 1;
+  static int usable = -1;                            // can a cluster of this size with the largest footprint be resident?
+  if (usable < 0) {
+    usable = 0;
+    if (cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GNC_MAX_DYN_SMEM) == cudaSuccess &&
+        (CL <= 8 || cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(CL, 1, 1);
+      q.blockDim = dim3(GNC_THREADS, 1, 1);
+      q.dynamicSmemBytes = GNC_MAX_DYN_SMEM;
+      cudaLaunchAttribute a[1];
+      a[0].id = cudaLaunchAttributeClusterDimension;
+      a[0].val.clusterDim.x = CL;
+      a[0].val.clusterDim.y = 1;
+      a[0].val.clusterDim.z = 1;
+      q.attrs = a;
+      q.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, gn_cluster_kernel, &q) == cudaSuccess && nclusters >= 1) usable = 1;
+    }
+    (void)cudaGetLastError();
+  }
+  if (!usable) return 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CL, n, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  count_launch();
+  LECO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gn_cluster_kernel, BF(x), BFW(y), reinterpret_cast<float2*>(stats), BF(gamma),
+                                     BF(beta), hw, C, G, eps, silu, vpp, rows_per));
+  return 0;
+}
+}  // namespace leco
+
+extern "C" int leco_group_norm_v3(const void* x, void* y, void* stats, const void* gamma, const void* beta, int n, int hw,
+                                  int C, int G, float eps, int silu, void* workspace, void* counters, void* stream) {
+  LECO_REQUIRE(x && y && stats && gamma && beta && workspace && counters, "leco_group_norm_v3: null pointer");
+  LECO_REQUIRE(C % 8 == 0 && G > 0 && G <= GN_MAX_GROUPS && C % G == 0, "leco_group_norm_v3: C=%d G=%d unsupported", C, G);
+  const int rc = launch_gn_cluster(x, y, stats, gamma, beta, n, hw, C, G, eps, silu, STREAM(stream));
+  if (rc <= 0) return rc;
+  return leco_group_norm_v2(x, y, stats, gamma, beta, n, hw, C, G, eps, silu, workspace, counters, stream);
 }
 
 extern "C" int leco_group_norm_bwd(const void* x, const void* dz, void* dx, const void* stats, const void* gamma,

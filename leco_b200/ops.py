@@ -375,7 +375,9 @@ def _gn_workspace(dev, n, G):
 GN_FUSED = int(__import__('os').environ.get('LECO_GN_FUSED', '0'))   # 1: single-launch GroupNorm forward (grid barrier); measured 245.4 vs 244.1 ms / iteration for the two-launch path, so off by default
 # "v2": the statistics kernel finishes mean / rstd (last block per sample), the normalise kernel only reads them;
 # "v1": the round-1 pair (every normalise block re-folds the partial sums)
-GN_IMPL = __import__('os').environ.get('LECO_GN_IMPL', 'v2')
+# "v3" (default): one launch, a thread-block cluster per sample (falls back to v2 inside the library when a sample does
+# not fit one cluster's shared memory; LECO_GN_CLUSTER=0/8/16 picks the cluster size)
+GN_IMPL = __import__('os').environ.get('LECO_GN_IMPL', 'v3')
 _GN_BARRIERS = {}
 _GN_COUNTERS = {}
 
@@ -404,6 +406,11 @@ def group_norm(x: torch.Tensor, n: int, hw: int, gamma: torch.Tensor, beta: torc
     y = torch.empty_like(x)
     stats = torch.empty((n, groups, 2), device=x.device, dtype=torch.float32)
     ws = torch.empty(int(_lib().leco_group_norm_workspace_bytes(n, groups)), device=x.device, dtype=torch.uint8)
+    if GN_IMPL == "v3" and not GN_FUSED and n <= 4096:
+        capi.check(_lib().leco_group_norm_v3(_ptr(x), _ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), n, hw, C, groups,
+                                             eps, int(silu_act), _ptr(ws), _ptr(_gn_counters(x.device)), _stream()),
+                   "leco_group_norm_v3")
+        return y, stats
     if GN_IMPL == "v2" and not GN_FUSED and n <= 4096:
         capi.check(_lib().leco_group_norm_v2(_ptr(x), _ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), n, hw, C, groups,
                                              eps, int(silu_act), _ptr(ws), _ptr(_gn_counters(x.device)), _stream()),

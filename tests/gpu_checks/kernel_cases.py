@@ -44,7 +44,10 @@ def case_norms():
     from leco_b200 import ops
     from tests import torch_backend as tb
     res = {}
-    for (n, hw, c) in ((2, 4096, 320), (3, 256, 1280), (2, 64, 2560), (4, 4, 64), (2, 1024, 960)):
+    # (2, 100, 320): rows not a multiple of the cluster size (ragged / empty CTAs of the one-launch cluster kernel);
+    # (1, 4096, 640): a sample too large for one cluster's shared memory (two-launch path inside leco_group_norm_v3)
+    for (n, hw, c) in ((2, 4096, 320), (3, 256, 1280), (2, 64, 2560), (4, 4, 64), (2, 1024, 960), (2, 100, 320),
+                       (1, 4096, 640), (5, 1024, 1280)):
         x = _rand((n * hw, c), seed=1) * 1.5 + 0.3
         gm, bt = _rand((c,), 0.2, 2) + 1.0, _rand((c,), 0.2, 3)
         for silu in (True, False):
