@@ -550,6 +550,25 @@ __device__ __forceinline__ uint32_t gnc_cluster_size() {
   return r;
 }
 __device__ __forceinline__ void gnc_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// SiLU with ONE special-function op: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx: relative error 2^-11, below the
+// bf16 rounding of the result).  The exp + reciprocal form costs two; with a sample's rows concentrated on one cluster
+// the MUFU pipe (16 / clk / SM) is what the normalise phase waits for.
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+// second barrier of the kernel: pure "I have finished reading my peers' shared memory", no data is published
+__device__ __forceinline__ void gnc_cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+// streaming 16-byte load (read once, never written by this kernel)
+__device__ __forceinline__ v8 gnc_ldg_stream(const void* p) {
+  v8 q;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+               : "l"(p));
+  return q;
+}
 __device__ __forceinline__ void gnc_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // float2 at the same shared-memory offset in CTA `rank` of this cluster
 __device__ __forceinline__ float2 gnc_ld_peer_f2(const float2* local, uint32_t rank) {
@@ -560,39 +579,46 @@ __device__ __forceinline__ float2 gnc_ld_peer_f2(const float2* local, uint32_t r
   return v;
 }
 
+// grid (CL, parts, n), cluster (CL, 1, 1): cluster (part, n) owns channels [part*Cs, (part+1)*Cs) = Gs whole groups of
+// sample n.  Splitting the channels over `parts` clusters puts 2-4x as many SMs on a batch of 4 samples (the SiLU is
+// MUFU work and the copies are per-SM L2 bandwidth: both scale with the number of SMs that take part).
 __global__ void __launch_bounds__(GNC_THREADS)
 gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, float2* __restrict__ stats,
-                  const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta, int hw, int C, int G,
-                  float eps, int silu, int vpp, int rows_per) {
+                  const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta, int hw, int C, int Cs,
+                  int G, int Gs, float eps, int silu, int vpp, int rows_per) {
   pdl_entry();
-  extern __shared__ __align__(16) uint8_t gnc_smem[];     // [2][R][C] floats (reduction scratch) | [rows_per][C] bf16
+  extern __shared__ __align__(16) uint8_t gnc_smem[];     // [2][R][Cs] floats (reduction scratch) | [rows_per][Cs] bf16
   __shared__ float2 part[GN_MAX_GROUPS];                  // this CTA's (sum, sum^2) per group; read by the whole cluster
-  __shared__ float2 gath[GNC_MAX_CL][GN_MAX_GROUPS];
+  __shared__ float2 gath[GNC_MAX_CL * GN_MAX_GROUPS];     // [CL][Gs]
   __shared__ float2 ms[GN_MAX_GROUPS];
-  const int n = blockIdx.y;
+  const int n = blockIdx.z, c0 = blockIdx.y * Cs;
   const uint32_t rank = gnc_cluster_rank(), CL = gnc_cluster_size();
   const int R = blockDim.x / vpp;
   const int v = threadIdx.x % vpp, rl = threadIdx.x / vpp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;    // FULL warps only
   const int r0 = (int)rank * rows_per, r1 = min(hw, r0 + rows_per);
-  const int cpg = C / G;
+  const int cpg = Cs / Gs;
   float* red = reinterpret_cast<float*>(gnc_smem);
-  v8* slab = reinterpret_cast<v8*>(gnc_smem + (size_t)2 * R * C * sizeof(float));
+  v8* slab = reinterpret_cast<v8*>(gnc_smem + (size_t)2 * R * Cs * sizeof(float));
   // ---------------- phase 1: this CTA's rows -> shared memory, per-thread channel sums on the way
   {
     float s1[8], s2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
     if (rl < R) {
-      const __nv_bfloat16* base = x + ((size_t)n * hw) * C + v * 8;
+      const __nv_bfloat16* base = x + ((size_t)n * hw) * C + c0 + v * 8;
       int r = r0 + rl;
       for (; r + 7 * R < r1; r += 8 * R) {  // eight independent 16-byte loads in flight per thread
+        // (volatile asm + barrier: with plain loads the compiler sank every load down to its shared-memory store, one
+        // load in flight per thread -- first GPU run of this kernel: 19 us for 10 MB, no better than two launches)
         v8 q[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) q[u] = *reinterpret_cast<const v8*>(base + (size_t)(r + u * R) * C);
+        for (int u = 0; u < 8; ++u) q[u] = gnc_ldg_stream(base + (size_t)(r + u * R) * C);
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int u = 0; u < 8; ++u) slab[(size_t)(r + u * R - r0) * vpp + v] = q[u];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          slab[(size_t)(r + u * R - r0) * vpp + v] = q[u];
           float f[8];
           up8(q[u], f);
 #pragma unroll
@@ -602,8 +628,23 @@ gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
           }
         }
       }
+      for (; r + R < r1; r += 2 * R) {
+        const v8 qa = gnc_ldg_stream(base + (size_t)r * C);
+        const v8 qb = gnc_ldg_stream(base + (size_t)(r + R) * C);
+        asm volatile("" ::: "memory");
+        slab[(size_t)(r - r0) * vpp + v] = qa;
+        slab[(size_t)(r + R - r0) * vpp + v] = qb;
+        float f[8], g[8];
+        up8(qa, f);
+        up8(qb, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += f[j] + g[j];
+          s2[j] = fmaf(f[j], f[j], fmaf(g[j], g[j], s2[j]));
+        }
+      }
       for (; r < r1; r += R) {
-        const v8 q = *reinterpret_cast<const v8*>(base + (size_t)r * C);
+        const v8 q = gnc_ldg_stream(base + (size_t)r * C);
         slab[(size_t)(r - r0) * vpp + v] = q;
         float f[8];
         up8(q, f);
@@ -613,8 +654,8 @@ gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
           s2[j] = fmaf(f[j], f[j], s2[j]);
         }
       }
-      float* d1 = red + (size_t)rl * C + v * 8;
-      float* d2 = red + (size_t)(R + rl) * C + v * 8;
+      float* d1 = red + (size_t)rl * Cs + v * 8;
+      float* d2 = red + (size_t)(R + rl) * Cs + v * 8;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         d1[j] = s1[j];
@@ -626,12 +667,12 @@ gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
   // ---------------- phase 2: ordered fold of the R x cpg parked values of each group (lanes stride, fixed xor tree)
   if (warp < nwarps) {
     const int items = R * cpg;
-    for (int g = warp; g < G; g += nwarps) {
+    for (int g = warp; g < Gs; g += nwarps) {
       float a = 0.f, b = 0.f;
       for (int i = lane; i < items; i += 32) {
         const int q = i / cpg, c = g * cpg + (i - q * cpg);
-        a += red[(size_t)q * C + c];
-        b += red[(size_t)(R + q) * C + c];
+        a += red[(size_t)q * Cs + c];
+        b += red[(size_t)(R + q) * Cs + c];
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -644,24 +685,24 @@ gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
   __syncthreads();
   gnc_cluster_arrive();          // release: part[] of every CTA is visible cluster-wide after the wait
   gnc_cluster_wait();
-  if (warp < nwarps) {
-    for (uint32_t w = warp; w < CL; w += nwarps)
-      for (int g = lane; g < G; g += 32) gath[w][g] = gnc_ld_peer_f2(&part[g], w);
+  for (int t = threadIdx.x; t < (int)CL * Gs; t += blockDim.x) {
+    const int w = t / Gs, g = t - w * Gs;
+    gath[t] = gnc_ld_peer_f2(&part[g], (uint32_t)w);
   }
   __syncthreads();
-  gnc_cluster_arrive();          // "done reading my peers": nobody leaves before every reader has (wait at the end)
-  if (threadIdx.x < G) {
+  gnc_cluster_arrive_relaxed();  // "done reading my peers": nobody leaves before every reader has (wait at the end)
+  if (threadIdx.x < Gs) {
     float a = 0.f, b = 0.f;
-    for (uint32_t w = 0; w < CL; ++w) {
-      a += gath[w][threadIdx.x].x;
-      b += gath[w][threadIdx.x].y;
+    for (uint32_t w = 0; w < CL; ++w) {           // rank order: every CTA of the cluster computes the same bits
+      a += gath[w * Gs + threadIdx.x].x;
+      b += gath[w * Gs + threadIdx.x].y;
     }
     const float cnt = (float)hw * (float)cpg;
     const float mean = a / cnt;
     const float var = fmaxf(b / cnt - mean * mean, 0.f);
     const float2 m = make_float2(mean, rsqrtf(var + eps));
     ms[threadIdx.x] = m;
-    if (rank == 0) stats[(size_t)n * G + threadIdx.x] = m;
+    if (rank == 0) stats[(size_t)n * G + blockIdx.y * Gs + threadIdx.x] = m;
   }
   __syncthreads();
   // ---------------- phase 3: normalise (+SiLU) out of shared memory
@@ -669,8 +710,8 @@ gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
     float sc[8], sh[8];
     {
       float gm[8], bt[8];
-      up8(__ldg(reinterpret_cast<const v8*>(gamma + v * 8)), gm);
-      up8(__ldg(reinterpret_cast<const v8*>(beta + v * 8)), bt);
+      up8(__ldg(reinterpret_cast<const v8*>(gamma + c0 + v * 8)), gm);
+      up8(__ldg(reinterpret_cast<const v8*>(beta + c0 + v * 8)), bt);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float2 m = ms[(v * 8 + j) / cpg];
@@ -678,7 +719,7 @@ gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
         sh[j] = fmaf(-m.x, sc[j], bt[j]);
       }
     }
-    __nv_bfloat16* yb = y + ((size_t)n * hw) * C + v * 8;
+    __nv_bfloat16* yb = y + ((size_t)n * hw) * C + c0 + v * 8;
     int r = r0 + rl;
     for (; r + 3 * R < r1; r += 4 * R) {
 #pragma unroll
@@ -688,7 +729,7 @@ gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           f[j] = fmaf(f[j], sc[j], sh[j]);
-          if (silu) f[j] = silu_fast(f[j]);
+          if (silu) f[j] = silu_tanh(f[j]);
         }
         *reinterpret_cast<v8*>(yb + (size_t)(r + u * R) * C) = pk8(f);
       }
@@ -699,7 +740,7 @@ gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         f[j] = fmaf(f[j], sc[j], sh[j]);
-        if (silu) f[j] = silu_fast(f[j]);
+        if (silu) f[j] = silu_tanh(f[j]);
       }
       *reinterpret_cast<v8*>(yb + (size_t)r * C) = pk8(f);
     }
@@ -1038,19 +1079,30 @@ static int launch_gn_cluster(const void* x, void* y, void* stats, const void* ga
                              int C, int G, float eps, int silu, cudaStream_t stream) {
   const int CL = gnc_cluster_size_cfg();
   if (CL == 0 || n > 65535) return 1;
-  const int vpp = C / 8;
-  if (vpp > GNC_THREADS) return 1;
-  int R = GNC_THREADS / vpp;
-  if (R < 1) R = 1;
+  // channel parts: the fewest that let a CTA's rows fit shared memory, then more while the launch still fits the SMs
+  static const int env_parts = [] { const char* e = getenv("LECO_GN_PARTS"); return e ? atoi(e) : 0; }();
+  int parts = 0, vpp = 0, R = 0, rows_per = (hw + CL - 1) / CL;
+  size_t smem = 0;
+  for (int pc = 1; pc <= 4; pc *= 2) {
+    if (G % pc || (C / pc) % 8 || (C / pc) % (G / pc)) break;
+    const int cs = C / pc, vp = cs / 8;
+    if (vp > GNC_THREADS) continue;
+    int r = GNC_THREADS / vp;
+    if (r < 1) r = 1;
+    if (vp * r < 32) break;
+    const size_t sm = (size_t)2 * r * cs * sizeof(float) + (size_t)rows_per * cs * 2;
+    if (sm > GNC_MAX_DYN_SMEM) continue;
+    if (parts && (env_parts ? pc > env_parts : (long long)n * CL * pc > sm_count())) break;
+    parts = pc; vpp = vp; R = r; smem = sm;
+  }
+  if (!parts) return 1;
   const int threads = vpp * R;
-  if (threads < 32) return 1;
-  const int rows_per = (hw + CL - 1) / CL;
-  const size_t smem = (size_t)2 * R * C * sizeof(float) + (size_t)rows_per * C * 2;
-  if (smem > GNC_MAX_DYN_SMEM) return 1;
   static int usable = -1;                            // can a cluster of this size with the largest footprint be resident?
   if (usable < 0) {
     usable = 0;
     if (cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GNC_MAX_DYN_SMEM) == cudaSuccess &&
+        // same shared-memory carve-out as the GEMMs around it, whatever this launch needs: no reconfiguration of the SMs
+        cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
         (CL <= 8 || cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)) {
       cudaLaunchConfig_t q = {};
       q.gridDim = dim3(CL, 1, 1);
@@ -1070,7 +1122,7 @@ static int launch_gn_cluster(const void* x, void* y, void* stats, const void* ga
   }
   if (!usable) return 1;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(CL, n, 1);
+  cfg.gridDim = dim3(CL, parts, n);
   cfg.blockDim = dim3(threads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
@@ -1085,7 +1137,7 @@ static int launch_gn_cluster(const void* x, void* y, void* stats, const void* ga
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   count_launch();
   LECO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gn_cluster_kernel, BF(x), BFW(y), reinterpret_cast<float2*>(stats), BF(gamma),
-                                     BF(beta), hw, C, G, eps, silu, vpp, rows_per));
+                                     BF(beta), hw, C, C / parts, G, G / parts, eps, silu, vpp, rows_per));
   return 0;
 }
 }  // namespace leco
