@@ -708,6 +708,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_ts_kernel(const 
         f2_unpack(f2_add(f2_add(rsp0, rsp1), f2_add(rsp2, rsp3)), lo, hi);
         rs0 = lo + hi;
       }
+      // Observe every pv_done phase once and in order (a parity wait is only meaningful while the barrier is in the
+      // awaited phase or the next one): the PV of this warpgroup's previous tile was issued a whole softmax period ago,
+      // so this returns at once, and the final wait below can no longer alias onto an older phase (the failure mode
+      // seen in flash_attn_fwd_wide_kernel's first GPU run, where one warpgroup follows every tile).
+      if constexpr (!first) mbar_wait(&pv_done[wg], ((j - 2) >> 1) & 1);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

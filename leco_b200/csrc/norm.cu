@@ -666,13 +666,15 @@ gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
   __syncthreads();
   // ---------------- phase 2: ordered fold of the R x cpg parked values of each group (lanes stride, fixed xor tree)
   if (warp < nwarps) {
-    const int items = R * cpg;
     for (int g = warp; g < Gs; g += nwarps) {
       float a = 0.f, b = 0.f;
-      for (int i = lane; i < items; i += 32) {
-        const int q = i / cpg, c = g * cpg + (i - q * cpg);
-        a += red[(size_t)q * Cs + c];
-        b += red[(size_t)(R + q) * Cs + c];
+      for (int co = lane; co < cpg; co += 32) {       // lane = channel of the group (consecutive banks), rows in order
+        const float* p1 = red + g * cpg + co;
+        const float* p2 = p1 + (size_t)R * Cs;
+        for (int q = 0; q < R; ++q) {
+          a += p1[(size_t)q * Cs];
+          b += p2[(size_t)q * Cs];
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -1065,62 +1067,79 @@ extern "C" int leco_group_norm_v2(const void* x, void* y, void* stats, const voi
 // SD2.x / SDXL UNets at <= 64 samples' worth of 32x32 latents, and the 320-channel ones at 64x64), the two-launch v2 pair
 // otherwise.  LECO_GN_CLUSTER=0 disables the cluster path, =8 uses clusters of 8 (portable size).
 namespace leco {
+// LECO_GN_CLUSTER: 0 = never use the cluster kernel, 8 / 16 = only that cluster size, unset = choose per launch
 static int gnc_cluster_size_cfg() {
   static const int v = [] {
     const char* e = getenv("LECO_GN_CLUSTER");
-    const int c = e ? atoi(e) : GNC_MAX_CL;
-    return (c == 0 || c == 2 || c == 4 || c == 8 || c == 16) ? c : GNC_MAX_CL;
+    const int c = e ? atoi(e) : -1;
+    return (c == 0 || c == 8 || c == 16) ? c : -1;
   }();
   return v;
 }
 constexpr size_t GNC_MAX_DYN_SMEM = 216 * 1024;      // + ~9.5 KB static: under the 227 KB per-CTA limit
+// How many clusters of `cl` CTAs with the largest footprint can be resident at once (ncu: 7 of 16 on a B200, some GPCs
+// expose fewer than 16 SMs).  A launch with more clusters than that runs in two waves and loses to the two-launch path.
+static int gnc_max_active(int cl) {
+  static int cache[2] = {-1, -1};
+  int& slot = cache[cl == 16 ? 1 : 0];
+  if (slot >= 0) return slot;
+  slot = 0;
+  static bool attrs = false, attrs_ok = false;
+  if (!attrs) {
+    attrs = true;
+    attrs_ok = cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GNC_MAX_DYN_SMEM) == cudaSuccess &&
+               // same shared-memory carve-out as the GEMMs around it, whatever this launch needs: no SM reconfiguration
+               cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
+               cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+  }
+  if (attrs_ok) {
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(cl, 1, 1);
+    q.blockDim = dim3(GNC_THREADS, 1, 1);
+    q.dynamicSmemBytes = GNC_MAX_DYN_SMEM;
+    cudaLaunchAttribute a[1];
+    a[0].id = cudaLaunchAttributeClusterDimension;
+    a[0].val.clusterDim.x = cl;
+    a[0].val.clusterDim.y = 1;
+    a[0].val.clusterDim.z = 1;
+    q.attrs = a;
+    q.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, gn_cluster_kernel, &q) == cudaSuccess && nclusters >= 1) slot = nclusters;
+  }
+  (void)cudaGetLastError();
+  return slot;
+}
 // 0 = launched; 1 = shape not eligible (caller falls back); <0 = error
 static int launch_gn_cluster(const void* x, void* y, void* stats, const void* gamma, const void* beta, int n, int hw,
                              int C, int G, float eps, int silu, cudaStream_t stream) {
-  const int CL = gnc_cluster_size_cfg();
-  if (CL == 0 || n > 65535) return 1;
-  // channel parts: the fewest that let a CTA's rows fit shared memory, then more while the launch still fits the SMs
-  static const int env_parts = [] { const char* e = getenv("LECO_GN_PARTS"); return e ? atoi(e) : 0; }();
-  int parts = 0, vpp = 0, R = 0, rows_per = (hw + CL - 1) / CL;
+  const int forced = gnc_cluster_size_cfg();
+  if (forced == 0 || n > 65535) return 1;
+  // channel parts (clusters per sample): measured slower than one cluster per sample at every UNet shape (8 clusters
+  // do not fit the 7 resident ones, and the row segments get short), so only on request (LECO_GN_PARTS = 2 / 4)
+  static const int max_parts = [] { const char* e = getenv("LECO_GN_PARTS"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
+  int CL = 0, parts = 0, vpp = 0, R = 0, rows_per = 0;
   size_t smem = 0;
-  for (int pc = 1; pc <= 4; pc *= 2) {
-    if (G % pc || (C / pc) % 8 || (C / pc) % (G / pc)) break;
-    const int cs = C / pc, vp = cs / 8;
-    if (vp > GNC_THREADS) continue;
-    int r = GNC_THREADS / vp;
-    if (r < 1) r = 1;
-    if (vp * r < 32) break;
-    const size_t sm = (size_t)2 * r * cs * sizeof(float) + (size_t)rows_per * cs * 2;
-    if (sm > GNC_MAX_DYN_SMEM) continue;
-    if (parts && (env_parts ? pc > env_parts : (long long)n * CL * pc > sm_count())) break;
-    parts = pc; vpp = vp; R = r; smem = sm;
+  for (int cl = 16; cl >= 8 && !parts; cl >>= 1) {
+    if (forced > 0 && cl != forced) continue;
+    const int resident = gnc_max_active(cl);
+    const int rp = (hw + cl - 1) / cl;
+    for (int pc = 1; pc <= 4 && pc <= max_parts; pc *= 2) {
+      if (G % pc || (C / pc) % 8 || (C / pc) % (G / pc)) break;
+      const int cs = C / pc, vp = cs / 8;
+      if (vp > GNC_THREADS) continue;
+      int r = GNC_THREADS / vp;
+      if (r < 1) r = 1;
+      if (vp * r < 32) break;
+      const size_t sm = (size_t)2 * r * cs * sizeof(float) + (size_t)rp * cs * 2;
+      if (sm > GNC_MAX_DYN_SMEM) continue;
+      if ((long long)n * pc > resident) break;          // would need a second wave of clusters
+      CL = cl; parts = pc; vpp = vp; R = r; smem = sm; rows_per = rp;
+      break;
+    }
   }
   if (!parts) return 1;
   const int threads = vpp * R;
-  static int usable = -1;                            // can a cluster of this size with the largest footprint be resident?
-  if (usable < 0) {
-    usable = 0;
-    if (cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GNC_MAX_DYN_SMEM) == cudaSuccess &&
-        // same shared-memory carve-out as the GEMMs around it, whatever this launch needs: no reconfiguration of the SMs
-        cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
-        (CL <= 8 || cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)) {
-      cudaLaunchConfig_t q = {};
-      q.gridDim = dim3(CL, 1, 1);
-      q.blockDim = dim3(GNC_THREADS, 1, 1);
-      q.dynamicSmemBytes = GNC_MAX_DYN_SMEM;
-      cudaLaunchAttribute a[1];
-      a[0].id = cudaLaunchAttributeClusterDimension;
-      a[0].val.clusterDim.x = CL;
-      a[0].val.clusterDim.y = 1;
-      a[0].val.clusterDim.z = 1;
-      q.attrs = a;
-      q.numAttrs = 1;
-      int nclusters = 0;
-      if (cudaOccupancyMaxActiveClusters(&nclusters, gn_cluster_kernel, &q) == cudaSuccess && nclusters >= 1) usable = 1;
-    }
-    (void)cudaGetLastError();
-  }
-  if (!usable) return 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CL, parts, n);
   cfg.blockDim = dim3(threads, 1, 1);
