@@ -467,6 +467,7 @@ __device__ __forceinline__ void ex2_poly2(uint64_t x2, float& r0, float& r1) {
   r1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 
+template <int POLY = FT_POLY_PAIRS>
 __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_ts_kernel(const __grid_constant__ FlashParams p) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
@@ -680,7 +681,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_attn_fwd_ts_kernel(const 
               // packed path: FFMA2 scale/shift, 2 x MUFU (or the FMA-pipe cubic), FADD2 row sum, 3-input max, F2FP
               const uint64_t x2 = f2_fma(f2_pack_bits(sv[i], sv[i + 1]), c2, nmb2);
               float p0, p1;
-              if ((FT_POLY_PAIRS >> u) & 1) {
+              if ((POLY >> u) & 1) {
                 ex2_poly2(x2, p0, p1);
               } else {
                 float x0, x1;
@@ -1181,7 +1182,10 @@ static int flash_fwd_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
   static bool attr_set = false;
   if (!attr_set) {
     LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+    LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_ts_kernel<FT_POLY_PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+    LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_ts_kernel<0b0000>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+    LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_ts_kernel<0b1010>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+    LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_ts_kernel<0b1110>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
     LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwCfg<2>::SMEM));
     LECO_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_wide_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwCfg<3>::SMEM));
     attr_set = true;
@@ -1195,7 +1199,15 @@ static int flash_fwd_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
   else if (d > FA_D)
     LECO_LAUNCH(flash_attn_fwd_wide_kernel<2>, grid, FW_THREADS, FwCfg<2>::SMEM, reinterpret_cast<cudaStream_t>(stream), p);
   else if (use_ts)
-    LECO_LAUNCH(flash_attn_fwd_ts_kernel, grid, FA_THREADS, FT_SMEM, reinterpret_cast<cudaStream_t>(stream), p);
+  {
+    // LECO_FLASH_POLY = 0 / 1 / 2 / 3: that many quarters of the exponentials on the FMA pipe (A/B switch; default 1/4)
+    static const int poly = [] { const char* e = getenv("LECO_FLASH_POLY"); return e ? atoi(e) : 1; }();
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (poly == 0) LECO_LAUNCH(flash_attn_fwd_ts_kernel<0b0000>, grid, FA_THREADS, FT_SMEM, st, p);
+    else if (poly == 2) LECO_LAUNCH(flash_attn_fwd_ts_kernel<0b1010>, grid, FA_THREADS, FT_SMEM, st, p);
+    else if (poly == 3) LECO_LAUNCH(flash_attn_fwd_ts_kernel<0b1110>, grid, FA_THREADS, FT_SMEM, st, p);
+    else LECO_LAUNCH(flash_attn_fwd_ts_kernel<FT_POLY_PAIRS>, grid, FA_THREADS, FT_SMEM, st, p);
+  }
   else
     LECO_LAUNCH(flash_attn_fwd_kernel, grid, FA_THREADS, FA_SMEM, reinterpret_cast<cudaStream_t>(stream), p);
   LECO_CHECK_CUDA(cudaGetLastError());
