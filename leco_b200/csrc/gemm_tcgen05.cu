@@ -409,40 +409,67 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-// split-K finalize: out = bf16(ws + bias + rowbias + residual); the workspace is zeroed again on the way
-__global__ void splitk_finalize_kernel(const GemmParams p) {
+// split-K finalize: out = bf16(ws + bias + rowbias + residual); the workspace is zeroed again on the way.
+// Two vectors per thread with every load issued before the first store (the stores to ws / d could alias the later
+// loads as far as the compiler knows), 32-bit index arithmetic: the in-graph timeline showed 6-11 us per call for
+// 1-5 MB of workspace, i.e. latency, not bandwidth.
+__device__ __forceinline__ void splitk_fin_load(const GemmParams& p, int i, int vpr, int& m, int& col, float4& v, uint2& qr,
+                                                uint2& qrb) {
+  m = i / vpr;
+  col = (i - m * vpr) * 4;
+  v = *reinterpret_cast<const float4*>(p.ws + (size_t)m * p.ldws + col);
+  qr = make_uint2(0u, 0u);
+  qrb = make_uint2(0u, 0u);
+  if (p.residual) qr = *reinterpret_cast<const uint2*>(p.residual + (size_t)m * p.ldr + col);
+  if (p.rowbias) qrb = *reinterpret_cast<const uint2*>(p.rowbias + (size_t)(m / p.rows_per_group) * p.ld_rowbias + col);
+}
+__device__ __forceinline__ void splitk_fin_store(const GemmParams& p, int m, int col, const float4& v, const uint2& qr,
+                                                 const uint2& qrb) {
+  *reinterpret_cast<float4*>(p.ws + (size_t)m * p.ldws + col) = make_float4(0.f, 0.f, 0.f, 0.f);
+  float f[4] = {v.x, v.y, v.z, v.w};
+  if (p.bias) {
+    const uint2 q = *reinterpret_cast<const uint2*>(p.bias + col);
+    f[0] += bf16_lo(q.x); f[1] += bf16_hi(q.x); f[2] += bf16_lo(q.y); f[3] += bf16_hi(q.y);
+  }
+  f[0] = (f[0] + bf16_lo(qrb.x)) + bf16_lo(qr.x);   // same order as the in-kernel epilogue; absent terms were loaded
+  f[1] = (f[1] + bf16_hi(qrb.x)) + bf16_hi(qr.x);   // as zeros
+  f[2] = (f[2] + bf16_lo(qrb.y)) + bf16_lo(qr.y);
+  f[3] = (f[3] + bf16_hi(qrb.y)) + bf16_hi(qr.y);
+  uint2 o;
+  o.x = pack_bf16(f[0], f[1]);
+  o.y = pack_bf16(f[2], f[3]);
+  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.d) + (size_t)m * p.ldd + col) = o;
+}
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const GemmParams p) {
   pdl_entry();
   const int vpr = p.N / 4;
-  const long long total = (long long)p.M * vpr;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long m = i / vpr;
-    const int col = (int)(i % vpr) * 4;
-    float4* w = reinterpret_cast<float4*>(p.ws + m * p.ldws + col);
-    float4 v = *w;
-    *w = make_float4(0.f, 0.f, 0.f, 0.f);
-    float f[4] = {v.x, v.y, v.z, v.w};
-    auto add4 = [&](const __nv_bfloat16* src) {
-      const uint2 q = *reinterpret_cast<const uint2*>(src);
-      f[0] += bf16_lo(q.x);
-      f[1] += bf16_hi(q.x);
-      f[2] += bf16_lo(q.y);
-      f[3] += bf16_hi(q.y);
-    };
-    if (p.bias) add4(p.bias + col);
-    if (p.rowbias) add4(p.rowbias + (m / p.rows_per_group) * p.ld_rowbias + col);
-    if (p.residual) add4(p.residual + m * p.ldr + col);
-    uint2 o;
-    o.x = pack_bf16(f[0], f[1]);
-    o.y = pack_bf16(f[2], f[3]);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.d) + m * p.ldd + col) = o;
+  const int total = p.M * vpr;                          // < 2^31: checked by the launcher
+  const int stride = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < total; i += 2 * stride) {
+    int m0, c0, m1, c1;
+    float4 v0, v1;
+    uint2 r0, r1, b0, b1;
+    splitk_fin_load(p, i, vpr, m0, c0, v0, r0, b0);
+    splitk_fin_load(p, i + stride, vpr, m1, c1, v1, r1, b1);
+    splitk_fin_store(p, m0, c0, v0, r0, b0);
+    splitk_fin_store(p, m1, c1, v1, r1, b1);
+  }
+  if (i < total) {
+    int m0, c0;
+    float4 v0;
+    uint2 r0, b0;
+    splitk_fin_load(p, i, vpr, m0, c0, v0, r0, b0);
+    splitk_fin_store(p, m0, c0, v0, r0, b0);
   }
 }
 void count_launch();
 static int launch_splitk_finalize(const GemmParams& p, cudaStream_t stream) {
   const long long total = (long long)p.M * (p.N / 4);
-  long long blocks = (total + 255) / 256;
+  LECO_REQUIRE(total < (1LL << 31), "split-K finalize: %lld vectors", total);
+  long long blocks = (total + 511) / 512;               // two vectors per thread
   if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
   count_launch();
   LECO_LAUNCH(splitk_finalize_kernel, (int)blocks, 256, 0, stream, p);
   LECO_CHECK_CUDA(cudaGetLastError());
