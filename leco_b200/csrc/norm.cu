@@ -23,7 +23,7 @@ __device__ __forceinline__ v8 pk8(const float (&f)[8]) {
   return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
 __device__ __forceinline__ float dsilu_f(float y) {
-  const float s = 1.0f / (1.0f + __expf(-y));
+  const float s = __fdividef(1.0f, 1.0f + __expf(-y));
   return s * (1.0f + y * (1.0f - s));
 }
 
@@ -46,15 +46,28 @@ __device__ __forceinline__ void gn_block_group_sums(float* red, const float (&s1
     }
   }
   __syncthreads();
+  // one (full) warp per group: lane = channel of the group (consecutive banks), rows in order, fixed xor tree.  (One
+  // THREAD per group walked R * cpg values serially: ~2 us of the statistics kernels' fixed latency.)
   const int cpg = C / G;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    float a = 0.f, b = 0.f;
-    for (int q = 0; q < R; ++q)
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        a += red[(size_t)q * C + c];
-        b += red[(size_t)(R + q) * C + c];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  if (warp < nwarps) {
+    for (int g = warp; g < G; g += nwarps) {
+      float a = 0.f, b = 0.f;
+      for (int co = lane; co < cpg; co += 32) {
+        const float* p1 = red + g * cpg + co;
+        const float* p2 = p1 + (size_t)R * C;
+        for (int q = 0; q < R; ++q) {
+          a += p1[(size_t)q * C];
+          b += p2[(size_t)q * C];
+        }
       }
-    dst[g] = make_float2(a, b);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (lane == 0) dst[g] = make_float2(a, b);
+    }
   }
 }
 // Ordered fold of the per-split partials of sample n: warp w handles groups w, w+nwarps, ...; lanes stride the splits,
@@ -774,21 +787,37 @@ __global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const _
     up8(__ldg(reinterpret_cast<const v8*>(gamma + v * 8)), gm);
     up8(__ldg(reinterpret_cast<const v8*>(beta + v * 8)), bt);
     const size_t off = ((size_t)n * hw) * C + v * 8;
-    for (int r = r0 + rl; r < r1; r += R) {
+    float2 mj[8];                                   // this thread's 8 channels: (mean, rstd) of their groups
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mj[j] = ms[(v * 8 + j) / cpg];
+    auto row = [&](const v8& qx, const v8& qd) {
       float f[8], d[8];
-      up8(*reinterpret_cast<const v8*>(x + off + (size_t)r * C), f);
-      up8(*reinterpret_cast<const v8*>(dz + off + (size_t)r * C), d);
+      up8(qx, f);
+      up8(qd, d);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float2 m = ms[(v * 8 + j) / cpg];
-        const float xh = (f[j] - m.x) * m.y;
+        const float xh = (f[j] - mj[j].x) * mj[j].y;
         float dy = d[j];
         if (silu) dy *= dsilu_f(xh * gm[j] + bt[j]);
         const float g = dy * gm[j];
         s1[j] += g;
         s2[j] = fmaf(g, xh, s2[j]);
       }
+    };
+    int r = r0 + rl;
+    for (; r + 3 * R < r1; r += 4 * R) {            // eight independent 16-byte loads in flight per thread
+      v8 qx[4], qd[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                 // (volatile asm: the compiler sinks plain loads to their first use)
+        qx[u] = gnc_ldg_stream(x + off + (size_t)(r + u * R) * C);
+        qd[u] = gnc_ldg_stream(dz + off + (size_t)(r + u * R) * C);
+      }
+      asm volatile("" ::: "memory");
+#pragma unroll
+      for (int u = 0; u < 4; ++u) row(qx[u], qd[u]);
     }
+    for (; r < r1; r += R)
+      row(*reinterpret_cast<const v8*>(x + off + (size_t)r * C), *reinterpret_cast<const v8*>(dz + off + (size_t)r * C));
   }
   gn_block_group_sums(gn_red, s1, s2, v, rl, R, C, G, partial + ((size_t)n * splits + sp) * G);
 }
@@ -816,12 +845,11 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
   const int vpp = C / 8;
   const long long total = (long long)hw * vpp;
   const size_t base = (size_t)n * hw * C;
-  for (long long i = blockIdx.y * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.y * blockDim.x) {
-    const int v = (int)(i % vpp);
+  auto one = [&](long long i, const v8& qx, const v8& qd) {
+    const int v = (int)((unsigned long long)i % (unsigned)vpp);
     float f[8], d[8], gm[8], bt[8];
-    up8(*reinterpret_cast<const v8*>(x + base + i * 8), f);
-    up8(*reinterpret_cast<const v8*>(dz + base + i * 8), d);
+    up8(qx, f);
+    up8(qd, d);
     up8(__ldg(reinterpret_cast<const v8*>(gamma + v * 8)), gm);
     up8(__ldg(reinterpret_cast<const v8*>(beta + v * 8)), bt);
 #pragma unroll
@@ -835,7 +863,17 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
       f[j] = m.y * (gg - gs[g].x - xh * gs[g].y);
     }
     *reinterpret_cast<v8*>(dx + base + i * 8) = pk8(f);
+  };
+  const long long stride = (long long)gridDim.y * blockDim.x;
+  long long i = blockIdx.y * (long long)blockDim.x + threadIdx.x;
+  for (; i + stride < total; i += 2 * stride) {     // two vectors (four 16-byte loads) in flight per thread
+    const v8 xa = gnc_ldg_stream(x + base + i * 8), da = gnc_ldg_stream(dz + base + i * 8);
+    const v8 xb = gnc_ldg_stream(x + base + (i + stride) * 8), db = gnc_ldg_stream(dz + base + (i + stride) * 8);
+    asm volatile("" ::: "memory");
+    one(i, xa, da);
+    one(i + stride, xb, db);
   }
+  if (i < total) one(i, gnc_ldg_stream(x + base + i * 8), gnc_ldg_stream(dz + base + i * 8));
 }
 
 // ---------------------------------------------------------------- LayerNorm
