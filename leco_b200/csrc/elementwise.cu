@@ -3,6 +3,8 @@
 // stride-2 im2col/col2im, batched transpose, row softmax (fwd/bwd) and axpy.  All are
 // coalesced 16-byte-vector kernels; none of them is worth a tensor core.
 #include "../../include/leco_b200.h"
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace leco {
@@ -80,6 +82,73 @@ __global__ void conv_in_kernel(const TIn* __restrict__ x, const __nv_bfloat16* _
           }
         }
     *reinterpret_cast<bf16x8*>(y + pix * cout + g * 8) = pack8(acc);
+  }
+}
+
+// Four consecutive pixels of a row per thread (w % 4 == 0): every 8-channel weight slice read from shared memory feeds
+// 4 x 8 FMAs instead of 8, and the 3 x 6 input patch of a channel is loaded once for the four outputs.  The one-pixel
+// kernel above was bound by its shared-memory weight reads (72 LDS.128 per 288 FMAs): 74 us per UNet forward at
+// 4 x 64 x 64 -> 320, 1 % of a denoise step (in-graph timeline).  Same accumulation order per output: same bits.
+template <typename TIn>
+__global__ void __launch_bounds__(256, 2)
+conv_in4_kernel(const TIn* __restrict__ x, const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ bias,
+                __nv_bfloat16* __restrict__ y, int n, int h, int wd, int cout) {
+  pdl_entry();
+  extern __shared__ float s_w[];  // [36][cout] + bias[cout]
+  float* s_b = s_w + 36 * cout;
+  for (int i = threadIdx.x; i < 36 * cout; i += blockDim.x) {   // consecutive threads -> consecutive banks
+    const int k = i / cout, o = i - k * cout;
+    s_w[i] = __bfloat162float(w[o * 36 + k]);
+  }
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) s_b[i] = bias ? __bfloat162float(bias[i]) : 0.f;
+  __syncthreads();
+  const int groups = cout / 8, qpr = wd / 4;
+  const long long total = 1LL * n * h * qpr * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long q = i / groups;
+    const int px0 = (int)(q % qpr) * 4;
+    const int py = (int)((q / qpr) % h);
+    const int img = (int)(q / ((long long)qpr * h));
+    float acc[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[p][j] = s_b[g * 8 + j];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = py + ky - 1;
+        float xv[6];
+        const TIn* row = x + ((1LL * img * 4 + c) * h + yy) * wd;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+          const int xx = px0 - 1 + t;
+          xv[t] = (yy >= 0 && yy < h && xx >= 0 && xx < wd) ? static_cast<float>(row[xx]) : 0.f;   // zero padding
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4* wr = reinterpret_cast<const float4*>(s_w + (c * 9 + ky * 3 + kx) * cout + g * 8);
+          const float4 w0 = wr[0], w1 = wr[1];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float v = xv[p + kx];
+            acc[p][0] = fmaf(v, w0.x, acc[p][0]);
+            acc[p][1] = fmaf(v, w0.y, acc[p][1]);
+            acc[p][2] = fmaf(v, w0.z, acc[p][2]);
+            acc[p][3] = fmaf(v, w0.w, acc[p][3]);
+            acc[p][4] = fmaf(v, w1.x, acc[p][4]);
+            acc[p][5] = fmaf(v, w1.y, acc[p][5]);
+            acc[p][6] = fmaf(v, w1.z, acc[p][6]);
+            acc[p][7] = fmaf(v, w1.w, acc[p][7]);
+          }
+        }
+      }
+    const long long pix0 = ((long long)img * h + py) * wd + px0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) *reinterpret_cast<bf16x8*>(y + (pix0 + p) * cout + g * 8) = pack8(acc[p]);
   }
 }
 
@@ -530,6 +599,19 @@ extern "C" int leco_conv_in(const void* x, int x_is_fp32, const void* w, const v
   int grid = grid_for(work, 256);
   if (grid > 148 * 4) grid = 148 * 4;  // each block re-stages the weights: keep the grid modest
   count_launch();
+  static const bool quad = [] { const char* e = getenv("LECO_CONV_IN_QUAD"); return !(e && e[0] == '0'); }();
+  if (quad && wd % 4 == 0) {           // four pixels per thread (LECO_CONV_IN_QUAD=0: the one-pixel kernel, for A/B runs)
+    int grid4 = grid_for(work / 4, 256);
+    if (grid4 > 148 * 2) grid4 = 148 * 2;
+    if (x_is_fp32)
+      LECO_LAUNCH(conv_in4_kernel<float>, grid4, 256, smem, STREAM(stream), reinterpret_cast<const float*>(x), BF(w), BF(bias),
+                  BFW(y), n, h, wd, cout);
+    else
+      LECO_LAUNCH(conv_in4_kernel<__nv_bfloat16>, grid4, 256, smem, STREAM(stream), BF(x), BF(w), BF(bias), BFW(y), n, h, wd,
+                  cout);
+    LECO_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (x_is_fp32)
     LECO_LAUNCH(conv_in_kernel<float>, grid, 256, smem, STREAM(stream), reinterpret_cast<const float*>(x), BF(w), BF(bias),
                                                               BFW(y), n, h, wd, cout);

@@ -134,6 +134,12 @@ def case_elementwise():
     w, b = _rand((64, 4, 3, 3), 0.3, 2), _rand((64,), 0.1, 3)
     res["conv_in_f32"] = _cmp(ops.conv_in(x, w, b), tb.conv_in(x.cpu(), w.cpu(), b.cpu()))
     res["conv_in_bf16"] = _cmp(ops.conv_in(x.bfloat16(), w, b), tb.conv_in(x.bfloat16().cpu(), w.cpu(), b.cpu()))
+    # width not a multiple of 4: the one-pixel-per-thread kernel; 64x64 -> 320: the UNet's own conv_in shape
+    x2 = _rand((2, 4, 10, 18), seed=8, dtype=torch.float32)
+    res["conv_in_w18"] = _cmp(ops.conv_in(x2, w, b), tb.conv_in(x2.cpu(), w.cpu(), b.cpu()))
+    x3 = _rand((2, 4, 64, 64), seed=9, dtype=torch.float32)
+    w3, b3 = _rand((320, 4, 3, 3), 0.3, 10), _rand((320,), 0.1, 11)
+    res["conv_in_64_320"] = _cmp(ops.conv_in(x3, w3, b3), tb.conv_in(x3.cpu(), w3.cpu(), b3.cpu()))
     xa = _rand((3 * 16 * 24, 64), seed=4)
     wo, bo = _rand((4, 9, 64), 0.05, 5), _rand((4,), 0.1, 6)
     res["conv_out"] = _cmp(ops.conv_out(xa, wo, bo, 3, 16, 24), tb.conv_out(xa.cpu(), wo.cpu(), bo.cpu(), 3, 16, 24))
