@@ -37,7 +37,7 @@ REQUIRED = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step
             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"]
 
 
-@pytest.mark.parametrize("name", ["r1_final_bench.json", "r1_bench_2gpu.json"])
+@pytest.mark.parametrize("name", ["r1_final_bench.json", "r1_bench_2gpu.json", "r2ai_final_bench.json"])
 def test_committed_bench_lines_follow_the_contract(name):
     line = json.load(open(os.path.join(ROOT, "profiles", name)))
     for k in REQUIRED:

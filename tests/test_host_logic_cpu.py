@@ -296,3 +296,51 @@ def test_optimizer_args_parsing_and_save_cadence():
     assert parse_optimizer_args("weight_decay=0.1 betas=(0.9,0.99)") == {"weight_decay": 0.1, "betas": (0.9, 0.99)}
     saves = [i for i in range(500) if i % 200 == 0 and i != 0 and i != 499]
     assert saves == [200, 400]
+
+
+def test_attention_dispatch_rule(monkeypatch):
+    """Which attention path a call takes (leco_b200/ops.py::attention): the fused forward covers head dims <= 192 on
+    every no-grad pass (SD1.5's 80 / 160 included), the fused backward head dims <= 64 only, and the deterministic
+    switch keeps the materialised path on the grad pass (the fused backward reduces dQ with fp32 atomics)."""
+    from leco_b200 import ops
+    calls = []
+    monkeypatch.setattr(ops, "flash_attention", lambda *a, **k: calls.append("flash") or "o")
+    monkeypatch.setattr(ops, "flash_attention_lse", lambda *a, **k: calls.append("flash_lse") or ("o", "lse"))
+    monkeypatch.setattr(ops, "attention_v0", lambda *a, **k: calls.append("v0") or ("o", None))
+    monkeypatch.setattr(ops, "ATTENTION_IMPL", "flash")
+    monkeypatch.setattr(ops, "ATTENTION_BWD_IMPL", "flash")
+    monkeypatch.setattr(ops, "FLASH_WIDE_MAX_D", 192)
+    monkeypatch.setattr(ops, "FLASH_V_MODE", 0)
+    monkeypatch.setattr(ops, "_DETERMINISTIC", [False])
+
+    def path(d, grad):
+        calls.clear()
+        ops.attention(None, None, None, 2, 64, 64, 8, d, d ** -0.5, grad)
+        return calls[-1]
+
+    assert [path(d, False) for d in (40, 64, 80, 160, 192)] == ["flash"] * 5
+    assert path(200, False) == "v0" and path(44, False) == "v0"          # too wide / not a multiple of 8
+    assert path(64, True) == "flash_lse" and path(40, True) == "flash_lse"
+    assert path(80, True) == "v0" and path(160, True) == "v0"            # grad pass: fused backward covers d <= 64
+    monkeypatch.setattr(ops, "_DETERMINISTIC", [True])
+    assert path(64, True) == "v0" and path(64, False) == "flash"
+    monkeypatch.setattr(ops, "_DETERMINISTIC", [False])
+    monkeypatch.setattr(ops, "FLASH_WIDE_MAX_D", 64)                     # LECO_FLASH_WIDE=0
+    assert path(80, False) == "v0" and path(64, False) == "flash"
+    monkeypatch.setattr(ops, "FLASH_WIDE_MAX_D", 192)
+    monkeypatch.setattr(ops, "FLASH_V_MODE", 1)                          # the wide kernel takes V in place only
+    assert path(80, False) == "v0" and path(64, False) == "flash"
+
+
+def test_timeline_attribution_by_end_times():
+    """tests/gpu_checks/timeline_step.py::table charges a kernel with the time by which it extends the timeline (a
+    PDL kernel starts while its predecessor still runs), and reports time with no kernel resident as idle."""
+    from tests.gpu_checks.timeline_step import table
+    ev = [{"name": "a", "ts": 0.0, "dur": 10.0},      # 0..10
+          {"name": "b", "ts": 2.0, "dur": 11.0},      # starts under a (PDL), ends at 13: extends the timeline by 3
+          {"name": "c", "ts": 4.0, "dur": 5.0},       # entirely hidden: 0
+          {"name": "a", "ts": 20.0, "dur": 5.0}]      # 7 us with nothing resident, then 5
+    md = table(ev, "t")
+    rows = {l.split("|")[1].strip(" `"): [c.strip() for c in l.split("|")[2:]] for l in md.splitlines() if l.startswith("| `")}
+    assert "span: 0.025 ms" in md and "idle (no kernel resident): 0.007 ms" in md and "busy: 0.018 ms" in md
+    assert rows["a"][0] == "2" and float(rows["a"][1]) == 0.015 and rows["b"][1] == "0.003" and rows["c"][1] == "0.000"
