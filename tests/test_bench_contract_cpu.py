@@ -80,3 +80,19 @@ def test_reference_arm_runs_complete_iterations_and_keeps_the_contract():
     assert m["k"] == 1 and m["iterations"] == 2 and m["s_per_iteration"] > m["s_denoise_step"] > 0
     assert abs(p["latents_per_s"] - m["prompt_batch"] / (25 * m["s_denoise_step"] + m["s_rest_of_iteration"])) < 1e-9
     assert line["e2e"] == {"value": line["value"], "unit": "latents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_both_arms_default_to_the_same_workload_and_idle_ranks_exit_clean():
+    """N=1 -> BASELINE configs[1], N>1 -> configs[4] for our arm AND the reference arm; under torchrun only rank 0 of the
+    reference arm works, the other ranks exit 0 without output; an SDXL reference request answers `unavailable`."""
+    import subprocess
+    import sys
+    assert bench.default_workload(1) == "sd21" and bench.default_workload(2) == bench.default_workload(8) == "sd21_b4"
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    pr = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert pr.returncode == 0 and pr.stdout.strip() == ""
+    pr = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "sdxl"],
+                        capture_output=True, text=True, timeout=120, cwd=ROOT)
+    line = json.loads(pr.stdout.strip().splitlines()[-1])
+    assert pr.returncode == 0 and line["impl"] == "reference" and "unavailable" in line
