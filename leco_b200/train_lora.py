@@ -32,8 +32,21 @@ def parse_optimizer_args(s: Optional[str]) -> dict:
     return out
 
 
+def share_seed(device) -> int:
+    """The data-parallel rule needs every rank to make the SAME draws (adapter init, prompt pair, k, global noise,
+    SURVEY §8e); the reference never seeds, so rank 0's seed is broadcast and installed everywhere (torch.manual_seed
+    also seeds the CUDA generator that the stochastic schedulers' step noise comes from)."""
+    import torch.distributed as dist
+    seed = torch.tensor([torch.initial_seed() % (1 << 62)], dtype=torch.int64, device=device)
+    dist.broadcast(seed, src=0)
+    torch.manual_seed(int(seed.item()))
+    return int(seed.item())
+
+
 def train(config, prompts, *, device="cuda", rank: int = 0, world_size: int = 1,
           on_iteration: Optional[Callable[[int, float], None]] = None, xl: bool = False) -> List[float]:
+    if world_size > 1:
+        share_seed(device)
     save_path = Path(config.save.path)
     weight_dtype = config_util.parse_precision(config.train.precision)
     save_weight_dtype = config_util.parse_precision(config.train.precision)      # sic (SURVEY Q7)
@@ -103,6 +116,13 @@ def train(config, prompts, *, device="cuda", rank: int = 0, world_size: int = 1,
     return losses
 
 
+def dist_env(env=None):
+    """(rank, world size, local rank) as torchrun exports them; (0, 1, 0) for a plain `python -m` launch."""
+    import os
+    env = os.environ if env is None else env
+    return int(env.get("RANK", "0")), int(env.get("WORLD_SIZE", "1")), int(env.get("LOCAL_RANK", "0"))
+
+
 def main(args=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--config_file", required=True, help="Config file for training.")
@@ -110,7 +130,19 @@ def main(args=None):
     a = ap.parse_args(args)
     config = config_util.load_config_from_yaml(a.config_file)
     prompts = config_util.load_prompts_from_yaml(config.prompts_file)
-    train(config, prompts, xl=a.xl)
+    # data parallel: `python -m torch.distributed.run --nproc-per-node N -m leco_b200.train_lora ...` —
+    # one process per GPU, each prompt's batch_size is the GLOBAL batch and is split over the ranks
+    rank, world, local = dist_env()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    try:
+        train(config, prompts, xl=a.xl, device=device, rank=rank, world_size=world)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -67,3 +67,30 @@ def test_two_rank_gradient_equals_single_process(tmp_path):
     assert abs(got["loss"].item() - want_loss.item()) < 1e-6 * abs(want_loss.item()) + 1e-9
     rel = (got["flat"] - want_flat).norm() / want_flat.norm()
     assert rel < 1e-4, rel
+
+
+def _seed_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from leco_b200 import train_lora
+    torch.manual_seed(1000 + rank)                 # ranks start out different, as un-seeded processes do
+    seed = train_lora.share_seed(torch.device("cpu"))
+    draws = (torch.randint(0, 1 << 30, (4,)), torch.randn(3))
+    torch.save({"seed": seed, "draws": draws}, out + str(rank))
+    dist.destroy_process_group()
+
+
+def test_ranks_share_rank0_seed(tmp_path):
+    """leco_b200.train_lora.train() under torchrun: every rank installs rank 0's seed before any draw."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "seed")
+    mp.spawn(_seed_worker, args=(2, port, out), nprocs=2, join=True)
+    a, b = torch.load(out + "0"), torch.load(out + "1")
+    assert a["seed"] == b["seed"] == 1000
+    assert torch.equal(a["draws"][0], b["draws"][0]) and torch.equal(a["draws"][1], b["draws"][1])
+    from leco_b200 import train_lora
+    assert train_lora.dist_env({"RANK": "3", "WORLD_SIZE": "8", "LOCAL_RANK": "3"}) == (3, 8, 3)
+    assert train_lora.dist_env({}) == (0, 1, 0)
