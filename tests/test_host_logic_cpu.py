@@ -177,6 +177,44 @@ def test_reference_lora_network_patches_engine_tree():
         assert sum(len(s.members) for s in sites) == n
 
 
+@pytest.mark.skipif(not reference_available(), reason="reference sources only exist in the build container")
+@pytest.mark.parametrize("arch,c3lier,rank", [("tiny21", False, 4), ("tiny15", True, 8)])
+def test_saved_file_is_byte_identical_to_the_reference_export(tmp_path, arch, c3lier, rank):
+    """north_star: '.safetensors export stays bit-compatible'.  The reference's OWN LoRANetwork.save_weights (lora.py:212-229)
+    on the oracle UNet and the mirror's on the engine tree, same seed, same (trained-looking) weights: the two files are
+    the same BYTES (header order, dtypes, shapes, tensor data), for lierla and for c3lier (3x3 conv adapters)."""
+    from oracle.ref_loader import load_reference
+    ref = load_reference()
+    eng, ora = EngineUNet(SPECS[arch], backend=torch_backend), build_unet(arch)
+    saved_m, saved_r = list(plora.DEFAULT_TARGET_REPLACE), list(ref.lora.DEFAULT_TARGET_REPLACE)
+    try:
+        if c3lier:                                   # train_lora.py:44-46
+            plora.DEFAULT_TARGET_REPLACE += plora.UNET_TARGET_REPLACE_MODULE_CONV
+            ref.lora.DEFAULT_TARGET_REPLACE += ref.lora.UNET_TARGET_REPLACE_MODULE_CONV
+        with contextlib.redirect_stdout(io.StringIO()):
+            torch.manual_seed(5)
+            a = plora.LoRANetwork(eng, rank=rank, multiplier=1.0, alpha=1.0)
+            torch.manual_seed(5)
+            b = ref.lora.LoRANetwork(ora, rank=rank, multiplier=1.0, alpha=1.0)
+    finally:
+        plora.DEFAULT_TARGET_REPLACE[:] = saved_m
+        ref.lora.DEFAULT_TARGET_REPLACE[:] = saved_r
+    g = torch.Generator().manual_seed(9)
+    for la, lb in zip(a.unet_loras, b.unet_loras):   # lora_up is zero at init: give both the same non-trivial values
+        w = 0.1 * torch.randn(la.lora_up.weight.shape, generator=g)
+        la.lora_up.weight.data.copy_(w)
+        lb.lora_up.weight.data.copy_(w)
+    for dtype in (torch.bfloat16, None):
+        fa, fb = str(tmp_path / f"a_{dtype}.safetensors"), str(tmp_path / f"b_{dtype}.safetensors")
+        a.save_weights(fa, dtype=dtype)
+        b.save_weights(fb, dtype=dtype)
+        assert open(fa, "rb").read() == open(fb, "rb").read(), (arch, dtype)
+    # the metadata argument reaches the file header unchanged too
+    a.save_weights(str(tmp_path / "ma.safetensors"), dtype=torch.float16, metadata={"ss_network_dim": str(rank)})
+    b.save_weights(str(tmp_path / "mb.safetensors"), dtype=torch.float16, metadata={"ss_network_dim": str(rank)})
+    assert open(tmp_path / "ma.safetensors", "rb").read() == open(tmp_path / "mb.safetensors", "rb").read()
+
+
 def test_lr_scheduler_factory_matches_torch():
     """train_util.get_lr_scheduler (train_util.py:373-401) drives the fused optimizer's lr through the same torch
     scheduler classes and arguments; the reference steps it once per iteration (train_lora.py:281)."""
