@@ -8,11 +8,15 @@ encoding of `train_util.py:60-130`, for an offline sandbox.
     from `vocab.json`/`merges.txt`, `ClipTextEncoder` from `config.json` + weights, the UNet topology from
     `unet/config.json` and its weights from `diffusion_pytorch_model.safetensors|.bin` (the engine tree uses diffusers'
     parameter names, so keys match 1:1);
+  * a single-file checkpoint in the ORIGINAL (LDM) key layout, `.ckpt` / `.safetensors` — what the reference passes to
+    `from_single_file` (model_util.py:78-101, 173-197): UNet and text encoder(s) are converted key by key
+    (`leco_b200.ckpt_convert`).  The file holds no vocabulary (diffusers fetches it from the hub): `tokenizer/`
+    [+ `tokenizer_2/`] are read from the checkpoint's own directory or from `$LECO_TOKENIZER_DIR`;
   * a single .safetensors / .pt file holding a diffusers-format UNet state dict: UNet weights real, text side synthetic;
   * anything else (a hub name, an architecture name of `leco_b200.unet.SPECS`): seeded synthetic weights of the
     architecture the config flags select, and a stand-in text encoder that returns a seeded N(0,1) embedding per
     prompt string.  No checkpoint or vocabulary exists in this sandbox, so this is what every benchmark here runs;
-    the run says so on stdout.  (Single-file .ckpt conversion, model_util.py:131-197, is not built.)"""
+    the run says so on stdout."""
 from __future__ import annotations
 
 import json
@@ -147,9 +151,44 @@ def _load_unet(arch: str, name_or_path: str, device) -> Tuple[EngineUNet, str]:
         sd, where = _read_weights(os.path.join(name_or_path, "unet", "diffusion_pytorch_model"))
         return _engine_from_state(spec, sd, device), f"topology from unet/config.json, weights from {where}"
     if name_or_path and os.path.isfile(name_or_path):
-        sd, where = _read_weights(os.path.splitext(name_or_path)[0])
-        return _engine_from_state(SPECS[arch], sd, device), f"weights from {where}"
+        from . import ckpt_convert
+        layout, sd, encs = ckpt_convert.split_single_file(ckpt_convert.read_single_file(name_or_path),
+                                                          SPECS[arch].layers_per_block)
+        _SINGLE_FILE_TEXT[os.path.abspath(name_or_path)] = encs       # consumed by _single_file_text_side (one read)
+        return _engine_from_state(SPECS[arch], sd, device), f"weights from {name_or_path} ({layout} layout)"
     return build_engine(arch, device, seed=0), "synthetic seeded weights (no checkpoint available offline)"
+
+
+_SINGLE_FILE_TEXT = {}
+
+
+def _single_file_text_side(path: str, device, n_expected: int):
+    """(tokenizers, encoders) of an LDM-layout single-file checkpoint, or None when the file carries no text encoder
+    (a bare diffusers UNet).  model_util.py:78-101 / :173-197 get both from `from_single_file`; the vocabulary is not
+    in the file, so `tokenizer/` [`tokenizer_2/`] must sit beside it or under $LECO_TOKENIZER_DIR."""
+    from . import ckpt_convert
+    encs = _SINGLE_FILE_TEXT.pop(os.path.abspath(path), None)
+    if encs is None:
+        _, _, encs = ckpt_convert.split_single_file(ckpt_convert.read_single_file(path))
+    if not encs:
+        return None
+    if len(encs) != n_expected:
+        raise ValueError(f"{path}: {len(encs)} text encoder(s) in the file, this loop needs {n_expected} "
+                         f"({'load_models_xl' if n_expected == 2 else 'load_models'})")
+    roots = [os.path.dirname(os.path.abspath(path))] + ([os.environ["LECO_TOKENIZER_DIR"]]
+                                                        if os.environ.get("LECO_TOKENIZER_DIR") else [])
+    toks, models = [], []
+    for i, (sd, act, with_proj) in enumerate(encs):
+        sub = "tokenizer" if i == 0 else f"tokenizer_{i + 1}"
+        root = next((r for r in roots if os.path.isfile(os.path.join(r, sub, "vocab.json"))), None)
+        if root is None:
+            raise FileNotFoundError(f"single-file checkpoint {path}: no {sub}/vocab.json beside it or under "
+                                    f"$LECO_TOKENIZER_DIR (the reference downloads the CLIP vocabulary from the hub)")
+        toks.append(ClipTokenizer.from_pretrained(root, sub))
+        enc = ClipTextEncoder(ckpt_convert.clip_spec_from_state(sd, f"{os.path.basename(path)}:{i}", act, with_proj))
+        enc.load_state_dict(sd)
+        models.append(enc.to(device))
+    return toks, models
 
 
 def load_models(pretrained_model_name_or_path: str, scheduler_name: str = "ddim", v2: bool = False, v_pred: bool = False,
@@ -162,6 +201,10 @@ def load_models(pretrained_model_name_or_path: str, scheduler_name: str = "ddim"
         tokenizer = ClipTokenizer.from_pretrained(pretrained_model_name_or_path, "tokenizer")
         enc = ClipTextEncoder.from_pretrained(pretrained_model_name_or_path, "text_encoder", device=device)
         how += "; tokenizer + CLIP text encoder from the same directory"
+    elif os.path.isfile(pretrained_model_name_or_path or "") and \
+            (text := _single_file_text_side(pretrained_model_name_or_path, device, 1)) is not None:
+        (tokenizer,), (enc,) = text
+        how += "; CLIP text encoder converted from the same file, tokenizer from the directory beside it"
     else:
         tokenizer, enc = None, SyntheticTextEncoder(unet.spec.cross_attention_dim)
         how += "; stand-in text embeddings (no tokenizer / text encoder files)"
@@ -181,6 +224,10 @@ def load_models_xl(pretrained_model_name_or_path: str, scheduler_name: str = "dd
         encoders = [ClipTextEncoder.from_pretrained(d, "text_encoder", device=device),
                     ClipTextEncoder.from_pretrained(d, "text_encoder_2", device=device)]
         how += "; both tokenizers + CLIP text encoders from the same directory"
+    elif os.path.isfile(pretrained_model_name_or_path or "") and \
+            (text := _single_file_text_side(pretrained_model_name_or_path, device, 2)) is not None:
+        tokenizers, encoders = text
+        how += "; both CLIP text encoders converted from the same file, tokenizers from the directory beside it"
     else:
         enc = SyntheticTextEncoder(unet.spec.cross_attention_dim, unet.spec.add_text_dim)
         tokenizers, encoders = [None, None], [enc, enc]
