@@ -43,10 +43,53 @@ def share_seed(device) -> int:
     return int(seed.item())
 
 
+def _json(obj) -> str:
+    """`.json()` of the reference's pydantic objects, or the same for the dataclass mirror."""
+    if hasattr(obj, "json"):
+        return obj.json()
+    import dataclasses
+    import json
+    return json.dumps(dataclasses.asdict(obj) if dataclasses.is_dataclass(obj) else vars(obj), default=str)
+
+
+class RunLogger:
+    """The logging side of the reference's driver: `metadata` printed under `logging.verbose` (train_lora.py:38-49),
+    `wandb.init(project="LECO_<save.name>", config=metadata)` and one `wandb.log({"loss", "iteration", "lr"})` per
+    iteration under `logging.use_wandb` (:51-52, :274-277).  Only rank 0 logs; `needs_loss` tells the loop whether it has
+    to read the loss back (a device synchronisation the plain loop avoids)."""
+
+    def __init__(self, config, prompts, rank: int = 0, wandb_module=None):
+        self.metadata = {"prompts": ",".join(_json(p) for p in prompts), "config": _json(config)}
+        self.verbose = bool(config.logging.verbose) and rank == 0
+        self.wandb = None
+        if self.verbose:
+            print(self.metadata)
+        if config.logging.use_wandb and rank == 0:
+            if wandb_module is None:
+                import wandb as wandb_module
+            self.wandb = wandb_module
+            self.wandb.init(project=f"LECO_{config.save.name}", config=self.metadata)
+
+    @property
+    def needs_loss(self) -> bool:
+        return self.verbose or self.wandb is not None
+
+    def iteration(self, i: int, loss: float, lr: float, k: int):
+        if self.wandb is not None:
+            self.wandb.log({"loss": loss, "iteration": i, "lr": lr})
+        if self.verbose:
+            print(f"iteration {i}: loss*1k {loss * 1000:.4f} lr {lr:.3e} k {k}")
+
+    def finish(self):
+        if self.wandb is not None and hasattr(self.wandb, "finish"):
+            self.wandb.finish()
+
+
 def train(config, prompts, *, device="cuda", rank: int = 0, world_size: int = 1,
           on_iteration: Optional[Callable[[int, float], None]] = None, xl: bool = False) -> List[float]:
     if world_size > 1:
         share_seed(device)
+    log = RunLogger(config, prompts, rank)
     save_path = Path(config.save.path)
     weight_dtype = config_util.parse_precision(config.train.precision)
     save_weight_dtype = config_util.parse_precision(config.train.precision)      # sic (SURVEY Q7)
@@ -96,14 +139,14 @@ def train(config, prompts, *, device="cuda", rank: int = 0, world_size: int = 1,
                           world_size=world_size)
     losses = []
     for i in range(config.train.iterations):
+        lr_now = trainer.optimizer.lr        # the rate this iteration steps with (= lr_scheduler.get_last_lr()[0], :276)
         loss = trainer.iteration()
-        if on_iteration is not None or config.logging.verbose:
+        if on_iteration is not None or log.needs_loss:
             v = float(loss.item())           # reading the loss synchronises; the plain loop never does
             losses.append(v)
             if on_iteration is not None:
                 on_iteration(i, v)
-            if config.logging.verbose:
-                print(f"iteration {i}: loss*1k {v * 1000:.4f} lr {trainer.last['lr']:.3e} k {trainer.last['k']}")
+            log.iteration(i, v, lr_now, trainer.last["k"])
         if i % config.save.per_steps == 0 and i != 0 and i != config.train.iterations - 1 and rank == 0:
             print("Saving...")
             save_path.mkdir(parents=True, exist_ok=True)
@@ -112,6 +155,7 @@ def train(config, prompts, *, device="cuda", rank: int = 0, world_size: int = 1,
         print("Saving...")
         save_path.mkdir(parents=True, exist_ok=True)
         network.save_weights(str(save_path / f"{config.save.name}_last.safetensors"), dtype=save_weight_dtype)
+    log.finish()
     print("Done.")
     return losses
 

@@ -336,6 +336,55 @@ def test_optimizer_args_parsing_and_save_cadence():
     assert saves == [200, 400]
 
 
+def test_run_logger_mirrors_the_reference_logging(capsys):
+    """train_lora.py:38-52, 274-277: metadata = {"prompts": joined .json(), "config": .json()}, printed when verbose;
+    wandb.init(project="LECO_<name>", config=metadata) and wandb.log({"loss", "iteration", "lr"}) per iteration; only
+    rank 0 logs, and the loop reads the loss back only when something consumes it."""
+    from types import SimpleNamespace as NS
+    from leco_b200 import config_util
+    from leco_b200.train_lora import RunLogger
+
+    class FakeWandb:
+        def __init__(self):
+            self.calls = []
+
+        def init(self, **kw):
+            self.calls.append(("init", kw))
+
+        def log(self, d):
+            self.calls.append(("log", d))
+
+        def finish(self):
+            self.calls.append(("finish", None))
+
+    def cfg(verbose, use_wandb):
+        return NS(logging=NS(verbose=verbose, use_wandb=use_wandb), save=NS(name="van_gogh"), json=lambda: '{"c": 1}')
+    prompts = [NS(json=lambda: '{"target": "van gogh"}'), NS(json=lambda: '{"target": "cat"}')]
+    quiet = RunLogger(cfg(False, False), prompts)
+    assert not quiet.needs_loss and capsys.readouterr().out == ""
+    w = FakeWandb()
+    log = RunLogger(cfg(True, True), prompts, rank=0, wandb_module=w)
+    assert log.needs_loss and log.metadata == {"prompts": '{"target": "van gogh"},{"target": "cat"}', "config": '{"c": 1}'}
+    assert w.calls == [("init", {"project": "LECO_van_gogh", "config": log.metadata})]
+    assert str(log.metadata) in capsys.readouterr().out
+    log.iteration(3, 0.25, 1e-4, 17)
+    log.finish()
+    assert w.calls[1:] == [("log", {"loss": 0.25, "iteration": 3, "lr": 1e-4}), ("finish", None)]
+    assert "iteration 3" in capsys.readouterr().out
+    w2 = FakeWandb()
+    other = RunLogger(cfg(True, True), prompts, rank=1, wandb_module=w2)      # data parallel: ranks > 0 stay silent
+    assert not other.needs_loss and w2.calls == [] and capsys.readouterr().out == ""
+    # the mirror's own config / prompt objects serialise too
+    if reference_available():
+        import json
+        from leco_b200.train_lora import _json
+        root = config_util.load_config_from_yaml("/root/reference/examples/config.yaml")
+        ps = config_util.load_prompts_from_yaml("/root/reference/examples/prompts.yaml")
+        assert json.loads(_json(root))["train"]["iterations"] == root.train.iterations
+        assert json.loads(_json(ps[0]))["target"] == ps[0].target
+        assert RunLogger(root, ps).metadata["config"] == _json(root)
+
+
 def test_attention_dispatch_rule(monkeypatch):
     """Which attention path a call takes (leco_b200/ops.py::attention): the fused forward covers head dims <= 192 on
     every no-grad pass (SD1.5's 80 / 160 included), the fused backward head dims <= 64 only, and the deterministic
