@@ -215,3 +215,43 @@ def test_repack_keeps_adapter_sites_and_sees_new_weights():
     assert all(a is b for a, b in zip(sites0, eng.lora_sites()))
     assert not torch.allclose(y0, y1)
     assert (y1 - ref).abs().max().item() < 2e-4 * ref.abs().max().item() + 1e-5
+
+
+def test_reference_loop_body_on_the_engine_equals_the_oracle_iteration():
+    """The reference's loop body (oracle/leco_ref.leco_iteration = train_lora.py:141-302, pinned against the reference)
+    driving the ENGINE tree through `unet(...).sample`, `with network:`, `loss.backward()`, torch AdamW — the drop-in seam,
+    here with the torch double in fp32 — gives the oracle's k draws, losses and adapter weights (GPU twin:
+    tests/test_gpu_parity.py::test_reference_loop_body_drives_the_engine_through_the_drop_in_surface)."""
+    from leco_b200 import lora as plora
+    from oracle.sched_ref import create_noise_scheduler
+    from leco_b200.synthetic import prompt_embedding
+    arch = "tiny21"
+    D = CONFIGS[arch].cross_attention_dim
+    emb = {p: prompt_embedding(p, D) for p in ("van gogh", "")}
+
+    def run(engine: bool):
+        oracle = build_unet(arch, seed=0)
+        unet = _engine(arch, oracle) if engine else oracle
+        torch.manual_seed(1234)
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = (plora.LoRANetwork if engine else leco_ref.LoRANetworkRef)(unet, rank=4, multiplier=1.0, alpha=1.0)
+        pair = leco_ref.PromptPairRef(target=emb["van gogh"], positive=emb["van gogh"], unconditional=emb[""],
+                                      neutral=emb[""], guidance_scale=1.0, resolution=64, batch_size=2, action="erase")
+        opt = torch.optim.AdamW(net.prepare_optimizer_params(), lr=1e-3)
+        lrs = torch.optim.lr_scheduler.ConstantLR(opt, factor=1)
+        sched = create_noise_scheduler("ddim", "v_prediction")
+        torch.manual_seed(7)
+        losses, ks = [], []
+        for _ in range(3):
+            rec = {}
+            losses.append(leco_ref.leco_iteration(unet, sched, net, opt, lrs, [pair], max_denoising_steps=6, record=rec))
+            ks.append(rec["k"])
+        return losses, ks, [l.lora_up.weight.detach().clone() for l in net.unet_loras]
+    la, ka, ua = run(engine=True)
+    lb, kb, ub = run(engine=False)
+    assert ka == kb
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 2e-4 * abs(b), (la, lb)
+    num = sum((x - y).pow(2).sum().item() for x, y in zip(ua, ub)) ** 0.5
+    den = sum(y.pow(2).sum().item() for y in ub) ** 0.5
+    assert den > 0 and num / den < 2e-2, num / den

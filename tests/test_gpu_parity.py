@@ -430,3 +430,26 @@ def test_train_driver_from_a_checkpoint_directory(tmp_path, arch):
     losses = train_lora.train(config, settings, xl=xl, on_iteration=lambda i, v: seen.append(v))
     assert len(losses) == 3 and all(v == v and 0 < v < 50 for v in losses), losses
     assert (tmp_path / "output" / "out_last.safetensors").is_file()
+
+
+def test_reference_loop_body_drives_the_engine_through_the_drop_in_surface():
+    """the reference's loop body — train_lora.py:141-302 as restated statement for statement by
+    oracle/leco_ref.leco_iteration, which tests/test_oracle_pinned.py holds bit-equal to the reference's own train() —
+    runs UNMODIFIED on the GPU with the engine behind the reference's call surface: `unet(...).sample` inside
+    predict_noise / diffusion, `scheduler.step(...).prev_sample`, `with network:`, `loss.backward()`, torch.optim.AdamW
+    on the adapters' Parameters (the reference's files themselves do not travel to the GPU box).
+    Same k draws as the fp32 oracle, losses inside the measured bf16 tolerance, adapters move the same way."""
+    import torch
+    from __graft_entry__ import dropin_iterations, oracle_iterations
+    from tests.oracle_cache import cached
+    ref = cached("iters_tiny21", lambda: oracle_iterations(3))
+    yard = _bf16_yardstick("iters_tiny21", lambda **kw: oracle_iterations(3, **kw))
+    got = dropin_iterations(3)
+    assert got["k"] == ref["k"]
+    assert_losses_close(got["losses"], ref["losses"], yard["losses"])
+    num = den = 0.0
+    for wa, wb in zip(got["lora_up"], ref["lora_up"]):
+        wa, wb = wa.float().reshape(-1), wb.float().reshape(-1)
+        num += torch.dot(wa, wb).item()
+        den += (wa.norm() * wb.norm()).item()
+    assert den > 0 and num / den > 0.9, num / den
