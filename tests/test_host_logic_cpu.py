@@ -327,6 +327,23 @@ def test_config_mirror_parses_the_reference_examples_like_the_reference():
                 assert getattr(a, k) == v, (path, k)
 
 
+def test_shipped_example_config_parses_and_names_the_baseline_workload():
+    """examples/sd21_erase.yaml is BASELINE configs[1] in the driver's own format: every key is one the mirror (and the
+    reference's RootConfig) defines, and it selects the workload bench.py measures."""
+    from leco_b200 import config_util, train_util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    c = config_util.load_config_from_yaml(os.path.join(root, "examples", "sd21_erase.yaml"))
+    ps = config_util.load_prompts_from_yaml(os.path.join(root, "examples", "erase_prompts.yaml"))
+    assert (c.pretrained_model.name_or_path, c.pretrained_model.v2, c.pretrained_model.v_pred) == ("sd21", True, True)
+    assert (c.network.type, c.network.rank, c.train.precision, c.train.max_denoising_steps) == ("lierla", 4, "bfloat16", 50)
+    assert config_util.parse_precision(c.train.precision) == torch.bfloat16 and c.train.lr == 1e-4
+    train_util.get_optimizer(c.train.optimizer)               # a known optimizer name
+    assert (ps[0].target, ps[0].action, ps[0].batch_size, ps[0].resolution) == ("van gogh", "erase", 2, 512)
+    import bench
+    b = bench.CONFIGS["sd21"]
+    assert (b["arch"], b["rank"], b["batch"], b["res"]) == ("sd21", c.network.rank, ps[0].batch_size, ps[0].resolution)
+
+
 def test_optimizer_args_parsing_and_save_cadence():
     """train_lora.py:81-87 ("k=v k=v" through ast.literal_eval) and :292-309 (periodic saves skip i == 0 and the last)."""
     from leco_b200.train_lora import parse_optimizer_args
