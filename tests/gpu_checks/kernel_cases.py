@@ -483,8 +483,15 @@ def case_flash(nb, sq, skv, heads, d, cross=False, v_mode=0, perf=False, ts=None
     torch.cuda.synchronize()
     if nb * heads * sq * skv <= 2 * 8 * 1024 * 1024 * 4:
         oref, _ = tb.attention(qt.cpu(), kt.cpu(), vt.cpu(), nb, sq, skv, heads, d, scale, False)
-    else:  # big case: the (separately verified) materialised path is the reference
-        oref, _ = ops.attention_v0(qt, kt, vt, nb, sq, skv, heads, d, scale, False)
+    else:
+        # big case: an INDEPENDENT reference — stock torch attention in fp32 on the GPU (the fused
+        # bf16 backends do not take fp32, so this is torch's own math / memory-efficient path), one sample at a time
+        def heads_view(t, s):
+            return t.unflatten(0, (nb, s)).unflatten(2, (heads, d)).permute(0, 2, 1, 3).float()
+        q4, k4, v4 = heads_view(qt, sq), heads_view(kt, skv), heads_view(vt, skv)
+        oref = torch.cat([torch.nn.functional.scaled_dot_product_attention(q4[b:b + 1], k4[b:b + 1], v4[b:b + 1], scale=scale)
+                          for b in range(nb)], 0).permute(0, 2, 1, 3).reshape(nb * sq, C)
+        del q4, k4, v4
     res = _cmp(o, oref)
     if perf:
         def timeit(fn, iters=10):
