@@ -17,6 +17,11 @@ def get_random_noise(batch_size: int, height: int, width: int, generator: torch.
                        generator=generator, device="cpu")
 
 
+def apply_noise_offset(latents: torch.Tensor, noise_offset: float) -> torch.Tensor:
+    """train_util.py:36-40 (offset noise: one draw per sample and channel on the latents' device)."""
+    return latents + noise_offset * torch.randn((latents.shape[0], latents.shape[1], 1, 1), device=latents.device)
+
+
 def get_initial_latents(scheduler, n_imgs: int, height: int, width: int, n_prompts: int, generator=None):
     """train_util.py:43-57."""
     noise = get_random_noise(n_imgs, height, width, generator=generator).repeat(n_prompts, 1, 1, 1)
@@ -43,6 +48,18 @@ def diffusion(unet, scheduler, latents, text_embeddings, total_timesteps: int = 
         eps = predict_noise(unet, scheduler, timestep, latents, text_embeddings, **kwargs)
         latents = scheduler.step(eps, timestep, latents).prev_sample
     return latents
+
+
+def rescale_noise_cfg(noise_cfg: torch.Tensor, noise_pred_text: torch.Tensor, guidance_rescale: float = 0.0):
+    """train_util.py:196-214 ("Common Diffusion Noise Schedules and Sample Steps are Flawed", section 3.4): match the
+    guided prediction's per-sample std to the text branch's, then blend by `guidance_rescale`.  Plain torch on whatever
+    device the predictions live on; the reference's XL loop computes it and discards the result, so it is
+    not on the training path."""
+    dims = list(range(1, noise_pred_text.ndim))
+    std_text = noise_pred_text.std(dim=dims, keepdim=True)
+    std_cfg = noise_cfg.std(dim=list(range(1, noise_cfg.ndim)), keepdim=True)
+    rescaled = noise_cfg * (std_text / std_cfg)
+    return guidance_rescale * rescaled + (1 - guidance_rescale) * noise_cfg
 
 
 def predict_noise_xl(unet, scheduler, timestep, latents, text_embeddings, add_text_embeddings, add_time_ids,
@@ -143,3 +160,37 @@ def get_lr_scheduler(name, optimizer, max_iterations, lr_min, **kwargs):
     if isinstance(optimizer, torch.optim.Optimizer):
         return ctor(optimizer)
     return _LrProxy(optimizer, ctor)
+
+
+def get_random_resolution_in_bucket(bucket_resolution: int = 512):
+    """train_util.py:404-416 (randint's upper bound is exclusive: the bucket size itself is never drawn)."""
+    lo, hi = (bucket_resolution // 2) // 64, bucket_resolution // 64
+    height = torch.randint(lo, hi, (1,)).item() * 64
+    width = torch.randint(lo, hi, (1,)).item() * 64
+    return height, width
+
+
+# ---- the prompt-encoding functions of train_util.py:60-130 live beside the loaders (model_util); same names here ----
+def text_tokenize(tokenizer, prompts):
+    from . import model_util
+    return model_util.text_tokenize(tokenizer, prompts)
+
+
+def text_encode(text_encoder, tokens):
+    from . import model_util
+    return model_util.text_encode(text_encoder, tokens)
+
+
+def encode_prompts(tokenizer, text_encoder, prompts):
+    from . import model_util
+    return model_util.encode_prompts(tokenizer, text_encoder, prompts)
+
+
+def text_encode_xl(text_encoder, tokens, num_images_per_prompt: int = 1):
+    from . import model_util
+    return model_util.text_encode_xl(text_encoder, tokens, num_images_per_prompt)
+
+
+def encode_prompts_xl(tokenizers, text_encoders, prompts, num_images_per_prompt: int = 1):
+    from . import model_util
+    return model_util.encode_prompts_xl(tokenizers, text_encoders, prompts, num_images_per_prompt)

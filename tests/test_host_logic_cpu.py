@@ -344,6 +344,37 @@ def test_shipped_example_config_parses_and_names_the_baseline_workload():
     assert (b["arch"], b["rank"], b["batch"], b["res"]) == ("sd21", c.network.rank, ps[0].batch_size, ps[0].resolution)
 
 
+@pytest.mark.skipif(not reference_available(), reason="reference sources only exist in the build container")
+def test_train_util_surface_is_complete_and_the_small_helpers_equal_the_reference():
+    """Every function the reference's train_util.py defines exists under the same name in leco_b200.train_util, and the
+    ones that are plain arithmetic / RNG draws (apply_noise_offset :36-40, get_initial_latents :43-57, concat_embeddings
+    :133-138, rescale_noise_cfg :196-214, get_add_time_ids :295-330, get_random_resolution_in_bucket :404-416) return
+    the reference's values bit for bit and leave the global generator in the same state."""
+    import inspect
+    import re
+    from types import SimpleNamespace as NS
+    from leco_b200 import train_util as tu
+    from oracle.ref_loader import load_reference
+    ref = load_reference().train_util
+    names = set(re.findall(r"^def (\w+)", open(inspect.getsourcefile(ref)).read(), re.M))
+    assert names and not [n for n in names if not callable(getattr(tu, n, None))]
+    sched = NS(init_noise_sigma=14.6)
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+    u, c = torch.randn(1, 77, 16, generator=g), torch.randn(1, 77, 16, generator=g)
+    calls = [lambda m: m.apply_noise_offset(a, 0.1), lambda m: m.get_initial_latents(sched, 2, 256, 320, 3),
+             lambda m: m.get_random_noise(3, 128, 192), lambda m: m.concat_embeddings(u, c, 3),
+             lambda m: m.rescale_noise_cfg(a, b, guidance_rescale=0.7), lambda m: m.get_add_time_ids(320, 256, dynamic_crops=True),
+             lambda m: torch.tensor(m.get_random_resolution_in_bucket(512)), lambda m: torch.tensor(m.get_random_resolution_in_bucket(384))]
+    for i, f in enumerate(calls):
+        torch.manual_seed(100 + i)
+        want, state_want = f(ref), torch.get_rng_state()
+        torch.manual_seed(100 + i)
+        got, state_got = f(tu), torch.get_rng_state()
+        assert got.shape == want.shape and got.dtype == want.dtype and torch.equal(got, want), i
+        assert torch.equal(state_got, state_want), i
+
+
 def test_optimizer_args_parsing_and_save_cadence():
     """train_lora.py:81-87 ("k=v k=v" through ast.literal_eval) and :292-309 (periodic saves skip i == 0 and the last)."""
     from leco_b200.train_lora import parse_optimizer_args
