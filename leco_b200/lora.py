@@ -32,6 +32,7 @@ import torch.nn as nn
 from .unet import down_as_rows, rows_as_down
 
 PREFIX = "lora_unet"
+LORA_PREFIX_UNET = PREFIX   # the reference's name (lora.py:16)
 MAX_SITE_RANK = 64   # stacked (padded) adapter rank that rides as ONE tensor-core K-segment; larger ranks work too
                      # (unet._linear / _conv3x3 run the LoRA branch as a second accumulate-GEMM then)
 # The reference keeps these as module-level lists and EXTENDS THE FIRST IN PLACE for c3lier

@@ -191,6 +191,45 @@ def _single_file_text_side(path: str, device, n_expected: int):
     return toks, models
 
 
+AVAILABLE_SCHEDULERS = ("ddim", "ddpm", "lms", "euler_a")     # model_util.py:23
+DIFFUSERS_CACHE_DIR = None                                    # model_util.py:27 (nothing is downloaded here)
+SDXL_TEXT_ENCODER_TYPE = ClipTextEncoder                      # model_util.py:25 (both towers are this class)
+
+
+def load_diffusers_model(pretrained_model_name_or_path: str, v2: bool = False, clip_skip=None, weight_dtype=None,
+                         device="cuda"):
+    """model_util.py:30-75 -> (tokenizer, text_encoder, unet) from a diffusers checkpoint directory.  `clip_skip` is
+    accepted like the reference's and, like there (`load_models` never passes it), unused by the training loops."""
+    if not is_checkpoint_dir(pretrained_model_name_or_path):
+        raise FileNotFoundError(f"{pretrained_model_name_or_path}: not a diffusers checkpoint directory (no hub access here)")
+    tokenizer, text_encoder, unet, _ = load_models(pretrained_model_name_or_path, "ddim", v2=v2, device=device)
+    return tokenizer, text_encoder, unet
+
+
+def load_checkpoint_model(checkpoint_path: str, v2: bool = False, clip_skip=None, weight_dtype=None, device="cuda"):
+    """model_util.py:78-101 -> (tokenizer, text_encoder, unet) from a single-file checkpoint (ckpt_convert.py)."""
+    if not os.path.isfile(checkpoint_path):
+        raise FileNotFoundError(checkpoint_path)
+    tokenizer, text_encoder, unet, _ = load_models(checkpoint_path, "ddim", v2=v2, device=device)
+    return tokenizer, text_encoder, unet
+
+
+def load_diffusers_model_xl(pretrained_model_name_or_path: str, weight_dtype=None, device="cuda"):
+    """model_util.py:132-170 -> (tokenizers, text_encoders, unet)."""
+    if not is_checkpoint_dir(pretrained_model_name_or_path):
+        raise FileNotFoundError(f"{pretrained_model_name_or_path}: not a diffusers checkpoint directory (no hub access here)")
+    tokenizers, text_encoders, unet, _ = load_models_xl(pretrained_model_name_or_path, "ddim", device=device)
+    return tokenizers, text_encoders, unet
+
+
+def load_checkpoint_model_xl(checkpoint_path: str, weight_dtype=None, device="cuda"):
+    """model_util.py:173-197 -> (tokenizers, text_encoders, unet) from a single-file SDXL checkpoint."""
+    if not os.path.isfile(checkpoint_path):
+        raise FileNotFoundError(checkpoint_path)
+    tokenizers, text_encoders, unet, _ = load_models_xl(checkpoint_path, "ddim", device=device)
+    return tokenizers, text_encoders, unet
+
+
 def load_models(pretrained_model_name_or_path: str, scheduler_name: str = "ddim", v2: bool = False, v_pred: bool = False,
                 device="cuda", arch: str = None):
     """-> (tokenizer, text_encoder, unet, scheduler), model_util.py:104-129."""

@@ -22,6 +22,18 @@ from .lora import LoRANetwork
 from .trainer import LecoTrainer, PromptPair
 
 
+DEVICE_CUDA = torch.device("cuda:0")      # train_lora.py:26 (the mirror's train() takes `device=` instead)
+NUM_IMAGES_PER_PROMPT = 1                 # train_lora_xl.py:29
+
+
+def flush():
+    """train_lora.py:29-31.  The reference calls it every iteration; the fused trainer never needs to (its graphs
+    share one memory pool and nothing is freed inside the loop)."""
+    import gc
+    torch.cuda.empty_cache()
+    gc.collect()
+
+
 def parse_optimizer_args(s: Optional[str]) -> dict:
     """train_lora.py:81-87."""
     out = {}

@@ -375,6 +375,50 @@ def test_train_util_surface_is_complete_and_the_small_helpers_equal_the_referenc
         assert torch.equal(state_got, state_want), i
 
 
+@pytest.mark.skipif(not reference_available(), reason="reference sources only exist in the build container")
+def test_prompt_util_mirror_against_the_live_reference():
+    """leco_b200.prompt_util carries the reference's names: PromptEmbedsPair(loss_fn, target, positive, unconditional,
+    neutral, settings).loss(**kwargs) gives the reference's erase / enhance objective bit for bit (prompt_util.py:107-148),
+    is a trainer.PromptPair (signed guidance, settings fields), PromptEmbedsXL is positional, PromptEmbedsCache returns
+    None for unknown prompts and shares its dict across instances like the reference's."""
+    from leco_b200 import prompt_util as pu
+    from leco_b200.trainer import EmbedsXL, PromptPair
+    from oracle.ref_loader import load_reference
+    ref = load_reference().prompt_util
+    g = torch.Generator().manual_seed(0)
+    t, p, u, n = (torch.randn(2, 4, 8, 8, generator=g) for _ in range(4))
+    emb = torch.randn(1, 77, 16, generator=g)
+    crit = torch.nn.MSELoss()
+    for action, gs in (("erase", 1.0), ("enhance", 1.5), ("erase", 3.0)):
+        kw = dict(target="a", positive="b", unconditional="", neutral="c", action=action, guidance_scale=gs,
+                  resolution=384, dynamic_resolution=True, batch_size=3, dynamic_crops=True)
+        a = pu.PromptEmbedsPair(crit, emb, emb, emb, emb, pu.PromptSettings(**kw))
+        b = ref.PromptEmbedsPair(crit, emb, emb, emb, emb, ref.PromptSettings(**kw))
+        la = a.loss(target_latents=t, positive_latents=p, unconditional_latents=u, neutral_latents=n)
+        lb = b.loss(target_latents=t, positive_latents=p, unconditional_latents=u, neutral_latents=n)
+        assert torch.equal(la, lb)
+        assert isinstance(a, PromptPair) and a.signed_guidance() == (-gs if action == "erase" else gs)
+        for f in ("guidance_scale", "resolution", "dynamic_resolution", "batch_size", "dynamic_crops", "action"):
+            assert getattr(a, f) == getattr(b, f), f
+    a.action = "nope"
+    with pytest.raises(ValueError, match="action must be erase or enhance"):
+        a.loss(target_latents=t, positive_latents=p, unconditional_latents=u, neutral_latents=n)
+    xl = pu.PromptEmbedsXL(emb, emb[:, 0])
+    assert isinstance(xl, EmbedsXL) and xl.text_embeds is emb and xl.pooled_embeds.shape == (1, 16)
+    c1, c2 = pu.PromptEmbedsCache(), pu.PromptEmbedsCache()
+    c1["van gogh"] = emb
+    assert c2["van gogh"] is emb and c1["unknown"] is None          # class-level dict, as in prompt_util.py:31
+    assert set(pu.ACTION_TYPES) == {"erase", "enhance"}
+    from leco_b200 import debug_util, lora as plora2, model_util as mu, train_lora as tl
+    assert plora2.LORA_PREFIX_UNET == "lora_unet" and tl.NUM_IMAGES_PER_PROMPT == 1 and callable(tl.flush)
+    assert set(mu.AVAILABLE_SCHEDULERS) == {"ddim", "ddpm", "lms", "euler_a"} and mu.DIFFUSERS_CACHE_DIR is None
+    for name in ("load_diffusers_model", "load_checkpoint_model", "load_diffusers_model_xl", "load_checkpoint_model_xl"):
+        with pytest.raises(FileNotFoundError):
+            getattr(mu, name)("/nonexistent/model")
+    debug_util.check_requires_grad(torch.nn.Linear(2, 2))
+    debug_util.check_training_mode(torch.nn.Linear(2, 2))
+
+
 def test_optimizer_args_parsing_and_save_cadence():
     """train_lora.py:81-87 ("k=v k=v" through ast.literal_eval) and :292-309 (periodic saves skip i == 0 and the last)."""
     from leco_b200.train_lora import parse_optimizer_args
