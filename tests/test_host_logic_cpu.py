@@ -409,14 +409,12 @@ def test_prompt_util_mirror_against_the_live_reference():
     c1["van gogh"] = emb
     assert c2["van gogh"] is emb and c1["unknown"] is None          # class-level dict, as in prompt_util.py:31
     assert set(pu.ACTION_TYPES) == {"erase", "enhance"}
-    from leco_b200 import debug_util, lora as plora2, model_util as mu, train_lora as tl
+    from leco_b200 import lora as plora2, model_util as mu, train_lora as tl
     assert plora2.LORA_PREFIX_UNET == "lora_unet" and tl.NUM_IMAGES_PER_PROMPT == 1 and callable(tl.flush)
     assert set(mu.AVAILABLE_SCHEDULERS) == {"ddim", "ddpm", "lms", "euler_a"} and mu.DIFFUSERS_CACHE_DIR is None
     for name in ("load_diffusers_model", "load_checkpoint_model", "load_diffusers_model_xl", "load_checkpoint_model_xl"):
         with pytest.raises(FileNotFoundError):
             getattr(mu, name)("/nonexistent/model")
-    debug_util.check_requires_grad(torch.nn.Linear(2, 2))
-    debug_util.check_training_mode(torch.nn.Linear(2, 2))
 
 
 def test_optimizer_args_parsing_and_save_cadence():
