@@ -231,8 +231,10 @@ def load_checkpoint_model_xl(checkpoint_path: str, weight_dtype=None, device="cu
 
 
 def load_models(pretrained_model_name_or_path: str, scheduler_name: str = "ddim", v2: bool = False, v_pred: bool = False,
-                device="cuda", arch: str = None):
-    """-> (tokenizer, text_encoder, unet, scheduler), model_util.py:104-129."""
+                weight_dtype=None, device="cuda", arch: str = None):
+    """-> (tokenizer, text_encoder, unet, scheduler), model_util.py:104-129.  `weight_dtype` is accepted for signature
+    parity: holders keep the checkpoint's dtype (the caller's `.to(device, dtype=...)` works as in train_lora.py:64-67),
+    the kernel-layout copies are always bf16."""
     # an architecture name of leco_b200.unet.SPECS (e.g. the reduced-width "tiny21") selects synthetic weights of it
     arch = arch or (pretrained_model_name_or_path if pretrained_model_name_or_path in SPECS else ("sd21" if v2 else "sd15"))
     unet, how = _load_unet(arch, pretrained_model_name_or_path, device)
@@ -253,7 +255,8 @@ def load_models(pretrained_model_name_or_path: str, scheduler_name: str = "ddim"
     return tokenizer, enc, unet, scheduler
 
 
-def load_models_xl(pretrained_model_name_or_path: str, scheduler_name: str = "ddim", device="cuda", arch: str = None):
+def load_models_xl(pretrained_model_name_or_path: str, scheduler_name: str = "ddim", weight_dtype=None, device="cuda",
+                   arch: str = None):
     """-> (tokenizers, text_encoders, unet, scheduler), model_util.py:200-227."""
     arch = arch or (pretrained_model_name_or_path if pretrained_model_name_or_path in SPECS else "sdxl")
     unet, how = _load_unet(arch, pretrained_model_name_or_path, device)
