@@ -210,6 +210,11 @@ int leco_adamw_flat(void* params_bf16, float* grads, void* exp_avg, void* exp_av
  *   device array of {int64 src_off, dst_off; int32 rows, cols, r0, c0} (32x32 tiles). */
 int leco_optim_flat(void* params_bf16, float* grads, void* exp_avg, void* exp_avg_sq, int state_is_fp32,
                     const void* mask_u8, const float* hyper16_dev, int64_t n, int zero_grad, void* stream);
+/* leco_optim_flat_master: the same optimizers for `train.precision: float32` (config_util.py:62-83): fp32 master
+ *   parameters and fp32 moments updated as torch does on fp32 tensors (no intermediate rounding); `shadow_bf16` receives
+ *   the bf16 copy of every updated parameter = the operand buffer the GEMM kernels read.  hyper16_dev as above. */
+int leco_optim_flat_master(float* master, void* shadow_bf16, float* grads, float* exp_avg, float* exp_avg_sq,
+                           const void* mask_u8, const float* hyper16_dev, int64_t n, int zero_grad, void* stream);
 int leco_transpose_tiles(const void* src, void* dst, const void* tiles, int n_tiles, void* stream);
 int leco_guided_step(const float* eps_pair, const float* x, float* x_out, float* guided_out, const float* coef_dev,
                      int64_t half_numel, void* stream);

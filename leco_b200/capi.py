@@ -109,6 +109,7 @@ _OPS: list[tuple[str, list]] = [
     ("leco_tn_reduce", [P, L, P, L, P, L, L, I, I, F, I, P]),
     ("leco_adamw_flat", [P, P, P, P, I, P, P, L, I, P]),
     ("leco_optim_flat", [P, P, P, P, I, P, P, L, I, P]),
+    ("leco_optim_flat_master", [P, P, P, P, P, P, P, L, I, P]),
     ("leco_transpose_tiles", [P, P, P, I, P]),
     ("leco_set_deterministic", [I]),
     ("leco_guided_step", [P, P, P, P, P, L, P]),

@@ -272,6 +272,55 @@ __global__ void optim_flat_kernel(__nv_bfloat16* __restrict__ p, float* __restri
   }
 }
 
+// fp32 training precision (`train.precision: float32`, config_util.py:62-83; the notebook's setting): the adapters are
+// fp32 MASTER parameters with fp32 moments — torch.optim.AdamW / Adam / lion_pytorch on fp32 tensors, no intermediate
+// rounding — and every step also writes the bf16 operand copy the tensor-core kernels read (`shadow`).
+__global__ void optim_flat_master_kernel(float* __restrict__ p, __nv_bfloat16* __restrict__ shadow,
+                                         float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                         const uint8_t* __restrict__ mask, const float* __restrict__ hyper,
+                                         long long n, int zero_grad) {
+  pdl_entry();
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], step = hyper[5],
+              gs = hyper[6];
+  const int mode = (int)hyper[7];
+  float step_size = hyper[8], bc2_sqrt = hyper[9], decay = hyper[10], omb1 = hyper[11], omb2 = hyper[12];
+  if (step_size == 0.f) step_size = lr / (1.0f - powf(b1, step));
+  if (bc2_sqrt == 0.f) bc2_sqrt = sqrtf(1.0f - powf(b2, step));
+  if (decay == 0.f) decay = 1.0f - lr * wd;
+  if (omb1 == 0.f) omb1 = 1.0f - b1;
+  if (omb2 == 0.f) omb2 = 1.0f - b2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (mask && !mask[i]) {
+      if (zero_grad) g[i] = 0.f;
+      continue;
+    }
+    float grad = g[i] * gs;
+    float w = p[i];
+    const float m0 = m[i];
+    if (mode == 2) {              // lion_pytorch.update_fn
+      if (wd != 0.f) w *= decay;
+      const float u = fmaf(omb1, grad, m0 * b1);
+      w -= lr * ((u > 0.f) ? 1.f : ((u < 0.f) ? -1.f : 0.f));
+      m[i] = fmaf(omb2, grad, m0 * b2);
+    } else {
+      if (mode == 1) {            // torch.optim.Adam: L2 decay enters the gradient
+        if (wd != 0.f) grad = fmaf(wd, w, grad);
+      } else if (wd != 0.f) {     // AdamW: decoupled decay
+        w *= decay;
+      }
+      const float mi = m0 + omb1 * (grad - m0);          // exp_avg.lerp_(grad, 1 - beta1)
+      const float vi = fmaf(omb2 * grad, grad, v[i] * b2);
+      m[i] = mi;
+      v[i] = vi;
+      w -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    }
+    p[i] = w;
+    shadow[i] = __float2bfloat16(w);
+    if (zero_grad) g[i] = 0.f;
+  }
+}
+
 // One launch that transposes every [rows, cols] block listed in `tiles` (32x32 tiles of the adapter operands
 // ad [Kl,K] / bup [N,Kl] of all fused sites) from the flat parameter buffer into the flat transposed buffer:
 // the backward GEMMs need ad^T / bup^T, which only change at the optimizer step.
@@ -464,6 +513,20 @@ extern "C" int leco_optim_flat(void* params_bf16, float* grads, void* exp_avg, v
                                const void* mask_u8, const float* hyper16_dev, int64_t n, int zero_grad, void* stream) {
   LECO_REQUIRE(params_bf16 && grads && exp_avg && exp_avg_sq && hyper16_dev && n > 0, "leco_optim_flat: null / empty");
   return launch_optim(params_bf16, grads, exp_avg, exp_avg_sq, state_is_fp32, mask_u8, hyper16_dev, 16, n, zero_grad, stream);
+}
+
+extern "C" int leco_optim_flat_master(float* master, void* shadow_bf16, float* grads, float* exp_avg, float* exp_avg_sq,
+                                      const void* mask_u8, const float* hyper16_dev, int64_t n, int zero_grad,
+                                      void* stream) {
+  LECO_REQUIRE(master && shadow_bf16 && grads && exp_avg && exp_avg_sq && hyper16_dev && n > 0,
+               "leco_optim_flat_master: null / empty");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  count_launch();
+  LECO_LAUNCH(optim_flat_master_kernel, (int)blocks, 256, 0, STREAM(stream), master, BFW(shadow_bf16), grads, exp_avg,
+              exp_avg_sq, reinterpret_cast<const uint8_t*>(mask_u8), hyper16_dev, (long long)n, zero_grad);
+  LECO_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int leco_transpose_tiles(const void* src, void* dst, const void* tiles, int n_tiles, void* stream) {

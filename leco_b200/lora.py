@@ -19,6 +19,12 @@ site, see unet.LoraSite); every `lora_down.weight` / `lora_up.weight` Parameter 
 into it.  Consequences: the forward needs no packing, the backward accumulates straight
 into a flat fp32 gradient buffer, AdamW is one fused kernel over the flat buffer
 (`FlatAdamW`) and data-parallel training all-reduces that one buffer.
+
+`network.to(device, dtype=torch.float32)` (`train.precision: float32`, the notebook's setting) keeps the Parameters as
+views of a flat fp32 MASTER buffer instead; the bf16 operand buffer is then a copy the optimizer kernel rewrites with
+every step (`leco_optim_flat_master`) and `FlatState.refresh_transposed` re-derives after any other in-place edit.
+The tensor cores still compute on bf16 operands with fp32 accumulation — fp32 here is the precision of the adapter
+weights, their gradients and the optimizer state, not of the UNet arithmetic.
 """
 from __future__ import annotations
 
@@ -211,11 +217,20 @@ class LoRANetwork(nn.Module):
             raise NotImplementedError(
                 f"leco_b200: {len(self.unet_loras) - covered} adapters sit on layers without a fused engine site")
         dev, dt = p0.device, p0.dtype
-        st = FlatState(torch.zeros(total, device=dev, dtype=dt), torch.zeros(total + 8, device=dev, dtype=torch.float32),
-                       torch.zeros(total, device=dev, dtype=torch.uint8))
+        if dt not in (torch.bfloat16, torch.float32):
+            raise NotImplementedError(
+                f"leco_b200: adapters in {dt} are not supported — use network.to(device, dtype=torch.bfloat16) "
+                "(train.precision: bfloat16, every example config) or torch.float32 (fp32 master adapters); the "
+                "reference's README calls float16 unstable")
+        master = torch.zeros(total, device=dev, dtype=torch.float32) if dt == torch.float32 else None
+        st = FlatState(torch.zeros(total, device=dev, dtype=torch.bfloat16),
+                       torch.zeros(total + 8, device=dev, dtype=torch.float32),
+                       torch.zeros(total, device=dev, dtype=torch.uint8), master=master)
+        home = st.params if master is None else master      # where the Parameters live
         for s, (off, kl) in zip(sites, offsets):
             na, nb = kl * s.k_in, s.n_total * kl
-            ad, bup = st.params[off:off + na].view(kl, s.k_in), st.params[off + na:off + na + nb].view(s.n_total, kl)
+            op_ad, op_bup = st.params[off:off + na].view(kl, s.k_in), st.params[off + na:off + na + nb].view(s.n_total, kl)
+            ad, bup = home[off:off + na].view(kl, s.k_in), home[off + na:off + na + nb].view(s.n_total, kl)
             g_ad, g_bup = st.grads[off:off + na].view(kl, s.k_in), st.grads[off + na:off + na + nb].view(s.n_total, kl)
             m_ad, m_bup = st.mask[off:off + na].view(kl, s.k_in), st.mask[off + na:off + na + nb].view(s.n_total, kl)
             k0 = 0
@@ -230,7 +245,7 @@ class LoRANetwork(nn.Module):
                 m_ad[k0:k0 + r] = 1
                 m_bup[n0:n0 + n, k0:k0 + r] = 1
                 k0 += r
-            s.bind_native(ad, bup, g_ad, g_bup)
+            s.bind_native(op_ad, op_bup, g_ad, g_bup, home_ptr=ad.data_ptr())
         st.n_real = int(st.mask.sum().item())
         st.build_transposed(sites, offsets)
         self.flat = st
@@ -259,13 +274,15 @@ class LoRANetwork(nn.Module):
 
 
 class FlatState:
-    """Flat adapter storage: bf16 params, fp32 grads, uint8 mask (1 = a real LoRA element, 0 = operand
-    padding / off-block zero that must never be updated).  `grads` is a view of `grads_ext`, which carries one more
-    fp32 slot (`loss_slot`) so that data-parallel training reduces gradient and loss in ONE all-reduce."""
+    """Flat adapter storage: bf16 params (the GEMM operands), fp32 grads, uint8 mask (1 = a real LoRA element, 0 =
+    operand padding / off-block zero that must never be updated).  `grads` is a view of `grads_ext`, which carries one
+    more fp32 slot (`loss_slot`) so that data-parallel training reduces gradient and loss in ONE all-reduce.
+    `master` (fp32, same layout) exists for a float32 network: the Parameters are views of it and `params` is its
+    bf16 copy."""
 
-    def __init__(self, params, grads_ext, mask):
+    def __init__(self, params, grads_ext, mask, master=None):
         n = params.numel()
-        self.params, self.grads_ext, self.mask = params, grads_ext, mask
+        self.params, self.grads_ext, self.mask, self.master = params, grads_ext, mask, master
         self.grads = grads_ext[:n]
         self.loss_slot = grads_ext[n:n + 1]
         self.n_real = 0
@@ -290,10 +307,23 @@ class FlatState:
         self._tiles = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(self.params.device)
         self.refresh_transposed()
 
+    @property
+    def home(self):
+        """The buffer the Parameters are views of (what an optimizer updates, what save_weights reads)."""
+        return self.params if self.master is None else self.master
+
+    def refresh_operands(self):
+        """float32 network: re-derive the bf16 operand buffer from the fp32 master (one launch).  A no-op for a bf16
+        network, whose Parameters ARE the operands."""
+        if self.master is not None:
+            from . import ops
+            ops.cast_f32_to_bf16(self.master, out=self.params)
+
     def refresh_transposed(self):
-        """Bring every site's (ad^T, bup^T) up to date with the parameters: ONE kernel launch.  Called before every
-        pass that differentiates (LecoTrainer.iteration, EngineUNet.forward under autograd), so in-place parameter
-        edits by any optimizer / loader are picked up."""
+        """Bring every site's operands and (ad^T, bup^T) up to date with the parameters: one kernel launch (two for a
+        float32 network).  Called before every pass that differentiates (LecoTrainer.iteration, EngineUNet.forward
+        under autograd), so in-place parameter edits by any optimizer / loader are picked up."""
+        self.refresh_operands()
         if self.params_t is not None:
             from . import ops
             ops.transpose_tiles(self.params, self.params_t, self._tiles, self._n_tiles)
@@ -307,7 +337,8 @@ class FlatOptimizer:
     form — torch.optim.AdamW / torch.optim.Adam / lion_pytorch.Lion — as ONE fused kernel over the flat LoRA buffer.
     Optimizer state lives in the parameter dtype like the reference's (`network.to(dtype)` precedes the optimizer,
     train_lora.py:78-89) and the kernel then rounds where torch's foreach implementation rounds; `state_fp32=True`
-    keeps fp32 moments instead (no intermediate rounding).  `param_groups[0]["lr"]` is read at every step, so any
+    keeps fp32 moments instead (no intermediate rounding); a float32 network (fp32 master parameters) always has fp32
+    moments and is stepped as torch steps fp32 tensors.  `param_groups[0]["lr"]` is read at every step, so any
     torch.optim.lr_scheduler-style driver works (train_lora.py:281)."""
 
     def __init__(self, flat: FlatState, name: str = "adamw", lr=1e-3, betas=None, eps=1e-8, weight_decay=None,
@@ -323,12 +354,12 @@ class FlatOptimizer:
         if weight_decay is None:
             weight_decay = 1e-2 if name == "adamw" else 0.0
         self.flat = flat
-        sd = torch.float32 if state_fp32 else flat.params.dtype
+        sd = torch.float32 if (state_fp32 or flat.master is not None) else flat.params.dtype
         self.exp_avg = torch.zeros_like(flat.params, dtype=sd)
         self.exp_avg_sq = torch.zeros_like(flat.params, dtype=sd) if self.mode != 2 else self.exp_avg
         self.step_count = 0
         self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
-        self.param_groups = [dict(self.defaults, params=[flat.params])]
+        self.param_groups = [dict(self.defaults, params=[flat.home])]
         self.hyper = torch.zeros(16, device=flat.params.device, dtype=torch.float32)
 
     @property
@@ -350,8 +381,12 @@ class FlatOptimizer:
         # pageable source: the copy is staged before this call returns, so the host values can change
         self.hyper.copy_(torch.tensor([lr, b1, b2, eps, wd, float(t), grad_scale, float(self.mode),
                                        lr / bc1, bc2 ** 0.5, 1 - lr * wd, 1 - b1, 1 - b2, 0, 0, 0], dtype=torch.float32))
-        ops.optim_flat(self.flat.params, self.flat.grads, self.exp_avg, self.exp_avg_sq, self.flat.mask, self.hyper,
-                       zero_grad=True)
+        if self.flat.master is not None:     # float32 network: fp32 master + moments, bf16 operands rewritten in-pass
+            ops.optim_flat_master(self.flat.master, self.flat.params, self.flat.grads, self.exp_avg, self.exp_avg_sq,
+                                  self.flat.mask, self.hyper, zero_grad=True)
+        else:
+            ops.optim_flat(self.flat.params, self.flat.grads, self.exp_avg, self.exp_avg_sq, self.flat.mask, self.hyper,
+                           zero_grad=True)
 
     def zero_grad(self):
         self.flat.grads.zero_()

@@ -477,6 +477,16 @@ def optim_flat(params, grads, exp_avg, exp_avg_sq, mask, hyper16, zero_grad=True
                                       params.numel(), int(zero_grad), _stream()), "leco_optim_flat")
 
 
+def optim_flat_master(master, shadow, grads, exp_avg, exp_avg_sq, mask, hyper16, zero_grad=True):
+    """leco_optim_flat_master: fp32 master parameters + fp32 moments, bf16 operand copy written in the same pass."""
+    assert hyper16.numel() >= 16 and hyper16.dtype == torch.float32
+    assert master.dtype == exp_avg.dtype == exp_avg_sq.dtype == torch.float32 and shadow.dtype == BF16
+    assert master.numel() == shadow.numel() == exp_avg.numel()
+    capi.check(_lib().leco_optim_flat_master(_ptr(master), _ptr(shadow), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq),
+                                             _ptr(mask), _ptr(hyper16), master.numel(), int(zero_grad), _stream()),
+               "leco_optim_flat_master")
+
+
 def transpose_tiles(src_flat, dst_flat, tiles, n_tiles):
     capi.check(_lib().leco_transpose_tiles(_ptr(src_flat), _ptr(dst_flat), _ptr(tiles), int(n_tiles), _stream()),
                "leco_transpose_tiles")
@@ -534,8 +544,9 @@ def axpby(x, y, a: float, b: float):
     return out
 
 
-def cast_f32_to_bf16(x):
-    y = torch.empty(x.shape, device=x.device, dtype=BF16)
+def cast_f32_to_bf16(x, out=None):
+    y = torch.empty(x.shape, device=x.device, dtype=BF16) if out is None else out
+    assert x.dtype == torch.float32 and y.dtype == BF16 and y.numel() == x.numel() and x.is_contiguous() and y.is_contiguous()
     capi.check(_lib().leco_cast_f32_to_bf16(_ptr(x), _ptr(y), x.numel(), _stream()), "leco_cast")
     return y
 

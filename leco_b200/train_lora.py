@@ -105,9 +105,12 @@ def train(config, prompts, *, device="cuda", rank: int = 0, world_size: int = 1,
     save_path = Path(config.save.path)
     weight_dtype = config_util.parse_precision(config.train.precision)
     save_weight_dtype = config_util.parse_precision(config.train.precision)      # sic
-    if weight_dtype != torch.bfloat16:
-        raise NotImplementedError("leco_b200 kernels run the UNet in bf16 (train.precision: bfloat16); the reference's "
-                                  "README calls fp16 unstable and fp32 is the CPU-oracle configuration")
+    if weight_dtype == torch.float16:
+        raise NotImplementedError("train.precision: float16 is not supported (the reference's README calls it unstable); "
+                                  "use bfloat16 (every example config) or float32")
+    # bfloat16: adapters, gradients' rounding and optimizer state in bf16 like the reference's bf16 run (train_lora.py:78-89).
+    # float32 (the notebook's setting): fp32 master adapters + fp32 optimizer state, saved as fp32; the frozen UNet still
+    # runs on the bf16 tensor cores with fp32 accumulation (leco_b200.lora module docstring).
     if xl:
         tokenizer, text_encoder, unet, scheduler = model_util.load_models_xl(
             config.pretrained_model.name_or_path, scheduler_name=config.train.noise_scheduler, device=device)

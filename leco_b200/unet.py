@@ -309,14 +309,18 @@ class LoraSite:
         self.g_ad = self.g_bup = None
         self._versions = None
         self._native = False
+        self._home_ptr = None
         self.ranks = None
         self.static_t = None   # (ad^T, bup^T) static views (leco_b200.lora.FlatState.build_transposed)
         self.flat_state = None
 
-    def bind_native(self, ad, bup, g_ad, g_bup):
+    def bind_native(self, ad, bup, g_ad, g_bup, home_ptr=None):
         """The adapter Parameters are views of `ad`/`bup` (leco_b200.lora flat layout): no packing,
-        gradients accumulate straight into the flat fp32 buffer."""
+        gradients accumulate straight into the flat fp32 buffer.  For a float32 network the Parameters are views of
+        the fp32 master instead (`home_ptr` = where this site's first Parameter starts there) and `ad`/`bup` are the
+        bf16 copies FlatState keeps current."""
         self.ad, self.bup, self.g_ad, self.g_bup = ad, bup, g_ad, g_bup
+        self._home_ptr = ad.data_ptr() if home_ptr is None else home_ptr
         self.ranks = [a.lora_down.weight.shape[0] for a in self.adapters()]
         self._native = True
 
@@ -343,7 +347,7 @@ class LoraSite:
 
     def refresh(self, ads, device, dtype):
         if self._native:
-            if ads[0].lora_down.weight.data_ptr() == self.ad.data_ptr():
+            if ads[0].lora_down.weight.data_ptr() == self._home_ptr:
                 return self.ad, self.bup
             self._native = False  # parameters were re-homed (e.g. .to()): fall back to packing
             self.ad = self.bup = self.g_ad = self.g_bup = None
@@ -1012,6 +1016,9 @@ class EngineUNet(nn.Module):
                     params += [a.lora_down.weight, a.lora_up.weight]
             eps = _EngineFn.apply(self, x_in, t, ctx2d, added_cond_kwargs, sites, *params)
         else:
+            # a float32 network's operands are a bf16 COPY of its Parameters: bring it up to date (whoever stepped them)
+            for fs in {id(st.flat_state): st.flat_state for st in sites if st.flat_state is not None}.values():
+                fs.refresh_operands()
             eps = self.run(x_in, t, ctx2d, added_cond_kwargs, None)
         return SimpleNamespace(sample=eps.to(sample.dtype))
 

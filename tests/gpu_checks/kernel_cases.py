@@ -374,6 +374,73 @@ def case_optimizers():
     return _merge(res)
 
 
+def case_optimizers_master():
+    """leco_optim_flat_master (`train.precision: float32`: fp32 master adapters + fp32 moments) vs the reference's
+    optimizer objects on fp32 parameters — torch.optim.AdamW / Adam and the lion_pytorch rule — to fp32 rounding, and
+    the bf16 operand copy it writes in the same pass == the master rounded to bf16, exactly."""
+    import torch
+    from leco_b200 import lora as plora
+    res = {}
+    n = 200000
+    g32 = [_rand((n,), 0.01 * (1 + s), 40 + s, torch.float32) for s in range(6)]
+    mask = (torch.rand(n, generator=torch.Generator().manual_seed(3)) < 0.9).to(torch.uint8).cuda()
+    p_init = _rand((n,), 0.05, 3, torch.float32)
+
+    def ours(name, steps, gscale=1.0, **kw):
+        master = p_init.clone()
+        flat = plora.FlatState(master.bfloat16(), torch.zeros(n + 8, device="cuda"), mask, master=master)
+        opt = plora.FlatOptimizer(flat, name, **kw)
+        assert opt.exp_avg.dtype == torch.float32 and opt.param_groups[0]["params"][0] is master
+        for s in range(steps):
+            flat.grads.copy_(g32[s] / gscale)
+            opt.step(grad_scale=gscale)
+        assert float(flat.grads.abs().max()) == 0.0      # zero_grad
+        return flat
+
+    def theirs(make, steps):
+        pt = torch.nn.Parameter(p_init.clone())
+        opt = make([pt])
+        for s in range(steps):
+            pt.grad = g32[s] * mask
+            opt.step()
+        return torch.where(mask.bool(), pt.data, p_init)
+
+    def lion_ref(steps, lr=1e-4, b1=0.9, b2=0.99, wd=0.0):
+        p = p_init.clone()
+        m = torch.zeros_like(p)
+        for s in range(steps):
+            g = g32[s]
+            p.mul_(1 - lr * wd)
+            upd = m.clone().mul_(b1).add(g, alpha=1 - b1).sign_()
+            p.add_(upd, alpha=-lr)
+            m.mul_(b2).add_(g, alpha=1 - b2)
+        return torch.where(mask.bool(), p, p_init)
+
+    for tag, name, kw, ref in (
+            ("adamw", "adamw", dict(lr=1e-3), lambda: theirs(lambda ps: torch.optim.AdamW(ps, lr=1e-3), 6)),
+            ("adamw_wd", "adamw", dict(lr=1e-4, weight_decay=0.1),
+             lambda: theirs(lambda ps: torch.optim.AdamW(ps, lr=1e-4, weight_decay=0.1), 6)),
+            ("adam_wd", "adam", dict(lr=1e-3, weight_decay=0.01),
+             lambda: theirs(lambda ps: torch.optim.Adam(ps, lr=1e-3, weight_decay=0.01), 6)),
+            ("lion_wd", "lion", dict(lr=1e-4, weight_decay=0.1), lambda: lion_ref(6, wd=0.1))):
+        flat = ours(name, 6, **kw)
+        want = ref()
+        # the update itself (lr-sized), not the 0.05-sized weights, is what must agree: error relative to the total movement.
+        # lion's sign() may flip where |u| sits at fp32 rounding level: a 1e-3 fraction of full-step disagreements is allowed
+        moved = (want - p_init).abs().max().item()
+        err = (flat.master - want).abs()
+        rel = (err.max().item() / moved) if name != "lion" else float((err > 0.1 * moved).float().mean().item())
+        shadow_exact = bool(torch.equal(flat.params, flat.master.bfloat16()))
+        untouched = bool(torch.equal(flat.master[~mask.bool()], p_init[~mask.bool()]))
+        res[f"{tag}_fp32_master"] = {"rel": rel, "ok": rel < 1e-3 and shadow_exact and untouched, "shadow_exact": shadow_exact,
+                                     "masked_untouched": untouched, "max_abs_err": err.max().item(), "ref_absmax": moved}
+    a = ours("adamw", 4, gscale=0.5, lr=1e-3)
+    b = ours("adamw", 4, gscale=1.0, lr=1e-3)
+    d = (a.master - b.master).abs().max().item()
+    res["grad_scale"] = {"rel": d, "ok": d < 1e-7, "max_abs_err": d, "ref_absmax": 1.0}
+    return _merge(res)
+
+
 def case_transpose_tiles():
     """FlatState.refresh_transposed: every site's static (ad^T, bup^T) equals the transposed operand, exactly."""
     import torch
@@ -744,6 +811,7 @@ CASES = [
     ("elementwise", case_elementwise, {}),
     ("training_kernels", case_training_kernels, {}),
     ("optimizers", case_optimizers, {}),
+    ("optimizers_master", case_optimizers_master, {}),
     ("sched_step", case_sched_step, {}),
     ("transpose_tiles", case_transpose_tiles, {}),
     ("determinism", case_determinism, {}),

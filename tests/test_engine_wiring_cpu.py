@@ -255,3 +255,121 @@ def test_reference_loop_body_on_the_engine_equals_the_oracle_iteration():
     num = sum((x - y).pow(2).sum().item() for x, y in zip(ua, ub)) ** 0.5
     den = sum(y.pow(2).sum().item() for y in ub) ** 0.5
     assert den > 0 and num / den < 2e-2, num / den
+
+
+def _stub_flat_kernels(monkeypatch):
+    """bind_flat / FlatState call three kernels through leco_b200.ops; on the CPU they are replaced by their documented
+    semantics (include/leco_b200.h: leco_transpose_tiles, leco_cast_f32_to_bf16) so the host-side bookkeeping — which
+    buffer the Parameters live in, what the kernels are handed — can be checked without a GPU."""
+    import struct
+    from leco_b200 import ops
+
+    def transpose_tiles(src, dst, tiles, n_tiles):
+        raw = bytes(tiles.cpu().numpy().tobytes())
+        seen = set()
+        for i in range(n_tiles):
+            so, do, rows, cols, _, _ = struct.unpack_from("<qqiiii", raw, 32 * i)
+            if (so, rows, cols) in seen:
+                continue
+            seen.add((so, rows, cols))
+            dst[do:do + rows * cols].copy_(src[so:so + rows * cols].view(rows, cols).t().reshape(-1))
+
+    def cast_f32_to_bf16(x, out=None):
+        y = x.bfloat16()
+        if out is None:
+            return y
+        out.copy_(y)
+        return out
+
+    monkeypatch.setattr(ops, "transpose_tiles", transpose_tiles)
+    monkeypatch.setattr(ops, "cast_f32_to_bf16", cast_f32_to_bf16)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bfloat16", "float32_master"])
+def test_flat_layout_bookkeeping(monkeypatch, dtype):
+    """leco_b200.lora.bind_flat on the c3lier topology (linear, 1x1 and 3x3 adapters, fused q/k/v sites): Parameters
+    become views of ONE flat buffer — the bf16 operand buffer for a bf16 network, the fp32 master for a float32 network
+    (`train.precision: float32`) whose bf16 operand copy is re-derived before every pass — values, forward, gradients and
+    the transposed operands unchanged by the re-homing."""
+    import leco_b200.lora as plora
+    _stub_flat_kernels(monkeypatch)
+    arch = "tiny15"
+    eng = _engine(arch, build_unet(arch))
+    x, ctx, _ = _inputs(arch, n=2, hw=8)
+    t = torch.tensor(261)
+    saved = list(plora.DEFAULT_TARGET_REPLACE)
+    try:
+        plora.DEFAULT_TARGET_REPLACE += plora.UNET_TARGET_REPLACE_MODULE_CONV
+        torch.manual_seed(11)
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = plora.LoRANetwork(eng, rank=4, multiplier=1.0, alpha=1.0)
+    finally:
+        plora.DEFAULT_TARGET_REPLACE[:] = saved
+    g = torch.Generator().manual_seed(2)
+    for l in net.unet_loras:
+        l.lora_up.weight.data = (torch.randn(l.lora_up.weight.shape, generator=g) * 0.05)
+    net.to(dtype=dtype)
+    for l in net.unet_loras:        # bf16-representable values: the operand copy of the float32 network is then exact
+        l.lora_down.weight.data = l.lora_down.weight.data.bfloat16().to(dtype)
+        l.lora_up.weight.data = l.lora_up.weight.data.bfloat16().to(dtype)
+    before = {k: v.detach().clone() for k, v in net.state_dict().items()}
+
+    def loss_and_grads():
+        for p in net.parameters():
+            p.grad = None
+        with net:
+            y = eng(x, t, encoder_hidden_states=ctx).sample
+            (y.float() ** 2).mean().backward()
+        return y.detach(), [p.grad.detach().clone() for p in net.parameters()]
+
+    y0, g0 = loss_and_grads()                 # packing path: no flat layout yet
+    assert net.flat is None and all(gr.dtype == dtype for gr in g0)
+
+    flat = net.bind_flat()
+    assert (flat.master is None) == (dtype == torch.bfloat16)
+    home = flat.home
+    assert home.dtype == dtype and flat.params.dtype == torch.bfloat16 and flat.grads.dtype == torch.float32
+    lo, hi = home.data_ptr(), home.data_ptr() + home.numel() * home.element_size()
+    for k, v in net.state_dict().items():
+        if k.endswith("weight"):
+            assert lo <= v.data_ptr() < hi, k                       # a view of the flat buffer
+        assert torch.equal(v, before[k]), k                          # same values, same shapes
+    assert torch.equal(flat.params, home.bfloat16())                 # what the kernels read
+    assert int(flat.mask.sum()) == sum(p.numel() for p in net.parameters()) == flat.n_real
+    assert torch.equal(home[flat.mask == 0], torch.zeros_like(home[flat.mask == 0]))   # operand padding stays zero
+    for s in eng.lora_sites():
+        if s.adapters() is not None:
+            assert s._native and s.ad.dtype == torch.bfloat16
+            assert torch.equal(s.static_t[0], s.ad.t()) and torch.equal(s.static_t[1], s.bup.t())
+
+    y1, g1 = loss_and_grads()                 # native path: operands and fp32 gradient accumulators inside the flat buffers
+    assert all(s._native for s in eng.lora_sites() if s.adapters() is not None)      # still bound after a pass
+    assert torch.allclose(y1, y0, rtol=1e-4, atol=1e-5)
+    for a, b in zip(g1, g0):
+        assert a.dtype == dtype
+        assert torch.allclose(a.float(), b.float(), rtol=2e-2, atol=1e-6 + 1e-2 * b.float().abs().max().item())
+
+    # an in-place edit by ANY optimizer (here: by hand) reaches the next pass, with or without autograd
+    with torch.no_grad():
+        net.unet_loras[0].lora_up.weight.add_(0.25)
+        net.unet_loras[-1].lora_down.weight.mul_(2.0)
+        with net:
+            y2 = eng(x, t, encoder_hidden_states=ctx).sample
+    assert torch.equal(flat.params, home.bfloat16())
+    assert not torch.allclose(y2, y1)
+    assert torch.equal(net.unet_loras[0].lora_up.weight, before[net.unet_loras[0].lora_name + ".lora_up.weight"] + 0.25)
+
+    # the optimizer object steps the buffer the Parameters live in, with fp32 moments for a float32 network
+    opt = plora.FlatOptimizer(flat, "adamw", lr=1e-3)
+    assert opt.param_groups[0]["params"][0] is home
+    assert opt.exp_avg.dtype == (torch.float32 if dtype == torch.float32 else torch.bfloat16)
+
+
+def test_flat_layout_rejects_float16_adapters(monkeypatch):
+    import leco_b200.lora as plora
+    _stub_flat_kernels(monkeypatch)
+    eng = _engine("tiny21", build_unet("tiny21"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = plora.LoRANetwork(eng, rank=4).to(dtype=torch.float16)
+    with pytest.raises(NotImplementedError, match="float16"):
+        net.bind_flat()

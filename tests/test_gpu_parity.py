@@ -72,19 +72,23 @@ def test_engine_not_worse_than_reference_numerics():
     assert e_engine < 1.5 * e_bf16 + 1e-3, (e_engine, e_bf16)
 
 
-@pytest.mark.parametrize("graphs,state_fp32", [(False, True), (True, True), (True, False)],
-                         ids=["eager", "cuda_graphs", "cuda_graphs_bf16_optimizer_state"])
-def test_leco_iteration_matches_oracle(graphs, state_fp32):
+@pytest.mark.parametrize("graphs,state_fp32,net_fp32", [(False, True, False), (True, True, False), (True, False, False),
+                                                        (True, True, True)],
+                         ids=["eager", "cuda_graphs", "cuda_graphs_bf16_optimizer_state", "cuda_graphs_float32_network"])
+def test_leco_iteration_matches_oracle(graphs, state_fp32, net_fp32):
     """Three full LECO iterations (denoise loop, 4 predictions, erase loss, backward, AdamW) on the GPU
     vs oracle/leco_ref.leco_iteration (fp32 CPU, pinned against the reference's train loop) on the same
     seeds.  Tolerance: measured (bf16 torch execution of the same oracle, __graft_entry__.loss_tolerance).
-    The third variant runs the default / benchmarked optimizer (bf16 moments, the reference's rounding points)."""
+    The third variant runs the default / benchmarked optimizer (bf16 moments, the reference's rounding points); the
+    fourth `train.precision: float32` (fp32 master adapters stepped by leco_optim_flat_master)."""
     import torch
     from __graft_entry__ import engine_trainer, oracle_iterations
     from tests.oracle_cache import cached
     ref = cached("iters_tiny21", lambda: oracle_iterations(3))
     yard = _bf16_yardstick("iters_tiny21", lambda **kw: oracle_iterations(3, **kw))
-    trainer, net = engine_trainer(use_graphs=graphs, state_fp32=state_fp32)
+    trainer, net = engine_trainer(use_graphs=graphs, state_fp32=state_fp32, net_dtype=torch.float32 if net_fp32 else None)
+    if net_fp32:
+        assert net.flat.master is not None and net.unet_loras[0].lora_up.weight.dtype == torch.float32
     torch.manual_seed(7)
     got, ks = [], []
     for _ in range(3):
@@ -99,6 +103,8 @@ def test_leco_iteration_matches_oracle(graphs, state_fp32):
         num += torch.dot(wa, wb).item()
         den += (wa.norm() * wb.norm()).item()
     assert num / den > 0.9, num / den
+    if net_fp32:     # the operands the kernels read are the bf16 copy of the fp32 master, kept current by the optimizer
+        assert torch.equal(net.flat.params, net.flat.master.bfloat16())
 
 
 @pytest.mark.parametrize("graphs", [False, True], ids=["eager", "cuda_graphs"])
@@ -338,11 +344,13 @@ def test_data_parallel_two_gpus_nccl():
     assert res["ok"], res
 
 
-def test_train_driver_runs_an_examples_style_config(tmp_path):
+@pytest.mark.parametrize("precision", ["bfloat16", "float32"])
+def test_train_driver_runs_an_examples_style_config(tmp_path, precision):
     """`leco_b200.train_lora.train(config, prompts)` = the reference's driver (train_lora.py:34-321) on the fused trainer:
     a YAML with exactly the keys of examples/config.yaml / examples/prompts.yaml (architecture swapped for the
     reduced-width twin, lion + cosine as in examples/unreal_config.yaml) trains, follows the cosine LR schedule, writes
-    the periodic and final .safetensors files with the kohya key set, and the saved file loads back."""
+    the periodic and final .safetensors files with the kohya key set, and the saved file loads back.  precision =
+    float32 is the notebook's setting (train.ipynb): fp32 master adapters, saved as fp32 (train_lora.py:55)."""
     import torch
     import yaml
     from leco_b200 import config_util, train_lora
@@ -350,7 +358,7 @@ def test_train_driver_runs_an_examples_style_config(tmp_path):
     cfg = {"prompts_file": str(tmp_path / "prompts.yaml"),
            "pretrained_model": {"name_or_path": "tiny21", "v2": True, "v_pred": True},
            "network": {"type": "lierla", "rank": 4, "alpha": 1.0, "training_method": "full"},
-           "train": {"precision": "bfloat16", "noise_scheduler": "ddim", "iterations": 5, "lr": "1e-4", "optimizer": "lion",
+           "train": {"precision": precision, "noise_scheduler": "ddim", "iterations": 5, "lr": "1e-4", "optimizer": "lion",
                      "optimizer_args": "weight_decay=0.01", "lr_scheduler": "cosine", "max_denoising_steps": 8},
            "save": {"name": "van_gogh", "path": str(tmp_path / "output"), "per_steps": 2, "precision": "bfloat16"},
            "logging": {"use_wandb": False, "verbose": False}, "other": {"use_xformers": True}}
@@ -368,7 +376,8 @@ def test_train_driver_runs_an_examples_style_config(tmp_path):
     assert out == ["van_gogh_2steps.safetensors", "van_gogh_4steps.safetensors", "van_gogh_last.safetensors"] or \
         out == ["van_gogh_2steps.safetensors", "van_gogh_last.safetensors"], out     # i == iterations-1 is skipped
     sd = load_file(str(tmp_path / "output" / "van_gogh_last.safetensors"))
-    assert len(sd) == 192 * 3 and all(v.dtype == torch.bfloat16 for k, v in sd.items() if "lora_" in k.split(".")[-2])
+    want = config_util.parse_precision(precision)
+    assert len(sd) == 192 * 3 and all(v.dtype == want for k, v in sd.items() if "lora_" in k.split(".")[-2])
     up = [v for k, v in sd.items() if k.endswith("lora_up.weight")]
     assert any(float(u.abs().max()) > 0 for u in up)           # lion moved the zero-initialised lora_up
 
@@ -432,19 +441,22 @@ def test_train_driver_from_a_checkpoint_directory(tmp_path, arch):
     assert (tmp_path / "output" / "out_last.safetensors").is_file()
 
 
-def test_reference_loop_body_drives_the_engine_through_the_drop_in_surface():
+@pytest.mark.parametrize("net_fp32", [False, True], ids=["bfloat16", "float32_network"])
+def test_reference_loop_body_drives_the_engine_through_the_drop_in_surface(net_fp32):
     """the reference's loop body — train_lora.py:141-302 as restated statement for statement by
     oracle/leco_ref.leco_iteration, which tests/test_oracle_pinned.py holds bit-equal to the reference's own train() —
     runs UNMODIFIED on the GPU with the engine behind the reference's call surface: `unet(...).sample` inside
     predict_noise / diffusion, `scheduler.step(...).prev_sample`, `with network:`, `loss.backward()`, torch.optim.AdamW
     on the adapters' Parameters (the reference's files themselves do not travel to the GPU box).
-    Same k draws as the fp32 oracle, losses inside the measured bf16 tolerance, adapters move the same way."""
+    Same k draws as the fp32 oracle, losses inside the measured bf16 tolerance, adapters move the same way.
+    float32_network: `train.precision: float32` — torch's AdamW steps fp32 Parameters (views of the flat fp32 master),
+    the engine re-derives its bf16 operands before every pass."""
     import torch
     from __graft_entry__ import dropin_iterations, oracle_iterations
     from tests.oracle_cache import cached
     ref = cached("iters_tiny21", lambda: oracle_iterations(3))
     yard = _bf16_yardstick("iters_tiny21", lambda **kw: oracle_iterations(3, **kw))
-    got = dropin_iterations(3)
+    got = dropin_iterations(3, net_dtype=torch.float32 if net_fp32 else None)
     assert got["k"] == ref["k"]
     assert_losses_close(got["losses"], ref["losses"], yard["losses"])
     num = den = 0.0
