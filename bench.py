@@ -380,6 +380,29 @@ def kernel_rooflines(cfg, dev, burst, how):
     return out
 
 
+def scaling_base(name, dev, k, steps):
+    """One GPU on the per-GPU share of the sharded workload (`name`, = what every rank of an N > 1 run executes minus
+    the all-reduce): latents/s with the latent noise resident in HBM, CUDA events, 3 warm-up iterations."""
+    import torch
+    cfg = CONFIGS[name]
+    lat = cfg["res"] // 8
+    tr, _ = build_trainer(name, cfg, dev, 0, 1, cfg["batch"])
+    for _ in range(3):
+        tr.iteration(fixed_k=k)
+    noise = torch.randn((cfg["batch"], 4, lat, lat), device=dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tr.iteration(fixed_k=k, device_noise=noise)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) / 1000.0
+    return {"workload": config_dict(name, cfg, 1, k, cfg["batch"])["workload"], "name": name, "n_gpus": 1,
+            "value": cfg["batch"] * steps / sec, "unit": "latents/s", "steps": steps, "ms_per_step": 1000.0 * sec / steps,
+            "note": "N > 1 lines run this workload per GPU: scaling efficiency at N = value(N) / (N x this value)"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -500,6 +523,14 @@ def run_ours(args):
             line["allreduce"] = {"device_us_per_step": None if ar_ms is None else 1000.0 * ar_ms,
                                  "bytes": int(net.flat.grads_ext.numel() * 4),
                                  "what": "ONE ncclAllReduce of the flat fp32 LoRA gradient with the loss in its last slot"}
+        if world == 1 and args.config is None and not args.no_scaling_base:
+            # The sharded runs (N > 1) use configs[4]'s per-GPU share (prompt batch 4 per GPU), this N=1 line configs[1]
+            # (prompt batch 2): the like-for-like base of the 1 -> N curve is the configs[4] share on ONE GPU, measured
+            # here after everything else (a failure cannot touch the numbers above).
+            try:
+                line["scaling_base"] = scaling_base(default_workload(2), dev, k, max(3, min(args.steps, 5)))
+            except Exception as e:
+                line["scaling_base"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline and cfg["arch"] != "sdxl":
             # bounded sample: ONE complete iteration of the CPU path at k=1, prompt batch 1
             t_den, t_tot, cores = cpu_reference_iterations(cfg, 1, 1, 1)
@@ -523,6 +554,7 @@ def main():
     ap.add_argument("--k", type=int, default=25, help="fixed number of denoise steps per iteration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
+    ap.add_argument("--no-scaling-base", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
