@@ -96,3 +96,17 @@ def test_both_arms_default_to_the_same_workload_and_idle_ranks_exit_clean():
                         capture_output=True, text=True, timeout=120, cwd=ROOT)
     line = json.loads(pr.stdout.strip().splitlines()[-1])
     assert pr.returncode == 0 and line["impl"] == "reference" and "unavailable" in line
+
+
+def test_committed_scaling_base_is_the_sharded_workload_on_one_gpu():
+    """The N = 1 line (configs[1], prompt batch 2) and the N > 1 lines (configs[4] share, batch 4 per GPU) are different
+    workloads; `scaling_base` in the N = 1 line is the latter on ONE GPU, so the 1 -> N curve has a like-for-like base."""
+    import bench
+    one = json.load(open(os.path.join(ROOT, "profiles", "r2am_bench_scaling_base.json")))
+    two = json.load(open(os.path.join(ROOT, "profiles", "r2aj_bench_2gpu_sd21_b4_final.json")))
+    sb = one["scaling_base"]
+    assert one["config"]["name"] == bench.default_workload(1) and sb["name"] == bench.default_workload(2) == two["config"]["name"]
+    assert sb["n_gpus"] == 1 and sb["unit"] == one["unit"]
+    assert abs(sb["value"] - bench.CONFIGS[sb["name"]]["batch"] * 1000.0 / sb["ms_per_step"]) < 1e-6
+    eff = two["value"] / (two["n_gpus"] * sb["value"])
+    assert 0.9 < eff <= 1.02, eff          # like for like; value(2) / (2 x value(1)) of the mixed workloads would read 1.28
