@@ -101,7 +101,7 @@ class LecoTrainer:
                  hoist_cross_kv: bool = True):
         if network.flat is None:
             raise RuntimeError("LecoTrainer needs the flat LoRA layout: move the network to CUDA first "
-                               "(network.to('cuda', dtype=torch.bfloat16))")
+                               "(network.to('cuda', dtype=torch.bfloat16), or torch.float32 for fp32 master adapters)")
         self.unet, self.network, self.scheduler = unet, network, scheduler
         self.pairs = list(prompt_pairs)
         self.max_steps = max_denoising_steps
