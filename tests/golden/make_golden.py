@@ -112,14 +112,16 @@ other:
 """
 
 
-def run_reference_train(arch: str, iters: int, max_steps: int, v_pred: bool):
+def run_reference_train(arch: str, iters: int, max_steps: int, v_pred: bool, unet=None):
+    """The reference's UNMODIFIED train_lora.train(config, prompts) on the CPU; `model_util.load_models` is the one
+    patched seam and returns `unet` (default: the oracle UNet; tests also pass the engine)."""
     ref = load_reference()
     import importlib
     os.environ.setdefault("WANDB_MODE", "disabled")
     train_lora = importlib.import_module("train_lora")
     assert os.path.abspath(train_lora.__file__).startswith("/root/reference")
     cfg = CONFIGS[arch]
-    unet = build_unet(arch, seed=0)
+    unet = build_unet(arch, seed=0) if unet is None else unet
 
     class _Dummy:
         def to(self, *a, **k):
@@ -213,8 +215,9 @@ def synthetic_embedding_xl(prompt: str, dim: int, pooled_dim: int):
     return torch.randn((1, 77, dim), generator=g), torch.randn((1, pooled_dim), generator=g)
 
 
-def run_reference_train_xl(arch: str, iters: int, max_steps: int):
-    """The reference's unmodified train_lora_xl.train() (train_lora_xl.py:40-385) on the oracle SDXL-topology UNet."""
+def run_reference_train_xl(arch: str, iters: int, max_steps: int, unet=None):
+    """The reference's unmodified train_lora_xl.train() (train_lora_xl.py:40-385) on the oracle SDXL-topology UNet
+    (or on `unet`: tests pass the engine)."""
     ref = load_reference()
     import importlib
     os.environ.setdefault("WANDB_MODE", "disabled")
@@ -222,7 +225,7 @@ def run_reference_train_xl(arch: str, iters: int, max_steps: int):
     assert os.path.abspath(tx.__file__).startswith("/root/reference")
     cfg = CONFIGS[arch]
     pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
-    unet = build_unet(arch, seed=0)
+    unet = build_unet(arch, seed=0) if unet is None else unet
 
     class _Dummy:
         def to(self, *a, **k):

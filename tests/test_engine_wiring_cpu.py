@@ -373,3 +373,35 @@ def test_flat_layout_rejects_float16_adapters(monkeypatch):
         net = plora.LoRANetwork(eng, rank=4).to(dtype=torch.float16)
     with pytest.raises(NotImplementedError, match="float16"):
         net.bind_flat()
+
+
+from oracle.ref_loader import reference_available  # noqa: E402
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference sources only exist in the build container")
+@pytest.mark.parametrize("xl", [False, True], ids=["train_lora", "train_lora_xl"])
+def test_the_reference_train_py_runs_unmodified_on_the_engine(xl):
+    """VERDICT r1 row ns5 with the reference's OWN files: `/root/reference/train_lora.py::train(config, prompts)` — its
+    config / prompt parsing, its `LoRANetwork` (lora.py) patching the engine's tree, its `train_util.diffusion` /
+    `predict_noise`, `PromptEmbedsPair.loss`, `loss.backward()`, torch AdamW, `save_weights` — runs UNMODIFIED with
+    `model_util.load_models` returning the engine (the one binding of INTEGRATION.md section 1; here the torch double in
+    fp32, `train.precision: float32`).  Same k draws, losses and saved adapter file as the same function on the oracle
+    UNet (= the run tests/golden/leco_train_golden.json was made from).  train_lora_xl: `train_lora_xl.py::train` the
+    same way (pooled text embedding + add_time_ids through `added_cond_kwargs`; the harness works around the two
+    reference bugs tests/golden/make_golden.py documents)."""
+    from tests.golden import make_golden as mg
+    arch, iters, max_steps = ("tinyxl", 3, 6) if xl else ("tiny21", 3, 6)
+    run = (lambda **kw: mg.run_reference_train_xl(arch, iters, max_steps, **kw)) if xl else \
+        (lambda **kw: mg.run_reference_train(arch, iters, max_steps, True, **kw))
+    ref_losses, ref_ks, ref_sd, _ = run()
+    losses, ks, sd, _ = run(unet=_engine(arch, build_unet(arch, seed=0)))
+    assert ks == ref_ks and len(losses) == len(ref_losses) == iters
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) <= 2e-4 * abs(b), (losses, ref_losses)
+    assert list(sd) == list(ref_sd) and len(sd) % 3 == 0 and len(sd) >= 3 * 16     # kohya key set in the reference's order
+    num = sum((sd[k].float() - ref_sd[k].float()).pow(2).sum().item() for k in sd if k.endswith("lora_up.weight")) ** 0.5
+    den = sum(ref_sd[k].float().pow(2).sum().item() for k in sd if k.endswith("lora_up.weight")) ** 0.5
+    assert den > 0 and num / den < 2e-2, num / den
+    for k in sd:
+        if k.endswith("lora_down.weight"):
+            assert torch.allclose(sd[k], ref_sd[k], rtol=1e-3, atol=1e-4), k
