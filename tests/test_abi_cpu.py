@@ -65,3 +65,46 @@ def test_argument_errors_come_back_as_codes_not_crashes():
     import pytest
     with pytest.raises(capi.LecoError):
         capi.check(-1, "leco_gemm_bf16")
+
+
+def test_header_is_plain_c_and_a_c_host_can_bind_it(tmp_path):
+    """The boundary is a C ABI (plain pointers and sizes, no C++ / torch types in the signatures): `include/leco_b200.h`
+    compiles as C99, and a C host that includes it, dlopens the library and calls through the declared prototypes gets
+    the version and the error convention (negative code + leco_last_error() text) without a GPU."""
+    import shutil
+    import subprocess
+    import pytest
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(inc, "leco_b200.h")], check=True)
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+#include "leco_b200.h"
+typedef int (*abi_fn)(void);
+typedef const char* (*err_fn)(void);
+typedef int (*opt_fn)(float*, void*, float*, float*, float*, const void*, const float*, int64_t, int, void*);
+int main(int argc, char** argv) {
+  void* h = dlopen(argv[1], RTLD_NOW);
+  if (!h) { fprintf(stderr, "%s\n", dlerror()); return 2; }
+  abi_fn abi = (abi_fn)dlsym(h, "leco_abi_version");
+  err_fn err = (err_fn)dlsym(h, "leco_last_error");
+  opt_fn opt = (opt_fn)dlsym(h, "leco_optim_flat_master");
+  opt_fn same = leco_optim_flat_master;   /* the header's prototype has exactly this type */
+  (void)same;
+  if (!abi || !err || !opt) return 3;
+  int rc = opt(NULL, NULL, NULL, NULL, NULL, NULL, NULL, 0, 1, NULL);
+  printf("%d %d %s\n", abi(), rc, err());
+  return (abi() == 2 && rc < 0 && strstr(err(), "leco_optim_flat_master") != NULL) ? 0 : 1;
+}
+''')
+    exe = tmp_path / "host"
+    # the prototype reference `same = leco_optim_flat_master` needs the symbol at link time: link against the library
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", f"-I{inc}", str(src), "-o", str(exe), "-ldl",
+                    capi.lib_path(), f"-Wl,-rpath,{os.path.dirname(capi.lib_path())}"], check=True)
+    out = subprocess.run([str(exe), capi.lib_path()], capture_output=True, text=True)
+    assert out.returncode == 0, (out.stdout, out.stderr)
